@@ -1,0 +1,160 @@
+/*
+ * optconpy_b200 — C ABI of the B200 (sm_100a) kernels behind the
+ * sadptprj_riclyap_adi interface that highlando/optconpy drives.
+ *
+ * The reference has no FFI of its own: its boundary is the Python module
+ * functions of sadptprj_riclyap_adi.{lin_alg_utils,proj_ric_utils} that
+ * optcont_main.py:13-14 and solve_dae_ric.py:3-4 import.  Each entry point below
+ * names the reference call site(s) whose numerical work it carries.  The Python
+ * shim optconpy_b200/{lin_alg_utils,proj_ric_utils}.py binds these with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ocb_status otherwise;
+ *     ocb_last_error() gives the message of the last failure on this thread.
+ *   - dense blocks are FP64, ROW-major, leading dimension in elements (ld >= k):
+ *     element (i, c) of an (n x k) block is ptr[i*ld + c].
+ *   - sparse matrices are CSR, int32 indices, FP64 values.
+ *   - pointers named d_* are DEVICE pointers (e.g. torch.Tensor.data_ptr()),
+ *     h_* are HOST pointers.  No torch types cross this boundary.
+ *   - stream is a cudaStream_t passed as void*; nothing uses a hidden stream.
+ */
+#ifndef OPTCONPY_B200_H
+#define OPTCONPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    OCB_OK = 0,
+    OCB_ERR_ARG = -1,      /* bad argument */
+    OCB_ERR_CUDA = -2,     /* CUDA runtime error (message has the detail) */
+    OCB_ERR_SINGULAR = -3, /* zero pivot / singular small system */
+    OCB_ERR_NOCONV = -4,   /* Jacobi eigen-solver hit its sweep limit */
+    OCB_ERR_CAPACITY = -5  /* a caller-provided buffer is too small */
+} ocb_status;
+
+const char* ocb_last_error(void);
+int ocb_version(void);
+/* number of kernel launches issued by this library since process start (bench.py: gpu_launches) */
+int64_t ocb_launch_count(void);
+
+/* ---- K2: CSR x dense block ---------------------------------------------------
+ * Y = alpha * S * X + beta * Y,  S (nrows x ncols) CSR, X (ncols x k), Y (nrows x k).
+ * Carries `MT*Zc`, `Mt*V` inside the ADI, `jmat*mic`, `tb_mat.T*Y`
+ * (solve_dae_ric.py:78,149,187; the SpMM of every ADI step). */
+int ocb_spmm(int64_t nrows, int64_t ncols,
+             const int32_t* d_rowptr, const int32_t* d_colidx, const double* d_vals,
+             const double* d_X, int64_t ldx, double* d_Y, int64_t ldy, int64_t k,
+             double alpha, double beta, void* stream);
+
+/* ---- K1: multi-RHS sparse triangular solves on an LU factorisation ------------
+ * Replaces the SuperLU solve behind spsla.factorized(...) that
+ * lau.solve_sadpnt_smw / pru.solve_proj_lyap_stein call once per column
+ * (solve_dae_ric.py:192-194; every ADI step).  The factorisation itself
+ * (Pr*A*Pc = L*U, L unit lower, both CSR on the host) is the separately timed
+ * setup step; ocb_lu_create analyses the dependency levels and uploads. */
+typedef struct ocb_lu ocb_lu;
+
+int ocb_lu_create(ocb_lu** out, int64_t n,
+                  const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
+                  const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
+                  const int32_t* h_perm_r, const int32_t* h_perm_c, void* stream);
+int ocb_lu_destroy(ocb_lu* lu);
+/* info[0..7] = n, nnz(L) strictly lower, nnz(U) incl. diagonal, #levels L, #levels U,
+ *              device bytes held, max level width L, max level width U */
+int ocb_lu_info(const ocb_lu* lu, int64_t* info8);
+/* bytes of device workspace ocb_lu_solve needs for k right-hand sides (0 if the
+ * column panel fits shared memory) */
+int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k);
+/* X[0:nrows_x, 0:k] = (A^-1 [B[0:nrows_b, 0:k]; 0])[0:nrows_x].  B and X may alias. */
+int ocb_lu_solve(const ocb_lu* lu, const double* d_B, int64_t ldb, int64_t nrows_b,
+                 double* d_X, int64_t ldx, int64_t nrows_x, int64_t k,
+                 void* d_ws, int64_t ws_bytes, void* stream);
+
+/* ---- K3: Gram product on FP64 tensor cores (DMMA) -----------------------------
+ * G (ka x kb) = Z^T W over n rows; deterministic (fixed split + ordered reduce).
+ * Carries np.dot(Z.T, M*Z), Z.T*tB, the factored norms
+ * (tests/test_units_compfacres_compress.py:85-86; solve_dae_ric.py:101,183,189). */
+int64_t ocb_gram_ws_bytes(int64_t n, int64_t ka, int64_t kb);
+int ocb_gram(const double* d_Z, int64_t ldz, int64_t ka,
+             const double* d_W, int64_t ldw, int64_t kb, int64_t n,
+             double* d_G, int64_t ldg, void* d_ws, int64_t ws_bytes, void* stream);
+
+/* C (n x kc) = alpha * Z (n x k) * T (k x kc) + beta * C   (DMMA; `Z*V_k`, `Z*(Z^T tB)`) */
+int ocb_tall_gemm(const double* d_Z, int64_t ldz, int64_t n, int64_t k,
+                  const double* d_T, int64_t ldt, int64_t kc,
+                  double* d_C, int64_t ldc, double alpha, double beta, void* stream);
+
+/* ---- K4: small symmetric eigen-decomposition (parallel cyclic Jacobi) ----------
+ * G (k x k, symmetric, destroyed) = V diag(lam) V^T, lam sorted descending,
+ * V row-major with eigenvectors in its columns.  Cooperative launch. */
+int ocb_sym_eig(double* d_G, int64_t ldg, int64_t k, double* d_lam, double* d_V, int64_t ldv,
+                int32_t* h_sweeps, void* stream);
+
+/* ---- K3+K4: pru.compress_Zsvd (solve_dae_ric.py:162; optcont_main.py:498) -------
+ * Zc = Z V_keep with the singular values > thresh, at most kmax (kmax <= 0: no cap;
+ * thresh < 0: no threshold).  Rank-revealing pivoted Cholesky of Z^T Z (relative
+ * stop eta), Jacobi on the r x r core, two tall products.  h_info[0]=kept columns,
+ * [1]=Cholesky rank r, [2]=Jacobi sweeps; d_sigma (optional, >= rmax) gets the
+ * singular values of the core. */
+int64_t ocb_compress_ws_bytes(int64_t n, int64_t K, int64_t rmax);
+int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K,
+                 double thresh, int64_t kmax, double eta, int64_t rmax,
+                 double* d_Zc, int64_t ldzc, int64_t zc_capacity_cols,
+                 double* d_sigma, int64_t* h_info3,
+                 void* d_ws, int64_t ws_bytes, void* stream);
+
+/* ---- K6/K7 + the LR-ADI loop: pru.solve_proj_lyap_stein -------------------------
+ * (tests/test_units_compfacres_compress.py:62-64; called by
+ * pru.proj_alg_ric_newtonadi, solve_dae_ric.py:152-159, optcont_main.py:488-492).
+ * Li-White recurrence on saddle-point solves with per-shift LU handles:
+ *   V_1 = sqrt(-2 mu_1) S_1(W),  V_i = sqrt(mu_i/mu_{i-1}) (V_{i-1} - (mu_i+mu_{i-1}) S_i(Mt V_{i-1})),
+ *   S_i(R) = first NV rows of (A_i - Ue Ve)^-1 [R; 0],  A_i = [[At + mu_i Mt, J^T],[J, 0]].
+ * Low-rank part (optional, m columns): Ue = [d_Ufb (NV x m dense); 0],
+ * Ve = [Vt (m x NV) CSR, 0]  applied by Sherman-Morrison-Woodbury.
+ * Blocks V_i are written side by side into d_Z (NV x ldz), block i at column i*k.
+ * Stops after step i when ||V_i||_F / ||[V_1..V_i]||_F <= reltol or i == maxsteps.
+ * h_relnorms (maxsteps doubles) receives the ratios; *h_steps the number of blocks. */
+int64_t ocb_adi_ws_bytes(int64_t n_sad, int64_t k, int64_t m, int64_t nshifts,
+                         ocb_lu* const* lus);
+int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts,
+                int64_t NV, int64_t NP,
+                const int32_t* d_Mt_rowptr, const int32_t* d_Mt_colidx, const double* d_Mt_vals,
+                const double* d_W, int64_t ldw, int64_t k,
+                const double* d_Ufb, int64_t ldu, int64_t m,
+                const int32_t* d_Vt_rowptr, const int32_t* d_Vt_colidx, const double* d_Vt_vals,
+                int64_t maxsteps, double reltol,
+                double* d_Z, int64_t ldz, int64_t z_capacity_cols,
+                double* h_relnorms, int64_t* h_steps,
+                void* d_ws, int64_t ws_bytes, void* stream);
+
+/* One saddle-point solve with SMW low-rank update: lau.solve_sadpnt_smw
+ * (solve_dae_ric.py:192-194; optcont_main.py:510-514), lau.app_prj_via_sadpnt
+ * (optcont_main.py:405-408).  X (n_sad x k) = (A - Ue Ve)^-1 [B (nrows_b x k); 0]. */
+int64_t ocb_smw_solve_ws_bytes(const ocb_lu* lu, int64_t k, int64_t m);
+int ocb_smw_solve(const ocb_lu* lu, int64_t NV,
+                  const double* d_B, int64_t ldb, int64_t nrows_b, int64_t k,
+                  const double* d_Ufb, int64_t ldu, int64_t m,
+                  const int32_t* d_Vt_rowptr, const int32_t* d_Vt_colidx, const double* d_Vt_vals,
+                  double* d_X, int64_t ldx, int64_t nrows_x,
+                  void* d_ws, int64_t ws_bytes, void* stream);
+
+/* ---- K5: pru.get_mTzzTtb (solve_dae_ric.py:101,183,189; optcont_main.py:505-506) --
+ * Out (NV x m) = alpha * Mt * (Z * (Z^T tB)),  Z (NV x kz), tB (NV x m) dense. */
+int64_t ocb_feedback_ws_bytes(int64_t NV, int64_t kz, int64_t m);
+int ocb_feedback(const int32_t* d_Mt_rowptr, const int32_t* d_Mt_colidx, const double* d_Mt_vals,
+                 int64_t NV, const double* d_Z, int64_t ldz, int64_t kz,
+                 const double* d_tB, int64_t ldb, int64_t m,
+                 double* d_Out, int64_t ldo, double alpha,
+                 void* d_ws, int64_t ws_bytes, void* stream);
+
+/* sum of squares of an (n x k) block -> *d_out (one double); deterministic */
+int ocb_sqnorm(const double* d_X, int64_t ldx, int64_t n, int64_t k, double* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTCONPY_B200_H */

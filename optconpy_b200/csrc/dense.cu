@@ -1,0 +1,457 @@
+// K3 / K4: the dense contractions of the hot path, on the FP64 tensor pipe (DMMA.8x8x4),
+// and the small on-device symmetric eigen-solver.
+//
+//   gram       G = Z^T W            flops 2*n*ka*kb, bytes 8*n*(ka+kb) + 8*ka*kb
+//   tall_gemm  C = Z T              flops 2*n*k*kc,  bytes 8*n*(k+kc)
+//   sym_eig    parallel cyclic two-sided Jacobi, cooperative launch (grid.sync per round)
+//   small_inv  Gauss-Jordan with partial pivoting for the m x m SMW core (m <= 32)
+#include "common.cuh"
+#include <cooperative_groups.h>
+#include <math.h>
+#include <algorithm>
+
+namespace cg = cooperative_groups;
+
+namespace ocb {
+
+// ---------------------------------------------------------------------------------
+// Gram: CTA tile 64 x 64 of G, 8 warps (each 16 x 32 = 2 x 4 DMMA tiles), rows split
+// over blockIdx.z; partial tiles go to a workspace and are summed in fixed order.
+// ---------------------------------------------------------------------------------
+constexpr int GR_TM = 64, GR_TN = 64, GR_RK = 32, GR_LD = 72;  // 72 % 16 == 8: conflict-free frags
+
+__global__ void __launch_bounds__(256) gram_partial_kernel(const double* __restrict__ Z, int64_t ldz,
+                                                          int64_t ka, const double* __restrict__ W,
+                                                          int64_t ldw, int64_t kb, int64_t n,
+                                                          int64_t rows_per_split,
+                                                          double* __restrict__ P /*[split][ka][kb]*/) {
+    __shared__ double Zs[GR_RK * GR_LD];
+    __shared__ double Ws[GR_RK * GR_LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t a0 = (int64_t)blockIdx.x * GR_TM, b0 = (int64_t)blockIdx.y * GR_TN;
+    const int64_t r_beg = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t r_end = min(n, r_beg + rows_per_split);
+    const int m0 = (warp & 3) * 16, n0 = (warp >> 2) * 32;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int64_t r0 = r_beg; r0 < r_end; r0 += GR_RK) {
+        // stage 32 rows x 64 cols of each operand (coalesced 512-byte row segments)
+        for (int e = tid; e < GR_RK * GR_TM; e += 256) {
+            const int rr = e >> 6, cc = e & 63;
+            const int64_t r = r0 + rr;
+            double zv = 0.0, wv = 0.0;
+            if (r < r_end) {
+                if (a0 + cc < ka) zv = __ldg(Z + r * ldz + a0 + cc);
+                if (b0 + cc < kb) wv = __ldg(W + r * ldw + b0 + cc);
+            }
+            Zs[rr * GR_LD + cc] = zv;
+            Ws[rr * GR_LD + cc] = wv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GR_RK / 4; ++kk) {
+            const int kr = kk * 4 + (lane & 3);
+            double af[2], bf[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = Zs[kr * GR_LD + m0 + i * 8 + (lane >> 2)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = Ws[kr * GR_LD + n0 + j * 8 + (lane >> 2)];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+    double* Pz = P + (int64_t)blockIdx.z * ka * kb;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t gr = a0 + m0 + i * 8 + (lane >> 2);
+            const int64_t gc = b0 + n0 + j * 8 + 2 * (lane & 3);
+            if (gr < ka) {
+                if (gc < kb) Pz[gr * kb + gc] = acc[i][j][0];
+                if (gc + 1 < kb) Pz[gr * kb + gc + 1] = acc[i][j][1];
+            }
+        }
+}
+
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ P, int64_t ka,
+                                                         int64_t kb, int nsplit,
+                                                         double* __restrict__ G, int64_t ldg) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ka * kb) return;
+    double s = 0.0;
+    for (int z = 0; z < nsplit; ++z) s += P[(int64_t)z * ka * kb + e];
+    G[(e / kb) * ldg + (e % kb)] = s;
+}
+
+static void gram_plan(int64_t n, int64_t ka, int64_t kb, int* nsplit, int64_t* rps) {
+    const int64_t tiles = ((ka + GR_TM - 1) / GR_TM) * ((kb + GR_TN - 1) / GR_TN);
+    int64_t want = (4 * (int64_t)148 + tiles - 1) / tiles;        // ~4 CTAs per SM in total
+    const int64_t maxsplit = (n + 4 * GR_RK - 1) / (4 * GR_RK);   // >= 128 rows per split
+    want = std::max<int64_t>(1, std::min(want, std::max<int64_t>(1, maxsplit)));
+    int64_t r = (n + want - 1) / want;
+    r = align_up(std::max<int64_t>(r, 1), GR_RK);
+    *rps = r;
+    *nsplit = (int)std::max<int64_t>(1, (n + r - 1) / r);
+}
+
+int gram_impl(const double* Z, int64_t ldz, int64_t ka, const double* W, int64_t ldw, int64_t kb,
+              int64_t n, double* G, int64_t ldg, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    if (ka == 0 || kb == 0) return OCB_OK;
+    int nsplit;
+    int64_t rps;
+    gram_plan(n, ka, kb, &nsplit, &rps);
+    const int64_t need = (int64_t)nsplit * ka * kb * 8;
+    if (!ws || ws_bytes < need) {
+        set_error("gram: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+        return OCB_ERR_CAPACITY;
+    }
+    dim3 grid((unsigned)((ka + GR_TM - 1) / GR_TM), (unsigned)((kb + GR_TN - 1) / GR_TN), nsplit);
+    gram_partial_kernel<<<grid, 256, 0, st>>>(Z, ldz, ka, W, ldw, kb, n, rps, (double*)ws);
+    OCB_LAUNCH_CHECK();
+    gram_reduce_kernel<<<(unsigned)((ka * kb + 255) / 256), 256, 0, st>>>((const double*)ws, ka, kb,
+                                                                         nsplit, G, ldg);
+    OCB_LAUNCH_CHECK();
+    return OCB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// tall_gemm: C (n x kc) = alpha Z (n x k) T (k x kc) + beta C.
+// CTA tile 64 rows x 64 cols, 8 warps (16 x 32 each), inner dimension in chunks of 32.
+// ---------------------------------------------------------------------------------
+constexpr int TG_LDZ = 36;  // 36 % 16 == 4
+
+__global__ void __launch_bounds__(256) tall_gemm_kernel(const double* __restrict__ Z, int64_t ldz,
+                                                       int64_t n, int64_t k,
+                                                       const double* __restrict__ T, int64_t ldt,
+                                                       int64_t kc, double* __restrict__ C,
+                                                       int64_t ldc, double alpha, double beta) {
+    __shared__ double Zs[64 * TG_LDZ];
+    __shared__ double Ts[32 * GR_LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 64, c0 = (int64_t)blockIdx.y * 64;
+    const int m0 = (warp & 3) * 16, n0 = (warp >> 2) * 32;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int64_t k0 = 0; k0 < k; k0 += 32) {
+        for (int e = tid; e < 64 * 32; e += 256) {
+            const int rr = e >> 5, cc = e & 31;
+            double v = 0.0;
+            if (r0 + rr < n && k0 + cc < k) v = __ldg(Z + (r0 + rr) * ldz + k0 + cc);
+            Zs[rr * TG_LDZ + cc] = v;
+        }
+        for (int e = tid; e < 32 * 64; e += 256) {
+            const int rr = e >> 6, cc = e & 63;
+            double v = 0.0;
+            if (k0 + rr < k && c0 + cc < kc) v = __ldg(T + (k0 + rr) * ldt + c0 + cc);
+            Ts[rr * GR_LD + cc] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            double af[2], bf[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                af[i] = Zs[(m0 + i * 8 + (lane >> 2)) * TG_LDZ + kk * 4 + (lane & 3)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                bf[j] = Ts[(kk * 4 + (lane & 3)) * GR_LD + n0 + j * 8 + (lane >> 2)];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t gr = r0 + m0 + i * 8 + (lane >> 2);
+            const int64_t gc = c0 + n0 + j * 8 + 2 * (lane & 3);
+            if (gr < n) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (gc + u < kc) {
+                        double r = alpha * acc[i][j][u];
+                        if (beta != 0.0) r = fma(beta, C[gr * ldc + gc + u], r);
+                        C[gr * ldc + gc + u] = r;
+                    }
+                }
+            }
+        }
+}
+
+int tall_gemm_impl(const double* Z, int64_t ldz, int64_t n, int64_t k, const double* T, int64_t ldt,
+                   int64_t kc, double* C, int64_t ldc, double alpha, double beta, cudaStream_t st) {
+    if (n == 0 || kc == 0) return OCB_OK;
+    dim3 grid((unsigned)((n + 63) / 64), (unsigned)((kc + 63) / 64));
+    tall_gemm_kernel<<<grid, 256, 0, st>>>(Z, ldz, n, k, T, ldt, kc, C, ldc, alpha, beta);
+    OCB_LAUNCH_CHECK();
+    return OCB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Parallel cyclic Jacobi (two-sided), round-robin pairing, one cooperative kernel.
+// ---------------------------------------------------------------------------------
+constexpr int EIG_MAXK = 2048;
+__device__ double g_eig_c[EIG_MAXK / 2], g_eig_s[EIG_MAXK / 2];
+__device__ int g_eig_p[EIG_MAXK / 2], g_eig_q[EIG_MAXK / 2];
+__device__ double g_eig_part[2 * 1024];
+__device__ int g_eig_rank[EIG_MAXK];
+__device__ int g_eig_sweeps;
+
+__global__ void __launch_bounds__(256) jacobi_kernel(double* __restrict__ G, int64_t ldg, int k,
+                                                    double* __restrict__ lam,
+                                                    double* __restrict__ V, int64_t ldv,
+                                                    int max_sweeps, double tol2) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[2][8];
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
+    const int kp = (k + 1) & ~1;  // padded to even; index k (if odd) is a bye
+    const int np = kp / 2;
+    // V = I
+    for (int64_t e = gtid; e < (int64_t)k * k; e += gsize) {
+        const int r = (int)(e / k), c = (int)(e % k);
+        V[(int64_t)r * ldv + c] = (r == c) ? 1.0 : 0.0;
+    }
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        // ---- convergence measure: off(G)^2 vs diag(G)^2, deterministic two-stage sum
+        double off = 0.0, dg = 0.0;
+        for (int64_t e = gtid; e < (int64_t)k * k; e += gsize) {
+            const int r = (int)(e / k), c = (int)(e % k);
+            const double v = G[(int64_t)r * ldg + c];
+            if (r == c) dg = fma(v, v, dg); else off = fma(v, v, off);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            off += __shfl_xor_sync(0xffffffffu, off, o);
+            dg += __shfl_xor_sync(0xffffffffu, dg, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            red[0][threadIdx.x >> 5] = off;
+            red[1][threadIdx.x >> 5] = dg;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0, b = 0.0;
+            for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+            g_eig_part[2 * blockIdx.x] = a;
+            g_eig_part[2 * blockIdx.x + 1] = b;
+        }
+        grid.sync();
+        double toff = 0.0, tdg = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) {
+            toff += g_eig_part[2 * b];
+            tdg += g_eig_part[2 * b + 1];
+        }
+        if (toff <= tol2 * tdg) break;  // identical decision in every thread
+        for (int round = 0; round < kp - 1; ++round) {
+            // ---- phase A: rotations of this round's disjoint pairs
+            for (int64_t t = gtid; t < np; t += gsize) {
+                int p, q;
+                if (t == 0) { p = kp - 1; q = round; }
+                else {
+                    p = (round + (int)t) % (kp - 1);
+                    q = (round - (int)t + (kp - 1)) % (kp - 1);
+                }
+                if (p > q) { const int tmp = p; p = q; q = tmp; }
+                double c = 1.0, s = 0.0;
+                if (q < k) {
+                    const double app = G[(int64_t)p * ldg + p], aqq = G[(int64_t)q * ldg + q];
+                    const double apq = 0.5 * (G[(int64_t)p * ldg + q] + G[(int64_t)q * ldg + p]);
+                    if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * sqrt(fabs(app * aqq))) {
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double tt = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(tt * tt + 1.0);
+                        s = tt * c;
+                    }
+                } else { q = -1; }
+                g_eig_p[t] = p; g_eig_q[t] = q; g_eig_c[t] = c; g_eig_s[t] = s;
+            }
+            grid.sync();
+            // ---- phase B: G <- J^T G J on 2x2 blocks, V <- V J on row pairs
+            const int64_t nblk = (int64_t)np * np;
+            for (int64_t e = gtid; e < nblk + (int64_t)k * np; e += gsize) {
+                if (e < nblk) {
+                    const int a = (int)(e / np), b = (int)(e % np);
+                    const int pa = g_eig_p[a], qa = g_eig_q[a], pb = g_eig_p[b], qb = g_eig_q[b];
+                    const double ca = g_eig_c[a], sa = g_eig_s[a], cb = g_eig_c[b], sb = g_eig_s[b];
+                    if (qa < 0 && qb < 0) {
+                        // single element, identity rotations
+                    } else if (qa < 0) {
+                        double* gp = G + (int64_t)pa * ldg;
+                        const double g0 = gp[pb], g1 = gp[qb];
+                        gp[pb] = cb * g0 - sb * g1;
+                        gp[qb] = sb * g0 + cb * g1;
+                    } else if (qb < 0) {
+                        double* g0p = G + (int64_t)pa * ldg + pb;
+                        double* g1p = G + (int64_t)qa * ldg + pb;
+                        const double g0 = *g0p, g1 = *g1p;
+                        *g0p = ca * g0 - sa * g1;
+                        *g1p = sa * g0 + ca * g1;
+                    } else {
+                        double* rp = G + (int64_t)pa * ldg;
+                        double* rq = G + (int64_t)qa * ldg;
+                        const double g00 = rp[pb], g01 = rp[qb], g10 = rq[pb], g11 = rq[qb];
+                        const double h00 = cb * g00 - sb * g01, h01 = sb * g00 + cb * g01;
+                        const double h10 = cb * g10 - sb * g11, h11 = sb * g10 + cb * g11;
+                        double n00 = ca * h00 - sa * h10, n10 = sa * h00 + ca * h10;
+                        double n01 = ca * h01 - sa * h11, n11 = sa * h01 + ca * h11;
+                        if (a == b) { n01 = 0.0; n10 = 0.0; }
+                        rp[pb] = n00; rp[qb] = n01; rq[pb] = n10; rq[qb] = n11;
+                    }
+                } else {
+                    const int64_t f = e - nblk;
+                    const int r = (int)(f / np), b = (int)(f % np);
+                    const int pb = g_eig_p[b], qb = g_eig_q[b];
+                    if (qb >= 0) {
+                        double* vr = V + (int64_t)r * ldv;
+                        const double cb = g_eig_c[b], sb = g_eig_s[b];
+                        const double v0 = vr[pb], v1 = vr[qb];
+                        vr[pb] = cb * v0 - sb * v1;
+                        vr[qb] = sb * v0 + cb * v1;
+                    }
+                }
+            }
+            grid.sync();
+        }
+    }
+    // ---- eigenvalues sorted descending; permute the columns of V through G as scratch
+    for (int64_t i = gtid; i < k; i += gsize) {
+        const double li = G[i * ldg + i];
+        int rank = 0;
+        for (int j = 0; j < k; ++j) {
+            const double lj = G[(int64_t)j * ldg + j];
+            rank += (lj > li) || (lj == li && j < i);
+        }
+        g_eig_rank[i] = rank;
+        lam[rank] = li;
+    }
+    if (gtid == 0) g_eig_sweeps = sweep;
+    grid.sync();
+    for (int64_t e = gtid; e < (int64_t)k * k; e += gsize) {
+        const int r = (int)(e / k), c = (int)(e % k);
+        G[(int64_t)r * ldg + g_eig_rank[c]] = V[(int64_t)r * ldv + c];
+    }
+    grid.sync();
+    for (int64_t e = gtid; e < (int64_t)k * k; e += gsize) {
+        const int r = (int)(e / k), c = (int)(e % k);
+        V[(int64_t)r * ldv + c] = G[(int64_t)r * ldg + c];
+    }
+}
+
+int sym_eig_impl(double* G, int64_t ldg, int64_t k, double* lam, double* V, int64_t ldv,
+                 int32_t* h_sweeps, cudaStream_t st) {
+    if (k == 0) { if (h_sweeps) *h_sweeps = 0; return OCB_OK; }
+    if (k > EIG_MAXK) { set_error("sym_eig: k=%lld > %d", (long long)k, EIG_MAXK); return OCB_ERR_ARG; }
+    int per_sm = 0;
+    OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_kernel, 256, 0));
+    const int64_t np = (k + 1) / 2;
+    const int64_t work = np * np + k * np;
+    int64_t blocks = (work + 255) / 256;
+    blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, std::min(per_sm, 4) * (int64_t)sm_count()));
+    blocks = std::min<int64_t>(blocks, 1024);
+    int kk = (int)k, max_sweeps = 40;
+    double tol2 = 1e-30;  // off(G)^2 <= tol2 * diag(G)^2
+    void* args[] = {&G, &ldg, &kk, &lam, &V, &ldv, &max_sweeps, &tol2};
+    OCB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3((unsigned)blocks), dim3(256), args, 0, st));
+    count_launch();
+    if (h_sweeps) {
+        int sw = 0;
+        OCB_CUDA(cudaMemcpyFromSymbolAsync(&sw, g_eig_sweeps, sizeof(int), 0, cudaMemcpyDeviceToHost, st));
+        OCB_CUDA(cudaStreamSynchronize(st));
+        *h_sweeps = sw;
+        if (sw >= max_sweeps) { set_error("sym_eig: no convergence in %d sweeps", max_sweeps); return OCB_ERR_NOCONV; }
+    }
+    return OCB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// m x m inverse (SMW core  (I - V A^-1 U)^-1 ), one warp, Gauss-Jordan with partial pivoting.
+// In: C (m x m row-major, ld) holds  V A^-1 U ; Out: Sinv = (I - C)^-1.  flag[0]=1 if singular.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) smw_core_inv_kernel(const double* __restrict__ C, int64_t ldc,
+                                                         int m, double* __restrict__ Sinv,
+                                                         int* __restrict__ flag) {
+    __shared__ double A[32][65];
+    const int lane = threadIdx.x;
+    for (int r = 0; r < m; ++r)
+        for (int c = lane; c < 2 * m; c += 32)
+            A[r][c] = (c < m) ? ((r == c ? 1.0 : 0.0) - C[(int64_t)r * ldc + c]) : ((c - m) == r ? 1.0 : 0.0);
+    __syncwarp();
+    for (int col = 0; col < m; ++col) {
+        int piv = col;
+        double best = fabs(A[col][col]);
+        for (int r = col + 1; r < m; ++r)
+            if (fabs(A[r][col]) > best) { best = fabs(A[r][col]); piv = r; }
+        if (best == 0.0) { if (lane == 0) *flag = 1; return; }
+        if (piv != col)
+            for (int c = lane; c < 2 * m; c += 32) { const double t = A[col][c]; A[col][c] = A[piv][c]; A[piv][c] = t; }
+        __syncwarp();
+        const double d = 1.0 / A[col][col];
+        __syncwarp();
+        for (int c = lane; c < 2 * m; c += 32) A[col][c] *= d;
+        __syncwarp();
+        for (int r = 0; r < m; ++r) {
+            if (r == col) continue;
+            const double f = A[r][col];
+            __syncwarp();
+            for (int c = lane; c < 2 * m; c += 32) A[r][c] = fma(-f, A[col][c], A[r][c]);
+            __syncwarp();
+        }
+    }
+    for (int r = 0; r < m; ++r)
+        for (int c = lane; c < m; c += 32) Sinv[r * m + c] = A[r][m + c];
+}
+
+int smw_core_inv(const double* C, int64_t ldc, int m, double* Sinv, int* flag, cudaStream_t st) {
+    if (m > 32) { set_error("SMW rank m=%d > 32", m); return OCB_ERR_ARG; }
+    smw_core_inv_kernel<<<1, 32, 0, st>>>(C, ldc, m, Sinv, flag);
+    OCB_LAUNCH_CHECK();
+    return OCB_OK;
+}
+
+}  // namespace ocb
+
+extern "C" {
+
+int64_t ocb_gram_ws_bytes(int64_t n, int64_t ka, int64_t kb) {
+    int nsplit;
+    int64_t rps;
+    ocb::gram_plan(n, std::max<int64_t>(ka, 1), std::max<int64_t>(kb, 1), &nsplit, &rps);
+    return (int64_t)nsplit * ka * kb * 8;
+}
+
+int ocb_gram(const double* d_Z, int64_t ldz, int64_t ka, const double* d_W, int64_t ldw, int64_t kb,
+             int64_t n, double* d_G, int64_t ldg, void* d_ws, int64_t ws_bytes, void* stream) {
+    OCB_ARG(ka >= 0 && kb >= 0 && n >= 0 && ldz >= ka && ldw >= kb && ldg >= kb, "gram sizes");
+    OCB_ARG(ka == 0 || kb == 0 || (d_Z && d_W && d_G), "gram null");
+    return ocb::gram_impl(d_Z, ldz, ka, d_W, ldw, kb, n, d_G, ldg, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int ocb_tall_gemm(const double* d_Z, int64_t ldz, int64_t n, int64_t k, const double* d_T, int64_t ldt,
+                  int64_t kc, double* d_C, int64_t ldc, double alpha, double beta, void* stream) {
+    OCB_ARG(n >= 0 && k >= 0 && kc >= 0 && ldz >= k && ldt >= kc && ldc >= kc, "tall_gemm sizes");
+    OCB_ARG(n == 0 || kc == 0 || (d_C && (k == 0 || (d_Z && d_T))), "tall_gemm null");
+    return ocb::tall_gemm_impl(d_Z, ldz, n, k, d_T, ldt, kc, d_C, ldc, alpha, beta, (cudaStream_t)stream);
+}
+
+int ocb_sym_eig(double* d_G, int64_t ldg, int64_t k, double* d_lam, double* d_V, int64_t ldv,
+                int32_t* h_sweeps, void* stream) {
+    OCB_ARG(k >= 0 && ldg >= k && ldv >= k, "sym_eig sizes");
+    OCB_ARG(k == 0 || (d_G && d_lam && d_V), "sym_eig null");
+    return ocb::sym_eig_impl(d_G, ldg, k, d_lam, d_V, ldv, h_sweeps, (cudaStream_t)stream);
+}
+}

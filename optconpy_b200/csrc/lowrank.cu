@@ -1,0 +1,606 @@
+// Low-rank factor machinery of the hot path:
+//   * compress_Zsvd  (rank-revealing pivoted Cholesky of Z^T Z  + Jacobi core + DMMA products)
+//   * the LR-ADI loop with Sherman-Morrison-Woodbury corrections (K6/K7 fused update + norm)
+//   * single SMW saddle-point solves, the feedback product  Mt (Z (Z^T tB)).
+#include "common.cuh"
+#include <math.h>
+#include <vector>
+#include <algorithm>
+
+struct ocb_lu;
+
+namespace ocb {
+// from the other translation units
+int spmm_launch(int64_t nrows, const int32_t* rp, const int32_t* ci, const double* va,
+                const double* X, int64_t ldx, double* Y, int64_t ldy, int64_t k, double alpha,
+                double beta, cudaStream_t st);
+int lu_solve_impl(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_b, double* X,
+                  int64_t ldx, int64_t nrows_x, int64_t k, void* ws, int64_t ws_bytes,
+                  cudaStream_t st);
+int gram_impl(const double* Z, int64_t ldz, int64_t ka, const double* W, int64_t ldw, int64_t kb,
+              int64_t n, double* G, int64_t ldg, void* ws, int64_t ws_bytes, cudaStream_t st);
+int tall_gemm_impl(const double* Z, int64_t ldz, int64_t n, int64_t k, const double* T, int64_t ldt,
+                   int64_t kc, double* C, int64_t ldc, double alpha, double beta, cudaStream_t st);
+int sym_eig_impl(double* G, int64_t ldg, int64_t k, double* lam, double* V, int64_t ldv,
+                 int32_t* h_sweeps, cudaStream_t st);
+int smw_core_inv(const double* C, int64_t ldc, int m, double* Sinv, int* flag, cudaStream_t st);
+
+// pinned host scratch for the few scalars that steer host-side loops
+static double* pinned_scratch() {
+    static double* p = nullptr;
+    if (!p) {
+        if (cudaHostAlloc((void**)&p, 16384, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+    }
+    return p;
+}
+
+// =================================================================================
+// compress_Zsvd
+// =================================================================================
+struct CholState {
+    double d0max;  // largest initial column norm^2
+    double dp;     // pivot value of the current step
+    int piv;       // pivot column of the current step
+    int done;      // 1 once the stop rule fired
+    int rank;      // number of Cholesky columns produced
+    int pad;
+};
+
+constexpr int CH_THREADS = 512, CH_WARPS = 16;
+
+// sum over rows of Z[i][j] * Z[i][p] for 32 columns j per CTA (p < 0: Z[i][j]^2).
+// 16 warps stride the rows; fixed-order shared-memory reduction => deterministic.
+__device__ __forceinline__ double col_dot_block(const double* __restrict__ Z, int64_t ldz, int64_t n,
+                                                int64_t K, int64_t j, int p, double (*red)[33]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc = 0.0;
+    if (j < K) {
+        int64_t i = warp;
+        // 4 independent row streams per warp for memory-level parallelism
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (; i + 3 * CH_WARPS < n; i += 4 * CH_WARPS) {
+            const double* r0 = Z + i * ldz;
+            const double* r1 = r0 + (int64_t)CH_WARPS * ldz;
+            const double* r2 = r1 + (int64_t)CH_WARPS * ldz;
+            const double* r3 = r2 + (int64_t)CH_WARPS * ldz;
+            const double z0 = __ldg(r0 + j), z1 = __ldg(r1 + j), z2 = __ldg(r2 + j), z3 = __ldg(r3 + j);
+            const double p0 = p < 0 ? z0 : __ldg(r0 + p), p1 = p < 0 ? z1 : __ldg(r1 + p);
+            const double p2 = p < 0 ? z2 : __ldg(r2 + p), p3 = p < 0 ? z3 : __ldg(r3 + p);
+            a0 = fma(z0, p0, a0); a1 = fma(z1, p1, a1); a2 = fma(z2, p2, a2); a3 = fma(z3, p3, a3);
+        }
+        for (; i < n; i += CH_WARPS) {
+            const double z0 = __ldg(Z + i * ldz + j);
+            const double p0 = p < 0 ? z0 : __ldg(Z + i * ldz + p);
+            a0 = fma(z0, p0, a0);
+        }
+        acc = (a0 + a1) + (a2 + a3);
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    double s = 0.0;
+    if (warp == 0)
+        for (int w = 0; w < CH_WARPS; ++w) s += red[w][lane];
+    return s;  // valid in warp 0
+}
+
+__global__ void __launch_bounds__(CH_THREADS) chol_colsq_kernel(const double* __restrict__ Z, int64_t ldz,
+                                                               int64_t n, int64_t K, double* __restrict__ d) {
+    __shared__ double red[CH_WARPS][33];
+    const int64_t j = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    const double s = col_dot_block(Z, ldz, n, K, j, -1, red);
+    if (threadIdx.x < 32 && j < K) d[j] = s;
+}
+
+__global__ void __launch_bounds__(1024) chol_pick_kernel(const double* __restrict__ d, int64_t K, int t,
+                                                        int rmax, double eta, CholState* st) {
+    __shared__ double bv[32];
+    __shared__ int bi[32];
+    if (st->done) return;
+    double best = -1.0;
+    int arg = -1;
+    for (int64_t j = threadIdx.x; j < K; j += blockDim.x) {
+        const double v = d[j];
+        if (v > best) { best = v; arg = (int)j; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ov > best || (ov == best && oi >= 0 && (arg < 0 || oi < arg))) { best = ov; arg = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = arg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w)
+            if (bv[w] > best || (bv[w] == best && bi[w] >= 0 && (arg < 0 || bi[w] < arg))) { best = bv[w]; arg = bi[w]; }
+        if (t == 0) st->d0max = best;
+        if (t >= rmax || arg < 0 || !(best > eta * st->d0max) || !(best > 0.0)) {
+            st->done = 1;
+            st->rank = t;
+        } else {
+            st->piv = arg;
+            st->dp = best;
+        }
+    }
+}
+
+// column t of the Cholesky factor: Rt[j][t] = (z_j . z_p - sum_{s<t} Rt[p][s] Rt[j][s]) / sqrt(dp)
+__global__ void __launch_bounds__(CH_THREADS) chol_col_kernel(const double* __restrict__ Z, int64_t ldz,
+                                                             int64_t n, int64_t K, int t,
+                                                             double* __restrict__ Rt, int64_t ldr,
+                                                             double* __restrict__ d,
+                                                             const CholState* __restrict__ st) {
+    __shared__ double red[CH_WARPS][33];
+    __shared__ double rp[1024];
+    if (st->done) return;
+    const int p = st->piv;
+    const double dp = st->dp;
+    for (int s = threadIdx.x; s < t; s += CH_THREADS) rp[s] = Rt[(int64_t)p * ldr + s];
+    const int64_t j = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    const double g = col_dot_block(Z, ldz, n, K, j, p, red);  // contains a __syncthreads
+    if (threadIdx.x < 32 && j < K) {
+        const double* rj = Rt + j * ldr;
+        double s0 = 0.0, s1 = 0.0;
+        int s = 0;
+        for (; s + 1 < t; s += 2) { s0 = fma(rp[s], rj[s], s0); s1 = fma(rp[s + 1], rj[s + 1], s1); }
+        if (s < t) s0 = fma(rp[s], rj[s], s0);
+        const double row = (g - (s0 + s1)) / sqrt(dp);
+        Rt[j * ldr + t] = row;
+        d[j] = (j == p) ? -1.0 : d[j] - row * row;
+    }
+}
+
+__global__ void scale_cols_kernel(const double* __restrict__ U, int64_t ldu, int r, int kk,
+                                  const double* __restrict__ lam, double* __restrict__ Us, int64_t lds) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r * kk) return;
+    const int i = e / kk, j = e % kk;
+    Us[(int64_t)i * lds + j] = U[(int64_t)i * ldu + j] / sqrt(lam[j]);
+}
+
+struct CompressWs {
+    double *d, *Rt, *S, *U, *lam, *Us, *T, *gws;
+    CholState* st;
+    int64_t gws_bytes;
+};
+
+static int64_t compress_carve(void* ws, int64_t bytes, int64_t n, int64_t K, int64_t rmax, CompressWs* o) {
+    WsCarver c(ws, bytes);
+    CompressWs w;
+    w.st = c.take<CholState>(1);
+    w.d = c.take<double>(K);
+    w.Rt = c.take<double>(K * rmax);
+    w.S = c.take<double>(rmax * rmax);
+    w.U = c.take<double>(rmax * rmax);
+    w.lam = c.take<double>(rmax);
+    w.Us = c.take<double>(rmax * rmax);
+    w.T = c.take<double>(K * rmax);
+    w.gws_bytes = ocb_gram_ws_bytes(K, rmax, rmax);
+    w.gws = (double*)c.take<char>(w.gws_bytes);
+    if (o) *o = w;
+    return c.off + 256;
+}
+
+}  // namespace ocb
+
+extern "C" {
+
+int64_t ocb_compress_ws_bytes(int64_t n, int64_t K, int64_t rmax) {
+    return ocb::compress_carve(nullptr, 0, n, K, rmax, nullptr);
+}
+
+int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K, double thresh, int64_t kmax,
+                 double eta, int64_t rmax, double* d_Zc, int64_t ldzc, int64_t zc_capacity_cols,
+                 double* d_sigma, int64_t* h_info3, void* d_ws, int64_t ws_bytes, void* stream) {
+    using namespace ocb;
+    OCB_ARG(n >= 0 && K >= 0 && ldz >= K && rmax >= 1 && rmax <= 1024, "compress sizes");
+    OCB_ARG(d_Z && d_Zc && h_info3 && d_ws, "compress null");
+    OCB_ARG(eta > 0.0 && eta < 1e-6, "compress eta");
+    cudaStream_t st = (cudaStream_t)stream;
+    h_info3[0] = h_info3[1] = h_info3[2] = 0;
+    if (K == 0 || n == 0) return OCB_OK;
+    rmax = std::min<int64_t>(rmax, std::min(K, n));
+    CompressWs w;
+    const int64_t need = compress_carve(d_ws, ws_bytes, n, K, rmax, &w);
+    if (need > ws_bytes) {
+        set_error("compress: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+        return OCB_ERR_CAPACITY;
+    }
+    double* hp = pinned_scratch();
+    OCB_ARG(hp != nullptr, "pinned scratch allocation failed");
+    OCB_CUDA(cudaMemsetAsync(w.st, 0, sizeof(CholState), st));
+    const unsigned cblocks = (unsigned)((K + 31) / 32);
+    chol_colsq_kernel<<<cblocks, CH_THREADS, 0, st>>>(d_Z, ldz, n, K, w.d);
+    OCB_LAUNCH_CHECK();
+    CholState* hst = (CholState*)hp;
+    int t = 0;
+    bool done = false;
+    while (!done) {
+        const int batch_end = (int)std::min<int64_t>(rmax, t + 32);
+        for (; t < batch_end; ++t) {
+            chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
+            OCB_LAUNCH_CHECK();
+            chol_col_kernel<<<cblocks, CH_THREADS, 0, st>>>(d_Z, ldz, n, K, t, w.Rt, rmax, w.d, w.st);
+            OCB_LAUNCH_CHECK();
+        }
+        if (t >= rmax) {  // closes the factorisation at rank rmax if the rule never fired
+            chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
+            OCB_LAUNCH_CHECK();
+        }
+        OCB_CUDA(cudaMemcpyAsync(hst, w.st, sizeof(CholState), cudaMemcpyDeviceToHost, st));
+        OCB_CUDA(cudaStreamSynchronize(st));
+        done = hst->done != 0;
+    }
+    const int r = hst->rank;
+    h_info3[1] = r;
+    if (r == 0) return OCB_OK;
+    // core: S = R R^T (r x r) = Rt^T Rt, eigen-decomposition, sigma = sqrt(lam)
+    int rc = gram_impl(w.Rt, rmax, r, w.Rt, rmax, r, K, w.S, rmax, w.gws, w.gws_bytes, st);
+    if (rc) return rc;
+    int32_t sweeps = 0;
+    rc = sym_eig_impl(w.S, rmax, r, w.lam, w.U, rmax, &sweeps, st);
+    if (rc) return rc;
+    h_info3[2] = sweeps;
+    double* hlam = hp + 64;
+    OCB_ARG(r <= 1900, "compress: rank above pinned scratch");
+    OCB_CUDA(cudaMemcpyAsync(hlam, w.lam, r * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OCB_CUDA(cudaStreamSynchronize(st));
+    int keep = 0;
+    for (int i = 0; i < r; ++i) {
+        const double sg = hlam[i] > 0.0 ? sqrt(hlam[i]) : 0.0;
+        if (sg > 0.0 && (thresh < 0.0 || sg > thresh)) ++keep; else break;
+    }
+    if (kmax > 0) keep = (int)std::min<int64_t>(keep, kmax);
+    h_info3[0] = keep;
+    if (d_sigma) {
+        for (int i = 0; i < r; ++i) hlam[i] = hlam[i] > 0.0 ? sqrt(hlam[i]) : 0.0;
+        OCB_CUDA(cudaMemcpyAsync(d_sigma, hlam, r * sizeof(double), cudaMemcpyHostToDevice, st));
+        OCB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (keep == 0) return OCB_OK;
+    if (keep > zc_capacity_cols || ldzc < keep) {
+        set_error("compress: %d columns kept but capacity is %lld", keep, (long long)zc_capacity_cols);
+        return OCB_ERR_CAPACITY;
+    }
+    scale_cols_kernel<<<(r * keep + 255) / 256, 256, 0, st>>>(w.U, rmax, r, keep, w.lam, w.Us, rmax);
+    OCB_LAUNCH_CHECK();
+    // T (K x keep) = Rt (K x r) Us (r x keep);  Zc = Z T
+    rc = tall_gemm_impl(w.Rt, rmax, K, r, w.Us, rmax, keep, w.T, rmax, 1.0, 0.0, st);
+    if (rc) return rc;
+    return tall_gemm_impl(d_Z, ldz, n, K, w.T, rmax, keep, d_Zc, ldzc, 1.0, 0.0, st);
+}
+}
+
+// =================================================================================
+// LR-ADI
+// =================================================================================
+namespace ocb {
+
+// S2 (m x k) = Sinv (m x m) * small (m x k)
+__global__ void smw_s2_kernel(const double* __restrict__ Sinv, int m, const double* __restrict__ small,
+                              int64_t k, double* __restrict__ S2) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)m * k) return;
+    const int r = (int)(e / k);
+    const int64_t c = e % k;
+    double s = 0.0;
+    for (int l = 0; l < m; ++l) s = fma(Sinv[r * m + l], small[(int64_t)l * k + c], s);
+    S2[e] = s;
+}
+
+__device__ unsigned int g_upd_counter = 0;
+
+// Vnew = a*Vold + b*(Y + AiU*S2);  *nrm2 = ||Vnew||_F^2  (per-CTA partials, last CTA sums in order)
+template <int MMAX>
+__global__ void __launch_bounds__(256) adi_update_kernel(const double* __restrict__ Vold, int64_t ldv,
+                                                        const double* __restrict__ Y, int64_t ldy,
+                                                        const double* __restrict__ AiU, int64_t lda, int m,
+                                                        const double* __restrict__ S2,
+                                                        double* __restrict__ Vnew, int64_t ldn,
+                                                        int64_t nrows, int64_t k, double a, double b,
+                                                        double* __restrict__ partials,
+                                                        double* __restrict__ nrm2) {
+    __shared__ double red[8];
+    __shared__ bool last;
+    const int64_t total = nrows * k;
+    double acc = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / k, c = e - i * k;
+        double x = Y[i * ldy + c];
+        if (MMAX > 0) {
+            const double* ai = AiU + i * lda;
+            for (int l = 0; l < m; ++l) x = fma(ai[l], S2[(int64_t)l * k + c], x);
+        }
+        double v = b * x;
+        if (Vold) v = fma(a, Vold[i * ldv + c], v);
+        if (Vnew) Vnew[i * ldn + c] = v;
+        acc = fma(v, v, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        partials[blockIdx.x] = s;
+        __threadfence();
+        const unsigned int done = atomicAdd(&g_upd_counter, 1u);
+        last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned int bI = 0; bI < gridDim.x; ++bI) s += ((volatile double*)partials)[bI];
+        *nrm2 = s;
+        g_upd_counter = 0;
+    }
+}
+
+constexpr int UPD_MAXBLOCKS = 1024;
+
+static int adi_update(const double* Vold, int64_t ldv, const double* Y, int64_t ldy, const double* AiU,
+                      int64_t lda, int m, const double* S2, double* Vnew, int64_t ldn, int64_t nrows,
+                      int64_t k, double a, double b, double* partials, double* nrm2, cudaStream_t st) {
+    const int64_t total = nrows * k;
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(UPD_MAXBLOCKS, (total + 1023) / 1024));
+    if (m > 0)
+        adi_update_kernel<1><<<blocks, 256, 0, st>>>(Vold, ldv, Y, ldy, AiU, lda, m, S2, Vnew, ldn, nrows, k, a, b, partials, nrm2);
+    else
+        adi_update_kernel<0><<<blocks, 256, 0, st>>>(Vold, ldv, Y, ldy, AiU, lda, 0, S2, Vnew, ldn, nrows, k, a, b, partials, nrm2);
+    OCB_LAUNCH_CHECK();
+    return OCB_OK;
+}
+
+struct SmwWs {
+    double *AiU;      // [nshifts][nrows_aiu][m]
+    double *Sinv;     // [nshifts][m][m]
+    double *core;     // [m][m]
+    double *small;    // [m][k]
+    double *S2;       // [m][k]
+    int* flag;
+};
+
+// prepare the SMW pieces of one factorisation: AiU = A^-1 [U;0] (first nrows rows), Sinv
+static int smw_prepare(const ocb_lu* lu, int64_t NV, const double* Ufb, int64_t ldu, int m,
+                       const int32_t* vt_rp, const int32_t* vt_ci, const double* vt_va,
+                       double* AiU, int64_t nrows_aiu, double* core, double* Sinv, int* flag,
+                       void* lws, int64_t lws_bytes, cudaStream_t st) {
+    int rc = lu_solve_impl(lu, Ufb, ldu, NV, AiU, m, nrows_aiu, m, lws, lws_bytes, st);
+    if (rc) return rc;
+    // core = Vt (m x NV) * AiU[:NV]  (m x m)
+    rc = spmm_launch(m, vt_rp, vt_ci, vt_va, AiU, m, core, m, m, 1.0, 0.0, st);
+    if (rc) return rc;
+    return smw_core_inv(core, m, m, Sinv, flag, st);
+}
+
+}  // namespace ocb
+
+extern "C" {
+
+int64_t ocb_adi_ws_bytes(int64_t n_sad, int64_t k, int64_t m, int64_t nshifts, ocb_lu* const* lus) {
+    using namespace ocb;
+    int64_t lws = 0;
+    for (int64_t i = 0; i < nshifts; ++i)
+        lws = std::max(lws, ocb_lu_solve_ws_bytes(lus[i], std::max(k, m)));
+    WsCarver c(nullptr, 0);
+    c.take<double>(n_sad * k);                   // T = Mt V
+    c.take<double>(n_sad * k);                   // Y
+    c.take<double>(UPD_MAXBLOCKS);               // partials
+    c.take<double>(8);                           // norm
+    c.take<int>(8);                              // flag
+    c.take<double>(nshifts * n_sad * std::max<int64_t>(m, 1));
+    c.take<double>(nshifts * m * m + 1);
+    c.take<double>(m * m + 1);
+    c.take<double>(m * k + 1);
+    c.take<double>(m * k + 1);
+    c.take<char>(lws);
+    return c.off + 256;
+}
+
+int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int64_t NV, int64_t NP,
+                const int32_t* d_Mt_rowptr, const int32_t* d_Mt_colidx, const double* d_Mt_vals,
+                const double* d_W, int64_t ldw, int64_t k, const double* d_Ufb, int64_t ldu, int64_t m,
+                const int32_t* d_Vt_rowptr, const int32_t* d_Vt_colidx, const double* d_Vt_vals,
+                int64_t maxsteps, double reltol, double* d_Z, int64_t ldz, int64_t z_capacity_cols,
+                double* h_relnorms, int64_t* h_steps, void* d_ws, int64_t ws_bytes, void* stream) {
+    using namespace ocb;
+    OCB_ARG(lus && h_shifts && nshifts >= 1 && NV >= 1 && NP >= 0 && k >= 1, "adi sizes");
+    OCB_ARG(d_Mt_rowptr && d_W && d_Z && h_relnorms && h_steps && d_ws, "adi null");
+    OCB_ARG(m == 0 || (d_Ufb && d_Vt_rowptr && m <= 32 && ldu >= m), "adi low-rank part");
+    OCB_ARG(maxsteps >= 1 && ldw >= k, "adi steps/ld");
+    for (int64_t i = 0; i < nshifts; ++i) OCB_ARG(h_shifts[i] < 0.0, "adi shifts must be negative reals");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_sad = NV + NP;
+    const int64_t need = ocb_adi_ws_bytes(n_sad, k, m, nshifts, lus);
+    if (ws_bytes < need) {
+        set_error("adi: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+        return OCB_ERR_CAPACITY;
+    }
+    int64_t lws_bytes = 0;
+    for (int64_t i = 0; i < nshifts; ++i)
+        lws_bytes = std::max(lws_bytes, ocb_lu_solve_ws_bytes(lus[i], std::max(k, m)));
+    WsCarver c(d_ws, ws_bytes);
+    double* T = c.take<double>(n_sad * k);
+    double* Y = c.take<double>(n_sad * k);
+    double* partials = c.take<double>(UPD_MAXBLOCKS);
+    double* dnorm = c.take<double>(8);
+    int* flag = c.take<int>(8);
+    double* AiU = c.take<double>(nshifts * n_sad * std::max<int64_t>(m, 1));
+    double* Sinv = c.take<double>(nshifts * m * m + 1);
+    double* core = c.take<double>(m * m + 1);
+    double* small = c.take<double>(m * k + 1);
+    double* S2 = c.take<double>(m * k + 1);
+    void* lws = c.take<char>(lws_bytes);
+    double* hp = pinned_scratch();
+    OCB_ARG(hp != nullptr, "pinned scratch allocation failed");
+    OCB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 8, st));
+    std::vector<char> prepared(nshifts, 0);
+    (void)T;
+
+    double z_nsq = 0.0;
+    int64_t step = 0;
+    *h_steps = 0;
+    while (step < maxsteps) {
+        if ((step + 1) * k > z_capacity_cols || (step + 1) * k > ldz) {
+            set_error("adi: Z capacity (%lld cols) exhausted at step %lld", (long long)z_capacity_cols,
+                      (long long)step);
+            return OCB_ERR_CAPACITY;
+        }
+        const int64_t i = step % nshifts, ip = (step + nshifts - 1) % nshifts;
+        const ocb_lu* lu = lus[i];
+        int rc;
+        if (m > 0 && !prepared[i]) {
+            rc = smw_prepare(lu, NV, d_Ufb, ldu, (int)m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals,
+                             AiU + i * NV * m, NV, core, Sinv + i * m * m, flag, lws, lws_bytes, st);
+            if (rc) return rc;
+            prepared[i] = 1;
+        }
+        const double* Vprev = step > 0 ? d_Z + (step - 1) * k : nullptr;
+        double* Vnew = d_Z + step * k;
+        if (step == 0) {
+            rc = lu_solve_impl(lu, d_W, ldw, NV, Y, k, NV, k, lws, lws_bytes, st);
+        } else {
+            rc = spmm_launch(NV, d_Mt_rowptr, d_Mt_colidx, d_Mt_vals, Vprev, ldz, T, k, k, 1.0, 0.0, st);
+            if (rc) return rc;
+            rc = lu_solve_impl(lu, T, k, NV, Y, k, NV, k, lws, lws_bytes, st);
+        }
+        if (rc) return rc;
+        if (m > 0) {
+            rc = spmm_launch(m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals, Y, k, small, k, k, 1.0, 0.0, st);
+            if (rc) return rc;
+            smw_s2_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, st>>>(Sinv + i * m * m, (int)m, small, k, S2);
+            OCB_LAUNCH_CHECK();
+        }
+        double a, b;
+        if (step == 0) { a = 0.0; b = sqrt(-2.0 * h_shifts[0]); }
+        else {
+            const double cs = sqrt(h_shifts[i] / h_shifts[ip]);
+            a = cs;
+            b = -cs * (h_shifts[i] + h_shifts[ip]);
+        }
+        rc = adi_update(Vprev, ldz, Y, k, AiU + i * NV * m, m, (int)m, S2, Vnew, ldz, NV, k, a, b,
+                        partials, dnorm, st);
+        if (rc) return rc;
+        OCB_CUDA(cudaMemcpyAsync(hp, dnorm, sizeof(double), cudaMemcpyDeviceToHost, st));
+        OCB_CUDA(cudaMemcpyAsync(hp + 1, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OCB_CUDA(cudaStreamSynchronize(st));
+        if (*(int*)(hp + 1) != 0) {
+            set_error("adi: singular Sherman-Morrison-Woodbury core at shift %lld", (long long)i);
+            return OCB_ERR_SINGULAR;
+        }
+        const double v_nsq = hp[0];
+        z_nsq += v_nsq;
+        const double rel = z_nsq > 0.0 ? sqrt(v_nsq / z_nsq) : 0.0;
+        h_relnorms[step] = rel;
+        ++step;
+        *h_steps = step;
+        if (!(rel > reltol)) break;
+    }
+    return OCB_OK;
+}
+
+int64_t ocb_smw_solve_ws_bytes(const ocb_lu* lu, int64_t k, int64_t m) {
+    using namespace ocb;
+    int64_t n = 0;
+    if (lu) { int64_t info[8]; ocb_lu_info(lu, info); n = info[0]; }
+    WsCarver c(nullptr, 0);
+    c.take<double>(n * k);
+    c.take<double>(n * std::max<int64_t>(m, 1));
+    c.take<double>(m * m + 1);
+    c.take<double>(m * m + 1);
+    c.take<double>(m * k + 1);
+    c.take<double>(m * k + 1);
+    c.take<double>(UPD_MAXBLOCKS);
+    c.take<double>(8);
+    c.take<int>(8);
+    c.take<char>(ocb_lu_solve_ws_bytes(lu, std::max(k, m)));
+    return c.off + 256;
+}
+
+int ocb_smw_solve(const ocb_lu* lu, int64_t NV, const double* d_B, int64_t ldb, int64_t nrows_b, int64_t k,
+                  const double* d_Ufb, int64_t ldu, int64_t m, const int32_t* d_Vt_rowptr,
+                  const int32_t* d_Vt_colidx, const double* d_Vt_vals, double* d_X, int64_t ldx,
+                  int64_t nrows_x, void* d_ws, int64_t ws_bytes, void* stream) {
+    using namespace ocb;
+    OCB_ARG(lu && d_B && d_X && k >= 1 && ldb >= k && ldx >= k, "smw_solve args");
+    OCB_ARG(m == 0 || (d_Ufb && d_Vt_rowptr && m <= 32 && ldu >= m), "smw_solve low-rank part");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t info[8];
+    ocb_lu_info(lu, info);
+    const int64_t n = info[0];
+    OCB_ARG(NV <= n && nrows_b <= n && nrows_x <= n, "smw_solve sizes");
+    const int64_t need = ocb_smw_solve_ws_bytes(lu, k, m);
+    if (!d_ws || ws_bytes < need) {
+        set_error("smw_solve: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+        return OCB_ERR_CAPACITY;
+    }
+    const int64_t lws_bytes = ocb_lu_solve_ws_bytes(lu, std::max(k, m));
+    WsCarver c(d_ws, ws_bytes);
+    double* Y = c.take<double>(n * k);
+    double* AiU = c.take<double>(n * std::max<int64_t>(m, 1));
+    double* core = c.take<double>(m * m + 1);
+    double* Sinv = c.take<double>(m * m + 1);
+    double* small = c.take<double>(m * k + 1);
+    double* S2 = c.take<double>(m * k + 1);
+    double* partials = c.take<double>(UPD_MAXBLOCKS);
+    double* dnorm = c.take<double>(8);
+    int* flag = c.take<int>(8);
+    void* lws = c.take<char>(lws_bytes);
+    if (m == 0) return lu_solve_impl(lu, d_B, ldb, nrows_b, d_X, ldx, nrows_x, k, lws, lws_bytes, st);
+    double* hp = pinned_scratch();
+    OCB_ARG(hp != nullptr, "pinned scratch allocation failed");
+    OCB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 8, st));
+    int rc = smw_prepare(lu, NV, d_Ufb, ldu, (int)m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals, AiU, n, core,
+                         Sinv, flag, lws, lws_bytes, st);
+    if (rc) return rc;
+    rc = lu_solve_impl(lu, d_B, ldb, nrows_b, Y, k, n, k, lws, lws_bytes, st);
+    if (rc) return rc;
+    rc = spmm_launch(m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals, Y, k, small, k, k, 1.0, 0.0, st);
+    if (rc) return rc;
+    smw_s2_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, st>>>(Sinv, (int)m, small, k, S2);
+    OCB_LAUNCH_CHECK();
+    rc = adi_update(nullptr, 0, Y, k, AiU, m, (int)m, S2, d_X, ldx, nrows_x, k, 0.0, 1.0, partials, dnorm, st);
+    if (rc) return rc;
+    OCB_CUDA(cudaMemcpyAsync(hp + 1, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OCB_CUDA(cudaStreamSynchronize(st));
+    if (*(int*)(hp + 1) != 0) {
+        set_error("smw_solve: singular Sherman-Morrison-Woodbury core");
+        return OCB_ERR_SINGULAR;
+    }
+    return OCB_OK;
+}
+
+int64_t ocb_feedback_ws_bytes(int64_t NV, int64_t kz, int64_t m) {
+    using namespace ocb;
+    WsCarver c(nullptr, 0);
+    c.take<double>(kz * m + 1);
+    c.take<double>(NV * m + 1);
+    c.take<char>(ocb_gram_ws_bytes(NV, kz, m));
+    return c.off + 256;
+}
+
+int ocb_feedback(const int32_t* d_Mt_rowptr, const int32_t* d_Mt_colidx, const double* d_Mt_vals, int64_t NV,
+                 const double* d_Z, int64_t ldz, int64_t kz, const double* d_tB, int64_t ldb, int64_t m,
+                 double* d_Out, int64_t ldo, double alpha, void* d_ws, int64_t ws_bytes, void* stream) {
+    using namespace ocb;
+    OCB_ARG(d_Mt_rowptr && d_Z && d_tB && d_Out && NV >= 1 && kz >= 1 && m >= 1, "feedback args");
+    OCB_ARG(ldz >= kz && ldb >= m && ldo >= m, "feedback ld");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t need = ocb_feedback_ws_bytes(NV, kz, m);
+    if (!d_ws || ws_bytes < need) {
+        set_error("feedback: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+        return OCB_ERR_CAPACITY;
+    }
+    WsCarver c(d_ws, ws_bytes);
+    double* ztb = c.take<double>(kz * m + 1);
+    double* tmp = c.take<double>(NV * m + 1);
+    const int64_t gws_bytes = ocb_gram_ws_bytes(NV, kz, m);
+    void* gws = c.take<char>(gws_bytes);
+    int rc = gram_impl(d_Z, ldz, kz, d_tB, ldb, m, NV, ztb, m, gws, gws_bytes, st);
+    if (rc) return rc;
+    rc = tall_gemm_impl(d_Z, ldz, NV, kz, ztb, m, m, tmp, m, 1.0, 0.0, st);
+    if (rc) return rc;
+    return spmm_launch(NV, d_Mt_rowptr, d_Mt_colidx, d_Mt_vals, tmp, m, d_Out, ldo, m, alpha, 0.0, st);
+}
+}

@@ -1,0 +1,195 @@
+"""Backward implicit-Euler stepper for the differential-algebraic Riccati equation.
+
+Python-3 restatement of the *caller* of the hot path, ``solve_flow_daeric``
+(reference ``solve_dae_ric.py:7-213``; it cannot be imported: Python 2 and it
+needs ``dolfin_navier_scipy``).  The numerical work is delegated to two
+modules with the reference's ``lin_alg_utils`` / ``proj_ric_utils`` interface,
+passed in as ``lau`` / ``pru``: by default the CUDA-backed ones of this package;
+the tests hand in the CPU oracle to obtain the reference trajectory with the
+very same driver.
+
+Semantics kept from the reference, in its order of operations:
+  * consistency check of C^T (``solve_dae_ric.py:75-83``),
+  * terminal values ``Zc = sqrt(gamma) M^-1 C~^T``, ``mtxtb = -M^T Zc Zc^T B~``
+    (``:92-101``), ``w(T) = M^-T gamma C~^T y*(T)`` (``:107-108``),
+  * per step: ``F_k^T = -(M^T/2 + tau (A^T + N^T))``, ``W_k = [M^T Zc, sqrt(tau) C~^T]``,
+    Newton-ADI, compression (``:147-165``); then the feed-forward solve
+    (``:173-194``) — including the quirk that the accumulated outer-Newton gain
+    ``cnsmtxtb`` is updated with the PREVIOUS step's ``mtxtb`` (``:181``) before
+    ``mtxtb`` is recomputed (``:189``),
+  * memoisation: a step whose ``__Z`` entry already exists is not recomputed
+    (``:143-145``).
+Storage goes through a ``store`` object (``NpyStore`` = the reference's
+``dou.save_npa`` / ``dou.load_npa`` on ``.npy`` files; ``MemStore`` keeps arrays
+in memory).
+"""
+import os
+import numpy as np
+
+__all__ = ['NpyStore', 'MemStore', 'solve_flow_daeric', 'default_datastr']
+
+
+class NpyStore(object):
+    """``dou.save_npa`` / ``dou.load_npa`` shim: ``np.save`` appends ``.npy``
+    (reference ``optcont_main.py:231`` loads ``veldict[t]+'.npy'``)."""
+
+    def save(self, arr, fstring):
+        d = os.path.dirname(fstring)
+        if d and not os.path.isdir(d):
+            os.makedirs(d)
+        np.save(fstring, arr)
+
+    def load(self, fstring):
+        try:
+            return np.load(fstring + '.npy')
+        except (IOError, OSError):
+            raise IOError(fstring)
+
+
+class MemStore(dict):
+    def save(self, arr, fstring):
+        self[fstring] = None if arr is None else np.array(arr, copy=True)
+
+    def load(self, fstring):
+        try:
+            return self[fstring]
+        except KeyError:
+            raise IOError(fstring)
+
+
+def default_datastr(time=None, meshp=None, nu=None, Nts=None, data_prfx='', **kw):
+    """``get_datastr`` of ``optcont_main.py:153-157``."""
+    return (data_prfx + 'time{0}_nu{1}_mesh{2}_Nts{3}').format(time, nu, meshp, Nts)
+
+
+def _terminal(lau, pru, mmat, bmat, cmat, mcmat, v_is_my, rmat, vmat, gamma):
+    if v_is_my and mcmat is not None:
+        tct = lau.apply_invsqrt_fromright(vmat, mcmat.T, output='dense')
+    else:
+        tct = lau.apply_sqrt_fromright(vmat, cmat.T, output='dense')
+    tb = lau.apply_invsqrt_fromright(rmat, bmat, output='sparse')
+    zc = np.sqrt(gamma)*lau.apply_massinv(mmat, tct)
+    return tct, tb, zc
+
+
+def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
+                      cmat=None, rhsv=None, rhsp=None,
+                      mcmat=None, v_is_my=False,
+                      rmat=None, vmat=None,
+                      gamma=1.0,
+                      tmesh=None, ystarvec=None,
+                      nwtn_adi_dict=None,
+                      curnwtnsdict=None,
+                      comprz_thresh=None, comprz_maxc=None, save_full_z=False,
+                      get_tdpart=None, gttdprtargs=None,
+                      get_datastr=None, gtdtstrargs=None,
+                      check_c_consist=True,
+                      lau=None, pru=None, store=None, verbose=False,
+                      stepinfo=None):
+    """Same keyword signature as the reference's ``solve_flow_daeric`` plus
+    ``lau``/``pru`` (backend modules), ``store`` and ``stepinfo`` (optional list
+    that receives per-step diagnostics).  Returns the ``feedbackthroughdict``
+    ``{t: dict(w=..., mtxtb=...)}`` of store keys."""
+    if lau is None or pru is None:
+        from . import lin_alg_utils as _lau, proj_ric_utils as _pru
+        lau, pru = lau or _lau, pru or _pru
+    store = NpyStore() if store is None else store
+    get_datastr = default_datastr if get_datastr is None else get_datastr
+    gtdtstrargs = {} if gtdtstrargs is None else gtdtstrargs
+    gttdprtargs = {} if gttdprtargs is None else gttdprtargs
+
+    if check_c_consist:
+        chk = mcmat if (v_is_my and mcmat is not None) else cmat
+        if chk is not None:
+            mic = lau.apply_massinv(mmat.T, chk.T)
+            if np.linalg.norm(jmat @ mic) > 1e-12:
+                raise Warning(('mcmat' if chk is mcmat else 'cmat') +
+                              '.T needs to be in the kernel of J*M.-1')
+
+    MT, AT, NV = mmat.T.tocsr(), amat.T.tocsr(), amat.shape[0]
+    tE = tmesh[-1]
+    gtdtstrargs.update(time=tE)
+    key = get_datastr(**gtdtstrargs)
+
+    tct_mat, tb_mat, Zc = _terminal(lau, pru, mmat, bmat, cmat, mcmat, v_is_my,
+                                    rmat, vmat, gamma)
+    mtxtb = -pru.get_mTzzTtb(MT, Zc, tb_mat)
+    store.save(Zc, key + '__Z')
+    store.save(mtxtb, key + '__mtxtb')
+    if ystarvec is not None:
+        wc = lau.apply_massinv(MT, gamma*np.dot(mcmat.T, ystarvec(tE)))
+        store.save(wc, key + '__w')
+    else:
+        wc = None
+    fbdict = {tE: dict(w=key + '__w', mtxtb=key + '__mtxtb')}
+    if curnwtnsdict is not None:
+        store.save(wc, curnwtnsdict[tE]['w'])
+        store.save(mtxtb, curnwtnsdict[tE]['mtxtb'])
+
+    for tk in range(len(tmesh)-2, -1, -1):
+        t = tmesh[tk]
+        cts = tmesh[tk+1] - t
+        if verbose:
+            print('Time is {0}, timestep is {1}'.format(t, cts))
+        gtdtstrargs.update(time=t)
+        key = get_datastr(**gtdtstrargs)
+        nmattd, rhsvtd = get_tdpart(time=t, **gttdprtargs)
+        NT = nmattd.T
+
+        cnsw, cnsmtxtb = None, None
+        if curnwtnsdict is not None:
+            try:
+                cnsw = store.load(curnwtnsdict[t]['w'])
+                cnsmtxtb = store.load(curnwtnsdict[t]['mtxtb'])
+            except IOError:
+                cnsw, cnsmtxtb = None, None
+
+        info = dict(t=t, tau=cts)
+        try:
+            Zc = store.load(key + '__Z')
+        except IOError:
+            ft_mat = -(0.5*MT + cts*(AT + NT))
+            w_mat = np.hstack([MT @ Zc, np.sqrt(cts)*tct_mat])
+            oldfb = np.sqrt(cts)*cnsmtxtb if cnsmtxtb is not None else None
+            nres = pru.proj_alg_ric_newtonadi(mmat=MT, amat=ft_mat, transposed=True,
+                                              mtxoldb=oldfb, jmat=jmat,
+                                              bmat=np.sqrt(cts)*tb_mat,
+                                              wmat=w_mat, z0=Zc,
+                                              nwtn_adi_dict=nwtn_adi_dict)
+            Zp = nres['zfac']
+            info.update(nwtn_upd_fnorms=nres.get('nwtn_upd_fnorms'),
+                        adi_steps=nres.get('adi_steps'), zp_cols=Zp.shape[1])
+            if comprz_maxc is not None or comprz_thresh is not None:
+                Zc = pru.compress_Zsvd(Zp, thresh=comprz_thresh, k=comprz_maxc)
+            else:
+                Zc = Zp
+            store.save(Zp if save_full_z else Zc, key + '__Z')
+        info.update(zc_cols=Zc.shape[1])
+
+        at_mat = MT + cts*(AT + NT)
+        ftilde = rhsvtd + rhsv
+        if cnsw is not None:
+            ftilde = rhsvtd + rhsv + cnsw
+        # NB (reference quirk, solve_dae_ric.py:181): uses the previous step's mtxtb
+        cnsmtxtb = cnsmtxtb + mtxtb if cnsmtxtb is not None else mtxtb
+
+        mtxft = pru.get_mTzzTtb(MT, Zc, ftilde)
+        fl1 = np.dot(mcmat.T, ystarvec(t))
+        rhswc = MT @ wc + cts*(fl1 - mtxft)
+        mtxtb = -pru.get_mTzzTtb(MT, Zc, tb_mat)
+        wc = lau.solve_sadpnt_smw(amat=at_mat, jmat=jmat,
+                                  umat=cts*cnsmtxtb, vmat=tb_mat.T,
+                                  rhsv=rhswc)[:NV]
+
+        if curnwtnsdict is not None:
+            cnsw = cnsw + wc if cnsw is not None else wc
+            cnsmtxtb = cnsmtxtb + mtxtb if cnsmtxtb is not None else mtxtb
+            store.save(cnsw, curnwtnsdict[t]['w'])
+            store.save(cnsmtxtb, curnwtnsdict[t]['mtxtb'])
+
+        store.save(wc, key + '__w')
+        store.save(mtxtb, key + '__mtxtb')
+        fbdict.update({t: dict(w=key + '__w', mtxtb=key + '__mtxtb')})
+        if stepinfo is not None:
+            stepinfo.append(info)
+    return fbdict

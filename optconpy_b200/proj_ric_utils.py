@@ -1,0 +1,208 @@
+"""CUDA-backed ``sadptprj_riclyap_adi.proj_ric_utils`` for the optconpy hot path.
+
+Module-level functions with the names, keyword arguments and return shapes of
+the reference's call sites:
+
+* ``solve_proj_lyap_stein``   ``tests/test_units_compfacres_compress.py:62-64``
+* ``proj_alg_ric_newtonadi``  ``optcont_main.py:488-492``, ``solve_dae_ric.py:152-159``
+* ``compress_Zsvd``           ``solve_dae_ric.py:162``, ``optcont_main.py:498``
+* ``get_mTzzTtb``             ``solve_dae_ric.py:101,183,189``, ``optcont_main.py:505-506``
+* ``comp_proj_lyap_res_norm`` ``tests/test_units_compfacres_compress.py:82,104``
+
+Host objects in, host objects out; the factor ``Z`` stays resident on the device
+between the Newton steps (``*_dev`` helpers work on torch tensors and are what
+the device-resident DRE loop uses).  The per-shift sparse LU factorisations are
+the separately timed host setup (``device.LU``); all solves, products, norms,
+the compression and the eigen-decomposition run in CUDA kernels.  No CPU fallback.
+"""
+import numpy as np
+import scipy.sparse as sps
+import torch
+
+from . import device as dv
+
+__all__ = ['solve_proj_lyap_stein', 'proj_alg_ric_newtonadi', 'compress_Zsvd',
+           'get_mTzzTtb', 'comp_proj_lyap_res_norm']
+
+DEFAULT_SHIFTS = [-30.0, -20.0, -10.0, -5.0, -3.0, -1.0]
+
+
+def _dense(a):
+    if sps.issparse(a):
+        return np.asarray(a.todense(), dtype=np.float64)
+    a = np.asarray(a, dtype=np.float64)
+    return a[:, None] if a.ndim == 1 else a
+
+
+class ShiftedFactors(object):
+    """Per-shift LU handles of ``[[At + mu Mt, J^T], [J, 0]]`` — the setup step that
+    ``north_star`` times separately.  Reused across the Newton steps of one
+    Riccati solve (the low-rank closed-loop part enters through SMW only)."""
+
+    def __init__(self, At, Mt, jmat, ms):
+        self.ms = [float(m) for m in ms]
+        self.NV, self.NP = At.shape[0], jmat.shape[0]
+        self.lus = [dv.LU(dv.sadpnt_matrix(At + mu*Mt, jmat)) for mu in self.ms]
+        self.Mt_dev = dv.DeviceCSR(Mt)
+
+
+def _stein_dev(fac, W, adi_dict, Ufb=None, Vt=None):
+    """LR-ADI on the device: W (NV x k) device block -> (Z device, rel norms)."""
+    return dv.adi_run(fac.lus, fac.ms, fac.NV, fac.NP, fac.Mt_dev, W,
+                      int(adi_dict['adi_max_steps']), float(adi_dict['adi_newZ_reltol']),
+                      Ufb=Ufb, Vt=Vt)
+
+
+def _transposed_pair(amat, mmat, transposed):
+    if transposed:
+        return sps.csr_matrix(amat), sps.csr_matrix(mmat)
+    return sps.csr_matrix(amat.T), sps.csr_matrix(mmat.T)
+
+
+def solve_proj_lyap_stein(amat=None, jmat=None, wmat=None, mmat=None,
+                          umat=None, vmat=None, transposed=False,
+                          adi_dict=dict(adi_max_steps=150, adi_newZ_reltol=1e-8),
+                          nwtn_adi_dict=None, **kw):
+    """Low-rank ADI for ``[F-UV]^T X M + M^T X [F-UV] + W W^T = 0`` on the
+    divergence-free subspace, ``X = Z Z^T``.  Returns
+    ``dict(zfac=Z, adi_rel_newZ_norms=[...])`` with ``Z`` a numpy array."""
+    dv.require_cuda()
+    if nwtn_adi_dict is not None:
+        adi_dict = nwtn_adi_dict
+    At, Mt = _transposed_pair(amat, mmat, transposed)
+    fac = ShiftedFactors(At, Mt, jmat, adi_dict.get('ms', DEFAULT_SHIFTS))
+    W = dv.to_dev(_dense(wmat))
+    Ufb = Vt = None
+    if umat is not None and vmat is not None:
+        # (F - U V)^T = F^T - V^T U^T: dense SMW factor V^T (NV x m), sparse factor U^T
+        Ufb = dv.to_dev(_dense(vmat).T)
+        Vt = dv.DeviceCSR(sps.csr_matrix(umat).T)
+    Z, rel = _stein_dev(fac, W, adi_dict, Ufb=Ufb, Vt=Vt)
+    return dict(zfac=dv.to_host(Z), adi_rel_newZ_norms=rel)
+
+
+def get_mTzzTtb(MT, Z, tB, output=None):
+    """``M^T (Z (Z^T tB))`` -> dense ndarray (NV, m)."""
+    dv.require_cuda()
+    Mt = MT if isinstance(MT, dv.DeviceCSR) else dv.DeviceCSR(MT)
+    out = dv.feedback(Mt, dv.to_dev(Z), dv.to_dev(_dense(tB)))
+    return dv.to_host(out)
+
+
+def _probe_vec(n, nwtn_adi_dict):
+    rng = np.random.default_rng(nwtn_adi_dict.get('probe_seed', 0))
+    vec = rng.standard_normal((n, 1))
+    return vec/np.linalg.norm(vec)
+
+
+def _fro(t):
+    return float(torch.sqrt((t*t).sum()).item())
+
+
+def newtonadi_dev(fac, Bd, Vt_b, W, z0, nwtn_adi_dict, mtxoldb=None):
+    """Newton-Kleinman with everything resident on the device.
+    fac: ShiftedFactors, Bd: dense device B (NV x m), Vt_b: DeviceCSR of B^T,
+    W: device (NV x p), z0: device factor or None.  Returns (Z device, info)."""
+    znc = z0
+    fnorms, adi_steps, rels = [], [], []
+    maxstp = int(nwtn_adi_dict['nwtn_max_steps'])
+    reltol = nwtn_adi_dict.get('nwtn_upd_reltol', 0.0)
+    abstol = nwtn_adi_dict.get('nwtn_upd_abstol', 0.0)
+    full = nwtn_adi_dict.get('full_upd_norm_check', False)
+    vec = None
+    stp = 0
+    while stp < maxstp:
+        if znc is None:
+            rhsadi, kfb = W, None
+        else:
+            kfb = dv.feedback(fac.Mt_dev, znc, Bd)               # M^T Z Z^T B
+            rhsadi = torch.cat([kfb, W], dim=1).contiguous()
+        if mtxoldb is not None:
+            kfb = -mtxoldb if kfb is None else kfb - mtxoldb
+        znn, rel = _stein_dev(fac, rhsadi, nwtn_adi_dict,
+                              Ufb=kfb, Vt=Vt_b if kfb is not None else None)
+        adi_steps.append(len(rel))
+        rels.append(rel)
+        if full:
+            gnn = dv.gram(znn, znn)
+            ref = _fro(gnn)
+            if znc is None:
+                upd = ref
+            else:
+                gnc, gcc = dv.gram(znn, znc), dv.gram(znc, znc)
+                upd = np.sqrt(abs(ref**2 - 2*_fro(gnc)**2 + _fro(gcc)**2))
+        else:
+            if vec is None:
+                vec = dv.to_dev(_probe_vec(znn.shape[0], nwtn_adi_dict))
+            nv = dv.tall_gemm(znn, dv.gram(znn, vec))
+            ref = _fro(nv)
+            if znc is None:
+                upd = ref
+            else:
+                upd = _fro(nv - dv.tall_gemm(znc, dv.gram(znc, vec)))
+        fnorms.append(upd)
+        znc = znn
+        stp += 1
+        if upd < abstol or upd < reltol*ref:
+            break
+    return znc, dict(nwtn_upd_fnorms=fnorms, adi_steps=adi_steps, adi_rel_norms=rels)
+
+
+def proj_alg_ric_newtonadi(mmat=None, amat=None, jmat=None,
+                           bmat=None, wmat=None, z0=None, mtxoldb=None,
+                           transposed=False,
+                           nwtn_adi_dict=dict(adi_max_steps=150, adi_newZ_reltol=1e-5,
+                                              nwtn_max_steps=14, nwtn_upd_reltol=1e-8),
+                           **kw):
+    """Newton-ADI for ``F^T X M + M^T X F - M^T X B B^T X M + W W^T = 0``,
+    ``X = Z Z^T`` (projected).  ``transposed=True``: ``mmat=M^T``, ``amat=F^T``.
+    Returns ``dict(zfac=Z, nwtn_upd_fnorms=[...], adi_steps=[...])``."""
+    dv.require_cuda()
+    At, Mt = _transposed_pair(amat, mmat, transposed)
+    fac = kw.get('_factors')
+    if fac is None:
+        fac = ShiftedFactors(At, Mt, jmat, nwtn_adi_dict.get('ms', DEFAULT_SHIFTS))
+    Bd = dv.to_dev(_dense(bmat))
+    Vt_b = dv.DeviceCSR(sps.csr_matrix(bmat).T)
+    W = dv.to_dev(_dense(wmat))
+    z0d = None if z0 is None else dv.to_dev(z0)
+    old = None if mtxoldb is None else dv.to_dev(_dense(mtxoldb))
+    Z, info = newtonadi_dev(fac, Bd, Vt_b, W, z0d, nwtn_adi_dict, mtxoldb=old)
+    if kw.get('_return_device'):
+        return dict(zfac=Z, **info)
+    return dict(zfac=dv.to_host(Z), **info)
+
+
+def compress_Zsvd(Z, k=None, thresh=None, shplot=False):
+    """Column compression ``Zc = Z V_k`` (singular values ``> thresh``, at most ``k``):
+    rank-revealing Cholesky of the Gram matrix, Jacobi eigen-solver and the two
+    tall products, all on the device."""
+    dv.require_cuda()
+    Zd = Z if isinstance(Z, torch.Tensor) else dv.to_dev(Z)
+    Zc, info = dv.compress(Zd, thresh=thresh, k=k)
+    if isinstance(Z, torch.Tensor):
+        return Zc
+    return dv.to_host(Zc)
+
+
+def comp_proj_lyap_res_norm(Z, amat=None, mmat=None, wmat=None, jmat=None,
+                            umat=None, vmat=None):
+    """SQUARED Frobenius norm of ``P^T (F^T Z Z^T M + M^T Z Z^T F + W W^T) P`` in
+    factored form (positional call ``(Z, F, M, W, J)``)."""
+    dv.require_cuda()
+    Ft, Mt = dv.DeviceCSR(sps.csr_matrix(amat.T)), dv.DeviceCSR(sps.csr_matrix(mmat.T))
+    Zd = dv.to_dev(Z)
+    ftz = Ft.matmul(Zd)
+    if umat is not None and vmat is not None:
+        utz = dv.DeviceCSR(sps.csr_matrix(umat).T).matmul(Zd)
+        ftz = ftz - dv.tall_gemm(dv.to_dev(_dense(vmat).T), utz)
+    mtz = Mt.matmul(Zd)
+    Wd = dv.to_dev(_dense(wmat))
+    stacked = torch.cat([ftz, mtz, Wd], dim=1).contiguous()
+    NV = mmat.shape[0]
+    lu = dv.LU(dv.sadpnt_matrix(mmat, jmat))
+    prj = dv.DeviceCSR(mmat).matmul(lu.solve(stacked, nrows_out=NV))    # P^T [..]
+    ka, kb = ftz.shape[1], mtz.shape[1]
+    G = dv.gram(prj, prj)
+    DG = torch.cat([G[ka:ka+kb, :], G[:ka, :], G[ka+kb:, :]], dim=0)
+    return float((DG*DG.t()).sum().item())

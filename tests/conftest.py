@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def cav10():
+    from optconpy_b200 import problems as pb
+    return pb.drivcav_problem(10, 1e-2)
+
+
+@pytest.fixture(scope='session')
+def cav6():
+    from optconpy_b200 import problems as pb
+    return pb.drivcav_problem(6, 1e-2)

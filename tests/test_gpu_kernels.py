@@ -1,0 +1,188 @@
+"""Kernel-level parity: every C-ABI entry point against numpy/scipy on seeded inputs.
+All calls go through the ctypes C ABI (optconpy_b200.device)."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import scipy.sparse.linalg as spsla
+
+pytestmark = pytest.mark.gpu
+
+
+def _relerr(a, b):
+    return np.linalg.norm(a - b)/max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope='module')
+def dv():
+    from optconpy_b200 import device
+    device.require_cuda()
+    return device
+
+
+@pytest.fixture(scope='module')
+def sad(cav10):
+    from optconpy_b200 import problems as pb, device
+    M, A, J = cav10['M'], cav10['A'], cav10['J']
+    Nc = pb.convection_matrix(cav10, pb.analytic_vortex)
+    Ft = -(0.5*M.T + 0.05*(A.T + Nc.T))
+    return device.sadpnt_matrix(Ft - 1.0*M.T, J)
+
+
+@pytest.mark.parametrize('k', [1, 5, 32, 33, 66, 130])
+def test_spmm(dv, cav10, k):
+    rng = np.random.default_rng(k)
+    S = cav10['J']                      # rectangular NP x NV
+    X = rng.standard_normal((S.shape[1], k))
+    Y0 = rng.standard_normal((S.shape[0], k))
+    Sd = dv.DeviceCSR(S)
+    Y = dv.to_host(Sd.matmul(dv.to_dev(X)))
+    assert _relerr(Y, S @ X) < 1e-14
+    out = dv.to_dev(Y0)
+    Sd.matmul(dv.to_dev(X), alpha=-0.5, beta=2.0, out=out)
+    assert _relerr(dv.to_host(out), -0.5*(S @ X) + 2.0*Y0) < 1e-14
+
+
+def test_spmm_strided_and_empty_rows(dv):
+    rng = np.random.default_rng(0)
+    S = sps.random(300, 200, density=0.02, random_state=1, format='csr')  # has empty rows
+    Xbig = rng.standard_normal((200, 40))
+    Xd = dv.to_dev(Xbig)[:, 3:20]       # non-contiguous view, ld = 40
+    Y = dv.to_host(dv.DeviceCSR(S).matmul(Xd))
+    assert _relerr(Y, S @ Xbig[:, 3:20]) < 1e-14
+
+
+@pytest.mark.parametrize('k', [1, 3, 4, 7, 66])
+def test_lu_solve_matches_superlu(dv, sad, k):
+    rng = np.random.default_rng(10 + k)
+    n = sad.shape[0]
+    B = rng.standard_normal((n, k))
+    ref = spsla.splu(sad).solve(B)       # the reference's factorisation (COLAMD default)
+    lu = dv.LU(sad)
+    X = dv.to_host(lu.solve(dv.to_dev(B)))
+    assert _relerr(X, ref) < 1e-11
+    assert np.linalg.norm(sad @ X - B)/np.linalg.norm(B) < 1e-12
+    # same factors as the oracle would use: default SuperLU options
+    lu2 = dv.LU(sad, lu_options={})
+    X2 = dv.to_host(lu2.solve(dv.to_dev(B)))
+    assert _relerr(X2, ref) < 1e-12
+
+
+def test_lu_solve_partial_rows(dv, sad, cav10):
+    rng = np.random.default_rng(3)
+    NV, n = cav10['NV'], sad.shape[0]
+    R = rng.standard_normal((NV, 9))
+    full = np.vstack([R, np.zeros((n - NV, 9))])
+    ref = spsla.splu(sad).solve(full)[:NV]
+    lu = dv.LU(sad)
+    X = dv.to_host(lu.solve(dv.to_dev(R), nrows_out=NV))
+    assert X.shape == (NV, 9)
+    assert _relerr(X, ref) < 1e-11
+    # in place
+    Rd = dv.to_dev(R)
+    lu.solve(Rd, nrows_out=NV, out=Rd)
+    assert _relerr(dv.to_host(Rd), ref) < 1e-11
+
+
+def test_lu_solve_global_panel_path(dv):
+    """n large enough that the column panel does not fit shared memory."""
+    from optconpy_b200 import problems as pb
+    p = pb.drivcav_problem(64, 1e-2)
+    S = dv.sadpnt_matrix(p['M'] + 0.01*p['A'], p['J'])
+    n = S.shape[0]
+    assert n*2*8 > 227*1024
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((n, 11))
+    lu = dv.LU(S)
+    X = dv.to_host(lu.solve(dv.to_dev(B)))
+    assert np.linalg.norm(S @ X - B)/np.linalg.norm(B) < 1e-11
+    ref = spsla.splu(S).solve(B)
+    assert _relerr(X, ref) < 1e-10
+
+
+@pytest.mark.parametrize('shape', [(722, 5, 5), (1000, 66, 66), (4802, 130, 8), (333, 7, 129)])
+def test_gram(dv, shape):
+    n, ka, kb = shape
+    rng = np.random.default_rng(n)
+    Z, W = rng.standard_normal((n, ka)), rng.standard_normal((n, kb))
+    G = dv.to_host(dv.gram(dv.to_dev(Z), dv.to_dev(W)))
+    assert _relerr(G, Z.T @ W) < 1e-13
+    G2 = dv.to_host(dv.gram(dv.to_dev(Z), dv.to_dev(W)))
+    assert np.array_equal(G, G2)         # deterministic
+
+
+@pytest.mark.parametrize('shape', [(722, 5, 3), (1000, 70, 66), (4802, 300, 50), (65, 33, 1)])
+def test_tall_gemm(dv, shape):
+    n, k, kc = shape
+    rng = np.random.default_rng(n)
+    Z, T = rng.standard_normal((n, k)), rng.standard_normal((k, kc))
+    Cm = dv.to_host(dv.tall_gemm(dv.to_dev(Z), dv.to_dev(T), alpha=0.5))
+    assert _relerr(Cm, 0.5*Z @ T) < 1e-13
+
+
+@pytest.mark.parametrize('k', [1, 2, 7, 64, 101, 256])
+def test_sym_eig(dv, k):
+    rng = np.random.default_rng(k)
+    A = rng.standard_normal((k + 20, k))*np.logspace(0, -6, k)[None, :]
+    G = A.T @ A
+    lam, V, sweeps = dv.sym_eig(dv.to_dev(G))
+    lam, V = dv.to_host(lam), dv.to_host(V)
+    ref = np.linalg.eigvalsh(G)[::-1]
+    assert np.max(np.abs(lam - ref)) < 1e-13*ref[0]
+    assert np.linalg.norm(V.T @ V - np.eye(k)) < 1e-12
+    assert np.linalg.norm(V @ np.diag(lam) @ V.T - G) < 1e-12*ref[0]*k
+    assert np.all(np.diff(lam) <= 0)
+
+
+def test_compress_matches_svd(dv):
+    rng = np.random.default_rng(7)
+    n, K, r = 900, 1500, 120
+    Z = (rng.standard_normal((n, r))*np.logspace(1, -9, r)[None, :]) @ rng.standard_normal((r, K))
+    s = np.linalg.svd(Z, compute_uv=False)
+    U, sv, Vt = np.linalg.svd(Z, full_matrices=False)
+    for thresh, k in ((5e-5, 50), (1e-6, None), (None, 17)):
+        keep = len(sv) if thresh is None else int(np.sum(sv > thresh))
+        keep = keep if k is None else min(keep, k)
+        ref = Z @ Vt[:keep].T
+        Zc, info = dv.compress(dv.to_dev(Z), thresh=thresh, k=k)
+        Zc = dv.to_host(Zc)
+        if thresh == 1e-6:
+            # the Gram route resolves singular values down to ~1e-7 sigma_max
+            assert abs(Zc.shape[1] - keep) <= 3
+        else:
+            assert Zc.shape[1] == keep
+        assert _relerr(Zc @ Zc.T, ref @ ref.T) < 1e-9
+        assert _relerr(dv.to_host(info['sigma'])[:10], s[:10]) < 1e-10
+
+
+def test_smw_solve(dv, sad, cav10):
+    rng = np.random.default_rng(2)
+    NV, n = cav10['NV'], sad.shape[0]
+    U = rng.standard_normal((NV, 8))*1e-2
+    V = sps.random(8, NV, density=0.05, random_state=3, format='csr')
+    R = rng.standard_normal((NV, 6))
+    Ue = np.vstack([U, np.zeros((n-NV, 8))])
+    Ve = sps.hstack([V, sps.csr_matrix((8, n-NV))]).tocsr()
+    ref = np.linalg.solve(sad.toarray() - Ue @ Ve.toarray(), np.vstack([R, np.zeros((n-NV, 6))]))
+    lu = dv.LU(sad)
+    X = dv.to_host(lu.smw_solve(dv.to_dev(R), NV, Ufb=dv.to_dev(U), Vt=dv.DeviceCSR(V)))
+    assert X.shape == (n, 6)
+    assert _relerr(X, ref) < 1e-10
+
+
+def test_feedback(dv, cav10):
+    rng = np.random.default_rng(4)
+    NV = cav10['NV']
+    Z = rng.standard_normal((NV, 37))
+    tB = rng.standard_normal((NV, 8))
+    MT = cav10['M'].T.tocsr()
+    out = dv.to_host(dv.feedback(dv.DeviceCSR(MT), dv.to_dev(Z), dv.to_dev(tB), alpha=-1.0))
+    assert _relerr(out, -(MT @ (Z @ (Z.T @ tB)))) < 1e-13
+
+
+def test_errors_are_loud(dv, sad):
+    from optconpy_b200 import _cabi
+    lu = dv.LU(sad)
+    import torch
+    B = torch.zeros((sad.shape[0] + 1, 2), dtype=torch.float64, device='cuda')
+    with pytest.raises(_cabi.OcbError):
+        lu.solve(B)

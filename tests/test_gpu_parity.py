@@ -1,0 +1,175 @@
+"""Path-level parity of the CUDA modules against the CPU oracle on the same seeded
+inputs: factor products Z Z^T and gains within 1e-9 relative Frobenius error, ADI
+iteration counts and relative-norm histories equal, DRE trajectories within 1e-8."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+pytestmark = pytest.mark.gpu
+
+TOL_FACTOR = 1e-9      # north_star: Z Z^T and feedback gains
+TOL_TRAJ = 1e-8        # north_star: DRE trajectory quantities
+
+
+def _relerr(a, b):
+    return np.linalg.norm(a - b)/max(np.linalg.norm(b), 1e-300)
+
+
+def _zzt_relerr(Za, Zb):
+    """||Za Za^T - Zb Zb^T||_F / ||Zb Zb^T||_F via small Gram matrices."""
+    gaa, gab, gbb = Za.T @ Za, Za.T @ Zb, Zb.T @ Zb
+    num = np.linalg.norm(gaa)**2 - 2*np.linalg.norm(gab)**2 + np.linalg.norm(gbb)**2
+    return np.sqrt(abs(num))/np.linalg.norm(gbb)
+
+
+@pytest.fixture(scope='module')
+def mods():
+    import optconpy_b200.lin_alg_utils as glau
+    import optconpy_b200.proj_ric_utils as gpru
+    from oracle import lin_alg_utils as olau, proj_ric_utils as opru
+    return glau, gpru, olau, opru
+
+
+@pytest.fixture(scope='module')
+def lyap_setup(cav10):
+    from optconpy_b200 import problems as pb
+    M, A, J = cav10['M'], cav10['A'], cav10['J']
+    Nc = pb.convection_matrix(cav10, pb.analytic_vortex)
+    tau = 0.05
+    F = -(0.5*M + tau*(A + Nc))
+    rng = np.random.default_rng(0)
+    W = rng.standard_normal((cav10['NV'], 5))
+    return M, F, J, W
+
+
+def test_lau_small_functions(mods, cav10):
+    glau, gpru, olau, opru = mods
+    M, J = cav10['M'], cav10['J']
+    rng = np.random.default_rng(1)
+    R = rng.standard_normal((cav10['NV'], 3))
+    assert _relerr(glau.apply_massinv(M, R), olau.apply_massinv(M, R)) < 1e-12
+    Rs = sps.random(cav10['NV'], 4, density=0.05, random_state=2, format='csr')
+    a, b = glau.apply_massinv(M, Rs, output='sparse'), olau.apply_massinv(M, Rs, output='sparse')
+    assert sps.issparse(a) and _relerr(a.toarray(), b.toarray()) < 1e-12
+    for tp in (True, False):
+        pa = glau.app_prj_via_sadpnt(amat=M, jmat=J, rhsv=R, transposedprj=tp)
+        pb_ = olau.app_prj_via_sadpnt(amat=M, jmat=J, rhsv=R, transposedprj=tp)
+        assert _relerr(pa, pb_) < 1e-11
+    # projector property: J M^-1 (P^T R) = 0
+    pt = glau.app_prj_via_sadpnt(amat=M, jmat=J, rhsv=R, transposedprj=True)
+    assert np.linalg.norm(J @ olau.apply_massinv(M, pt)) < 1e-11*np.linalg.norm(R)
+    assert _relerr(glau.mm_dnssps(M, R), M @ R) < 1e-14
+    Z1, Z2 = rng.standard_normal((cav10['NV'], 7)), rng.standard_normal((cav10['NV'], 4))
+    assert abs(glau.comp_sqfnrm_factrd_diff(Z1, Z2) - olau.comp_sqfnrm_factrd_diff(Z1, Z2)) \
+        < 1e-11*olau.comp_sqfnrm_factrd_sum(Z1, Z2)
+    assert abs(glau.comp_sqfnrm_factrd_sum(Z1, Z2) - olau.comp_sqfnrm_factrd_sum(Z1, Z2)) \
+        < 1e-11*olau.comp_sqfnrm_factrd_sum(Z1, Z2)
+
+
+def test_solve_sadpnt_smw(mods, cav10):
+    glau, gpru, olau, opru = mods
+    M, A, J = cav10['M'], cav10['A'], cav10['J']
+    rng = np.random.default_rng(3)
+    NV = cav10['NV']
+    rhs = rng.standard_normal((NV, 1))
+    U = rng.standard_normal((NV, 8))*1e-3
+    V = sps.random(8, NV, density=0.03, random_state=5, format='csr')
+    amat = M.T + 0.1*A.T
+    ref = olau.solve_sadpnt_smw(amat=amat, jmat=J, rhsv=rhs, umat=U, vmat=V)
+    got = glau.solve_sadpnt_smw(amat=amat, jmat=J, rhsv=rhs, umat=U, vmat=V)
+    assert got.shape == ref.shape == (NV + cav10['NP'], 1)
+    assert _relerr(got, ref) < 1e-10
+    ref0 = olau.solve_sadpnt_smw(amat=amat, jmat=J, rhsv=rhs)
+    got0 = glau.solve_sadpnt_smw(amat=amat, jmat=J, rhsv=rhs)
+    assert _relerr(got0, ref0) < 1e-10
+
+
+def test_stein_parity(mods, lyap_setup):
+    glau, gpru, olau, opru = mods
+    M, F, J, W = lyap_setup
+    d = dict(adi_max_steps=80, adi_newZ_reltol=1e-9, ms=[-5.0, -3.0, -2.0, -1.5, -1.3, -1.1, -1.0])
+    ref = opru.solve_proj_lyap_stein(amat=F, mmat=M, jmat=J, wmat=W, adi_dict=d)
+    got = gpru.solve_proj_lyap_stein(amat=F, mmat=M, jmat=J, wmat=W, adi_dict=d)
+    assert got['zfac'].shape == ref['zfac'].shape            # same iteration count
+    assert len(got['adi_rel_newZ_norms']) == len(ref['adi_rel_newZ_norms'])
+    assert np.allclose(got['adi_rel_newZ_norms'], ref['adi_rel_newZ_norms'], rtol=1e-7, atol=0)
+    assert _zzt_relerr(got['zfac'], ref['zfac']) < TOL_FACTOR
+    # the five identities of the reference's test, on the CUDA result
+    Z = got['zfac']
+    res_full = gpru.comp_proj_lyap_res_norm(Z, F, M, W, J)
+    res_ref = opru.comp_proj_lyap_res_norm(Z, F, M, W, J)
+    assert abs(res_full - res_ref) <= 1e-8*max(res_ref, 1e-300) + 1e-20
+    Zr = gpru.compress_Zsvd(Z, k=None, thresh=1e-6)
+    MtZ, MtZr = M.T @ Z, M.T @ Zr
+    assert np.allclose(np.linalg.norm(MtZ.T @ MtZ), np.linalg.norm(MtZr.T @ MtZr))
+    Pt = olau.app_prj_via_sadpnt(amat=M, jmat=J, rhsv=MtZr, transposedprj=True)
+    assert np.allclose(Pt, MtZr, atol=1e-8*np.abs(MtZr).max())
+
+
+def test_stein_transposed_with_lowrank(mods, lyap_setup, cav10):
+    glau, gpru, olau, opru = mods
+    M, F, J, W = lyap_setup
+    rng = np.random.default_rng(9)
+    NV = cav10['NV']
+    B = sps.random(NV, 8, density=0.02, random_state=4, format='csr')
+    K = rng.standard_normal((8, NV))*1e-2
+    d = dict(adi_max_steps=60, adi_newZ_reltol=1e-8, ms=[-5.0, -2.0, -1.0])
+    kw = dict(amat=F.T, mmat=M.T, jmat=J, wmat=W, umat=B, vmat=K, transposed=True, adi_dict=d)
+    ref, got = opru.solve_proj_lyap_stein(**kw), gpru.solve_proj_lyap_stein(**kw)
+    assert got['zfac'].shape == ref['zfac'].shape
+    assert _zzt_relerr(got['zfac'], ref['zfac']) < TOL_FACTOR
+
+
+def test_newtonadi_parity(mods, lyap_setup, cav10):
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import problems as pb
+    M, F, J, _ = lyap_setup
+    cs = pb.control_setup(cav10, olau, alphau=1e-4)
+    d = dict(adi_max_steps=120, adi_newZ_reltol=1e-9, nwtn_max_steps=12,
+             nwtn_upd_reltol=1e-9, nwtn_upd_abstol=1e-12, full_upd_norm_check=False,
+             ms=[-5.0, -3.0, -2.0, -1.5, -1.3, -1.1, -1.0])
+    tau = 0.05
+    kw = dict(mmat=M.T, amat=F.T, transposed=True, jmat=J, bmat=np.sqrt(tau)*cs['tb_mat'],
+              wmat=np.sqrt(tau)*cs['trct_mat'], z0=None, nwtn_adi_dict=d)
+    ref, got = opru.proj_alg_ric_newtonadi(**kw), gpru.proj_alg_ric_newtonadi(**kw)
+    assert got['adi_steps'] == ref['adi_steps']
+    assert len(got['nwtn_upd_fnorms']) == len(ref['nwtn_upd_fnorms'])
+    assert _zzt_relerr(got['zfac'], ref['zfac']) < TOL_FACTOR
+    for full in (True,):
+        d2 = dict(d, full_upd_norm_check=full, nwtn_max_steps=3)
+        kw2 = dict(kw, nwtn_adi_dict=d2, z0=ref['zfac'][:, :16])
+        r2, g2 = opru.proj_alg_ric_newtonadi(**kw2), gpru.proj_alg_ric_newtonadi(**kw2)
+        assert g2['adi_steps'] == r2['adi_steps']
+        assert np.allclose(g2['nwtn_upd_fnorms'], r2['nwtn_upd_fnorms'], rtol=1e-5, atol=1e-12)
+        assert _zzt_relerr(g2['zfac'], r2['zfac']) < TOL_FACTOR
+    # feedback gains
+    tb = cs['tb_mat']
+    ga, gb = gpru.get_mTzzTtb(M.T, got['zfac'], tb), opru.get_mTzzTtb(M.T, ref['zfac'], tb)
+    assert _relerr(ga, gb) < TOL_FACTOR
+    fv = np.random.default_rng(1).standard_normal((cav10['NV'], 1))
+    assert _relerr(gpru.get_mTzzTtb(M.T, got['zfac'], fv), opru.get_mTzzTtb(M.T, ref['zfac'], fv)) < TOL_FACTOR
+    # compressed factor products
+    zc_g = gpru.compress_Zsvd(got['zfac'], thresh=5e-5, k=50)
+    zc_o = opru.compress_Zsvd(ref['zfac'], thresh=5e-5, k=50)
+    assert zc_g.shape == zc_o.shape
+    assert _zzt_relerr(zc_g, zc_o) < TOL_FACTOR
+
+
+def test_dre_trajectory_parity(mods):
+    """Config 1 (driven cavity N=10, optcon_nse defaults), 3 backward steps."""
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import scenarios as sc, dre_stepper as ds
+    prob, cs, kw = sc.config1(olau, Nts=3)
+    so, sg = ds.MemStore(), ds.MemStore()
+    io, ig = [], []
+    fo = ds.solve_flow_daeric(lau=olau, pru=opru, store=so, stepinfo=io, **dict(kw, gtdtstrargs=dict(kw['gtdtstrargs'])))
+    fg = ds.solve_flow_daeric(lau=glau, pru=gpru, store=sg, stepinfo=ig, **dict(kw, gtdtstrargs=dict(kw['gtdtstrargs'])))
+    assert sorted(fo) == sorted(fg)
+    for a, b in zip(io, ig):
+        assert a['adi_steps'] == b['adi_steps']
+        assert a['zc_cols'] == b['zc_cols']
+    for t in fo:
+        assert _relerr(sg[fg[t]['mtxtb']], so[fo[t]['mtxtb']]) < TOL_TRAJ
+        assert _relerr(sg[fg[t]['w']], so[fo[t]['w']]) < TOL_TRAJ
+        ko = fo[t]['mtxtb'].replace('__mtxtb', '__Z')
+        assert _zzt_relerr(sg[ko], so[ko]) < TOL_FACTOR
