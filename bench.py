@@ -1,0 +1,334 @@
+"""Benchmark of the LR-ADI / projected-Riccati hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one backward time step of the differential Riccati recursion
+(``solve_dae_ric.py:122-211``): Newton-ADI for the projected ARE, factor compression,
+the two feedback products and the feed-forward saddle-point solve.  Workload at N=1 is
+BASELINE config[1]: driven cavity N=25 (NV 4802, NP 675) with the parameters of
+``run_optcont.py:12-41``; steps are taken backward from the terminal time.
+
+* ``value``  DRE steps/s with all inputs (matrices, per-shift LU factors) resident in HBM:
+             the device-resident loop ``dre_device.run_step``; CUDA events, max over ranks.
+* ``e2e``    the same steps through the reference-facing API
+             ``solve_flow_daeric(lau=<CUDA lau>, pru=<CUDA pru>)`` with host (scipy/numpy)
+             inputs and ``.npy`` outputs: host LU setup, H2D and D2H inside the timed region.
+* ``roofline``  the multi-RHS SpTRSM solve kernel: algorithmic bytes / mean
+             launch time measured with CUDA events around every launch of the timed steps.
+* ``cpu_baseline``  the scipy/SuperLU oracle (oracle/) on the first backward steps, host cores.
+N>1: one independent DRE replica per GPU (the backward recursion is sequential and a
+66-column block cannot fill one B200, see DESIGN.md "Multi-GPU"); value = all steps / max time.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'dre_backward_steps_per_s'
+UNIT = 'steps/s'
+WORKLOAD = 'drivcav N=25 (NV 4802, NP 675), run_optcont.py params: nu=5e-3, Nts=128, tE=0.2, ' \
+           'alphau=1e-7, gamma=1e-1, 7 ADI shifts, compress 5e-5/50; backward steps from t=tE'
+
+
+def _config(N):
+    return dict(workload=WORKLOAD, mesh_N=N, NV=2*(2*N-1)**2, NP=(N+1)**2-1,
+                parallelism='independent DRE replica per GPU',
+                l2_policy='inputs exceed L2: every step streams its own 8 LU factor sets '
+                          '(~200 MB) from HBM; no flush needed',
+                lu_setup='host SuperLU (MMD_AT_PLUS_A, symmetric mode), timed separately')
+
+
+class ClockSampler(object):
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=float(max(smax)) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def _measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def _ncu_traffic():
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get('sptrsm_dram_bytes_per_launch')
+        except Exception:
+            return None
+    return None
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path: the scipy/SuperLU oracle (the
+    reference's own sadptprj_riclyap_adi is absent), all host threads it can use
+    (SuperLU solves are serial; numpy parts use the BLAS threads)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import lin_alg_utils as olau, proj_ric_utils as opru
+    from optconpy_b200 import scenarios as sc, dre_stepper as ds
+    N = args.mesh
+    prob, cs, kw = sc.config2(olau, N=N)
+    S = args.warmup + args.steps
+    kw['tmesh'] = kw['tmesh'][-(S+1):]
+    stamps = []
+    budget = float(os.environ.get('OCB_REF_BUDGET_S', '420'))
+    t_start = time.perf_counter()
+
+    class Stop(Exception):
+        pass
+
+    def cb(tk):
+        stamps.append(time.perf_counter())
+        done = len(stamps)
+        if done > args.warmup and time.perf_counter() - t_start > budget and done < S:
+            raise Stop()
+    stamps.append(time.perf_counter())
+    try:
+        ds.solve_flow_daeric(lau=olau, pru=opru, store=ds.MemStore(), step_callback=cb, **kw)
+    except Stop:
+        pass
+    done = len(stamps) - 1
+    timed = done - args.warmup
+    if timed <= 0:
+        print(json.dumps(dict(impl='reference', unavailable='no timed step finished in budget')))
+        return
+    el = stamps[-1] - stamps[args.warmup]
+    val = timed/el
+    sample = 'backward steps %d..%d from t=tE of the same workload (full steps%s)' % (
+        args.warmup+1, args.warmup+timed, '' if timed == args.steps else
+        '; stopped early by the %.0f s budget' % budget)
+    out = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=timed,
+               warmup=args.warmup, ms_per_step=1e3*el/timed, higher_is_better=True,
+               scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+               config=_config(N), impl='reference',
+               cpu_baseline=dict(value=val, unit=UNIT, cores=os.cpu_count(), kind='port',
+                                 sample=sample,
+                                 note='SuperLU triangular solves are single-threaded; '
+                                      'dense parts use the BLAS threads'),
+               e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+               gpu_launches=0)
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--mesh', type=int, default=25)
+    ap.add_argument('--cpu-steps', type=int, default=2)
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    import optconpy_b200.lin_alg_utils as glau
+    import optconpy_b200.proj_ric_utils as gpru
+    from optconpy_b200 import scenarios as sc, dre_stepper as ds, dre_device as dd, device as dv
+    from optconpy_b200 import _cabi
+    import ctypes as C
+    lib = _cabi.load()
+    N, W, K = args.mesh, args.warmup, args.steps
+    S = W + K
+    prob, cs, kw = sc.config2(glau, N=N)
+    kw['tmesh'] = kw['tmesh'][-(S+1):]
+
+    # ---------------- value: device-resident loop, setup timed separately ----------------
+    dv.reset_stats()
+    t0 = time.perf_counter()
+    ctx = dd.context_from_kwargs(kw)
+    setups = dd.prepare_steps(ctx, kw, S)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    setup_stats = dict(dv.STATS)
+    info = []
+    for st in setups[:W]:
+        dd.run_step(ctx, st, info)
+    sampler = ClockSampler(local)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.ocb_prof_enable(1)
+    n0 = dv.launch_count()
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K+1)]
+    e0.record()
+    step_ev[0].record()
+    for i, st in enumerate(setups[W:]):
+        dd.run_step(ctx, st, info)
+        step_ev[i+1].record()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = dv.launch_count() - n0
+    tot_ms, nl, ab = C.c_double(0), C.c_int64(0), C.c_double(0)
+    _cabi.check(lib.ocb_prof_collect(C.byref(tot_ms), C.byref(nl), C.byref(ab)), 'prof')
+    lib.ocb_prof_enable(0)
+    ms = e0.elapsed_time(e1)
+    step_ms = [step_ev[i].elapsed_time(step_ev[i+1]) for i in range(K)]
+    tmax = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_max = float(tmax.item())
+    value = world*K/(ms_max*1e-3)
+    lu0 = setups[-1].fac.lus[0]
+    peak, peak_src = _measured_peak()
+    k_mean = (ab.value/max(nl.value, 1) - 12.0*(lu0.info['nnzL']+lu0.info['nnzU'])
+              - 16.0*(lu0.info['n']+1))/(32.0*lu0.info['n'])
+    achieved = ab.value/max(tot_ms.value, 1e-9)/1e6          # GB/s
+    roofline = dict(bound='hbm', kernel='sptrsm_stream_kernel', achieved=achieved, peak=peak,
+                    unit='GB/s', frac=achieved/peak, traffic=_ncu_traffic(), peak_source=peak_src,
+                    launches=int(nl.value), mean_launch_ms=tot_ms.value/max(nl.value, 1),
+                    kernel_share_of_step=tot_ms.value/ms, mean_rhs_cols=k_mean,
+                    alg_bytes_per_launch=ab.value/max(nl.value, 1),
+                    note='n=5477: the solve is dependency-latency bound, not bandwidth bound '
+                         '(DESIGN.md K1); nnzL+nnzU=%d, levels L/U=%d/%d'
+                         % (lu0.info['nnzL']+lu0.info['nnzU'], lu0.info['levelsL'],
+                            lu0.info['levelsU']))
+    solves = sum(i['solves'] for i in info[W:])
+
+    # ---------------- e2e: reference-facing API with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        tmp = tempfile.mkdtemp(prefix='ocb_bench_')
+        try:
+            prob2, cs2, kw2 = sc.config2(glau, N=N)
+            kw2['tmesh'] = kw2['tmesh'][-(S+1):]
+            kw2['gtdtstrargs'] = dict(kw2['gtdtstrargs'], data_prfx=os.path.join(tmp, 'tdst_'))
+            stamps, bytes_at = [], []
+
+            def cb(tk):
+                torch.cuda.synchronize()
+                stamps.append(time.perf_counter())
+                bytes_at.append((dv.STATS['h2d_bytes'], dv.STATS['d2h_bytes']))
+            dv.reset_stats()
+            barrier()
+            ds.solve_flow_daeric(lau=glau, pru=gpru, store=ds.NpyStore(), step_callback=cb, **kw2)
+            barrier()
+            el = stamps[W+K-1] - stamps[W-1] if W > 0 else stamps[K-1] - stamps[0]
+            tm = torch.tensor([el], dtype=torch.float64, device='cuda')
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            h2d = (bytes_at[W+K-1][0] - bytes_at[W-1][0])/K
+            d2h = (bytes_at[W+K-1][1] - bytes_at[W-1][1])/K
+            e2e = dict(value=world*K/float(tm.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
+                       d2h_bytes_per_step=int(d2h), ms_per_step=1e3*float(tm.item())/K,
+                       api='optconpy_b200.dre_stepper.solve_flow_daeric(lau, pru) with scipy/numpy '
+                           'inputs and .npy outputs; host LU setup inside the timed region',
+                       lu_factor_s_per_step=dv.STATS['lu_factor_s']/S,
+                       lu_analyse_upload_s_per_step=dv.STATS['lu_analyse_upload_s']/S)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+    # ---------------- CPU baseline (rank 0, N == 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import lin_alg_utils as olau, proj_ric_utils as opru
+        nc = max(1, min(args.cpu_steps, S))
+        prob3, cs3, kw3 = sc.config2(olau, N=N)
+        kw3['tmesh'] = kw3['tmesh'][-(nc+1):]
+        # the DRE recursion starts at tE: these are the same first nc backward steps
+        kw3['tmesh'] = np.concatenate([kw['tmesh'][-(nc+1):]])
+        t0 = time.perf_counter()
+        ds.solve_flow_daeric(lau=olau, pru=opru, store=ds.MemStore(), **kw3)
+        el = time.perf_counter() - t0
+        gsame = [i for i in info[:nc]]
+        cpu = dict(value=nc/el, unit=UNIT, cores=os.cpu_count(), kind='port',
+                   sample='backward steps 1..%d from t=tE of the same workload (oracle: '
+                          'scipy/SuperLU, one LU per shift per Newton step, whole-block '
+                          'lu.solve); the terminal-value solve is included' % nc,
+                   seconds=el, saddle_solves=sum(i['solves'] for i in gsame))
+
+    if rank == 0:
+        out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W,
+                   ms_per_step=ms_max/K, higher_is_better=True, scaling='weak', vs_baseline=None,
+                   dtype='f64', data='synthetic', config=_config(N), clocks=clocks,
+                   e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
+                   setup=dict(seconds_per_step=setup_s/S, lu_factor_s_per_step=setup_stats['lu_factor_s']/S,
+                              lu_analyse_upload_s_per_step=setup_stats['lu_analyse_upload_s']/S,
+                              factorisations_per_step=setup_stats['n_factor']/S,
+                              note='excluded from value, included in e2e'),
+                   saddle_solves_per_s=solves/(ms_max*1e-3),
+                   rhs_columns_per_s=sum(sum(a)*0 for a in []) or None,
+                   step_ms=step_ms,
+                   steps_info=[dict(tau=float(i['tau']), adi_steps=i['adi_steps'],
+                                    zp_cols=i['zp_cols'], zc_cols=i['zc_cols']) for i in info[W:]])
+        out.pop('rhs_columns_per_s')
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

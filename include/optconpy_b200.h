@@ -64,7 +64,8 @@ int ocb_lu_create(ocb_lu** out, int64_t n,
                   const int32_t* h_perm_r, const int32_t* h_perm_c, void* stream);
 int ocb_lu_destroy(ocb_lu* lu);
 /* info[0..7] = n, nnz(L) strictly lower, nnz(U) incl. diagonal, #levels L, #levels U,
- *              device bytes held, max level width L, max level width U */
+ *              device bytes held, column-panel width of the TMA-fed stream kernel (0 = generic
+ *              kernel in use), number of stream batches */
 int ocb_lu_info(const ocb_lu* lu, int64_t* info8);
 /* bytes of device workspace ocb_lu_solve needs for k right-hand sides (0 if the
  * column panel fits shared memory) */
@@ -73,6 +74,13 @@ int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k);
 int ocb_lu_solve(const ocb_lu* lu, const double* d_B, int64_t ldb, int64_t nrows_b,
                  double* d_X, int64_t ldx, int64_t nrows_x, int64_t k,
                  void* d_ws, int64_t ws_bytes, void* stream);
+
+/* Per-launch timing of the solve kernel: when enabled, every ocb_lu_solve launch (also the
+ * ones inside ocb_adi_run / ocb_smw_solve) is bracketed by CUDA events on its stream.
+ * ocb_prof_collect waits for them and returns the summed kernel time, the launch count and the
+ * summed ALGORITHMIC bytes (12*(nnzL+nnzU) + 16*(n+1) + 32*n*k per launch). */
+int ocb_prof_enable(int on);
+int ocb_prof_collect(double* total_ms, int64_t* launches, double* alg_bytes);
 
 /* ---- K3: Gram product on FP64 tensor cores (DMMA) -----------------------------
  * G (ka x kb) = Z^T W over n rows; deterministic (fixed split + ordered reduce).

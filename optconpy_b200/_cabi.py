@@ -21,6 +21,8 @@ PROTOTYPES = {
     'ocb_lu_info': (C.c_int, [vp, C.POINTER(i64)]),
     'ocb_lu_solve_ws_bytes': (i64, [vp, i64]),
     'ocb_lu_solve': (C.c_int, [vp, f64p, i64, i64, f64p, i64, i64, i64, vp, i64, vp]),
+    'ocb_prof_enable': (C.c_int, [C.c_int]),
+    'ocb_prof_collect': (C.c_int, [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
     'ocb_gram_ws_bytes': (i64, [i64, i64, i64]),
     'ocb_gram': (C.c_int, [f64p, i64, i64, f64p, i64, i64, i64, f64p, i64, vp, i64, vp]),
     'ocb_tall_gemm': (C.c_int, [f64p, i64, i64, i64, f64p, i64, i64, f64p, i64,

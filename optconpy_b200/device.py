@@ -125,29 +125,83 @@ class DeviceCSR(object):
         return out
 
 
+_POOL = dict(pool=None, workers=0)
+
+
+def _lu_pool():
+    """Process pool for the host LU setup (SuperLU holds the GIL).  OCB_LU_WORKERS=0
+    keeps everything in-process."""
+    import multiprocessing as mp
+    import os
+    want = os.environ.get('OCB_LU_WORKERS')
+    if want is None:
+        world = int(os.environ.get('WORLD_SIZE', '1'))
+        want = max(1, min(8, (os.cpu_count() or 1)//max(world, 1)))
+    want = int(want)
+    if want <= 1:
+        return None
+    if _POOL['pool'] is None or _POOL['workers'] != want:
+        if _POOL['pool'] is not None:
+            _POOL['pool'].terminate()
+        _POOL['pool'] = mp.get_context('spawn').Pool(want)
+        _POOL['workers'] = want
+    return _POOL['pool']
+
+
+def _csc_args(mat, opts):
+    m = sps.csc_matrix(mat, dtype=np.float64)
+    m.sum_duplicates()
+    return (m.data, m.indices, m.indptr, m.shape, opts)
+
+
+def factorize_many(mats, lu_options=None):
+    """Factorise several matrices (the shifts of one ADI) on the host, in parallel worker
+    processes when available, then analyse + upload each: the separately timed setup."""
+    from . import _lu_worker
+    require_cuda()
+    opts = dict(LU_OPTIONS if lu_options is None else lu_options)
+    t0 = time.perf_counter()
+    args = [_csc_args(m, opts) for m in mats]
+    pool = _lu_pool() if len(mats) > 1 else None
+    if pool is None:
+        arrs = [_lu_worker.factor_arrays(a) for a in args]
+        STATS['lu_factor_s'] += time.perf_counter() - t0
+        STATS['n_factor'] += len(mats)
+        return [LU(None, arrays=a, n=m.shape[0]) for a, m in zip(arrs, mats)]
+    from multiprocessing import shared_memory
+    res = pool.map(_lu_worker.factor_to_shm, args)
+    STATS['lu_factor_s'] += time.perf_counter() - t0
+    STATS['n_factor'] += len(mats)
+    out = []
+    for (name, layout), m in zip(res, mats):
+        shm = shared_memory.SharedMemory(name=name)
+        try:
+            arrs = [np.frombuffer(shm.buf, dtype=np.dtype(d), count=c, offset=o)
+                    for d, c, o in layout]
+            out.append(LU(None, arrays=arrs, n=m.shape[0]))   # uploads synchronously
+            del arrs
+        finally:
+            shm.close()
+            shm.unlink()
+    return out
+
+
 class LU(object):
     """Device-resident LU factorisation ``Pr A Pc = L U`` (handle of the C ABI)."""
 
-    def __init__(self, mat, lu_options=None):
+    def __init__(self, mat, lu_options=None, arrays=None, n=None):
         lib = require_cuda()
-        opts = dict(LU_OPTIONS if lu_options is None else lu_options)
-        t0 = time.perf_counter()
-        slu = spsla.splu(sps.csc_matrix(mat, dtype=np.float64), **opts)
+        if arrays is None:
+            from . import _lu_worker
+            opts = dict(LU_OPTIONS if lu_options is None else lu_options)
+            t0 = time.perf_counter()
+            arrays = _lu_worker.factor_arrays(_csc_args(mat, opts))
+            STATS['lu_factor_s'] += time.perf_counter() - t0
+            STATS['n_factor'] += 1
+            n = mat.shape[0]
         t1 = time.perf_counter()
-        L = sps.csr_matrix(slu.L)
-        U = sps.csr_matrix(slu.U)
-        L.sort_indices()
-        U.sort_indices()
-        n = mat.shape[0]
         self.n = n
-        arrs = [np.ascontiguousarray(L.indptr, dtype=np.int32),
-                np.ascontiguousarray(L.indices, dtype=np.int32),
-                np.ascontiguousarray(L.data, dtype=np.float64),
-                np.ascontiguousarray(U.indptr, dtype=np.int32),
-                np.ascontiguousarray(U.indices, dtype=np.int32),
-                np.ascontiguousarray(U.data, dtype=np.float64),
-                np.ascontiguousarray(slu.perm_r, dtype=np.int32),
-                np.ascontiguousarray(slu.perm_c, dtype=np.int32)]
+        arrs = arrays
         h = C.c_void_p()
         _cabi.check(lib.ocb_lu_create(C.byref(h), n, *[a.ctypes.data for a in arrs],
                                       stream_ptr()), 'ocb_lu_create')
@@ -156,12 +210,9 @@ class LU(object):
         info = (C.c_int64*8)()
         _cabi.check(lib.ocb_lu_info(h, info), 'ocb_lu_info')
         self.info = dict(n=info[0], nnzL=info[1], nnzU=info[2], levelsL=info[3],
-                         levelsU=info[4], device_bytes=info[5], maxwidthL=info[6],
-                         maxwidthU=info[7])
-        t2 = time.perf_counter()
-        STATS['lu_factor_s'] += t1 - t0
-        STATS['lu_analyse_upload_s'] += t2 - t1
-        STATS['n_factor'] += 1
+                         levelsU=info[4], device_bytes=info[5], stream_kp=info[6],
+                         stream_batches=info[7])
+        STATS['lu_analyse_upload_s'] += time.perf_counter() - t1
         STATS['h2d_bytes'] += sum(a.nbytes for a in arrs)
 
     def __del__(self):

@@ -85,7 +85,7 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
                       get_datastr=None, gtdtstrargs=None,
                       check_c_consist=True,
                       lau=None, pru=None, store=None, verbose=False,
-                      stepinfo=None):
+                      stepinfo=None, step_callback=None):
     """Same keyword signature as the reference's ``solve_flow_daeric`` plus
     ``lau``/``pru`` (backend modules), ``store`` and ``stepinfo`` (optional list
     that receives per-step diagnostics).  Returns the ``feedbackthroughdict``
@@ -192,4 +192,6 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         fbdict.update({t: dict(w=key + '__w', mtxtb=key + '__mtxtb')})
         if stepinfo is not None:
             stepinfo.append(info)
+        if step_callback is not None:
+            step_callback(tk)
     return fbdict

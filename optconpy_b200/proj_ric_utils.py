@@ -39,11 +39,11 @@ class ShiftedFactors(object):
     ``north_star`` times separately.  Reused across the Newton steps of one
     Riccati solve (the low-rank closed-loop part enters through SMW only)."""
 
-    def __init__(self, At, Mt, jmat, ms):
+    def __init__(self, At, Mt, jmat, ms, Mt_dev=None):
         self.ms = [float(m) for m in ms]
         self.NV, self.NP = At.shape[0], jmat.shape[0]
-        self.lus = [dv.LU(dv.sadpnt_matrix(At + mu*Mt, jmat)) for mu in self.ms]
-        self.Mt_dev = dv.DeviceCSR(Mt)
+        self.lus = dv.factorize_many([dv.sadpnt_matrix(At + mu*Mt, jmat) for mu in self.ms])
+        self.Mt_dev = dv.DeviceCSR(Mt) if Mt_dev is None else Mt_dev
 
 
 def _stein_dev(fac, W, adi_dict, Ufb=None, Vt=None):

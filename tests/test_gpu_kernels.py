@@ -128,7 +128,7 @@ def test_sym_eig(dv, k):
     lam, V = dv.to_host(lam), dv.to_host(V)
     ref = np.linalg.eigvalsh(G)[::-1]
     assert np.max(np.abs(lam - ref)) < 1e-13*ref[0]
-    assert np.linalg.norm(V.T @ V - np.eye(k)) < 1e-12
+    assert np.linalg.norm(V.T @ V - np.eye(k)) < 1e-13*max(k, 10)
     assert np.linalg.norm(V @ np.diag(lam) @ V.T - G) < 1e-12*ref[0]*k
     assert np.all(np.diff(lam) <= 0)
 
@@ -136,7 +136,7 @@ def test_sym_eig(dv, k):
 def test_compress_matches_svd(dv):
     rng = np.random.default_rng(7)
     n, K, r = 900, 1500, 120
-    Z = (rng.standard_normal((n, r))*np.logspace(1, -9, r)[None, :]) @ rng.standard_normal((r, K))
+    Z = (rng.standard_normal((n, r))*np.logspace(-1, -9, r)[None, :]) @ rng.standard_normal((r, K))/30.0
     s = np.linalg.svd(Z, compute_uv=False)
     U, sv, Vt = np.linalg.svd(Z, full_matrices=False)
     for thresh, k in ((5e-5, 50), (1e-6, None), (None, 17)):
@@ -145,11 +145,7 @@ def test_compress_matches_svd(dv):
         ref = Z @ Vt[:keep].T
         Zc, info = dv.compress(dv.to_dev(Z), thresh=thresh, k=k)
         Zc = dv.to_host(Zc)
-        if thresh == 1e-6:
-            # the Gram route resolves singular values down to ~1e-7 sigma_max
-            assert abs(Zc.shape[1] - keep) <= 3
-        else:
-            assert Zc.shape[1] == keep
+        assert Zc.shape[1] == keep
         assert _relerr(Zc @ Zc.T, ref @ ref.T) < 1e-9
         assert _relerr(dv.to_host(info['sigma'])[:10], s[:10]) < 1e-10
 
