@@ -148,7 +148,9 @@ def test_newtonadi_parity(mods, lyap_setup, cav10):
         kw2 = dict(kw, nwtn_adi_dict=d2, z0=ref['zfac'][:, :16])
         r2, g2 = opru.proj_alg_ric_newtonadi(**kw2), gpru.proj_alg_ric_newtonadi(**kw2)
         assert g2['adi_steps'] == r2['adi_steps']
-        assert np.allclose(g2['nwtn_upd_fnorms'], r2['nwtn_upd_fnorms'], rtol=1e-5, atol=1e-12)
+        # the full check is sqrt of a difference of squared norms: floor ~ sqrt(eps)*||X||
+        assert np.allclose(g2['nwtn_upd_fnorms'], r2['nwtn_upd_fnorms'], rtol=1e-5,
+                           atol=2e-7*r2['nwtn_upd_fnorms'][0])
         assert _zzt_relerr(g2['zfac'], r2['zfac']) < TOL_FACTOR
     # feedback gains
     tb = cs['tb_mat']

@@ -1,0 +1,106 @@
+"""CPU suite, part 3: host-side logic that needs no GPU — the synthetic problem generator
+(sizes of the reference), the squeezed time mesh (``optcont_main.py:141-150``), the restated
+driver's storage/memoisation semantics (``solve_dae_ric.py:143-145``), the ``.npy`` shim and
+the data-string naming (``optcont_main.py:153-157``), and the column partition."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from oracle import lin_alg_utils as olau, proj_ric_utils as opru
+from optconpy_b200 import problems as pb, scenarios as sc, dre_stepper as ds, parallel as par
+
+
+@pytest.mark.parametrize('N,NV,NP', [(10, 722, 120), (20, 3042, 440), (25, 4802, 675)])
+def test_problem_sizes_match_reference(N, NV, NP):
+    # NV = 2(2N-1)^2, NP = (N+1)^2 - 1; N=20 -> NV 3042 is recorded in debugstuff.py:30
+    assert 2*(2*N-1)**2 == NV and (N+1)**2 - 1 == NP
+    if N > 10:
+        return
+    prob = pb.drivcav_problem(N, 1e-2)
+    assert prob['NV'] == NV and prob['NP'] == NP
+    assert prob['M'].shape == (NV, NV) and prob['J'].shape == (NP, NV)
+
+
+def test_matrices_are_a_stokes_system(cav6):
+    M, A, J = cav6['M'], cav6['A'], cav6['J']
+    assert abs(M - M.T).max() < 1e-14 and abs(A - A.T).max() < 1e-12
+    assert np.linalg.eigvalsh(M.toarray()).min() > 0
+    assert np.linalg.eigvalsh(A.toarray()).min() > 0
+    assert np.linalg.matrix_rank(J.toarray()) == cav6['NP']      # last pressure row dropped
+    # convection matrix of a divergence-free field is (nearly) skew in the interior
+    Nc = pb.convection_matrix(cav6, pb.analytic_vortex, newton_term=False)
+    assert Nc.shape == M.shape and abs(Nc).max() > 0
+
+
+def test_squeezed_time_mesh():
+    t = pb.get_tint(0.0, 1.0, 6)
+    ref = (np.sin(np.linspace(-0.5*np.pi, 0.5*np.pi, 7)) + 1)*0.5
+    assert np.allclose(t, ref) and t[0] == 0.0 and np.isclose(t[-1], 1.0)
+    t2 = pb.get_tint(0.0, 0.2, 128)
+    d = np.diff(t2)
+    assert len(t2) == 129 and d.min() > 0 and d[0] < d[64] and d[-1] < d[64]
+    assert np.allclose(pb.get_tint(1.0, 3.0, 4, sqzmesh=False), np.linspace(1, 3, 5))
+
+
+def test_datastr_and_npy_store(tmp_path):
+    s = ds.default_datastr(time=0.5, meshp=10, nu=0.01, Nts=10, data_prfx='data/tdst_')
+    assert s == 'data/tdst_time0.5_nu0.01_mesh10_Nts10'
+    st = ds.NpyStore()
+    a = np.arange(6.0).reshape(3, 2)
+    key = str(tmp_path / 'sub' / 'x__Z')
+    st.save(a, key)
+    assert os.path.exists(key + '.npy')            # np.save appends .npy (optcont_main.py:231)
+    assert np.array_equal(st.load(key), a)
+    with pytest.raises(IOError):
+        st.load(str(tmp_path / 'missing'))
+
+
+def test_stepper_memoises_and_keeps_reference_order(cav6):
+    cs = pb.control_setup(cav6, olau, alphau=1e-4)
+    tmesh = pb.get_tint(0.0, 0.1, 2)
+    nd = dict(sc.DEFAULT_NWTN_ADI, adi_max_steps=60, nwtn_max_steps=4)
+    kw = sc.dre_kwargs(cav6, cs, tmesh, nd, 1e-3, sc._ystar_sin(cs['NY']))
+    store, info = ds.MemStore(), []
+    fb = ds.solve_flow_daeric(lau=olau, pru=opru, store=store, stepinfo=info, **kw)
+    assert sorted(fb) == sorted(tmesh)
+    for t in fb:
+        assert store[fb[t]['mtxtb']].shape == (cav6['NV'], 2*cs['NU'])
+        assert store[fb[t]['w']].shape == (cav6['NV'], 1)
+    # gain definition at the terminal time: mtxtb = -M^T Zc Zc^T tB (solve_dae_ric.py:101)
+    tE = tmesh[-1]
+    kE = fb[tE]['mtxtb'].replace('__mtxtb', '__Z')
+    tb = olau.apply_invsqrt_fromright(cs['R'], cs['b_mat'], output='sparse')
+    assert np.allclose(store[fb[tE]['mtxtb']],
+                       -opru.get_mTzzTtb(cav6['M'].T, store[kE], tb), rtol=1e-12, atol=1e-14)
+    # second run over the same store: every __Z entry loads, no Riccati solve is repeated
+    calls = []
+
+    class CountingPru(object):
+        def __getattr__(self, name):
+            if name == 'proj_alg_ric_newtonadi':
+                calls.append(name)
+            return getattr(opru, name)
+    fb2 = ds.solve_flow_daeric(lau=olau, pru=CountingPru(), store=store,
+                               **dict(kw, gtdtstrargs=dict(kw['gtdtstrargs'])))
+    assert not calls and fb2 == fb
+
+
+def test_inconsistent_output_operator_raises(cav6):
+    cs = pb.control_setup(cav6, olau, alphau=1e-4)
+    tmesh = pb.get_tint(0.0, 0.1, 1)
+    kw = sc.dre_kwargs(cav6, cs, tmesh, dict(sc.DEFAULT_NWTN_ADI), 1e-3, sc._ystar_sin(cs['NY']))
+    bad = sps.csr_matrix(np.random.default_rng(0).standard_normal(kw['mcmat'].shape))
+    with pytest.raises(Warning):                     # solve_dae_ric.py:79,83
+        ds.solve_flow_daeric(lau=olau, pru=opru, store=ds.MemStore(), **dict(kw, mcmat=bad))
+
+
+def test_column_slices_partition():
+    for k in (1, 7, 8, 66, 1024):
+        for world in (1, 2, 3, 8):
+            sl = [par.column_slice(k, r, world) for r in range(world)]
+            assert sl[0][0] == 0 and sl[-1][1] == k
+            assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+            w = [b - a for a, b in sl]
+            assert max(w) - min(w) <= 1
