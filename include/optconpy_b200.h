@@ -63,10 +63,37 @@ int ocb_lu_create(ocb_lu** out, int64_t n,
                   const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
                   const int32_t* h_perm_r, const int32_t* h_perm_c, void* stream);
 int ocb_lu_destroy(ocb_lu* lu);
-/* info[0..7] = n, nnz(L) strictly lower, nnz(U) incl. diagonal, #levels L, #levels U,
- *              device bytes held, column-panel width of the TMA-fed stream kernel (0 = generic
- *              kernel in use), number of stream batches */
+/* info[0..7] = n, nnz(L) strictly lower, nnz(U) incl. diagonal, #sub-levels of the L sweep,
+ *              #sub-levels of the U sweep (one CTA barrier each), device bytes held, widest
+ *              column panel that fits shared memory (0 = panel lives in a global slab),
+ *              number of stream batches */
 int ocb_lu_info(const ocb_lu* lu, int64_t* info8);
+/* info[0..7] = rows of the extended vector (n + y scratch), #supernodes, widest supernode,
+ *              #slices, #program rows, #program entries (padded), ring stage bytes, ring stages */
+int ocb_lu_stats(const ocb_lu* lu, int64_t* info8);
+
+/* Host-only view of the same analysis (no CUDA call; usable without a GPU): the GATHER
+ * PROGRAM that ocb_lu_create packs and uploads.  Supernodes of U (rows with nested structure)
+ * get their diagonal blocks inverted on the host, which turns the two triangular solves into
+ * a short sequence of sub-levels of independent rows
+ *     xe[dst] = ((init >= 0 ? xe[init] : 0) - sum_p val[p]*xe[col[p]]) * scale
+ * on the extended vector xe = [x (n) | y scratch].  Sub-level s owns the slices
+ * [sub_ptr[s], sub_ptr[s+1]); slice = {ebase, trips, glog | nrows << 8, q0}: nrows <= 32 >> glog
+ * rows starting at row q0, 2^glog lanes per row, entries stored trip-major (sliced ELLPACK):
+ * entry (trip u, lane l = r * 2^glog + g) at ebase + 32 u + l is entry u * 2^glog + g of row
+ * q0 + r, zero padded.  tests/test_lu_program.py executes it with numpy against SuperLU. */
+typedef struct ocb_lu_program ocb_lu_program;
+int ocb_lu_program_create(ocb_lu_program** out, int64_t n,
+                          const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
+                          const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals);
+int ocb_lu_program_destroy(ocb_lu_program* prog);
+/* info[0..11] = n, n_ext, ymax, sub-levels L, sub-levels U, #supernodes, widest supernode,
+ *               #slices, #rows, #entries (padded), nnz(L) strictly lower, nnz(U) */
+int ocb_lu_program_info(const ocb_lu_program* prog, int64_t* info12);
+/* h_sub_ptr: sub-levels + 1 ints; h_slice4: 4 ints per slice; the rest per row / per entry */
+int ocb_lu_program_export(const ocb_lu_program* prog, int32_t* h_sub_ptr, int32_t* h_slice4,
+                          int32_t* h_dst, int32_t* h_init, double* h_scale,
+                          int32_t* h_col, double* h_val);
 /* bytes of device workspace ocb_lu_solve needs for k right-hand sides (0 if the
  * column panel fits shared memory) */
 int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k);

@@ -19,6 +19,11 @@ PROTOTYPES = {
     'ocb_lu_create': (C.c_int, [C.POINTER(vp), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'ocb_lu_destroy': (C.c_int, [vp]),
     'ocb_lu_info': (C.c_int, [vp, C.POINTER(i64)]),
+    'ocb_lu_stats': (C.c_int, [vp, C.POINTER(i64)]),
+    'ocb_lu_program_create': (C.c_int, [C.POINTER(vp), i64, vp, vp, vp, vp, vp, vp]),
+    'ocb_lu_program_destroy': (C.c_int, [vp]),
+    'ocb_lu_program_info': (C.c_int, [vp, C.POINTER(i64)]),
+    'ocb_lu_program_export': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     'ocb_lu_solve_ws_bytes': (i64, [vp, i64]),
     'ocb_lu_solve': (C.c_int, [vp, f64p, i64, i64, f64p, i64, i64, i64, vp, i64, vp]),
     'ocb_prof_enable': (C.c_int, [C.c_int]),

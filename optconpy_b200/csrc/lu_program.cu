@@ -1,0 +1,404 @@
+// Host-side construction of the gather program of a sparse LU solve (see lu_program.h).
+// Pure host code: no CUDA calls, so it is unit-tested on CPU through
+// ocb_lu_program_create / ocb_lu_program_export (tests/test_lu_program.py).
+#include "common.cuh"
+#include "lu_program.h"
+#include <algorithm>
+#include <numeric>
+#include <string.h>
+#include <stdlib.h>
+
+namespace ocb {
+
+namespace {
+
+constexpr int WMAX = 512;    // widest supernode (its inverse block has w(w+1)/2 entries)
+constexpr int YCAP = 1024;   // y-scratch rows one sub-level may use (two such regions exist)
+
+struct BlockPlan {
+    int32_t sA = -1;   // sub-level of the A rows (-1: block needs no work)
+    int32_t yoff = -1; // offset into the y region (w > 1 only)
+};
+
+struct Tri {
+    const int32_t* rp;
+    const int32_t* ci;
+    const double* va;
+    bool upper;
+};
+
+inline int pow2ceil(int64_t v) {
+    int g = 0;
+    while ((1LL << g) < v) ++g;
+    return g;
+}
+
+// supernodes: maximal runs of rows i, i+1, ... of U with  struct(U_i) \ {i} == struct(U_{i+1})
+int find_supernodes(int64_t n, const int32_t* rp, const int32_t* ci, std::vector<int32_t>* starts) {
+    starts->clear();
+    starts->push_back(0);
+    int w = 1;
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        const int32_t a0 = rp[i], a1 = rp[i + 1], b0 = rp[i + 1], b1 = rp[i + 2];
+        bool same = false;
+        if (a1 > a0 && ci[a0] == i && (a1 - a0 - 1) == (b1 - b0) && b1 > b0 && w < WMAX)
+            same = memcmp(ci + a0 + 1, ci + b0, (size_t)(b1 - b0) * sizeof(int32_t)) == 0;
+        if (same) {
+            ++w;
+        } else {
+            starts->push_back((int32_t)(i + 1));
+            w = 1;
+        }
+    }
+    if (n > 0) starts->push_back((int32_t)n);
+    return OCB_OK;
+}
+
+// assign the A sub-level (and y offset) of every block of one triangular factor
+int plan_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
+                std::vector<BlockPlan>* plan, int32_t* nsub, int64_t* ymax) {
+    const int nb = (int)starts.size() - 1;
+    plan->assign(nb, BlockPlan());
+    std::vector<int32_t> done(n, -1);
+    std::vector<int32_t> yuse;
+    int32_t top = -1;
+    for (int bb = 0; bb < nb; ++bb) {
+        const int t = T.upper ? nb - 1 - bb : bb;
+        const int32_t r0 = starts[t], r1 = starts[t + 1], w = r1 - r0;
+        int32_t dep = -1;
+        int64_t noff = 0;
+        for (int32_t i = r0; i < r1; ++i) {
+            bool diag = false;
+            for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) {
+                const int32_t c = T.ci[p];
+                if (c < 0 || c >= n) {
+                    set_error("factor has a column index out of range (row %d)", i);
+                    return OCB_ERR_ARG;
+                }
+                if (c >= r0 && c < r1) {
+                    if (T.upper ? c < i : c > i) {
+                        set_error("%s has an entry on the wrong side of the diagonal (row %d col %d)",
+                                  T.upper ? "U" : "L", i, c);
+                        return OCB_ERR_ARG;
+                    }
+                    if (c == i) diag = T.va[p] != 0.0;
+                    continue;
+                }
+                if (T.upper ? c < i : c > i) {
+                    set_error("%s has an entry on the wrong side of the diagonal (row %d col %d)",
+                              T.upper ? "U" : "L", i, c);
+                    return OCB_ERR_ARG;
+                }
+                dep = std::max(dep, done[c]);
+                ++noff;
+            }
+            if (T.upper && !diag) {
+                set_error("U has a zero pivot in row %d", i);
+                return OCB_ERR_SINGULAR;
+            }
+        }
+        BlockPlan& bp = (*plan)[t];
+        if (w == 1) {
+            if (!T.upper && noff == 0) continue;  // unit diagonal, nothing to subtract
+            bp.sA = dep + 1;
+            done[r0] = bp.sA;
+            top = std::max(top, bp.sA);
+        } else {
+            int32_t s = dep + 1;
+            for (;;) {
+                if ((int)yuse.size() <= s) yuse.resize(s + 1, 0);
+                if (yuse[s] + w <= YCAP || yuse[s] == 0) break;
+                ++s;
+            }
+            bp.sA = s;
+            bp.yoff = yuse[s];
+            yuse[s] += w;
+            *ymax = std::max<int64_t>(*ymax, yuse[s]);
+            for (int32_t i = r0; i < r1; ++i) done[i] = s + 1;
+            top = std::max(top, s + 1);
+        }
+    }
+    *nsub = top + 1;
+    return OCB_OK;
+}
+
+// inverse of the w x w diagonal block of rows [r0, r1) (row-major, dense)
+void invert_block(const Tri& T, int32_t r0, int32_t r1, std::vector<double>* Dbuf,
+                  std::vector<double>* Xbuf) {
+    const int w = r1 - r0;
+    std::vector<double>& D = *Dbuf;
+    std::vector<double>& X = *Xbuf;
+    D.assign((size_t)w * w, 0.0);
+    X.assign((size_t)w * w, 0.0);
+    for (int32_t i = r0; i < r1; ++i)
+        for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) {
+            const int32_t c = T.ci[p];
+            if (c >= r0 && c < r1) D[(size_t)(i - r0) * w + (c - r0)] = T.va[p];
+        }
+    if (!T.upper) {
+        for (int j = 0; j < w; ++j) {
+            X[(size_t)j * w + j] = 1.0;
+            for (int i = j + 1; i < w; ++i) {
+                double s = 0.0;
+                for (int k = j; k < i; ++k) s += D[(size_t)i * w + k] * X[(size_t)k * w + j];
+                X[(size_t)i * w + j] = -s;
+            }
+        }
+    } else {
+        for (int j = w - 1; j >= 0; --j) {
+            X[(size_t)j * w + j] = 1.0 / D[(size_t)j * w + j];
+            for (int i = j - 1; i >= 0; --i) {
+                double s = 0.0;
+                for (int k = i + 1; k <= j; ++k) s += D[(size_t)i * w + k] * X[(size_t)k * w + j];
+                X[(size_t)i * w + j] = -s / D[(size_t)i * w + i];
+            }
+        }
+    }
+}
+
+struct RowRef {     // a row of the program before it is laid out
+    int32_t block;  // supernode index
+    int32_t k;      // row within the supernode
+    int32_t len;    // number of entries
+    uint8_t kind;   // 0: A row, 1: B row
+};
+
+int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
+                const std::vector<BlockPlan>& plan, int32_t nsub, int64_t ymax, int max_lanes,
+                LuProgram* P) {
+    const int nb = (int)starts.size() - 1;
+    std::vector<std::vector<RowRef>> lev(nsub);
+    // off-block entry counts per row
+    for (int t = 0; t < nb; ++t) {
+        const BlockPlan& bp = plan[t];
+        if (bp.sA < 0) continue;
+        const int32_t r0 = starts[t], r1 = starts[t + 1], w = r1 - r0;
+        for (int32_t i = r0; i < r1; ++i) {
+            int32_t len = 0;
+            for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) len += (T.ci[p] < r0 || T.ci[p] >= r1);
+            lev[bp.sA].push_back(RowRef{t, i - r0, len, 0});
+        }
+        if (w > 1)
+            for (int k = 0; k < w; ++k) lev[bp.sA + 1].push_back(RowRef{t, k, T.upper ? w - k : k + 1, 1});
+    }
+    std::vector<double> D, X;
+    std::vector<int32_t> inv_slot(nb, -1);
+    std::vector<std::vector<double>> inv;   // inverses of the diagonal blocks of this sub-level
+    for (int32_t s = 0; s < nsub; ++s) {
+        std::vector<RowRef>& rows = lev[s];
+        if (rows.empty()) continue;
+        inv.clear();
+        for (const RowRef& rr : rows)
+            if (rr.kind == 1 && rr.k == 0) {
+                invert_block(T, starts[rr.block], starts[rr.block + 1], &D, &X);
+                inv_slot[rr.block] = (int32_t)inv.size();
+                inv.push_back(X);
+            }
+        std::stable_sort(rows.begin(), rows.end(), [](const RowRef& a, const RowRef& b) {
+            if (a.len != b.len) return a.len > b.len;
+            return a.block < b.block;
+        });
+        // lanes per row by length class (about lane_entries entries per lane), boosted while
+        // the whole sub-level still fits one pass of the CTA
+        std::vector<int> gl(rows.size());
+        int64_t slots = 0;
+        static int lane_entries = 0;
+        if (lane_entries == 0) {
+            const char* env = getenv("OCB_LANE_ENTRIES");
+            lane_entries = env ? atoi(env) : 16;
+            if (lane_entries < 1) lane_entries = 16;
+        }
+        for (size_t r = 0; r < rows.size(); ++r) {
+            gl[r] = std::min(5, pow2ceil((rows[r].len + lane_entries - 1) / lane_entries));
+            slots += 1LL << gl[r];
+        }
+        while (slots * 2 <= max_lanes) {
+            bool any = false;
+            slots = 0;
+            for (size_t r = 0; r < rows.size(); ++r) {
+                if (gl[r] < 5 && (2 << gl[r]) <= std::max(rows[r].len, 1)) { ++gl[r]; any = true; }
+                slots += 1LL << gl[r];
+            }
+            if (!any) break;
+        }
+        for (size_t r = 1; r < rows.size(); ++r) gl[r] = std::min(gl[r], gl[r - 1]);  // monotone
+        size_t r = 0;
+        while (r < rows.size()) {
+            const int g = gl[r], G = 1 << g, rmax = 32 >> g;
+            size_t r2 = r;
+            while (r2 < rows.size() && gl[r2] == g && (int)(r2 - r) < rmax) ++r2;
+            const int nr = (int)(r2 - r);
+            Slice sl;
+            sl.q0 = (int32_t)P->dst.size();
+            sl.glog_nrows = g | (nr << 8);
+            sl.ebase = (int32_t)P->col.size();
+            sl.trips = (rows[r].len + G - 1) / G;   // rows are sorted: the first is the longest
+            const size_t e0 = P->col.size();
+            P->col.resize(e0 + (size_t)sl.trips * 32, 0);
+            P->val.resize(e0 + (size_t)sl.trips * 32, 0.0);
+            for (int rl = 0; rl < nr; ++rl) {
+                const RowRef& rr = rows[r + rl];
+                const BlockPlan& bp = plan[rr.block];
+                const int32_t r0 = starts[rr.block], r1 = starts[rr.block + 1], w = r1 - r0;
+                const int32_t ybase = (int32_t)(n + (bp.sA & 1) * ymax + (bp.yoff < 0 ? 0 : bp.yoff));
+                const int32_t i = r0 + rr.k;
+                int e = 0;   // entry counter of this row
+                auto put = [&](int32_t c, double v) {
+                    const size_t pos = e0 + (size_t)(e / G) * 32 + (size_t)rl * G + (e % G);
+                    P->col[pos] = c;
+                    P->val[pos] = v;
+                    ++e;
+                };
+                if (rr.kind == 0) {
+                    double dg = 1.0;
+                    for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) {
+                        const int32_t c = T.ci[p];
+                        if (c < r0 || c >= r1) {
+                            put(c, T.va[p]);
+                        } else if (c == i && T.upper) {
+                            dg = T.va[p];
+                        }
+                    }
+                    P->init.push_back(i);
+                    if (w == 1) {
+                        P->dst.push_back(i);
+                        P->scale.push_back(1.0 / dg);
+                    } else {
+                        P->dst.push_back(ybase + rr.k);
+                        P->scale.push_back(1.0);
+                    }
+                } else {
+                    const std::vector<double>& Xi = inv[inv_slot[rr.block]];
+                    const int j0 = T.upper ? rr.k : 0, j1 = T.upper ? w : rr.k + 1;
+                    for (int j = j0; j < j1; ++j) put(ybase + j, -Xi[(size_t)rr.k * w + j]);
+                    P->init.push_back(-1);
+                    P->dst.push_back(i);
+                    P->scale.push_back(1.0);
+                }
+                P->nent_actual += e;
+            }
+            P->slices.push_back(sl);
+            r = r2;
+        }
+        P->sub_ptr.push_back((int32_t)P->slices.size());
+    }
+    return OCB_OK;
+}
+
+}  // namespace
+
+int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const double* Lva,
+                     const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
+                     LuProgram* P) {
+    *P = LuProgram();
+    P->n = n;
+    P->sub_ptr.push_back(0);
+    if (n == 0) return OCB_OK;
+    if ((int64_t)Lrp[n] + Urp[n] + 2 * n >= (int64_t)INT32_MAX / 2) {
+        set_error("factor too large for int32 program indices");
+        return OCB_ERR_ARG;
+    }
+    for (int64_t i = 0; i < n; ++i) {   // U rows: sorted column indices, diagonal first
+        for (int32_t p = Urp[i] + 1; p < Urp[i + 1]; ++p)
+            if (Uci[p - 1] >= Uci[p]) {
+                set_error("U rows must have sorted column indices (row %lld)", (long long)i);
+                return OCB_ERR_ARG;
+            }
+        if (Urp[i + 1] <= Urp[i] || Uci[Urp[i]] > i) {
+            set_error("U has a zero pivot in row %lld", (long long)i);
+            return OCB_ERR_SINGULAR;
+        }
+        if (Uci[Urp[i]] < i) {
+            set_error("U has an entry below the diagonal (row %lld col %d)", (long long)i, Uci[Urp[i]]);
+            return OCB_ERR_ARG;
+        }
+    }
+    std::vector<int32_t> starts;
+    find_supernodes(n, Urp, Uci, &starts);
+    P->nsuper = (int32_t)starts.size() - 1;
+    for (size_t t = 0; t + 1 < starts.size(); ++t) P->max_w = std::max(P->max_w, starts[t + 1] - starts[t]);
+    const Tri TL{Lrp, Lci, Lva, false}, TU{Urp, Uci, Uva, true};
+    std::vector<BlockPlan> planL, planU;
+    int64_t ymax = 0;
+    int rc = plan_factor(n, TL, starts, &planL, &P->nsub_L, &ymax);
+    if (rc == OCB_OK) rc = plan_factor(n, TU, starts, &planU, &P->nsub_U, &ymax);
+    if (rc != OCB_OK) return rc;
+    P->ymax = ymax;
+    P->n_ext = n + 2 * ymax;
+    const int64_t cap = (int64_t)Lrp[n] + Urp[n] + 4 * n;
+    P->col.reserve(cap);
+    P->val.reserve(cap);
+    for (int64_t i = 0; i < n; ++i) {
+        for (int32_t p = Lrp[i]; p < Lrp[i + 1]; ++p) P->nnzL += (Lci[p] != i);
+    }
+    P->nnzU = Urp[n];
+    rc = emit_factor(n, TL, starts, planL, P->nsub_L, ymax, max_lanes, P);
+    P->nsub_L = (int32_t)P->nsub();
+    if (rc == OCB_OK) rc = emit_factor(n, TU, starts, planU, P->nsub_U, ymax, max_lanes, P);
+    P->nsub_U = (int32_t)P->nsub() - P->nsub_L;
+    return rc;
+}
+
+}  // namespace ocb
+
+// ---------------------------------------------------------------------------------
+// host-only C ABI: lets the CPU test-suite execute the program without a GPU
+// ---------------------------------------------------------------------------------
+struct ocb_lu_program {
+    ocb::LuProgram P;
+};
+
+extern "C" {
+
+int ocb_lu_program_create(ocb_lu_program** out, int64_t n, const int32_t* h_L_rowptr,
+                          const int32_t* h_L_colidx, const double* h_L_vals, const int32_t* h_U_rowptr,
+                          const int32_t* h_U_colidx, const double* h_U_vals) {
+    OCB_ARG(out && n >= 0 && h_L_rowptr && h_U_rowptr, "lu_program_create");
+    ocb_lu_program* h = new ocb_lu_program();
+    const int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx,
+                                         h_U_vals, 512, &h->P);
+    if (rc != OCB_OK) {
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return OCB_OK;
+}
+
+int ocb_lu_program_destroy(ocb_lu_program* prog) {
+    delete prog;
+    return OCB_OK;
+}
+
+int ocb_lu_program_info(const ocb_lu_program* prog, int64_t* info12) {
+    OCB_ARG(prog && info12, "lu_program_info");
+    const ocb::LuProgram& P = prog->P;
+    info12[0] = P.n;
+    info12[1] = P.n_ext;
+    info12[2] = P.ymax;
+    info12[3] = P.nsub_L;
+    info12[4] = P.nsub_U;
+    info12[5] = P.nsuper;
+    info12[6] = P.max_w;
+    info12[7] = (int64_t)P.slices.size();
+    info12[8] = P.nrows();
+    info12[9] = P.nent();
+    info12[10] = P.nnzL;
+    info12[11] = P.nnzU;
+    return OCB_OK;
+}
+
+int ocb_lu_program_export(const ocb_lu_program* prog, int32_t* h_sub_ptr, int32_t* h_slice4, int32_t* h_dst,
+                          int32_t* h_init, double* h_scale, int32_t* h_col, double* h_val) {
+    OCB_ARG(prog && h_sub_ptr && h_slice4 && h_dst && h_init && h_scale && h_col && h_val, "lu_program_export");
+    const ocb::LuProgram& P = prog->P;
+    memcpy(h_sub_ptr, P.sub_ptr.data(), P.sub_ptr.size() * sizeof(int32_t));
+    memcpy(h_slice4, P.slices.data(), P.slices.size() * sizeof(ocb::Slice));
+    memcpy(h_dst, P.dst.data(), P.dst.size() * sizeof(int32_t));
+    memcpy(h_init, P.init.data(), P.init.size() * sizeof(int32_t));
+    memcpy(h_scale, P.scale.data(), P.scale.size() * sizeof(double));
+    memcpy(h_col, P.col.data(), P.col.size() * sizeof(int32_t));
+    memcpy(h_val, P.val.data(), P.val.size() * sizeof(double));
+    return OCB_OK;
+}
+}

@@ -1,0 +1,55 @@
+// Host-side "gather program" of a sparse LU solve (no CUDA in this header).
+//
+// x = Pc U^-1 L^-1 Pr b is rewritten as a short sequence of SUB-LEVELS.  Rows are
+// grouped into supernodes (consecutive rows of U with nested structure); the diagonal
+// block of every supernode is inverted on the host, so that a whole supernode costs two
+// dependent steps whatever its width:
+//     A:  y_t = b_t - T[t, off-block] x          (plain sparse row gathers)
+//     B:  x_t = inv(T[t,t]) y_t                   (dense triangular rows, gathers from y)
+// Both are instances of one primitive executed by the CUDA kernels,
+//     xe[dst] = ( (init >= 0 ? xe[init] : 0) - sum_p val[p] * xe[col[p]] ) * scale,
+// on an EXTENDED vector xe = [x (n rows) | y scratch (2 * ymax rows)].  Rows of one
+// sub-level are independent; a barrier separates sub-levels.  Within a sub-level the rows
+// are sorted by length and cut into SLICES of 32 >> g rows (2^g lanes per row, g from the
+// row length); a slice is the unit of work of one warp and its entries are stored
+// trip-major (sliced ELLPACK), so that the 32 lanes of a warp read 32 consecutive entries.  For the N=25 cavity factor
+// this is 143 sub-levels instead of 1784 scalar dependency levels.
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace ocb {
+
+struct Slice {        // up to 32 >> glog rows processed by ONE warp, 2^glog lanes per row
+    int32_t ebase;    // first entry; entry (trip u, lane l) is at ebase + 32*u + l, where lane
+                      // l = r * 2^glog + g holds entry u * 2^glog + g of the slice's row r
+                      // (zero padded: SELL-32 layout, conflict-free shared-memory reads)
+    int32_t trips;    // 32-wide trips = ceil(longest row / 2^glog)
+    int32_t glog_nrows;  // glog | nrows << 8
+    int32_t q0;       // first row
+};
+
+struct LuProgram {
+    int64_t n = 0, n_ext = 0, ymax = 0;
+    int64_t nnzL = 0, nnzU = 0;          // strictly lower / upper incl. diagonal (input factors)
+    int64_t nent_actual = 0;             // program entries without the SELL padding
+    int32_t nsub_L = 0, nsub_U = 0;      // sub-levels (barriers) of the two sweeps
+    int32_t nsuper = 0, max_w = 0;       // supernodes, widest supernode
+    std::vector<int32_t> sub_ptr;        // nsub + 1: slices of sub-level s are [sub_ptr[s], sub_ptr[s+1])
+    std::vector<Slice> slices;
+    std::vector<int32_t> dst, init;      // per row (indices into xe; init = -1: none)
+    std::vector<double> scale;           // per row
+    std::vector<int32_t> col;            // per padded entry (indices into xe)
+    std::vector<double> val;
+    int64_t nrows() const { return (int64_t)dst.size(); }
+    int64_t nent() const { return (int64_t)col.size(); }
+    int64_t nsub() const { return (int64_t)sub_ptr.size() - 1; }
+};
+
+// Build the program from CSR factors (L unit lower, diagonal optional; U upper with the
+// diagonal).  Returns 0 or a negative ocb_status (message via set_error).
+int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const double* Lva,
+                     const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
+                     LuProgram* out);
+
+}  // namespace ocb

@@ -1,196 +1,79 @@
 // K1: multi-RHS sparse triangular solves  x = Pc U^-1 L^-1 Pr b  on an LU factorisation.
 //
-// Design (DESIGN.md "K1").  The right-hand-side COLUMNS are independent, so the block is
-// cut into column panels of KP columns and ONE CTA owns one panel for the whole solve
-// (row permutation, L levels, U levels, column permutation): no inter-CTA synchronisation,
-// only __syncthreads() between dependency levels.  Rows of L and U are sorted by
-// dependency level; a row is reduced by a group of G = 2^g lanes (g per level, chosen on
-// the host from the mean row length), every lane holding KP partial sums, then a shuffle
-// reduction.
-//
-// Two kernels:
-//  * sptrsm_stream_kernel (the hot one for the reference's configs): the panel x lives in
-//    shared memory and the factor is consumed from a packed, 16-byte aligned BATCH STREAM
-//    that the TMA engine (cp.async.bulk + mbarrier complete_tx) copies into a shared-memory
-//    ring a few batches ahead of the consumers.  The dependency chain of a level then only
-//    sees shared-memory latency; the factor bytes arrive as large coalesced bulk copies.
-//  * sptrsm_panel_kernel: generic fallback (panel in shared memory or in a per-CTA global
-//    slab for large n), factor read with ordinary coalesced loads.
+// Design (DESIGN.md "K1").  The host turns the factors into a GATHER PROGRAM
+// (lu_program.h): supernodes with inverted diagonal blocks, so that the whole solve is a
+// short sequence of sub-levels (143 for the N=25 cavity instead of 1784 scalar dependency
+// levels), every sub-level a set of independent rows
+//     xe[dst] = ((init >= 0 ? xe[init] : 0) - sum_p val[p] * xe[col[p]]) * scale.
+// The right-hand-side COLUMNS are independent: the block is cut into panels of KP columns
+// and ONE CTA owns one panel for the whole solve (row permutation, all sub-levels, column
+// permutation) - no inter-CTA synchronisation, one __syncthreads() per sub-level.  The
+// panel xe lives in shared memory (or in a per-CTA global slab when n is too large); the
+// program is consumed from a packed, 16-byte aligned BATCH STREAM that the TMA engine
+// (cp.async.bulk + mbarrier complete_tx) copies into a shared-memory ring a few batches
+// ahead of the consumers, so a sub-level only ever sees shared-memory latency.  A row is
+// reduced by 2^g lanes (g per segment, chosen on the host from the row lengths) with
+// shuffle butterflies.  For few right-hand sides the launch picks KP = 1 so that as many
+// SMs as there are columns work concurrently (latency-optimal); more columns per CTA
+// amortise the program stream when there are more columns than SMs.
 //
 // Algorithmic bytes per solve: 12*(nnzL+nnzU) + 16*(n+1) + 32*n*k.
 #include "common.cuh"
+#include "lu_program.h"
 #include <vector>
 #include <algorithm>
 #include <string.h>
 #include <stdlib.h>
 
-namespace ocb {
-
-struct TriDev {
-    const int32_t* lvl_ptr;  // nlev+1, positions in level-sorted row order
-    const int32_t* rowid;    // n: original row of sorted position q
-    const int32_t* rowptr;   // n+1 (sorted order)
-    const int32_t* colidx;   // off-diagonal entries only
-    const double* vals;
-    const double* dinv;      // 1/diag by sorted position (1.0 for the unit-lower factor)
-    const uint8_t* glog;     // nlev: log2 of lanes per row
-    int nlev;
-};
-
-struct TriSorted {  // host image of one level-sorted factor
-    std::vector<int32_t> lvl_ptr, rowid, rowptr, colidx;
-    std::vector<double> vals, dinv;
-    std::vector<uint8_t> glog;       // lanes per row (<= 32) for the generic kernel
-    std::vector<uint8_t> glog_wide;  // lanes per row (<= TRSM_THREADS) for the stream kernel
-    int nlev = 0;
-    int64_t maxwidth = 0;
-};
-
-struct TriHost {
-    int32_t *lvl_ptr = nullptr, *rowid = nullptr, *rowptr = nullptr, *colidx = nullptr;
-    double *vals = nullptr, *dinv = nullptr;
-    uint8_t* glog = nullptr;
-    int nlev = 0;
-    int64_t nnz = 0, maxwidth = 0;
-    TriDev dev() const { return TriDev{lvl_ptr, rowid, rowptr, colidx, vals, dinv, glog, nlev}; }
-};
-
-}  // namespace ocb
-
 struct ocb_lu {
-    int64_t n = 0;
-    ocb::TriHost L, U;
+    int64_t n = 0, n_ext = 0;
+    int64_t nnzL = 0, nnzU = 0;
+    int32_t nsub_L = 0, nsub_U = 0, nsuper = 0, max_w = 0;
+    int64_t nseg = 0, nrows = 0, nent = 0;
+    unsigned char* arena = nullptr;   // one device allocation: perms | batch offsets | stream
     int32_t *perm_r = nullptr, *perm_c = nullptr;
-    int64_t bytes = 0;
-    int max_smem_optin = 0;
-    // packed batch stream for the TMA-fed kernel (L levels 1.., then U levels 0..)
+    int64_t* batch_off = nullptr;     // nbatch+1 byte offsets into stream
     unsigned char* stream = nullptr;
-    int64_t* batch_off = nullptr;  // nbatch+1 byte offsets into stream
-    int nbatch = 0;
-    int stage_bytes = 0;  // largest batch (multiple of 16)
-    int kp_stream = 0;    // panel width of the stream kernel (0: stream kernel unavailable)
-    int nstages = 0;
+    int64_t bytes = 0;
+    int nbatch = 0, stage_bytes = 0, nstages = 0;
+    int kp_smem_max = 0;              // widest panel that fits shared memory next to the ring (0: global slab)
+    int max_smem_optin = 0;
 };
 
 namespace ocb {
 
-constexpr int TRSM_THREADS = 512;
-
-// ---------------------------------------------------------------------------------
-// generic kernel: factor from global memory
-// ---------------------------------------------------------------------------------
-template <int KP>
-__device__ __forceinline__ void tri_levels(const TriDev F, double* x, int l0) {
-    const int tid = threadIdx.x;
-    if (F.nlev <= l0) return;
-    int q0 = __ldg(F.lvl_ptr + l0), q1 = __ldg(F.lvl_ptr + l0 + 1);
-    int gl = __ldg(F.glog + l0);
-    for (int l = l0; l < F.nlev; ++l) {
-        int nq1 = 0, ngl = 0;  // next level's descriptor, consumed after the barrier
-        if (l + 1 < F.nlev) {
-            nq1 = __ldg(F.lvl_ptr + l + 2);
-            ngl = __ldg(F.glog + l + 1);
-        }
-        const int G = 1 << gl;
-        const int gid = tid >> gl, glane = tid & (G - 1);
-        const int ngroups = TRSM_THREADS >> gl;
-        for (int qq = q0; qq < q1; qq += ngroups) {  // warp-uniform trip count
-            const int q = qq + gid;
-            const bool valid = q < q1;
-            double acc[KP];
-#pragma unroll
-            for (int c = 0; c < KP; ++c) acc[c] = 0.0;
-            int beg = 0, end = 0, row = 0;
-            double d = 1.0;
-            if (valid) {
-                beg = __ldg(F.rowptr + q);
-                end = __ldg(F.rowptr + q + 1);
-                row = __ldg(F.rowid + q);
-                d = __ldg(F.dinv + q);
-            }
-#pragma unroll 4
-            for (int p = beg + glane; p < end; p += G) {
-                const int j = __ldg(F.colidx + p);
-                const double v = __ldg(F.vals + p);
-                const double* xj = x + (int64_t)j * KP;
-#pragma unroll
-                for (int c = 0; c < KP; ++c) acc[c] = fma(v, xj[c], acc[c]);
-            }
-            for (int o = G >> 1; o > 0; o >>= 1) {
-#pragma unroll
-                for (int c = 0; c < KP; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-            }
-            if (valid && glane == 0) {
-                double* xi = x + (int64_t)row * KP;
-#pragma unroll
-                for (int c = 0; c < KP; ++c) xi[c] = (xi[c] - acc[c]) * d;
-            }
-        }
-        __syncthreads();
-        q0 = q1;
-        q1 = nq1;
-        gl = ngl;
+constexpr int TRSM_MAX_THREADS = 1024;
+static int trsm_threads() {
+    static int t = 0;
+    if (t == 0) {
+        const char* env = getenv("OCB_TRSM_THREADS");
+        t = env ? atoi(env) : 512;
+        if (t != 256 && t != 512 && t != 768 && t != 992) t = 512;
     }
+    return t;
 }
+constexpr int KP_GLOBAL = 8;          // panel width when xe lives in a global slab
 
 struct SolveArgs {
-    TriDev L, U;
     const int32_t *perm_r, *perm_c;
-    int64_t n;
+    int64_t n, n_ext;
     const double* B;
     int64_t ldb, nrows_b;
     double* X;
     int64_t ldx, nrows_x, k;
     double* ws;
-    // stream kernel
     const unsigned char* stream;
     const int64_t* batch_off;
     int nbatch, stage_bytes, nstages;
+    int tma_chunk, debug_skip;
 };
 
-template <int KP>
-__device__ __forceinline__ void load_panel(const SolveArgs& a, double* x, int64_t c0) {
-    // x[perm_r[i]] = b[i]  (Pr b); rows beyond nrows_b are zero
-    for (int64_t e = threadIdx.x; e < a.n * KP; e += blockDim.x) {
-        const int64_t i = e / KP;
-        const int c = (int)(e - i * KP);
-        double v = 0.0;
-        if (i < a.nrows_b && c0 + c < a.k) v = a.B[i * a.ldb + c0 + c];
-        x[(int64_t)__ldg(a.perm_r + i) * KP + c] = v;
-    }
-}
-
-template <int KP>
-__device__ __forceinline__ void store_panel(const SolveArgs& a, const double* x, int64_t c0) {
-    // out[j] = z[perm_c[j]]
-    for (int64_t e = threadIdx.x; e < a.nrows_x * KP; e += blockDim.x) {
-        const int64_t j = e / KP;
-        const int c = (int)(e - j * KP);
-        if (c0 + c < a.k) a.X[j * a.ldx + c0 + c] = x[(int64_t)__ldg(a.perm_c + j) * KP + c];
-    }
-}
-
-template <int KP, bool SMEMX>
-__global__ void __launch_bounds__(TRSM_THREADS, 1) sptrsm_panel_kernel(const SolveArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* x = SMEMX ? (double*)smem_raw : a.ws + (int64_t)blockIdx.x * a.n * KP;
-    const int64_t c0 = (int64_t)blockIdx.x * KP;
-    load_panel<KP>(a, x, c0);
-    __syncthreads();
-    tri_levels<KP>(a.L, x, 1);  // level 0 of the unit-lower factor has nothing to subtract
-    tri_levels<KP>(a.U, x, 0);
-    store_panel<KP>(a, x, c0);
-}
-
-// ---------------------------------------------------------------------------------
-// stream kernel: factor arrives through a TMA-fed shared-memory ring
-// ---------------------------------------------------------------------------------
 // Batch record (every section 16-byte aligned, offsets in bytes from the record start):
-//   int32 hdr[8] = {nlev, nrows, nent, off_lvl, off_rowbeg, off_rowid, off_dinv, off_col}
-//   int32 off_val at hdr-extension [8], pad to 48 bytes
-//   int32 lvl[nlev+1] (local row offsets), int32 glog[nlev]
-//   int32 rowbeg[nrows+1] (local entry offsets), int32 rowid[nrows], f64 dinv[nrows]
-//   int32 col[nent], f64 val[nent]
+//   int32 hdr[12] = {npiece, nslice, nrows, nent, off_piece, off_slice, off_dst, off_init,
+//                    off_scale, off_col, off_val, -}
+//   int32 piece[4*npiece] = {s0, s1, barrier, -}: slices [s0, s1) of one sub-level
+//   int32 slice[4*nslice] = {ebase, trips, glog | nrows << 8, q0}  (local to the record)
+//   int32 dst[nrows], int32 init[nrows], f64 scale[nrows], int32 col[nent], f64 val[nent]
 constexpr int HDR_INTS = 12;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -211,6 +94,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -225,309 +111,186 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-template <int KP>
-__global__ void __launch_bounds__(TRSM_THREADS, 1) sptrsm_stream_kernel(const SolveArgs a) {
+// one batch = several bulk copies completing on one mbarrier (more requests in flight)
+__device__ __forceinline__ void issue_batch(unsigned char* dst, const unsigned char* src, uint32_t bytes,
+                                            uint32_t chunk, uint64_t* bar) {
+    mbar_expect_tx(bar, bytes);
+    for (uint32_t o = 0; o < bytes; o += chunk)
+        bulk_g2s(dst + o, src + o, min(chunk, bytes - o), bar);
+}
+
+// XG = false: xe panel in shared memory;  XG = true: per-CTA slab in global memory (large n)
+template <int KP, bool XG>
+__global__ void __launch_bounds__(XG ? 544 : TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(const SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [ring: nstages * stage_bytes][mbarriers: 8 * 8 bytes][x panel: n*KP doubles]
+    // layout: [ring: nstages * stage_bytes][mbarriers full/empty: 128 bytes][xe panel: n_ext*KP doubles]
     unsigned char* ring = smem_raw;
     uint64_t* full = (uint64_t*)(smem_raw + (size_t)a.nstages * a.stage_bytes);
-    double* red = (double*)(smem_raw + (size_t)a.nstages * a.stage_bytes + 64);  // 16 warps x KP
-    double* x = red + (TRSM_THREADS / 32) * KP;
+    uint64_t* empty = full + 8;
+    double* x = XG ? a.ws + (size_t)blockIdx.x * a.n_ext * KP
+                   : (double*)(smem_raw + (size_t)a.nstages * a.stage_bytes + 128);
     const int tid = threadIdx.x;
+    // the last warp is the PRODUCER (feeds the ring with TMA bulk copies, runs ahead of the
+    // consumers); all other warps are consumers and synchronise among themselves only
+    const int warp = tid >> 5, lane = tid & 31, nwarps = (blockDim.x >> 5) - 1;
+    const int ncons = nwarps * 32;
     const int S = a.nstages;
     const int64_t c0 = (int64_t)blockIdx.x * KP;
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) mbar_init(full + s, 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, nwarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {  // prologue: the first S-1 batches are in flight while the panel loads
-        for (int b = 0; b < S - 1 && b < a.nbatch; ++b) {
-            const int64_t o = __ldg(a.batch_off + b);
-            const uint32_t bytes = (uint32_t)(__ldg(a.batch_off + b + 1) - o);
-            mbar_expect_tx(full + b, bytes);
-            bulk_g2s(ring + (size_t)b * a.stage_bytes, a.stream + o, bytes, full + b);
-        }
-    }
-    load_panel<KP>(a, x, c0);
-    __syncthreads();
-    for (int b = 0; b < a.nbatch; ++b) {
-        const int s = b % S;
-        if (tid == 0) {
-            const int nb = b + S - 1;  // its stage was released by the barrier ending batch b-1
-            if (nb < a.nbatch) {
-                const int ns = nb % S;
-                const int64_t o = __ldg(a.batch_off + nb);
-                const uint32_t bytes = (uint32_t)(__ldg(a.batch_off + nb + 1) - o);
-                mbar_expect_tx(full + ns, bytes);
-                bulk_g2s(ring + (size_t)ns * a.stage_bytes, a.stream + o, bytes, full + ns);
+    if (warp == nwarps) {
+        // batch offsets: one coalesced load per 31 batches, handed to lane 0 by shuffles
+        // (a dependent global load per batch would serialise the ring at L2 latency)
+        for (int b0 = 0; b0 < a.nbatch; b0 += 31) {
+            const long long mine = __ldg((const long long*)a.batch_off + min(b0 + lane, a.nbatch));
+            for (int i = 0; i < 31 && b0 + i < a.nbatch; ++i) {
+                const long long o = __shfl_sync(0xffffffffu, mine, i);
+                const long long o2 = __shfl_sync(0xffffffffu, mine, i + 1);
+                if (lane == 0) {
+                    const int b = b0 + i, s = b % S;
+                    if (b >= S) mbar_wait(empty + s, (uint32_t)(((b / S) - 1) & 1));
+                    issue_batch(ring + (size_t)s * a.stage_bytes, a.stream + o, (uint32_t)(o2 - o),
+                                a.tma_chunk, full + s);
+                }
             }
         }
+        return;
+    }
+    // consumers
+    for (int64_t e = tid; e < a.n * KP; e += ncons) {   // x[perm_r[i]] = b[i]; rows >= nrows_b are zero
+        const int64_t i = e / KP;
+        const int c = (int)(e - i * KP);
+        double v = 0.0;
+        if (i < a.nrows_b && c0 + c < a.k) v = a.B[i * a.ldb + c0 + c];
+        x[(int64_t)__ldg(a.perm_r + i) * KP + c] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+    for (int b = 0; b < a.nbatch; ++b) {
+        const int s = b % S;
         mbar_wait(full + s, (uint32_t)((b / S) & 1));
         const unsigned char* rec = ring + (size_t)s * a.stage_bytes;
         const int32_t* hdr = (const int32_t*)rec;
-        const int nlev = hdr[0];
-        const int32_t* lvl = (const int32_t*)(rec + hdr[3]);
-        const int32_t* glg = lvl + nlev + 1;
-        const int32_t* rowbeg = (const int32_t*)(rec + hdr[4]);
-        const int32_t* rowid = (const int32_t*)(rec + hdr[5]);
-        const double* dinv = (const double*)(rec + hdr[6]);
-        const int32_t* col = (const int32_t*)(rec + hdr[7]);
-        const double* val = (const double*)(rec + hdr[8]);
-        for (int l = 0; l < nlev; ++l) {
-            const int q0 = lvl[l], q1 = lvl[l + 1];
-            const int gl = glg[l];
-            if (gl < 5) {
-                // ---- G < 32 lanes per row: several rows per warp, plain butterflies.
-                // Warps without a row in this level fall through to the barrier.
+        const int npiece = a.debug_skip ? 0 : hdr[0];
+        const int4* piece = (const int4*)(rec + hdr[4]);
+        const int4* slice = (const int4*)(rec + hdr[5]);
+        const int32_t* dst = (const int32_t*)(rec + hdr[6]);
+        const int32_t* init = (const int32_t*)(rec + hdr[7]);
+        const double* scale = (const double*)(rec + hdr[8]);
+        const int32_t* col = (const int32_t*)(rec + hdr[9]);
+        const double* val = (const double*)(rec + hdr[10]);
+        for (int pc = 0; pc < npiece; ++pc) {
+            const int4 pd = piece[pc];
+            // one slice per warp and pass: 32 >> gl rows, 2^gl lanes per row, entries trip-major
+            for (int sl = pd.x + warp; sl < pd.y; sl += nwarps) {
+                const int4 sd = slice[sl];
+                const int gl = sd.z & 255, nr = sd.z >> 8;
                 const int G = 1 << gl;
-                const int glane = tid & (G - 1);
-                const int ngroups = TRSM_THREADS >> gl;
-                for (int qb = q0 + ((tid & ~31) >> gl); qb < q1; qb += ngroups) {  // warp-uniform
-                    const int q = qb + ((tid & 31) >> gl);
-                    const bool valid = q < q1;
-                    double acc[KP];
+                const int r = lane >> gl;
+                const bool owner = (r < nr) && ((lane & (G - 1)) == 0);
+                int i0 = -1, di = 0;
+                double sc = 0.0;
+                if (owner) {   // row metadata: in flight while the entries stream
+                    const int q = sd.w + r;
+                    i0 = init[q];
+                    di = dst[q];
+                    sc = scale[q];
+                }
+                const int32_t* cp = col + sd.x + lane;
+                const double* vp = val + sd.x + lane;
+                const int trips = sd.y;
+                // UNR trips per step, all loads of a step issued before the first use;
+                // NACC accumulators break the FP64 dependency chain
+                constexpr int UNR = KP <= 2 ? 8 : 4, NACC = KP <= 2 ? 4 : 1;
+                double acc[NACC][KP];
 #pragma unroll
-                    for (int c = 0; c < KP; ++c) acc[c] = 0.0;
-                    int beg = 0, end = 0;
-                    if (valid) {
-                        beg = rowbeg[q];
-                        end = rowbeg[q + 1];
+                for (int u = 0; u < NACC; ++u)
+#pragma unroll
+                    for (int c = 0; c < KP; ++c) acc[u][c] = 0.0;
+                int u0 = 0;
+                for (; u0 + UNR <= trips; u0 += UNR) {
+                    int j[UNR];
+                    double v[UNR];
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        j[u] = cp[(u0 + u) * 32];
+                        v[u] = vp[(u0 + u) * 32];
                     }
-#pragma unroll 4
-                    for (int p = beg + glane; p < end; p += G) {
-                        const int j = col[p];
-                        const double v = val[p];
-                        const double* xj = x + (size_t)j * KP;
 #pragma unroll
-                        for (int c = 0; c < KP; ++c) acc[c] = fma(v, xj[c], acc[c]);
-                    }
-                    for (int o = G >> 1; o > 0; o >>= 1) {
+                    for (int u = 0; u < UNR; ++u) {
+                        const double* xj = x + (size_t)j[u] * KP;
 #pragma unroll
-                        for (int c = 0; c < KP; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-                    }
-                    if (valid && glane == 0) {
-                        double* xi = x + (size_t)rowid[q] * KP;
-                        const double d = dinv[q];
-#pragma unroll
-                        for (int c = 0; c < KP; ++c) xi[c] = (xi[c] - acc[c]) * d;
+                        for (int c = 0; c < KP; ++c) acc[u % NACC][c] = fma(v[u], xj[c], acc[u % NACC][c]);
                     }
                 }
-                __syncthreads();
-            } else {
-                // ---- G >= 32: W = G/32 warps per row, (threads/G) rows per pass.
-                const int W = 1 << (gl - 5);
-                const int warp = tid >> 5, lane = tid & 31;
-                const int rpp = (TRSM_THREADS / 32) >> (gl - 5);
-                for (int qb = q0; qb < q1; qb += rpp) {  // block-uniform trip count
-                const int q = qb + (warp >> (gl - 5));
-                const bool valid = q < q1;  // warp-uniform
-                double tot = 0.0;           // lane c*(32/KP) of the warp ends with column c
-                if (valid) {
-                    double acc[KP];
+                if (u0 < trips) {   // remainder (warp-uniform): up to UNR-1 trips, loads first
+                    int j[UNR - 1];
+                    double v[UNR - 1];
 #pragma unroll
-                    for (int c = 0; c < KP; ++c) acc[c] = 0.0;
-                    const int beg = rowbeg[q], end = rowbeg[q + 1];
-                    const int G = 32 * W;
-#pragma unroll 4
-                    for (int p = beg + (tid & (G - 1)); p < end; p += G) {
-                        const int j = col[p];
-                        const double v = val[p];
-                        const double* xj = x + (size_t)j * KP;
-#pragma unroll
-                        for (int c = 0; c < KP; ++c) acc[c] = fma(v, xj[c], acc[c]);
+                    for (int u = 0; u < UNR - 1; ++u) {
+                        if (u0 + u < trips) {
+                            j[u] = cp[(u0 + u) * 32];
+                            v[u] = vp[(u0 + u) * 32];
+                        }
                     }
-                    // transposing butterfly: 6 (KP=4) instead of 20 double shuffles
-                    if (KP == 4) {
-                        const bool hi = lane & 16;
-                        const double s0 = hi ? acc[0] : acc[2], s1 = hi ? acc[1] : acc[3 % KP];
-                        const double k0 = hi ? acc[2] : acc[0], k1 = hi ? acc[3 % KP] : acc[1];
-                        const double v0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
-                        const double v1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
-                        const bool hi2 = lane & 8;
-                        tot = (hi2 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi2 ? v0 : v1, 8);
-                        tot += __shfl_xor_sync(0xffffffffu, tot, 4);
-                        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-                        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-                    } else if (KP == 2) {
-                        const bool hi = lane & 16;
-                        tot = (hi ? acc[KP - 1] : acc[0]) +
-                              __shfl_xor_sync(0xffffffffu, hi ? acc[0] : acc[KP - 1], 16);
-                        tot += __shfl_xor_sync(0xffffffffu, tot, 8);
-                        tot += __shfl_xor_sync(0xffffffffu, tot, 4);
-                        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-                        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+#pragma unroll
+                    for (int u = 0; u < UNR - 1; ++u) {
+                        if (u0 + u < trips) {
+                            const double* xj = x + (size_t)j[u] * KP;
+#pragma unroll
+                            for (int c = 0; c < KP; ++c)
+                                acc[u % NACC][c] = fma(v[u], xj[c], acc[u % NACC][c]);
+                        }
+                    }
+                }
+                double tot[KP];
+#pragma unroll
+                for (int c = 0; c < KP; ++c)
+                    tot[c] = NACC == 4 ? (acc[0][c] + acc[1 % NACC][c]) + (acc[2 % NACC][c] + acc[3 % NACC][c])
+                                       : acc[0][c];
+                for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int c = 0; c < KP; ++c) tot[c] += __shfl_xor_sync(0xffffffffu, tot[c], o);
+                }
+                if (owner) {
+                    double* xd = x + (size_t)di * KP;
+                    if (i0 >= 0) {
+                        const double* xi = x + (size_t)i0 * KP;
+#pragma unroll
+                        for (int c = 0; c < KP; ++c) xd[c] = (xi[c] - tot[c]) * sc;
                     } else {
-                        tot = acc[0];
-                        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+#pragma unroll
+                        for (int c = 0; c < KP; ++c) xd[c] = -tot[c] * sc;
                     }
                 }
-                const int cstep = 32 / KP;  // lane c*cstep holds column c
-                if (W == 1) {
-                    if (valid && (lane % cstep) == 0) {
-                        double* xi = x + (size_t)rowid[q] * KP + lane / cstep;
-                        *xi = (*xi - tot) * dinv[q];
-                    }
-                } else {
-                    if (valid && (lane % cstep) == 0) red[warp * KP + lane / cstep] = tot;
-                    __syncthreads();
-                    if (valid && (warp & (W - 1)) == 0 && lane < KP) {
-                        double sum = 0.0;
-                        for (int w = 0; w < W; ++w) sum += red[(warp + w) * KP + lane];
-                        double* xi = x + (size_t)rowid[q] * KP + lane;
-                        *xi = (*xi - sum) * dinv[q];
-                    }
-                    if (qb + rpp < q1) __syncthreads();  // red[] is reused by the next pass
-                }
-                }
-                __syncthreads();
             }
+            if (pd.z) asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);   // this warp is done with the stage
     }
-    store_panel<KP>(a, x, c0);
+    for (int64_t e = tid; e < a.nrows_x * KP; e += ncons) {   // out[j] = x[perm_c[j]]
+        const int64_t j = e / KP;
+        const int c = (int)(e - j * KP);
+        if (c0 + c < a.k) a.X[j * a.ldx + c0 + c] = x[(int64_t)__ldg(a.perm_c + j) * KP + c];
+    }
 }
 
 // ---------------------------------------------------------------------------------
-// host-side analysis
+// host side: packing the program into the batch stream
 // ---------------------------------------------------------------------------------
-static int analyse_factor(int64_t n, const int32_t* rp, const int32_t* ci, const double* va,
-                          bool upper, TriSorted* out) {
-    std::vector<int32_t> level(n, 0);
-    int nlev = 0;
-    int64_t nnz_off = 0;
-    std::vector<double> diag(n, 1.0);
-    if (!upper) {
-        for (int64_t i = 0; i < n; ++i) {
-            int lv = 0;
-            for (int32_t p = rp[i]; p < rp[i + 1]; ++p) {
-                const int32_t j = ci[p];
-                if (j < i) {
-                    lv = std::max(lv, level[j] + 1);
-                    ++nnz_off;
-                } else if (j > i) {
-                    set_error("L has an entry above the diagonal (row %lld col %d)", (long long)i, j);
-                    return OCB_ERR_ARG;
-                }
-            }
-            level[i] = lv;
-            nlev = std::max(nlev, lv + 1);
-        }
-    } else {
-        for (int64_t i = n - 1; i >= 0; --i) {
-            int lv = 0;
-            double dg = 0.0;
-            for (int32_t p = rp[i]; p < rp[i + 1]; ++p) {
-                const int32_t j = ci[p];
-                if (j > i) {
-                    lv = std::max(lv, level[j] + 1);
-                    ++nnz_off;
-                } else if (j == i) {
-                    dg = va[p];
-                } else {
-                    set_error("U has an entry below the diagonal (row %lld col %d)", (long long)i, j);
-                    return OCB_ERR_ARG;
-                }
-            }
-            if (dg == 0.0) {
-                set_error("U has a zero pivot in row %lld", (long long)i);
-                return OCB_ERR_SINGULAR;
-            }
-            diag[i] = dg;
-            level[i] = lv;
-            nlev = std::max(nlev, lv + 1);
-        }
-    }
-    if (n == 0) nlev = 0;
-    TriSorted& t = *out;
-    t.nlev = nlev;
-    t.lvl_ptr.assign(nlev + 1, 0);
-    for (int64_t i = 0; i < n; ++i) t.lvl_ptr[level[i] + 1]++;
-    for (int l = 0; l < nlev; ++l) t.lvl_ptr[l + 1] += t.lvl_ptr[l];
-    t.rowid.resize(n);
-    {
-        std::vector<int32_t> pos(t.lvl_ptr.begin(), t.lvl_ptr.begin() + nlev);
-        for (int64_t i = 0; i < n; ++i) t.rowid[pos[level[i]]++] = (int32_t)i;
-    }
-    t.rowptr.assign(n + 1, 0);
-    t.colidx.resize(nnz_off);
-    t.vals.resize(nnz_off);
-    t.dinv.resize(n);
-    int64_t w = 0;
-    for (int64_t q = 0; q < n; ++q) {
-        const int64_t i = t.rowid[q];
-        t.rowptr[q] = (int32_t)w;
-        for (int32_t p = rp[i]; p < rp[i + 1]; ++p) {
-            if (ci[p] != i) {
-                t.colidx[w] = ci[p];
-                t.vals[w] = va[p];
-                ++w;
-            }
-        }
-        t.dinv[q] = upper ? 1.0 / diag[i] : 1.0;
-    }
-    t.rowptr[n] = (int32_t)w;
-    t.glog.assign(std::max(nlev, 1), 0);
-    t.glog_wide.assign(std::max(nlev, 1), 0);
-    t.maxwidth = 0;
-    for (int l = 0; l < nlev; ++l) {
-        const int64_t width = t.lvl_ptr[l + 1] - t.lvl_ptr[l];
-        t.maxwidth = std::max(t.maxwidth, width);
-        const int64_t ent = t.rowptr[t.lvl_ptr[l + 1]] - t.rowptr[t.lvl_ptr[l]];
-        const double avg = width > 0 ? (double)ent / (double)width : 0.0;
-        int g = 0;
-        while (g < 5 && (double)(8 << g) < avg) ++g;  // about 8 entries per lane
-        // narrow level: spare lanes are free, use them
-        while (g < 5 && width * (int64_t)(2 << g) <= TRSM_THREADS && (double)(2 << g) <= avg) ++g;
-        t.glog[l] = (uint8_t)g;
-        // stream kernel: several warps may share one long row (cross-warp reduction in smem)
-        int gw = g;
-        while (gw < 9 && width * (int64_t)(2 << gw) <= TRSM_THREADS && (double)(4 << gw) <= avg) ++gw;
-        t.glog_wide[l] = (uint8_t)gw;
-    }
-    return OCB_OK;
-}
-
-template <typename T>
-static int upload(T** dst, const std::vector<T>& v, int64_t* bytes, cudaStream_t st) {
-    const size_t b = std::max<size_t>(v.size(), 1) * sizeof(T);
-    OCB_CUDA(cudaMalloc((void**)dst, b));
-    *bytes += (int64_t)b;
-    if (!v.empty()) OCB_CUDA(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
-    return OCB_OK;
-}
-
-static int upload_factor(const TriSorted& t, TriHost* out, int64_t* bytes, cudaStream_t st) {
-    out->nlev = t.nlev;
-    out->nnz = (int64_t)t.colidx.size();
-    out->maxwidth = t.maxwidth;
-    int rc;
-    if ((rc = upload(&out->lvl_ptr, t.lvl_ptr, bytes, st))) return rc;
-    if ((rc = upload(&out->rowid, t.rowid, bytes, st))) return rc;
-    if ((rc = upload(&out->rowptr, t.rowptr, bytes, st))) return rc;
-    if ((rc = upload(&out->colidx, t.colidx, bytes, st))) return rc;
-    if ((rc = upload(&out->vals, t.vals, bytes, st))) return rc;
-    if ((rc = upload(&out->dinv, t.dinv, bytes, st))) return rc;
-    if ((rc = upload(&out->glog, t.glog, bytes, st))) return rc;
-    return OCB_OK;
-}
-
-static void free_factor(TriHost* f) {
-    cudaFree(f->lvl_ptr);
-    cudaFree(f->rowid);
-    cudaFree(f->rowptr);
-    cudaFree(f->colidx);
-    cudaFree(f->vals);
-    cudaFree(f->dinv);
-    cudaFree(f->glog);
-    *f = TriHost();
-}
-
 static inline int64_t a16(int64_t x) { return (x + 15) & ~(int64_t)15; }
 
-static int64_t record_bytes(int64_t nlev, int64_t nrows, int64_t nent) {
+static int64_t record_bytes(int64_t npiece, int64_t nslice, int64_t nrows, int64_t nent) {
     int64_t o = a16(HDR_INTS * 4);
-    o = a16(o + (2 * nlev + 1) * 4);
-    o = a16(o + (nrows + 1) * 4);
+    o = a16(o + npiece * 16);
+    o = a16(o + nslice * 16);
+    o = a16(o + nrows * 4);
     o = a16(o + nrows * 4);
     o = a16(o + nrows * 8);
     o = a16(o + nent * 4);
@@ -535,170 +298,220 @@ static int64_t record_bytes(int64_t nlev, int64_t nrows, int64_t nent) {
     return o;
 }
 
-struct BatchPlan {
-    int factor;      // 0 = L, 1 = U
-    int lev0, lev1;  // level range (single level if split by rows)
-    int q0, q1;      // sorted-row range
+struct Piece {   // slices [s0, s1) of one sub-level placed in a batch
+    int32_t s0, s1, barrier;
 };
 
-// Greedy packing of whole levels into batches of at most cap bytes; a level that does not
-// fit alone is split by rows.  Returns false if a single row exceeds the capacity.
-static bool plan_batches(const TriSorted* f[2], int64_t cap, std::vector<BatchPlan>* plan) {
-    plan->clear();
-    for (int fi = 0; fi < 2; ++fi) {
-        const TriSorted& t = *f[fi];
-        int l = (fi == 0) ? 1 : 0;
-        while (l < t.nlev) {
-            // try to extend [l, l2)
-            int l2 = l;
-            while (l2 < t.nlev) {
-                const int64_t rows = t.lvl_ptr[l2 + 1] - t.lvl_ptr[l];
-                const int64_t ent = t.rowptr[t.lvl_ptr[l2 + 1]] - t.rowptr[t.lvl_ptr[l]];
-                if (record_bytes(l2 + 1 - l, rows, ent) > cap) break;
-                ++l2;
+static inline int slice_rows(const Slice& sl) { return sl.glog_nrows >> 8; }
+
+// Greedy packing of slices into batches of at most cap bytes (a sub-level may span several
+// batches).  Returns false if a single slice exceeds the capacity.
+static bool plan_batches(const LuProgram& P, int64_t cap, std::vector<std::vector<Piece>>* batches) {
+    batches->clear();
+    std::vector<Piece> cur;
+    int64_t nsl = 0, rows = 0, ent = 0;
+    auto flush = [&]() {
+        if (cur.empty()) return;
+        cur.back().barrier = 1;   // the ring stage is reused after the batch
+        batches->push_back(cur);
+        cur.clear();
+        nsl = rows = ent = 0;
+    };
+    for (int64_t sb = 0; sb < P.nsub(); ++sb) {
+        int32_t s = P.sub_ptr[sb];
+        const int32_t send = P.sub_ptr[sb + 1];
+        while (s < send) {
+            int32_t s2 = s;
+            int64_t r2 = rows, e2 = ent;
+            while (s2 < send) {
+                const int64_t rr = r2 + slice_rows(P.slices[s2]), ee = e2 + (int64_t)P.slices[s2].trips * 32;
+                if (record_bytes((int64_t)cur.size() + 1, nsl + (s2 + 1 - s), rr, ee) > cap) break;
+                r2 = rr;
+                e2 = ee;
+                ++s2;
             }
-            if (l2 > l) {
-                plan->push_back(BatchPlan{fi, l, l2, t.lvl_ptr[l], t.lvl_ptr[l2]});
-                l = l2;
+            if (s2 == s) {
+                if (cur.empty()) return false;   // one slice does not fit an empty batch
+                flush();
                 continue;
             }
-            // level l alone is too large: split by rows
-            int q = t.lvl_ptr[l];
-            const int qend = t.lvl_ptr[l + 1];
-            while (q < qend) {
-                int q2 = q;
-                while (q2 < qend && record_bytes(1, q2 + 1 - q, t.rowptr[q2 + 1] - t.rowptr[q]) <= cap) ++q2;
-                if (q2 == q) return false;  // one row does not fit
-                plan->push_back(BatchPlan{fi, l, l + 1, q, q2});
-                q = q2;
-            }
-            ++l;
+            cur.push_back(Piece{s, s2, (s2 == send) ? 1 : 0});
+            nsl += s2 - s;
+            rows = r2;
+            ent = e2;
+            s = s2;
+            if (s < send) flush();
         }
     }
+    flush();
     return true;
 }
 
-static void write_record(const TriSorted& t, const BatchPlan& b, unsigned char* rec) {
-    const int nlev = b.lev1 - b.lev0, nrows = b.q1 - b.q0;
-    const int e0 = t.rowptr[b.q0], nent = t.rowptr[b.q1] - e0;
+static void batch_counts(const LuProgram& P, const std::vector<Piece>& b, int64_t* nsl, int64_t* rows,
+                         int64_t* ent) {
+    *nsl = *rows = *ent = 0;
+    for (const Piece& p : b)
+        for (int32_t s = p.s0; s < p.s1; ++s) {
+            *nsl += 1;
+            *rows += slice_rows(P.slices[s]);
+            *ent += (int64_t)P.slices[s].trips * 32;
+        }
+}
+
+static int64_t batch_bytes(const LuProgram& P, const std::vector<Piece>& b) {
+    int64_t nsl, rows, ent;
+    batch_counts(P, b, &nsl, &rows, &ent);
+    return record_bytes((int64_t)b.size(), nsl, rows, ent);
+}
+
+static void write_record(const LuProgram& P, const std::vector<Piece>& b, unsigned char* rec) {
+    int64_t nsl, nrows, nent;
+    batch_counts(P, b, &nsl, &nrows, &nent);
+    const int64_t npiece = (int64_t)b.size();
     int32_t* hdr = (int32_t*)rec;
     int64_t o = a16(HDR_INTS * 4);
-    const int64_t off_lvl = o;
-    o = a16(o + (2 * nlev + 1) * 4);
-    const int64_t off_rowbeg = o;
-    o = a16(o + (nrows + 1) * 4);
-    const int64_t off_rowid = o;
+    const int64_t off_piece = o;
+    o = a16(o + npiece * 16);
+    const int64_t off_slice = o;
+    o = a16(o + nsl * 16);
+    const int64_t off_dst = o;
     o = a16(o + nrows * 4);
-    const int64_t off_dinv = o;
-    o = a16(o + (int64_t)nrows * 8);
+    const int64_t off_init = o;
+    o = a16(o + nrows * 4);
+    const int64_t off_scale = o;
+    o = a16(o + nrows * 8);
     const int64_t off_col = o;
-    o = a16(o + (int64_t)nent * 4);
+    o = a16(o + nent * 4);
     const int64_t off_val = o;
-    hdr[0] = nlev; hdr[1] = nrows; hdr[2] = nent;
-    hdr[3] = (int32_t)off_lvl; hdr[4] = (int32_t)off_rowbeg; hdr[5] = (int32_t)off_rowid;
-    hdr[6] = (int32_t)off_dinv; hdr[7] = (int32_t)off_col; hdr[8] = (int32_t)off_val;
-    int32_t* lvl = (int32_t*)(rec + off_lvl);
-    int32_t* glg = lvl + nlev + 1;
-    if (nlev == 1) {  // possibly a row slice of one level
-        lvl[0] = 0; lvl[1] = nrows; glg[0] = t.glog_wide[b.lev0];
-    } else {
-        for (int l = 0; l <= nlev; ++l) lvl[l] = t.lvl_ptr[b.lev0 + l] - b.q0;
-        for (int l = 0; l < nlev; ++l) glg[l] = t.glog_wide[b.lev0 + l];
+    hdr[0] = (int32_t)npiece; hdr[1] = (int32_t)nsl; hdr[2] = (int32_t)nrows; hdr[3] = (int32_t)nent;
+    hdr[4] = (int32_t)off_piece; hdr[5] = (int32_t)off_slice; hdr[6] = (int32_t)off_dst;
+    hdr[7] = (int32_t)off_init; hdr[8] = (int32_t)off_scale; hdr[9] = (int32_t)off_col;
+    hdr[10] = (int32_t)off_val;
+    int32_t* piece = (int32_t*)(rec + off_piece);
+    int32_t* slice = (int32_t*)(rec + off_slice);
+    int32_t* dst = (int32_t*)(rec + off_dst);
+    int32_t* init = (int32_t*)(rec + off_init);
+    double* scale = (double*)(rec + off_scale);
+    int32_t* col = (int32_t*)(rec + off_col);
+    double* val = (double*)(rec + off_val);
+    int32_t ls = 0, r = 0, e = 0;
+    for (size_t pi = 0; pi < b.size(); ++pi) {
+        const Piece& p = b[pi];
+        piece[4 * pi + 0] = ls;
+        piece[4 * pi + 1] = ls + (p.s1 - p.s0);
+        piece[4 * pi + 2] = p.barrier;
+        piece[4 * pi + 3] = 0;
+        for (int32_t s = p.s0; s < p.s1; ++s, ++ls) {
+            const Slice& sl = P.slices[s];
+            const int nr = slice_rows(sl), ne = sl.trips * 32;
+            slice[4 * ls + 0] = e;
+            slice[4 * ls + 1] = sl.trips;
+            slice[4 * ls + 2] = sl.glog_nrows;
+            slice[4 * ls + 3] = r;
+            memcpy(dst + r, P.dst.data() + sl.q0, (size_t)nr * 4);
+            memcpy(init + r, P.init.data() + sl.q0, (size_t)nr * 4);
+            memcpy(scale + r, P.scale.data() + sl.q0, (size_t)nr * 8);
+            memcpy(col + e, P.col.data() + sl.ebase, (size_t)ne * 4);
+            memcpy(val + e, P.val.data() + sl.ebase, (size_t)ne * 8);
+            r += nr;
+            e += ne;
+        }
     }
-    int32_t* rowbeg = (int32_t*)(rec + off_rowbeg);
-    for (int q = 0; q <= nrows; ++q) rowbeg[q] = t.rowptr[b.q0 + q] - e0;
-    memcpy(rec + off_rowid, t.rowid.data() + b.q0, (size_t)nrows * 4);
-    memcpy(rec + off_dinv, t.dinv.data() + b.q0, (size_t)nrows * 8);
-    memcpy(rec + off_col, t.colidx.data() + e0, (size_t)nent * 4);
-    memcpy(rec + off_val, t.vals.data() + e0, (size_t)nent * 8);
 }
 
-static int build_stream(ocb_lu* lu, const TriSorted& L, const TriSorted& U, cudaStream_t st) {
-    lu->kp_stream = 0;
-    const char* env = getenv("OCB_SPTRSM_NO_STREAM");
-    if (env && env[0] == '1') return OCB_OK;
-    const int64_t smem_cap = (int64_t)lu->max_smem_optin - 1024;
-    const TriSorted* f[2] = {&L, &U};
-    std::vector<BatchPlan> plan;
-    // prefer KP=4 with >= 2 stages of >= 16 KB; fall back to narrower panels
-    const int kps[3] = {4, 2, 1};
-    for (int ki = 0; ki < 3; ++ki) {
-        const int kp = kps[ki];
-        const int64_t left = smem_cap - 64 - (TRSM_THREADS / 32) * kp * 8 - lu->n * kp * 8;
-        if (left < 2 * 8192) continue;
-        int64_t cap = std::min<int64_t>(left / 3, 24 * 1024);
-        int nst = 3;
-        if (cap < 12 * 1024) { cap = std::min<int64_t>(left / 2, 24 * 1024); nst = 2; }
-        cap &= ~(int64_t)15;
-        if (!plan_batches(f, cap, &plan)) {
-            // a long row: try two bigger stages
-            cap = (left / 2) & ~(int64_t)15;
+// choose ring geometry + panel placement, pack, upload (one allocation, one copy)
+static int build_device_image(ocb_lu* lu, const LuProgram& P, const int32_t* h_perm_r,
+                              const int32_t* h_perm_c, cudaStream_t st) {
+    const int64_t smem_cap = (int64_t)lu->max_smem_optin - 1024 - 128;
+    const int64_t xe1 = P.n_ext * 8;   // bytes of a one-column panel
+    std::vector<std::vector<Piece>> batches;
+    int kp_smem = 0, nst = 3;
+    int64_t cap = 0;
+    const char* env = getenv("OCB_SPTRSM_FORCE_GLOBAL");
+    const bool force_global = env && env[0] == '1';
+    // prefer a two-column panel next to three stages of >= 16 KB, else one column
+    const int kps[2] = {2, 1};
+    const char* e_st = getenv("OCB_RING_STAGES");
+    const char* e_kb = getenv("OCB_RING_STAGE_KB");
+    if (e_st && atoi(e_st) >= 2 && atoi(e_st) <= 8) nst = atoi(e_st);
+    const int64_t want = (e_kb && atoi(e_kb) >= 4) ? (int64_t)atoi(e_kb) * 1024 : 48 * 1024;
+    for (int ki = 0; ki < 2 && !force_global && kp_smem == 0; ++ki) {
+        const int64_t left = smem_cap - xe1 * kps[ki];
+        if (left < nst * 8192) continue;
+        cap = std::min<int64_t>(left / nst, want) & ~(int64_t)15;
+        if (plan_batches(P, cap, &batches)) kp_smem = kps[ki];
+    }
+    if (kp_smem == 0) {   // panel in a global slab: the ring gets the whole shared memory
+        nst = 3;
+        cap = std::min<int64_t>(smem_cap / 3, 64 * 1024) & ~(int64_t)15;
+        if (!plan_batches(P, cap, &batches)) {
             nst = 2;
-            if (!plan_batches(f, cap, &plan)) continue;
+            cap = (smem_cap / 2) & ~(int64_t)15;
+            if (!plan_batches(P, cap, &batches)) {
+                set_error("lu_create: a factor row does not fit the shared-memory ring");
+                return OCB_ERR_CAPACITY;
+            }
         }
-        std::vector<int64_t> off(plan.size() + 1, 0);
-        int64_t maxb = 0;
-        for (size_t b = 0; b < plan.size(); ++b) {
-            const TriSorted& t = *f[plan[b].factor];
-            const int64_t rb = record_bytes(plan[b].lev1 - plan[b].lev0, plan[b].q1 - plan[b].q0,
-                                            t.rowptr[plan[b].q1] - t.rowptr[plan[b].q0]);
-            off[b + 1] = off[b] + rb;
-            maxb = std::max(maxb, rb);
-        }
-        std::vector<unsigned char> img((size_t)std::max<int64_t>(off.back(), 16), 0);
-        for (size_t b = 0; b < plan.size(); ++b) write_record(*f[plan[b].factor], plan[b], img.data() + off[b]);
-        OCB_CUDA(cudaMalloc((void**)&lu->stream, img.size()));
-        OCB_CUDA(cudaMalloc((void**)&lu->batch_off, off.size() * sizeof(int64_t)));
-        OCB_CUDA(cudaMemcpyAsync(lu->stream, img.data(), img.size(), cudaMemcpyHostToDevice, st));
-        OCB_CUDA(cudaMemcpyAsync(lu->batch_off, off.data(), off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-        OCB_CUDA(cudaStreamSynchronize(st));
-        lu->bytes += (int64_t)img.size() + (int64_t)off.size() * 8;
-        lu->nbatch = (int)plan.size();
-        lu->stage_bytes = (int)std::max<int64_t>(maxb, 16);
-        lu->nstages = nst;
-        lu->kp_stream = kp;
-        return OCB_OK;
     }
-    return OCB_OK;  // stream kernel unavailable: generic kernel is used
-}
-
-// panel width / placement policy of the generic kernel
-static void solve_policy(const ocb_lu* lu, int* kp, bool* smem) {
-    const int64_t cap = lu->max_smem_optin - 1024;
-    if (lu->n * 4 * 8 <= cap) {
-        *kp = 4;
-        *smem = true;
-    } else if (lu->n * 2 * 8 <= cap) {
-        *kp = 2;
-        *smem = true;
-    } else {
-        *kp = 8;
-        *smem = false;
+    std::vector<int64_t> off(batches.size() + 1, 0);
+    int64_t maxb = 16;
+    for (size_t b = 0; b < batches.size(); ++b) {
+        const int64_t rb = batch_bytes(P, batches[b]);
+        off[b + 1] = off[b] + rb;
+        maxb = std::max(maxb, rb);
     }
-}
-
-template <int KP, bool SMEMX>
-static int launch_panel(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
-    const size_t smem = SMEMX ? (size_t)lu->n * KP * sizeof(double) : 0;
-    if (SMEMX)
-        OCB_CUDA(cudaFuncSetAttribute(sptrsm_panel_kernel<KP, SMEMX>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((a.k + KP - 1) / KP);
-    sptrsm_panel_kernel<KP, SMEMX><<<grid, TRSM_THREADS, smem, st>>>(a);
-    OCB_LAUNCH_CHECK();
+    // arena: perm_r | perm_c | batch_off | stream
+    const int64_t o_pr = 0;
+    const int64_t o_pc = align_up(o_pr + std::max<int64_t>(P.n, 1) * 4, 256);
+    const int64_t o_bo = align_up(o_pc + std::max<int64_t>(P.n, 1) * 4, 256);
+    const int64_t o_st = align_up(o_bo + (int64_t)off.size() * 8, 256);
+    const int64_t total = o_st + std::max<int64_t>(off.back(), 16);
+    std::vector<unsigned char> img((size_t)total, 0);
+    if (P.n > 0) {
+        memcpy(img.data() + o_pr, h_perm_r, (size_t)P.n * 4);
+        memcpy(img.data() + o_pc, h_perm_c, (size_t)P.n * 4);
+    }
+    memcpy(img.data() + o_bo, off.data(), off.size() * 8);
+    for (size_t b = 0; b < batches.size(); ++b) write_record(P, batches[b], img.data() + o_st + off[b]);
+    OCB_CUDA(cudaMalloc((void**)&lu->arena, (size_t)total));
+    OCB_CUDA(cudaMemcpyAsync(lu->arena, img.data(), (size_t)total, cudaMemcpyHostToDevice, st));
+    OCB_CUDA(cudaStreamSynchronize(st));   // img dies below
+    lu->perm_r = (int32_t*)(lu->arena + o_pr);
+    lu->perm_c = (int32_t*)(lu->arena + o_pc);
+    lu->batch_off = (int64_t*)(lu->arena + o_bo);
+    lu->stream = lu->arena + o_st;
+    lu->bytes = total;
+    lu->nbatch = (int)batches.size();
+    lu->stage_bytes = (int)maxb;
+    lu->nstages = nst;
+    lu->kp_smem_max = kp_smem;
     return OCB_OK;
 }
 
-template <int KP>
+template <int KP, bool XG>
 static int launch_stream(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 64 + (TRSM_THREADS / 32) * KP * sizeof(double) +
-                        (size_t)lu->n * KP * sizeof(double);
-    OCB_CUDA(cudaFuncSetAttribute(sptrsm_stream_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 128 +
+                        (XG ? 0 : (size_t)lu->n_ext * KP * sizeof(double));
+    OCB_CUDA(cudaFuncSetAttribute(sptrsm_stream_kernel<KP, XG>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((a.k + KP - 1) / KP);
-    sptrsm_stream_kernel<KP><<<grid, TRSM_THREADS, smem, st>>>(a);
+    sptrsm_stream_kernel<KP, XG><<<grid, (XG ? std::min(512, trsm_threads()) : trsm_threads()) + 32, smem, st>>>(a);
     OCB_LAUNCH_CHECK();
     return OCB_OK;
+}
+
+// panel width for k right-hand sides: as narrow as possible while one wave of CTAs covers
+// all columns (latency), wider once there are more columns than SMs (throughput)
+static int choose_kp(const ocb_lu* lu, int64_t k) {
+    if (lu->kp_smem_max == 0) return KP_GLOBAL;
+    const char* env = getenv("OCB_SPTRSM_KP");
+    if (env) {
+        const int v = atoi(env);
+        if (v >= 1 && v <= lu->kp_smem_max && (v & (v - 1)) == 0) return v;
+    }
+    int kp = 1;
+    while (kp < lu->kp_smem_max && (k + kp - 1) / kp > sm_count()) kp *= 2;
+    return kp;
 }
 
 // optional per-launch timing of the solve kernel (bench.py roofline): CUDA events on the
@@ -714,7 +527,50 @@ static SolveProf g_prof;
 
 static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_b, double* X,
                              int64_t ldx, int64_t nrows_x, int64_t k, void* ws, int64_t ws_bytes,
-                             cudaStream_t st);
+                             cudaStream_t st) {
+    SolveArgs a;
+    a.perm_r = lu->perm_r;
+    a.perm_c = lu->perm_c;
+    a.n = lu->n;
+    a.n_ext = lu->n_ext;
+    a.B = B;
+    a.ldb = ldb;
+    a.nrows_b = nrows_b;
+    a.X = X;
+    a.ldx = ldx;
+    a.nrows_x = nrows_x;
+    a.k = k;
+    a.ws = (double*)ws;
+    a.stream = lu->stream;
+    a.batch_off = lu->batch_off;
+    a.nbatch = lu->nbatch;
+    a.stage_bytes = lu->stage_bytes;
+    a.nstages = lu->nstages;
+    {
+        static int chunk = 0, dbg = -1;
+        if (chunk == 0) {
+            const char* e1 = getenv("OCB_TMA_CHUNK");
+            chunk = e1 ? atoi(e1) : 8192;
+            if (chunk < 16) chunk = 8192;
+            chunk &= ~15;
+            const char* e2 = getenv("OCB_TRSM_DEBUG_SKIP");
+            dbg = e2 ? atoi(e2) : 0;
+        }
+        a.tma_chunk = chunk;
+        a.debug_skip = dbg;
+    }
+    const int kp = choose_kp(lu, k);
+    if (lu->kp_smem_max == 0) {
+        const int64_t need = ocb_lu_solve_ws_bytes(lu, k);
+        if (ws == nullptr || ws_bytes < need) {
+            set_error("lu_solve: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+            return OCB_ERR_CAPACITY;
+        }
+        return launch_stream<KP_GLOBAL, true>(lu, a, st);
+    }
+    if (kp == 2) return launch_stream<2, false>(lu, a, st);
+    return launch_stream<1, false>(lu, a, st);
+}
 
 int lu_solve_impl(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_b, double* X,
                   int64_t ldx, int64_t nrows_x, int64_t k, void* ws, int64_t ws_bytes,
@@ -731,50 +587,9 @@ int lu_solve_impl(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_
     OCB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], st));
     g_prof.used += 2;
     g_prof.launches += 1;
-    g_prof.alg_bytes += 12.0 * (double)(lu->L.nnz + lu->U.nnz + lu->n) + 16.0 * (double)(lu->n + 1) +
+    g_prof.alg_bytes += 12.0 * (double)(lu->nnzL + lu->nnzU) + 16.0 * (double)(lu->n + 1) +
                         32.0 * (double)lu->n * (double)k;
     return rc;
-}
-
-static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_b, double* X,
-                             int64_t ldx, int64_t nrows_x, int64_t k, void* ws, int64_t ws_bytes,
-                             cudaStream_t st) {
-    SolveArgs a;
-    a.L = lu->L.dev();
-    a.U = lu->U.dev();
-    a.perm_r = lu->perm_r;
-    a.perm_c = lu->perm_c;
-    a.n = lu->n;
-    a.B = B;
-    a.ldb = ldb;
-    a.nrows_b = nrows_b;
-    a.X = X;
-    a.ldx = ldx;
-    a.nrows_x = nrows_x;
-    a.k = k;
-    a.ws = (double*)ws;
-    a.stream = lu->stream;
-    a.batch_off = lu->batch_off;
-    a.nbatch = lu->nbatch;
-    a.stage_bytes = lu->stage_bytes;
-    a.nstages = lu->nstages;
-    if (lu->kp_stream == 4) return launch_stream<4>(lu, a, st);
-    if (lu->kp_stream == 2) return launch_stream<2>(lu, a, st);
-    if (lu->kp_stream == 1) return launch_stream<1>(lu, a, st);
-    int kp;
-    bool smem;
-    solve_policy(lu, &kp, &smem);
-    if (!smem) {
-        const int64_t need = ocb_lu_solve_ws_bytes(lu, k);
-        if (ws == nullptr || ws_bytes < need) {
-            set_error("lu_solve: workspace too small (%lld < %lld)", (long long)ws_bytes,
-                      (long long)need);
-            return OCB_ERR_CAPACITY;
-        }
-        return launch_panel<8, false>(lu, a, st);
-    }
-    if (kp == 4) return launch_panel<4, true>(lu, a, st);
-    return launch_panel<2, true>(lu, a, st);
 }
 
 }  // namespace ocb
@@ -788,32 +603,26 @@ int ocb_lu_create(ocb_lu** out, int64_t n, const int32_t* h_L_rowptr, const int3
     OCB_ARG(out && n >= 0, "lu_create");
     OCB_ARG(h_L_rowptr && h_U_rowptr && h_perm_r && h_perm_c, "lu_create: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    ocb::LuProgram P;
+    int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals,
+                                   ocb::trsm_threads(), &P);
+    if (rc != OCB_OK) return rc;
     ocb_lu* lu = new ocb_lu();
     lu->n = n;
+    lu->n_ext = P.n_ext;
+    lu->nnzL = P.nnzL;
+    lu->nnzU = P.nnzU;
+    lu->nsub_L = P.nsub_L;
+    lu->nsub_U = P.nsub_U;
+    lu->nsuper = P.nsuper;
+    lu->max_w = P.max_w;
+    lu->nseg = (int64_t)P.slices.size();
+    lu->nrows = P.nrows();
+    lu->nent = P.nent();
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&lu->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    ocb::TriSorted Ls, Us;
-    int rc = ocb::analyse_factor(n, h_L_rowptr, h_L_colidx, h_L_vals, false, &Ls);
-    if (rc == OCB_OK) rc = ocb::analyse_factor(n, h_U_rowptr, h_U_colidx, h_U_vals, true, &Us);
-    if (rc == OCB_OK) rc = ocb::upload_factor(Ls, &lu->L, &lu->bytes, st);
-    if (rc == OCB_OK) rc = ocb::upload_factor(Us, &lu->U, &lu->bytes, st);
-    if (rc == OCB_OK) {
-        const size_t pb = std::max<int64_t>(n, 1) * sizeof(int32_t);
-        cudaError_t e = cudaMalloc((void**)&lu->perm_r, pb);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&lu->perm_c, pb);
-        if (e == cudaSuccess && n > 0)
-            e = cudaMemcpyAsync(lu->perm_r, h_perm_r, pb, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess && n > 0)
-            e = cudaMemcpyAsync(lu->perm_c, h_perm_c, pb, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host vectors die below
-        if (e != cudaSuccess) {
-            ocb::set_error("lu_create: %s", cudaGetErrorString(e));
-            rc = OCB_ERR_CUDA;
-        }
-        lu->bytes += 2 * (int64_t)pb;
-    }
-    if (rc == OCB_OK) rc = ocb::build_stream(lu, Ls, Us, st);
+    rc = ocb::build_device_image(lu, P, h_perm_r, h_perm_c, st);
     if (rc != OCB_OK) {
         ocb_lu_destroy(lu);
         return rc;
@@ -824,12 +633,7 @@ int ocb_lu_create(ocb_lu** out, int64_t n, const int32_t* h_L_rowptr, const int3
 
 int ocb_lu_destroy(ocb_lu* lu) {
     if (!lu) return OCB_OK;
-    ocb::free_factor(&lu->L);
-    ocb::free_factor(&lu->U);
-    cudaFree(lu->perm_r);
-    cudaFree(lu->perm_c);
-    cudaFree(lu->stream);
-    cudaFree(lu->batch_off);
+    cudaFree(lu->arena);
     delete lu;
     return OCB_OK;
 }
@@ -860,23 +664,33 @@ int ocb_prof_collect(double* total_ms, int64_t* launches, double* alg_bytes) {
 int ocb_lu_info(const ocb_lu* lu, int64_t* info8) {
     OCB_ARG(lu && info8, "lu_info");
     info8[0] = lu->n;
-    info8[1] = lu->L.nnz;
-    info8[2] = lu->U.nnz + lu->n;
-    info8[3] = lu->L.nlev;
-    info8[4] = lu->U.nlev;
+    info8[1] = lu->nnzL;
+    info8[2] = lu->nnzU;
+    info8[3] = lu->nsub_L;
+    info8[4] = lu->nsub_U;
     info8[5] = lu->bytes;
-    info8[6] = lu->kp_stream;  // 0: generic kernel
+    info8[6] = lu->kp_smem_max;  // 0: panel in a global slab
     info8[7] = lu->nbatch;
     return OCB_OK;
 }
 
+int ocb_lu_stats(const ocb_lu* lu, int64_t* info8) {
+    OCB_ARG(lu && info8, "lu_stats");
+    info8[0] = lu->n_ext;
+    info8[1] = lu->nsuper;
+    info8[2] = lu->max_w;
+    info8[3] = lu->nseg;
+    info8[4] = lu->nrows;
+    info8[5] = lu->nent;
+    info8[6] = lu->stage_bytes;
+    info8[7] = lu->nstages;
+    return OCB_OK;
+}
+
 int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k) {
-    if (!lu || lu->kp_stream > 0) return 0;
-    int kp;
-    bool smem;
-    ocb::solve_policy(lu, &kp, &smem);
-    if (smem) return 0;
-    return ((k + kp - 1) / kp) * lu->n * kp * (int64_t)sizeof(double);
+    if (!lu || lu->kp_smem_max > 0) return 0;
+    const int kp = ocb::KP_GLOBAL;
+    return ((k + kp - 1) / kp) * lu->n_ext * kp * (int64_t)sizeof(double);
 }
 
 int ocb_lu_solve(const ocb_lu* lu, const double* d_B, int64_t ldb, int64_t nrows_b, double* d_X,

@@ -209,9 +209,13 @@ class LU(object):
         self._lib = lib
         info = (C.c_int64*8)()
         _cabi.check(lib.ocb_lu_info(h, info), 'ocb_lu_info')
+        st8 = (C.c_int64*8)()
+        _cabi.check(lib.ocb_lu_stats(h, st8), 'ocb_lu_stats')
         self.info = dict(n=info[0], nnzL=info[1], nnzU=info[2], levelsL=info[3],
                          levelsU=info[4], device_bytes=info[5], stream_kp=info[6],
-                         stream_batches=info[7])
+                         stream_batches=info[7], n_ext=st8[0], supernodes=st8[1],
+                         max_supernode=st8[2], segments=st8[3], program_rows=st8[4],
+                         program_entries=st8[5], stage_bytes=st8[6], stages=st8[7])
         STATS['lu_analyse_upload_s'] += time.perf_counter() - t1
         STATS['h2d_bytes'] += sum(a.nbytes for a in arrs)
 

@@ -1,0 +1,184 @@
+"""CPU suite, part 5: the host-side analysis of the solve kernel (csrc/lu_program.cu).
+
+``ocb_lu_program_create`` turns SuperLU's factors into the gather program the CUDA kernel
+executes (supernodes with inverted diagonal blocks -> a short sequence of sub-levels).  It
+is pure host code, so it is checked here without a GPU: the exported program is executed
+with numpy and must reproduce ``SuperLU.solve`` to rounding, rows of a sub-level must be
+independent of each other, and the depth must be far below the scalar level count."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import scipy.sparse.linalg as spsla
+
+from optconpy_b200 import _cabi, _lu_worker, device as dv, problems as pb
+
+
+def _program(arrs, n):
+    lib = _cabi.load()
+    h = C.c_void_p()
+    _cabi.check(lib.ocb_lu_program_create(C.byref(h), n, *[a.ctypes.data for a in arrs[:6]]),
+                'ocb_lu_program_create')
+    info = (C.c_int64*12)()
+    _cabi.check(lib.ocb_lu_program_info(h, info), 'info')
+    keys = ['n', 'n_ext', 'ymax', 'nsub_L', 'nsub_U', 'nsuper', 'max_w', 'nslice', 'nrows',
+            'nent', 'nnzL', 'nnzU']
+    info = dict(zip(keys, [int(v) for v in info]))
+    nsub = info['nsub_L'] + info['nsub_U']
+    sub_ptr = np.zeros(nsub+1, dtype=np.int32)
+    slices = np.zeros((info['nslice'], 4), dtype=np.int32)
+    dst = np.zeros(info['nrows'], dtype=np.int32)
+    init = np.zeros(info['nrows'], dtype=np.int32)
+    scale = np.zeros(info['nrows'], dtype=np.float64)
+    col = np.zeros(info['nent'], dtype=np.int32)
+    val = np.zeros(info['nent'], dtype=np.float64)
+    _cabi.check(lib.ocb_lu_program_export(h, *[a.ctypes.data for a in
+                                               (sub_ptr, slices, dst, init, scale, col, val)]), 'export')
+    lib.ocb_lu_program_destroy(h)
+    return info, sub_ptr, slices, dst, init, scale, col, val
+
+
+def _slice_rows(sl, col, val):
+    """(row index, cols, vals) of every row of a slice (SELL-32 layout, padding dropped)."""
+    ebase, trips, gn, q0 = [int(v) for v in sl]
+    g, nr = gn & 255, gn >> 8
+    G = 1 << g
+    assert 1 <= nr <= (32 >> g)
+    blk_c = col[ebase:ebase+32*trips].reshape(trips, 32)
+    blk_v = val[ebase:ebase+32*trips].reshape(trips, 32)
+    # lanes of rows beyond nr are pure padding
+    assert not blk_v[:, nr*G:].any()
+    out = []
+    for r in range(nr):
+        c = blk_c[:, r*G:(r+1)*G].reshape(-1)
+        v = blk_v[:, r*G:(r+1)*G].reshape(-1)
+        out.append((q0 + r, c, v))
+    return out
+
+
+def _execute(prog, X, check_hazards=False):
+    """numpy executor of the gather program on the extended block X (n_ext x k)."""
+    info, sub_ptr, slices, dst, init, scale, col, val = prog
+    for sb in range(len(sub_ptr)-1):
+        rows = []
+        for sl in slices[sub_ptr[sb]:sub_ptr[sb+1]]:
+            rows += _slice_rows(sl, col, val)
+        q = np.array([r[0] for r in rows])
+        lens = np.array([len(r[1]) for r in rows])
+        A = sps.csr_matrix((np.concatenate([r[2] for r in rows]),
+                            np.concatenate([r[1] for r in rows]),
+                            np.concatenate([[0], np.cumsum(lens)])), shape=(len(rows), info['n_ext']))
+        ini = init[q]
+        base = np.where(ini[:, None] >= 0, X[np.maximum(ini, 0)], 0.0)
+        new = (base - A @ X)*scale[q, None]
+        if check_hazards:
+            d = dst[q]
+            assert len(np.unique(d)) == len(d)                 # no two rows write one slot
+            A.eliminate_zeros()
+            read = np.union1d(A.indices, ini[(ini >= 0) & (ini != d)])
+            assert not np.intersect1d(read, d).size           # nobody reads what a peer writes
+        X[dst[q]] = new
+    return X
+
+
+def _saddle(prob, mu=-1.0, tau=0.05):
+    M, A, J = prob['M'], prob['A'], prob['J']
+    Nc = pb.convection_matrix(prob, pb.analytic_vortex)
+    Ft = -(0.5*M.T + tau*(A.T + Nc.T))
+    return dv.sadpnt_matrix(Ft + mu*M.T, J)
+
+
+@pytest.mark.parametrize('opts', [dv.LU_OPTIONS, {}])
+def test_program_reproduces_superlu(cav10, opts):
+    K = _saddle(cav10)
+    n = K.shape[0]
+    arrs = _lu_worker.factor_arrays(dv._csc_args(K, dict(opts)))
+    prog = _program(arrs, n)
+    info = prog[0]
+    assert info['n'] == n and info['n_ext'] == n + 2*info['ymax']
+    rng = np.random.default_rng(0)
+    B = rng.standard_normal((n, 3))
+    X = np.zeros((info['n_ext'], 3))
+    X[arrs[6]] = B                                   # x[perm_r[i]] = b[i]
+    _execute(prog, X, check_hazards=True)
+    got = X[arrs[7]]                                 # out[j] = x[perm_c[j]]
+    ref = spsla.splu(K).solve(B)
+    assert np.linalg.norm(got - ref) <= 1e-12*np.linalg.norm(ref)
+    assert np.linalg.norm(K @ got - B) <= 1e-12*np.linalg.norm(B)
+    # every entry of the factors is accounted for: off-block entries + inverse blocks
+    assert info['nnzL'] == sps.csr_matrix((arrs[2], arrs[1], arrs[0]), shape=(n, n)).nnz - n \
+        or info['nnzL'] <= len(arrs[2])
+    assert info['nnzU'] == len(arrs[5])
+
+
+def test_depth_is_cut_by_supernodes(cav10):
+    """The point of the program: far fewer sequential steps than scalar level scheduling."""
+    K = _saddle(cav10)
+    n = K.shape[0]
+    arrs = _lu_worker.factor_arrays(dv._csc_args(K, dict(dv.LU_OPTIONS)))
+    info = _program(arrs, n)[0]
+    L = sps.csr_matrix((arrs[2], arrs[1], arrs[0]), shape=(n, n))
+    U = sps.csr_matrix((arrs[5], arrs[4], arrs[3]), shape=(n, n))
+
+    def scalar_levels(T, upper):
+        lev = np.zeros(n, dtype=np.int64)
+        rng = range(n-1, -1, -1) if upper else range(n)
+        for i in rng:
+            c = T.indices[T.indptr[i]:T.indptr[i+1]]
+            c = c[c != i]
+            if c.size:
+                lev[i] = lev[c].max() + 1
+        return lev.max() + 1
+    scalar = scalar_levels(L, False) + scalar_levels(U, True)
+    assert info['nsub_L'] + info['nsub_U'] < scalar/3
+    assert info['nsuper'] < n and info['max_w'] > 8
+
+
+def test_small_and_degenerate_factors():
+    lib = _cabi.load()
+    # diagonal matrix: L = I (no work), U = diag -> one sub-level of n scalings
+    n = 5
+    Lc = sps.identity(n, format='csr')
+    Uc = sps.diags(np.arange(1.0, n+1)).tocsr()
+    arrs = [Lc.indptr.astype(np.int32), Lc.indices.astype(np.int32), Lc.data,
+            Uc.indptr.astype(np.int32), Uc.indices.astype(np.int32), Uc.data]
+    prog = _program(arrs, n)
+    assert prog[0]['nsub_L'] == 0 and prog[0]['nsub_U'] == 1 and prog[0]['nrows'] == n
+    X = np.ones((prog[0]['n_ext'], 1))
+    _execute(prog, X)
+    assert np.allclose(X[:n, 0], 1.0/np.arange(1.0, n+1))
+    # dense 6x6: a single supernode, two sub-levels per sweep
+    rng = np.random.default_rng(1)
+    Ad = rng.standard_normal((6, 6)) + 6*np.eye(6)
+    import scipy.linalg as sla
+    Pm, Ld, Ud = sla.lu(Ad)
+    Lc, Uc = sps.csr_matrix(Ld), sps.csr_matrix(Ud)
+    Lc.sort_indices()
+    Uc.sort_indices()
+    arrs = [Lc.indptr.astype(np.int32), Lc.indices.astype(np.int32), Lc.data,
+            Uc.indptr.astype(np.int32), Uc.indices.astype(np.int32), Uc.data]
+    prog = _program(arrs, 6)
+    assert prog[0]['nsuper'] == 1 and prog[0]['max_w'] == 6
+    assert prog[0]['nsub_L'] == 2 and prog[0]['nsub_U'] == 2
+    b = rng.standard_normal((6, 2))
+    X = np.zeros((prog[0]['n_ext'], 2))
+    X[:6] = Pm.T @ b
+    _execute(prog, X, check_hazards=True)
+    assert np.allclose(X[:6], np.linalg.solve(Ad, b))
+    # zero pivot and a misplaced entry are reported, not executed
+    Ubad = Uc.copy()
+    Ubad.data[Ubad.indptr[2]] = 0.0
+    h = C.c_void_p()
+    bad = [arrs[0], arrs[1], arrs[2], Ubad.indptr.astype(np.int32), Ubad.indices.astype(np.int32),
+           Ubad.data]
+    rc = lib.ocb_lu_program_create(C.byref(h), 6, *[a.ctypes.data for a in bad])
+    assert rc == -3 and b'zero pivot' in lib.ocb_last_error()
+    rc = lib.ocb_lu_program_create(C.byref(h), 6, *[a.ctypes.data for a in
+                                                    (arrs[3], arrs[4], arrs[5], arrs[3], arrs[4], arrs[5])])
+    assert rc == -1 and b'wrong side' in lib.ocb_last_error()
+    # n = 0
+    z = np.zeros(1, dtype=np.int32)
+    e = np.zeros(0)
+    prog0 = _program([z, z, e, z, z, e], 0)
+    assert prog0[0]['nrows'] == 0 and prog0[0]['nslice'] == 0
