@@ -46,7 +46,7 @@ def _config(N):
                 parallelism='independent DRE replica per GPU',
                 l2_policy='inputs exceed L2: every step streams its own 8 LU factor sets '
                           '(~200 MB) from HBM; no flush needed',
-                lu_setup='host SuperLU (MMD_AT_PLUS_A, symmetric mode), timed separately')
+                lu_setup='host SuperLU (MMD_AT_PLUS_A, symmetric mode) in worker processes, timed separately')
 
 
 class ClockSampler(object):
@@ -176,6 +176,7 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=2)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--phases', action='store_true', help='extra untimed pass with per-phase CUDA events + cProfile of the e2e loop (diagnostics on stderr)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -252,11 +253,20 @@ def main():
                     launches=int(nl.value), mean_launch_ms=tot_ms.value/max(nl.value, 1),
                     kernel_share_of_step=tot_ms.value/ms, mean_rhs_cols=k_mean,
                     alg_bytes_per_launch=ab.value/max(nl.value, 1),
-                    note='n=5477: the solve is dependency-latency bound, not bandwidth bound '
-                         '(DESIGN.md K1); nnzL+nnzU=%d, levels L/U=%d/%d'
+                    note='n=5477: every CTA streams the whole 15 MB program for its column; '
+                         'the kernel is bound by the per-SM stream + shared-memory gather rate, '
+                         'not by HBM (DESIGN.md K1); nnzL+nnzU=%d, sub-levels L/U=%d/%d'
                          % (lu0.info['nnzL']+lu0.info['nnzU'], lu0.info['levelsL'],
                             lu0.info['levelsU']))
     solves = sum(i['solves'] for i in info[W:])
+    phase_ms = None
+    if args.phases:        # diagnostics only: a separate, untimed pass over fresh steps
+        ctx2 = dd.context_from_kwargs(kw)
+        ph = dd._Phases()
+        for st in setups[:min(S, 4)]:
+            dd.run_step(ctx2, st, None, phases=ph)
+        phase_ms = {k: v/min(S, 4) for k, v in ph.collect().items()}
+        sys.stderr.write('phase ms per step: %s\n' % json.dumps(phase_ms))
 
     # ---------------- e2e: reference-facing API with host buffers ----------------
     e2e = None
@@ -274,7 +284,15 @@ def main():
                 bytes_at.append((dv.STATS['h2d_bytes'], dv.STATS['d2h_bytes']))
             dv.reset_stats()
             barrier()
+            if args.phases:
+                import cProfile
+                import pstats
+                prof = cProfile.Profile()
+                prof.enable()
             ds.solve_flow_daeric(lau=glau, pru=gpru, store=ds.NpyStore(), step_callback=cb, **kw2)
+            if args.phases:
+                prof.disable()
+                pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(45)
             barrier()
             el = stamps[W+K-1] - stamps[W-1] if W > 0 else stamps[K-1] - stamps[0]
             tm = torch.tensor([el], dtype=torch.float64, device='cuda')
@@ -286,8 +304,12 @@ def main():
                        d2h_bytes_per_step=int(d2h), ms_per_step=1e3*float(tm.item())/K,
                        api='optconpy_b200.dre_stepper.solve_flow_daeric(lau, pru) with scipy/numpy '
                            'inputs and .npy outputs; host LU setup inside the timed region',
-                       lu_factor_s_per_step=dv.STATS['lu_factor_s']/S,
-                       lu_analyse_upload_s_per_step=dv.STATS['lu_analyse_upload_s']/S)
+                       host_setup_per_step={k: (v/S) for k, v in dv.STATS.items()
+                                            if k.startswith('lu_') or k == 'n_factor'},
+                       lu_workers=dv._POOL['workers'],
+                       note='LU setup of step k-1 runs in worker processes while the GPU works '
+                            'on step k (dre_stepper look-ahead); lu_wait_s is what the main '
+                            'process still blocks on')
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
 
@@ -315,10 +337,13 @@ def main():
                    ms_per_step=ms_max/K, higher_is_better=True, scaling='weak', vs_baseline=None,
                    dtype='f64', data='synthetic', config=_config(N), clocks=clocks,
                    e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
-                   setup=dict(seconds_per_step=setup_s/S, lu_factor_s_per_step=setup_stats['lu_factor_s']/S,
-                              lu_analyse_upload_s_per_step=setup_stats['lu_analyse_upload_s']/S,
-                              factorisations_per_step=setup_stats['n_factor']/S,
-                              note='excluded from value, included in e2e'),
+                   setup=dict(seconds_per_step=setup_s/S,
+                              per_step={k: (v/S) for k, v in setup_stats.items()
+                                        if k.startswith('lu_') or k == 'n_factor'},
+                              note='wall seconds of the host setup (matrix assembly, SuperLU in '
+                                   'worker processes, analysis, upload) per step; excluded from '
+                                   'value, included in e2e; lu_factor_s / lu_worker_pack_s are '
+                                   'summed over the workers'),
                    saddle_solves_per_s=solves/(ms_max*1e-3),
                    rhs_columns_per_s=sum(sum(a)*0 for a in []) or None,
                    step_ms=step_ms,

@@ -63,6 +63,20 @@ int ocb_lu_create(ocb_lu** out, int64_t n,
                   const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
                   const int32_t* h_perm_r, const int32_t* h_perm_c, void* stream);
 int ocb_lu_destroy(ocb_lu* lu);
+/* The same in two halves, so that the analysis can run where the host LU ran (a worker
+ * process without a CUDA context): ocb_lu_pack_host builds the self-describing device image
+ * (malloc'ed; release with ocb_host_free) for a GPU with max_smem_optin bytes of opt-in shared
+ * memory per block; ocb_lu_create_from_image uploads it with one copy into d_arena (bytes long,
+ * 256-byte aligned, owned by the caller and kept alive until ocb_lu_destroy; NULL: the library
+ * allocates and frees its own). */
+int ocb_lu_pack_host(int64_t n,
+                     const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
+                     const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
+                     const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin,
+                     unsigned char** out_image, int64_t* out_bytes);
+void ocb_host_free(void* p);
+int ocb_lu_create_from_image(ocb_lu** out, const unsigned char* h_image, int64_t bytes,
+                             void* d_arena, void* stream);
 /* info[0..7] = n, nnz(L) strictly lower, nnz(U) incl. diagonal, #sub-levels of the L sweep,
  *              #sub-levels of the U sweep (one CTA barrier each), device bytes held, widest
  *              column panel that fits shared memory (0 = panel lives in a global slab),
@@ -71,6 +85,9 @@ int ocb_lu_info(const ocb_lu* lu, int64_t* info8);
 /* info[0..7] = rows of the extended vector (n + y scratch), #supernodes, widest supernode,
  *              #slices, #program rows, #program entries (padded), ring stage bytes, ring stages */
 int ocb_lu_stats(const ocb_lu* lu, int64_t* info8);
+/* debugging aid (OCB_TRSM_TRACE=1): SM clock of CTA 0 after the panel load and after every
+ * sub-level barrier of the most recent solve */
+int ocb_debug_trace(int64_t* h_out, int64_t count);
 
 /* Host-only view of the same analysis (no CUDA call; usable without a GPU): the GATHER
  * PROGRAM that ocb_lu_create packs and uploads.  Supernodes of U (rows with nested structure)

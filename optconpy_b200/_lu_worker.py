@@ -1,5 +1,10 @@
-"""Host sparse-LU worker (setup step).  Imports numpy/scipy only, so it can run in
-spawned worker processes without touching CUDA or torch."""
+"""Host sparse-LU worker (setup step).  Imports numpy/scipy and the C library through
+ctypes only, never torch and never initialises CUDA, so it can run in spawned worker
+processes: SuperLU factorisation, then the host half of ``ocb_lu_create``
+(``ocb_lu_pack_host``: supernodes, inverted diagonal blocks, packed batch stream)."""
+import ctypes as C
+import time
+
 import numpy as np
 import scipy.sparse as sps
 import scipy.sparse.linalg as spsla
@@ -8,7 +13,7 @@ import scipy.sparse.linalg as spsla
 def factor_arrays(args):
     """(data, indices, indptr, shape, lu_options) of a CSC matrix ->
     int32/FP64 CSR arrays of L and U plus the two permutations."""
-    data, indices, indptr, shape, opts = args
+    data, indices, indptr, shape, opts = args[:5]
     mat = sps.csc_matrix((data, indices, indptr), shape=shape)
     slu = spsla.splu(mat, **opts)
     L = sps.csr_matrix(slu.L)
@@ -25,19 +30,38 @@ def factor_arrays(args):
             np.ascontiguousarray(slu.perm_c, dtype=np.int32)]
 
 
-def factor_to_shm(args):
-    """Pool entry point: factorise and hand the arrays back through one POSIX shared-memory
-    block (avoids pickling ~13 MB per factor through a pipe).  Returns (name, layout)."""
-    from multiprocessing import shared_memory
+def pack_image(arrs, n, smem_optin):
+    """Host half of ``ocb_lu_create``: returns the device image as a uint8 array."""
+    from optconpy_b200 import _cabi
+    lib = _cabi.load()
+    img, nbytes = C.c_void_p(), C.c_int64(0)
+    _cabi.check(lib.ocb_lu_pack_host(n, *[a.ctypes.data for a in arrs], int(smem_optin),
+                                     C.byref(img), C.byref(nbytes)), 'ocb_lu_pack_host')
+    try:
+        buf = np.ctypeslib.as_array(C.cast(img, C.POINTER(C.c_uint8)), shape=(nbytes.value,)).copy()
+    finally:
+        lib.ocb_host_free(img)
+    return buf
+
+
+def factor_image(args):
+    """(data, indices, indptr, shape, lu_options, smem_optin) -> (image, seconds factor,
+    seconds analyse+pack)."""
+    t0 = time.perf_counter()
     arrs = factor_arrays(args)
-    layout, off = [], 0
-    for a in arrs:
-        off = (off + 63) & ~63
-        layout.append((a.dtype.str, a.size, off))
-        off += a.nbytes
-    shm = shared_memory.SharedMemory(create=True, size=max(off, 64))
-    for a, (_, _, o) in zip(arrs, layout):
-        np.frombuffer(shm.buf, dtype=a.dtype, count=a.size, offset=o)[:] = a
+    t1 = time.perf_counter()
+    img = pack_image(arrs, args[3][0], args[5])
+    return img, t1 - t0, time.perf_counter() - t1
+
+
+def factor_image_to_shm(args):
+    """Pool entry point: factorise, analyse, pack and hand the image back through one POSIX
+    shared-memory block (no pickling of ~15 MB through a pipe).
+    Returns (name, nbytes, seconds factor, seconds analyse+pack)."""
+    from multiprocessing import shared_memory
+    img, tf, tp = factor_image(args)
+    shm = shared_memory.SharedMemory(create=True, size=max(img.nbytes, 64))
+    np.frombuffer(shm.buf, dtype=np.uint8, count=img.nbytes)[:] = img
     name = shm.name
     shm.close()
-    return name, layout
+    return name, img.nbytes, tf, tp

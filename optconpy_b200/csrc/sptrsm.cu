@@ -31,24 +31,28 @@ struct ocb_lu {
     int32_t nsub_L = 0, nsub_U = 0, nsuper = 0, max_w = 0;
     int64_t nseg = 0, nrows = 0, nent = 0;
     unsigned char* arena = nullptr;   // one device allocation: perms | batch offsets | stream
+    bool arena_owned = false;         // false: the caller provided (and keeps) the buffer
     int32_t *perm_r = nullptr, *perm_c = nullptr;
-    int64_t* batch_off = nullptr;     // nbatch+1 byte offsets into stream
-    unsigned char* stream = nullptr;
+    // the program is dealt to CL cluster ranks: rank r streams its own batches
+    int cl = 1;
+    int64_t* batch_off[8] = {nullptr};   // nbatch[r]+1 byte offsets into stream[r]
+    unsigned char* stream[8] = {nullptr};
+    int nbatch[8] = {0};
     int64_t bytes = 0;
-    int nbatch = 0, stage_bytes = 0, nstages = 0;
+    int stage_bytes = 0, nstages = 0;
     int kp_smem_max = 0;              // widest panel that fits shared memory next to the ring (0: global slab)
     int max_smem_optin = 0;
 };
 
 namespace ocb {
 
-constexpr int TRSM_MAX_THREADS = 1024;
+constexpr int TRSM_MAX_THREADS = 544;   // 16 consumer warps + the producer warp
 static int trsm_threads() {
     static int t = 0;
     if (t == 0) {
         const char* env = getenv("OCB_TRSM_THREADS");
         t = env ? atoi(env) : 512;
-        if (t != 256 && t != 512 && t != 768 && t != 992) t = 512;
+        if (t != 128 && t != 256 && t != 384 && t != 512) t = 512;
     }
     return t;
 }
@@ -62,10 +66,12 @@ struct SolveArgs {
     double* X;
     int64_t ldx, nrows_x, k;
     double* ws;
-    const unsigned char* stream;
-    const int64_t* batch_off;
-    int nbatch, stage_bytes, nstages;
+    const unsigned char* stream[8];
+    const int64_t* batch_off[8];
+    int nbatch[8];
+    int stage_bytes, nstages;
     int tma_chunk, debug_skip;
+    long long* trace;   // debug: clock64() of CTA 0 after every sub-level barrier (null: off)
 };
 
 // Batch record (every section 16-byte aligned, offsets in bytes from the record start):
@@ -111,6 +117,58 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() {
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_C:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_C;\n"
+        "bra WAIT_LOOP_C;\n"
+        "DONE_C:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Sub-level barrier of a cluster: the consumers of this CTA meet at a named barrier, then ONE
+// thread publishes the CTA's (local and remote) panel writes with a single cluster-scope
+// fence and arrives once on the level barrier of every rank; everybody waits (acquire) on the
+// barrier of the own CTA, which completes after CL arrivals.
+template <int CL>
+__device__ __forceinline__ void cluster_level_barrier(uint64_t* lvlbar, uint32_t& phase, int ncons, int tid) {
+    asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+    if (tid == 0) {
+        fence_acq_rel_cluster();
+#pragma unroll
+        for (int r = 0; r < CL; ++r) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(lvlbar), r));
+    }
+    mbar_wait_cluster(lvlbar, phase & 1);
+    ++phase;
+}
+
 // one batch = several bulk copies completing on one mbarrier (more requests in flight)
 __device__ __forceinline__ void issue_batch(unsigned char* dst, const unsigned char* src, uint32_t bytes,
                                             uint32_t chunk, uint64_t* bar) {
@@ -120,49 +178,69 @@ __device__ __forceinline__ void issue_batch(unsigned char* dst, const unsigned c
 }
 
 // XG = false: xe panel in shared memory;  XG = true: per-CTA slab in global memory (large n)
-template <int KP, bool XG>
-__global__ void __launch_bounds__(XG ? 544 : TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(const SolveArgs a) {
+// CL > 1: a thread-block CLUSTER of CL CTAs owns one column panel.  The slices of every
+// sub-level are dealt to the CL ranks, so each CTA streams and gathers only 1/CL of the
+// program; every CTA keeps a full copy of the panel xe in its shared memory, results are
+// written to all CL copies through distributed shared memory (st.shared::cluster) and the
+// sub-level barrier is an mbarrier in every CTA that all consumer warps of the cluster
+// arrive on (release/acquire at cluster scope).
+template <int KP, bool XG, int CL>
+__global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(const SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [ring: nstages * stage_bytes][mbarriers full/empty: 128 bytes][xe panel: n_ext*KP doubles]
+    // layout: [ring: nstages * stage_bytes][mbarriers full/empty/level: 192 bytes][xe panel: n_ext*KP doubles]
     unsigned char* ring = smem_raw;
     uint64_t* full = (uint64_t*)(smem_raw + (size_t)a.nstages * a.stage_bytes);
     uint64_t* empty = full + 8;
-    double* x = XG ? a.ws + (size_t)blockIdx.x * a.n_ext * KP
-                   : (double*)(smem_raw + (size_t)a.nstages * a.stage_bytes + 128);
+    uint64_t* lvlbar = full + 16;
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
+    const int64_t panel = (int64_t)blockIdx.x / CL;
+    double* x = XG ? a.ws + (size_t)panel * a.n_ext * KP
+                   : (double*)(smem_raw + (size_t)a.nstages * a.stage_bytes + 192);
     const int tid = threadIdx.x;
     // the last warp is the PRODUCER (feeds the ring with TMA bulk copies, runs ahead of the
     // consumers); all other warps are consumers and synchronise among themselves only
     const int warp = tid >> 5, lane = tid & 31, nwarps = (blockDim.x >> 5) - 1;
     const int ncons = nwarps * 32;
     const int S = a.nstages;
-    const int64_t c0 = (int64_t)blockIdx.x * KP;
+    const int64_t c0 = panel * KP;
+    const int nbatch = a.nbatch[rank];
+    const int64_t* batch_off = a.batch_off[rank];
+    const unsigned char* stream = a.stream[rank];
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, nwarps);
         }
+        mbar_init(lvlbar, CL);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // every CTA's barriers exist before anyone arrives remotely
     if (warp == nwarps) {
         // batch offsets: one coalesced load per 31 batches, handed to lane 0 by shuffles
         // (a dependent global load per batch would serialise the ring at L2 latency)
-        for (int b0 = 0; b0 < a.nbatch; b0 += 31) {
-            const long long mine = __ldg((const long long*)a.batch_off + min(b0 + lane, a.nbatch));
-            for (int i = 0; i < 31 && b0 + i < a.nbatch; ++i) {
+        for (int b0 = 0; b0 < nbatch; b0 += 31) {
+            const long long mine = __ldg((const long long*)batch_off + min(b0 + lane, nbatch));
+            for (int i = 0; i < 31 && b0 + i < nbatch; ++i) {
                 const long long o = __shfl_sync(0xffffffffu, mine, i);
                 const long long o2 = __shfl_sync(0xffffffffu, mine, i + 1);
                 if (lane == 0) {
                     const int b = b0 + i, s = b % S;
                     if (b >= S) mbar_wait(empty + s, (uint32_t)(((b / S) - 1) & 1));
-                    issue_batch(ring + (size_t)s * a.stage_bytes, a.stream + o, (uint32_t)(o2 - o),
+                    issue_batch(ring + (size_t)s * a.stage_bytes, stream + o, (uint32_t)(o2 - o),
                                 a.tma_chunk, full + s);
                 }
             }
         }
+        if (CL > 1) cluster_sync_all();   // stay until the cluster is done (peers write our smem)
         return;
     }
     // consumers
+    uint32_t xbase[CL];   // the panel copy of every rank, as cluster shared addresses
+#pragma unroll
+    for (int r = 0; r < CL; ++r) xbase[r] = CL > 1 ? mapa_u32(smem_u32(x), r) : 0;
+    uint32_t lvl_phase = 0;
+    int trace_n = 0;
     for (int64_t e = tid; e < a.n * KP; e += ncons) {   // x[perm_r[i]] = b[i]; rows >= nrows_b are zero
         const int64_t i = e / KP;
         const int c = (int)(e - i * KP);
@@ -170,8 +248,13 @@ __global__ void __launch_bounds__(XG ? 544 : TRSM_MAX_THREADS, 1) sptrsm_stream_
         if (i < a.nrows_b && c0 + c < a.k) v = a.B[i * a.ldb + c0 + c];
         x[(int64_t)__ldg(a.perm_r + i) * KP + c] = v;
     }
-    asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
-    for (int b = 0; b < a.nbatch; ++b) {
+    if (CL == 1) {
+        asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+    } else {   // nobody may write results into a panel copy that is still being loaded
+        cluster_level_barrier<CL>(lvlbar, lvl_phase, ncons, tid);
+    }
+    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[trace_n++] = clock64();
+    for (int b = 0; b < nbatch; ++b) {
         const int s = b % S;
         mbar_wait(full + s, (uint32_t)((b / S) & 1));
         const unsigned char* rec = ring + (size_t)s * a.stage_bytes;
@@ -258,27 +341,46 @@ __global__ void __launch_bounds__(XG ? 544 : TRSM_MAX_THREADS, 1) sptrsm_stream_
                     for (int c = 0; c < KP; ++c) tot[c] += __shfl_xor_sync(0xffffffffu, tot[c], o);
                 }
                 if (owner) {
-                    double* xd = x + (size_t)di * KP;
+                    double res[KP];
                     if (i0 >= 0) {
                         const double* xi = x + (size_t)i0 * KP;
 #pragma unroll
-                        for (int c = 0; c < KP; ++c) xd[c] = (xi[c] - tot[c]) * sc;
+                        for (int c = 0; c < KP; ++c) res[c] = (xi[c] - tot[c]) * sc;
                     } else {
 #pragma unroll
-                        for (int c = 0; c < KP; ++c) xd[c] = -tot[c] * sc;
+                        for (int c = 0; c < KP; ++c) res[c] = -tot[c] * sc;
+                    }
+                    if (CL == 1) {
+                        double* xd = x + (size_t)di * KP;
+#pragma unroll
+                        for (int c = 0; c < KP; ++c) xd[c] = res[c];
+                    } else {
+                        const uint32_t o = (uint32_t)di * (KP * 8);
+#pragma unroll
+                        for (int r = 0; r < CL; ++r)
+#pragma unroll
+                            for (int c = 0; c < KP; ++c) st_cluster_f64(xbase[r] + o + c * 8, res[c]);
                     }
                 }
             }
-            if (pd.z) asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+            if (pd.z) {
+                if (CL == 1) {
+                    asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+                } else {   // cluster-wide sub-level barrier among the consumer warps
+                    cluster_level_barrier<CL>(lvlbar, lvl_phase, ncons, tid);
+                }
+                if (a.trace && blockIdx.x == 0 && tid == 0 && trace_n < 4000) a.trace[trace_n++] = clock64();
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);   // this warp is done with the stage
     }
-    for (int64_t e = tid; e < a.nrows_x * KP; e += ncons) {   // out[j] = x[perm_c[j]]
+    for (int64_t e = tid + (int64_t)rank * ncons; e < a.nrows_x * KP; e += (int64_t)ncons * CL) {   // out[j] = x[perm_c[j]]
         const int64_t j = e / KP;
         const int c = (int)(e - j * KP);
         if (c0 + c < a.k) a.X[j * a.ldx + c0 + c] = x[(int64_t)__ldg(a.perm_c + j) * KP + c];
     }
+    if (CL > 1) cluster_sync_all();
 }
 
 // ---------------------------------------------------------------------------------
@@ -306,37 +408,45 @@ static inline int slice_rows(const Slice& sl) { return sl.glog_nrows >> 8; }
 
 // Greedy packing of slices into batches of at most cap bytes (a sub-level may span several
 // batches).  Returns false if a single slice exceeds the capacity.
-static bool plan_batches(const LuProgram& P, int64_t cap, std::vector<std::vector<Piece>>* batches) {
+static bool plan_batches(const LuProgram& P, int64_t cap, int rank, int cl,
+                         std::vector<std::vector<Piece>>* batches) {
     batches->clear();
     std::vector<Piece> cur;
     int64_t nsl = 0, rows = 0, ent = 0;
     auto flush = [&]() {
         if (cur.empty()) return;
-        cur.back().barrier = 1;   // the ring stage is reused after the batch
         batches->push_back(cur);
         cur.clear();
         nsl = rows = ent = 0;
     };
+    // rank r of cl owns the slices s0 + r, s0 + r + cl, ... of every sub-level (sorted by
+    // decreasing work, so the deal is balanced); a Piece lists them as (first, end, stride cl)
     for (int64_t sb = 0; sb < P.nsub(); ++sb) {
-        int32_t s = P.sub_ptr[sb];
+        int32_t s = P.sub_ptr[sb] + rank;
         const int32_t send = P.sub_ptr[sb + 1];
+        if (s >= send) {   // nothing for this rank: it still takes part in the barrier
+            if (record_bytes((int64_t)cur.size() + 1, nsl, rows, ent) > cap) flush();
+            cur.push_back(Piece{s, s, 1});
+            continue;
+        }
         while (s < send) {
             int32_t s2 = s;
-            int64_t r2 = rows, e2 = ent;
+            int64_t r2 = rows, e2 = ent, n2 = nsl;
             while (s2 < send) {
                 const int64_t rr = r2 + slice_rows(P.slices[s2]), ee = e2 + (int64_t)P.slices[s2].trips * 32;
-                if (record_bytes((int64_t)cur.size() + 1, nsl + (s2 + 1 - s), rr, ee) > cap) break;
+                if (record_bytes((int64_t)cur.size() + 1, n2 + 1, rr, ee) > cap) break;
                 r2 = rr;
                 e2 = ee;
-                ++s2;
+                ++n2;
+                s2 += cl;
             }
             if (s2 == s) {
                 if (cur.empty()) return false;   // one slice does not fit an empty batch
                 flush();
                 continue;
             }
-            cur.push_back(Piece{s, s2, (s2 == send) ? 1 : 0});
-            nsl += s2 - s;
+            cur.push_back(Piece{s, s2, (s2 >= send) ? 1 : 0});
+            nsl = n2;
             rows = r2;
             ent = e2;
             s = s2;
@@ -347,26 +457,26 @@ static bool plan_batches(const LuProgram& P, int64_t cap, std::vector<std::vecto
     return true;
 }
 
-static void batch_counts(const LuProgram& P, const std::vector<Piece>& b, int64_t* nsl, int64_t* rows,
+static void batch_counts(const LuProgram& P, const std::vector<Piece>& b, int cl, int64_t* nsl, int64_t* rows,
                          int64_t* ent) {
     *nsl = *rows = *ent = 0;
     for (const Piece& p : b)
-        for (int32_t s = p.s0; s < p.s1; ++s) {
+        for (int32_t s = p.s0; s < p.s1; s += cl) {
             *nsl += 1;
             *rows += slice_rows(P.slices[s]);
             *ent += (int64_t)P.slices[s].trips * 32;
         }
 }
 
-static int64_t batch_bytes(const LuProgram& P, const std::vector<Piece>& b) {
+static int64_t batch_bytes(const LuProgram& P, const std::vector<Piece>& b, int cl) {
     int64_t nsl, rows, ent;
-    batch_counts(P, b, &nsl, &rows, &ent);
+    batch_counts(P, b, cl, &nsl, &rows, &ent);
     return record_bytes((int64_t)b.size(), nsl, rows, ent);
 }
 
-static void write_record(const LuProgram& P, const std::vector<Piece>& b, unsigned char* rec) {
+static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl, unsigned char* rec) {
     int64_t nsl, nrows, nent;
-    batch_counts(P, b, &nsl, &nrows, &nent);
+    batch_counts(P, b, cl, &nsl, &nrows, &nent);
     const int64_t npiece = (int64_t)b.size();
     int32_t* hdr = (int32_t*)rec;
     int64_t o = a16(HDR_INTS * 4);
@@ -397,11 +507,13 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, unsign
     int32_t ls = 0, r = 0, e = 0;
     for (size_t pi = 0; pi < b.size(); ++pi) {
         const Piece& p = b[pi];
+        int32_t cnt = 0;
+        for (int32_t s = p.s0; s < p.s1; s += cl) ++cnt;
         piece[4 * pi + 0] = ls;
-        piece[4 * pi + 1] = ls + (p.s1 - p.s0);
+        piece[4 * pi + 1] = ls + cnt;
         piece[4 * pi + 2] = p.barrier;
         piece[4 * pi + 3] = 0;
-        for (int32_t s = p.s0; s < p.s1; ++s, ++ls) {
+        for (int32_t s = p.s0; s < p.s1; s += cl, ++ls) {
             const Slice& sl = P.slices[s];
             const int nr = slice_rows(sl), ne = sl.trips * 32;
             slice[4 * ls + 0] = e;
@@ -419,99 +531,214 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, unsign
     }
 }
 
-// choose ring geometry + panel placement, pack, upload (one allocation, one copy)
-static int build_device_image(ocb_lu* lu, const LuProgram& P, const int32_t* h_perm_r,
-                              const int32_t* h_perm_c, cudaStream_t st) {
-    const int64_t smem_cap = (int64_t)lu->max_smem_optin - 1024 - 128;
+// Self-describing host image of a factorisation: [meta int64[32]] perm_r | perm_c | batch
+// offsets | batch stream.  Built without any CUDA call (worker processes build it next to the
+// host LU); ocb_lu_create_from_image uploads it with one allocation and one copy.
+constexpr int64_t IMG_MAGIC = 0x4f43424c55303032LL;   // "OCBLU002"
+enum { M_MAGIC = 0, M_TOTAL, M_N, M_NEXT, M_NNZL, M_NNZU, M_NSUBL, M_NSUBU, M_NSUPER, M_MAXW, M_NSLICE,
+       M_NROWS, M_NENT, M_OPR, M_OPC, M_CL, M_STAGEB, M_NSTAGES, M_KPSMEM,
+       M_OBO = 24, M_OST = 32, M_NBATCH = 40, M_COUNT = 48 };   // OBO/OST/NBATCH: one slot per cluster rank
+
+// choose ring geometry + panel placement and pack the image
+static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t* h_perm_c,
+                      int max_smem_optin, std::vector<unsigned char>* img_out) {
+    const int64_t smem_cap = (int64_t)max_smem_optin - 1024 - 192;
     const int64_t xe1 = P.n_ext * 8;   // bytes of a one-column panel
-    std::vector<std::vector<Piece>> batches;
-    int kp_smem = 0, nst = 3;
+    int kp_smem = 0, nst = 3, cl = 4;
     int64_t cap = 0;
     const char* env = getenv("OCB_SPTRSM_FORCE_GLOBAL");
     const bool force_global = env && env[0] == '1';
-    // prefer a two-column panel next to three stages of >= 16 KB, else one column
+    const char* e_cl = getenv("OCB_TRSM_CLUSTER");
+    if (e_cl) {
+        const int v = atoi(e_cl);
+        if (v == 1 || v == 2 || v == 4 || v == 8) cl = v;
+    }
+    std::vector<std::vector<Piece>> batches[8];
+    auto plan_all = [&](int64_t c, int ncl) {
+        for (int r = 0; r < ncl; ++r)
+            if (!plan_batches(P, c, r, ncl, &batches[r])) return false;
+        return true;
+    };
+    // prefer a two-column panel next to three stages, else one column
     const int kps[2] = {2, 1};
     const char* e_st = getenv("OCB_RING_STAGES");
     const char* e_kb = getenv("OCB_RING_STAGE_KB");
     if (e_st && atoi(e_st) >= 2 && atoi(e_st) <= 8) nst = atoi(e_st);
-    const int64_t want = (e_kb && atoi(e_kb) >= 4) ? (int64_t)atoi(e_kb) * 1024 : 48 * 1024;
+    const int64_t want = (e_kb && atoi(e_kb) >= 4) ? (int64_t)atoi(e_kb) * 1024 : 40 * 1024;
     for (int ki = 0; ki < 2 && !force_global && kp_smem == 0; ++ki) {
         const int64_t left = smem_cap - xe1 * kps[ki];
         if (left < nst * 8192) continue;
         cap = std::min<int64_t>(left / nst, want) & ~(int64_t)15;
-        if (plan_batches(P, cap, &batches)) kp_smem = kps[ki];
+        if (plan_all(cap, cl)) kp_smem = kps[ki];
     }
-    if (kp_smem == 0) {   // panel in a global slab: the ring gets the whole shared memory
+    if (kp_smem == 0) {   // panel in a global slab: one CTA per panel, the ring gets the shared memory
+        cl = 1;
         nst = 3;
         cap = std::min<int64_t>(smem_cap / 3, 64 * 1024) & ~(int64_t)15;
-        if (!plan_batches(P, cap, &batches)) {
+        if (!plan_all(cap, 1)) {
             nst = 2;
             cap = (smem_cap / 2) & ~(int64_t)15;
-            if (!plan_batches(P, cap, &batches)) {
+            if (!plan_all(cap, 1)) {
                 set_error("lu_create: a factor row does not fit the shared-memory ring");
                 return OCB_ERR_CAPACITY;
             }
         }
     }
-    std::vector<int64_t> off(batches.size() + 1, 0);
+    std::vector<int64_t> off[8];
     int64_t maxb = 16;
-    for (size_t b = 0; b < batches.size(); ++b) {
-        const int64_t rb = batch_bytes(P, batches[b]);
-        off[b + 1] = off[b] + rb;
-        maxb = std::max(maxb, rb);
+    for (int r = 0; r < cl; ++r) {
+        off[r].assign(batches[r].size() + 1, 0);
+        for (size_t b = 0; b < batches[r].size(); ++b) {
+            const int64_t rb = batch_bytes(P, batches[r][b], cl);
+            off[r][b + 1] = off[r][b] + rb;
+            maxb = std::max(maxb, rb);
+        }
     }
-    // arena: perm_r | perm_c | batch_off | stream
-    const int64_t o_pr = 0;
+    const int64_t o_pr = align_up(M_COUNT * 8, 256);
     const int64_t o_pc = align_up(o_pr + std::max<int64_t>(P.n, 1) * 4, 256);
-    const int64_t o_bo = align_up(o_pc + std::max<int64_t>(P.n, 1) * 4, 256);
-    const int64_t o_st = align_up(o_bo + (int64_t)off.size() * 8, 256);
-    const int64_t total = o_st + std::max<int64_t>(off.back(), 16);
-    std::vector<unsigned char> img((size_t)total, 0);
+    int64_t o = align_up(o_pc + std::max<int64_t>(P.n, 1) * 4, 256);
+    int64_t o_bo[8], o_st[8];
+    for (int r = 0; r < cl; ++r) {
+        o_bo[r] = o;
+        o = align_up(o + (int64_t)off[r].size() * 8, 256);
+    }
+    for (int r = 0; r < cl; ++r) {
+        o_st[r] = o;
+        o = align_up(o + std::max<int64_t>(off[r].back(), 16), 256);
+    }
+    const int64_t total = o;
+    std::vector<unsigned char>& img = *img_out;
+    img.assign((size_t)total, 0);
+    int64_t* meta = (int64_t*)img.data();
+    meta[M_MAGIC] = IMG_MAGIC; meta[M_TOTAL] = total; meta[M_N] = P.n; meta[M_NEXT] = P.n_ext;
+    meta[M_NNZL] = P.nnzL; meta[M_NNZU] = P.nnzU; meta[M_NSUBL] = P.nsub_L; meta[M_NSUBU] = P.nsub_U;
+    meta[M_NSUPER] = P.nsuper; meta[M_MAXW] = P.max_w; meta[M_NSLICE] = (int64_t)P.slices.size();
+    meta[M_NROWS] = P.nrows(); meta[M_NENT] = P.nent(); meta[M_OPR] = o_pr; meta[M_OPC] = o_pc;
+    meta[M_CL] = cl; meta[M_STAGEB] = maxb; meta[M_NSTAGES] = nst; meta[M_KPSMEM] = kp_smem;
+    for (int r = 0; r < cl; ++r) {
+        meta[M_OBO + r] = o_bo[r];
+        meta[M_OST + r] = o_st[r];
+        meta[M_NBATCH + r] = (int64_t)batches[r].size();
+    }
     if (P.n > 0) {
         memcpy(img.data() + o_pr, h_perm_r, (size_t)P.n * 4);
         memcpy(img.data() + o_pc, h_perm_c, (size_t)P.n * 4);
     }
-    memcpy(img.data() + o_bo, off.data(), off.size() * 8);
-    for (size_t b = 0; b < batches.size(); ++b) write_record(P, batches[b], img.data() + o_st + off[b]);
-    OCB_CUDA(cudaMalloc((void**)&lu->arena, (size_t)total));
-    OCB_CUDA(cudaMemcpyAsync(lu->arena, img.data(), (size_t)total, cudaMemcpyHostToDevice, st));
-    OCB_CUDA(cudaStreamSynchronize(st));   // img dies below
-    lu->perm_r = (int32_t*)(lu->arena + o_pr);
-    lu->perm_c = (int32_t*)(lu->arena + o_pc);
-    lu->batch_off = (int64_t*)(lu->arena + o_bo);
-    lu->stream = lu->arena + o_st;
-    lu->bytes = total;
-    lu->nbatch = (int)batches.size();
-    lu->stage_bytes = (int)maxb;
-    lu->nstages = nst;
-    lu->kp_smem_max = kp_smem;
-    return OCB_OK;
-}
-
-template <int KP, bool XG>
-static int launch_stream(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 128 +
-                        (XG ? 0 : (size_t)lu->n_ext * KP * sizeof(double));
-    OCB_CUDA(cudaFuncSetAttribute(sptrsm_stream_kernel<KP, XG>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((a.k + KP - 1) / KP);
-    sptrsm_stream_kernel<KP, XG><<<grid, (XG ? std::min(512, trsm_threads()) : trsm_threads()) + 32, smem, st>>>(a);
-    OCB_LAUNCH_CHECK();
-    return OCB_OK;
-}
-
-// panel width for k right-hand sides: as narrow as possible while one wave of CTAs covers
-// all columns (latency), wider once there are more columns than SMs (throughput)
-static int choose_kp(const ocb_lu* lu, int64_t k) {
-    if (lu->kp_smem_max == 0) return KP_GLOBAL;
-    const char* env = getenv("OCB_SPTRSM_KP");
-    if (env) {
-        const int v = atoi(env);
-        if (v >= 1 && v <= lu->kp_smem_max && (v & (v - 1)) == 0) return v;
+    for (int r = 0; r < cl; ++r) {
+        memcpy(img.data() + o_bo[r], off[r].data(), off[r].size() * 8);
+        for (size_t b = 0; b < batches[r].size(); ++b)
+            write_record(P, batches[r][b], cl, img.data() + o_st[r] + off[r][b]);
     }
+    return OCB_OK;
+}
+
+static int upload_image(ocb_lu* lu, const unsigned char* img, int64_t bytes, void* d_arena, cudaStream_t st) {
+    const int64_t* meta = (const int64_t*)img;
+    if (bytes < M_COUNT * 8 || meta[M_MAGIC] != IMG_MAGIC || meta[M_TOTAL] != bytes) {
+        set_error("lu_create_from_image: not a factor image (bad magic or size)");
+        return OCB_ERR_ARG;
+    }
+    lu->n = meta[M_N]; lu->n_ext = meta[M_NEXT]; lu->nnzL = meta[M_NNZL]; lu->nnzU = meta[M_NNZU];
+    lu->nsub_L = (int32_t)meta[M_NSUBL]; lu->nsub_U = (int32_t)meta[M_NSUBU];
+    lu->nsuper = (int32_t)meta[M_NSUPER]; lu->max_w = (int32_t)meta[M_MAXW];
+    lu->nseg = meta[M_NSLICE]; lu->nrows = meta[M_NROWS]; lu->nent = meta[M_NENT];
+    if (d_arena) {
+        if (((uintptr_t)d_arena & 255) != 0) {
+            set_error("lu_create_from_image: the device buffer must be 256-byte aligned");
+            return OCB_ERR_ARG;
+        }
+        lu->arena = (unsigned char*)d_arena;
+        lu->arena_owned = false;
+    } else {
+        OCB_CUDA(cudaMalloc((void**)&lu->arena, (size_t)bytes));
+        lu->arena_owned = true;
+    }
+    OCB_CUDA(cudaMemcpyAsync(lu->arena, img, (size_t)bytes, cudaMemcpyHostToDevice, st));
+    OCB_CUDA(cudaStreamSynchronize(st));   // the caller's buffer may go away
+    lu->perm_r = (int32_t*)(lu->arena + meta[M_OPR]);
+    lu->perm_c = (int32_t*)(lu->arena + meta[M_OPC]);
+    lu->cl = (int)meta[M_CL];
+    for (int r = 0; r < lu->cl; ++r) {
+        lu->batch_off[r] = (int64_t*)(lu->arena + meta[M_OBO + r]);
+        lu->stream[r] = lu->arena + meta[M_OST + r];
+        lu->nbatch[r] = (int)meta[M_NBATCH + r];
+    }
+    lu->bytes = bytes;
+    lu->stage_bytes = (int)meta[M_STAGEB];
+    lu->nstages = (int)meta[M_NSTAGES];
+    lu->kp_smem_max = (int)meta[M_KPSMEM];
+    return OCB_OK;
+}
+
+template <int KP, bool XG, int CL>
+static int launch_stream(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 192 +
+                        (XG ? 0 : (size_t)lu->n_ext * KP * sizeof(double));
+    OCB_CUDA(cudaFuncSetAttribute(sptrsm_stream_kernel<KP, XG, CL>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned npanels = (unsigned)((a.k + KP - 1) / KP);
+    const unsigned threads = (XG ? std::min(512, trsm_threads()) : trsm_threads()) + 32;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(npanels * CL, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    OCB_CUDA(cudaLaunchKernelEx(&cfg, sptrsm_stream_kernel<KP, XG, CL>, a));
+    g_launches.fetch_add(1);
+    return OCB_OK;
+}
+
+// clusters of CL CTAs (one CTA per SM at this shared-memory size) that can be resident at once
+template <int KP, int CL>
+static int max_clusters(const ocb_lu* lu) {
+    static int cache[9] = {0};
+    const int slot = KP;   // per (KP, CL) instantiation; shared memory is the same for one problem size
+    if (cache[slot] > 0) return cache[slot];
+    const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 192 + (size_t)lu->n_ext * KP * sizeof(double);
+    cudaFuncSetAttribute(sptrsm_stream_kernel<KP, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(CL * 64, 1, 1);
+    cfg.blockDim = dim3(trsm_threads() + 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, sptrsm_stream_kernel<KP, false, CL>, &cfg) != cudaSuccess || nc <= 0) {
+        cudaGetLastError();
+        nc = sm_count() / CL;
+    }
+    cache[slot] = nc;
+    return nc;
+}
+
+template <int CL>
+static int launch_cluster(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
+    // panel width: as narrow as possible while one wave of clusters covers all columns
     int kp = 1;
-    while (kp < lu->kp_smem_max && (k + kp - 1) / kp > sm_count()) kp *= 2;
-    return kp;
+    const char* env = getenv("OCB_SPTRSM_KP");
+    if (env && (atoi(env) == 1 || atoi(env) == 2) && atoi(env) <= lu->kp_smem_max) {
+        kp = atoi(env);
+    } else if (lu->kp_smem_max >= 2) {
+        const int cap1 = CL > 1 ? max_clusters<1, CL>(lu) : sm_count();
+        if (a.k > cap1) kp = 2;
+    }
+    if (kp == 2) return launch_stream<2, false, CL>(lu, a, st);
+    return launch_stream<1, false, CL>(lu, a, st);
 }
 
 // optional per-launch timing of the solve kernel (bench.py roofline): CUDA events on the
@@ -524,6 +751,7 @@ struct SolveProf {
     long long launches = 0;
 };
 static SolveProf g_prof;
+static long long* g_trace_buf = nullptr;
 
 static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_b, double* X,
                              int64_t ldx, int64_t nrows_x, int64_t k, void* ws, int64_t ws_bytes,
@@ -541,35 +769,49 @@ static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int
     a.nrows_x = nrows_x;
     a.k = k;
     a.ws = (double*)ws;
-    a.stream = lu->stream;
-    a.batch_off = lu->batch_off;
-    a.nbatch = lu->nbatch;
+    for (int r = 0; r < 8; ++r) {
+        a.stream[r] = lu->stream[r];
+        a.batch_off[r] = lu->batch_off[r];
+        a.nbatch[r] = lu->nbatch[r];
+    }
     a.stage_bytes = lu->stage_bytes;
     a.nstages = lu->nstages;
     {
         static int chunk = 0, dbg = -1;
         if (chunk == 0) {
             const char* e1 = getenv("OCB_TMA_CHUNK");
-            chunk = e1 ? atoi(e1) : 8192;
-            if (chunk < 16) chunk = 8192;
+            chunk = e1 ? atoi(e1) : 65536;
+            if (chunk < 16) chunk = 65536;
             chunk &= ~15;
             const char* e2 = getenv("OCB_TRSM_DEBUG_SKIP");
             dbg = e2 ? atoi(e2) : 0;
         }
         a.tma_chunk = chunk;
         a.debug_skip = dbg;
+        static long long* trace_buf = nullptr;
+        static int trace_on = -1;
+        if (trace_on < 0) {
+            const char* e3 = getenv("OCB_TRSM_TRACE");
+            trace_on = (e3 && e3[0] == '1') ? 1 : 0;
+            if (trace_on) cudaMalloc((void**)&trace_buf, 4096 * sizeof(long long));
+        }
+        a.trace = trace_on ? trace_buf : nullptr;
+        g_trace_buf = trace_buf;
     }
-    const int kp = choose_kp(lu, k);
     if (lu->kp_smem_max == 0) {
         const int64_t need = ocb_lu_solve_ws_bytes(lu, k);
         if (ws == nullptr || ws_bytes < need) {
             set_error("lu_solve: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
             return OCB_ERR_CAPACITY;
         }
-        return launch_stream<KP_GLOBAL, true>(lu, a, st);
+        return launch_stream<KP_GLOBAL, true, 1>(lu, a, st);
     }
-    if (kp == 2) return launch_stream<2, false>(lu, a, st);
-    return launch_stream<1, false>(lu, a, st);
+    switch (lu->cl) {
+        case 8: return launch_cluster<8>(lu, a, st);
+        case 4: return launch_cluster<4>(lu, a, st);
+        case 2: return launch_cluster<2>(lu, a, st);
+        default: return launch_cluster<1>(lu, a, st);
+    }
 }
 
 int lu_solve_impl(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_b, double* X,
@@ -596,33 +838,41 @@ int lu_solve_impl(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_
 
 extern "C" {
 
-int ocb_lu_create(ocb_lu** out, int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_colidx,
-                  const double* h_L_vals, const int32_t* h_U_rowptr, const int32_t* h_U_colidx,
-                  const double* h_U_vals, const int32_t* h_perm_r, const int32_t* h_perm_c,
-                  void* stream) {
-    OCB_ARG(out && n >= 0, "lu_create");
-    OCB_ARG(h_L_rowptr && h_U_rowptr && h_perm_r && h_perm_c, "lu_create: null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
+int ocb_lu_pack_host(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
+                     const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
+                     const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin,
+                     unsigned char** out_image, int64_t* out_bytes) {
+    OCB_ARG(n >= 0 && out_image && out_bytes, "lu_pack_host");
+    OCB_ARG(h_L_rowptr && h_U_rowptr && h_perm_r && h_perm_c, "lu_pack_host: null pointer");
+    OCB_ARG(max_smem_optin >= 48 * 1024, "lu_pack_host: shared-memory size");
     ocb::LuProgram P;
     int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals,
                                    ocb::trsm_threads(), &P);
     if (rc != OCB_OK) return rc;
+    std::vector<unsigned char> img;
+    rc = ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, &img);
+    if (rc != OCB_OK) return rc;
+    unsigned char* buf = (unsigned char*)malloc(img.size());
+    if (!buf) {
+        ocb::set_error("lu_pack_host: out of memory");
+        return OCB_ERR_CAPACITY;
+    }
+    memcpy(buf, img.data(), img.size());
+    *out_image = buf;
+    *out_bytes = (int64_t)img.size();
+    return OCB_OK;
+}
+
+void ocb_host_free(void* p) { free(p); }
+
+int ocb_lu_create_from_image(ocb_lu** out, const unsigned char* h_image, int64_t bytes, void* d_arena,
+                             void* stream) {
+    OCB_ARG(out && h_image && bytes > 0, "lu_create_from_image");
     ocb_lu* lu = new ocb_lu();
-    lu->n = n;
-    lu->n_ext = P.n_ext;
-    lu->nnzL = P.nnzL;
-    lu->nnzU = P.nnzU;
-    lu->nsub_L = P.nsub_L;
-    lu->nsub_U = P.nsub_U;
-    lu->nsuper = P.nsuper;
-    lu->max_w = P.max_w;
-    lu->nseg = (int64_t)P.slices.size();
-    lu->nrows = P.nrows();
-    lu->nent = P.nent();
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&lu->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    rc = ocb::build_device_image(lu, P, h_perm_r, h_perm_c, st);
+    const int rc = ocb::upload_image(lu, h_image, bytes, d_arena, (cudaStream_t)stream);
     if (rc != OCB_OK) {
         ocb_lu_destroy(lu);
         return rc;
@@ -631,9 +881,32 @@ int ocb_lu_create(ocb_lu** out, int64_t n, const int32_t* h_L_rowptr, const int3
     return OCB_OK;
 }
 
+int ocb_lu_create(ocb_lu** out, int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_colidx,
+                  const double* h_L_vals, const int32_t* h_U_rowptr, const int32_t* h_U_colidx,
+                  const double* h_U_vals, const int32_t* h_perm_r, const int32_t* h_perm_c,
+                  void* stream) {
+    OCB_ARG(out && n >= 0, "lu_create");
+    OCB_ARG(h_L_rowptr && h_U_rowptr && h_perm_r && h_perm_c, "lu_create: null pointer");
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (optin <= 0) {
+        ocb::set_error("lu_create: no CUDA device");
+        return OCB_ERR_CUDA;
+    }
+    unsigned char* img = nullptr;
+    int64_t bytes = 0;
+    int rc = ocb_lu_pack_host(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals, h_perm_r,
+                              h_perm_c, optin, &img, &bytes);
+    if (rc != OCB_OK) return rc;
+    rc = ocb_lu_create_from_image(out, img, bytes, nullptr, stream);
+    free(img);
+    return rc;
+}
+
 int ocb_lu_destroy(ocb_lu* lu) {
     if (!lu) return OCB_OK;
-    cudaFree(lu->arena);
+    if (lu->arena_owned) cudaFree(lu->arena);
     delete lu;
     return OCB_OK;
 }
@@ -670,7 +943,17 @@ int ocb_lu_info(const ocb_lu* lu, int64_t* info8) {
     info8[4] = lu->nsub_U;
     info8[5] = lu->bytes;
     info8[6] = lu->kp_smem_max;  // 0: panel in a global slab
-    info8[7] = lu->nbatch;
+    info8[7] = lu->nbatch[0];
+    return OCB_OK;
+}
+
+int ocb_debug_trace(int64_t* h_out, int64_t count) {
+    OCB_ARG(h_out && count > 0 && count <= 4096, "debug_trace");
+    if (!ocb::g_trace_buf) {
+        ocb::set_error("debug_trace: tracing is off (set OCB_TRSM_TRACE=1 before the first solve)");
+        return OCB_ERR_ARG;
+    }
+    OCB_CUDA(cudaMemcpy(h_out, ocb::g_trace_buf, (size_t)count * sizeof(long long), cudaMemcpyDeviceToHost));
     return OCB_OK;
 }
 

@@ -15,8 +15,12 @@ import torch
 from . import _cabi
 
 # Counters the bench reads (setup is timed separately, north_star).
-STATS = dict(lu_factor_s=0.0, lu_analyse_upload_s=0.0, n_factor=0,
-             h2d_bytes=0, d2h_bytes=0)
+STATS = dict(lu_factor_s=0.0,          # SuperLU seconds summed over the workers
+             lu_worker_pack_s=0.0,     # host analysis + packing seconds summed over the workers
+             lu_submit_s=0.0,          # main process: building + sending the CSC arguments
+             lu_wait_s=0.0,            # main process: blocked on a worker result
+             lu_analyse_upload_s=0.0,  # main process: image upload + handle creation
+             n_factor=0, h2d_bytes=0, d2h_bytes=0)
 
 # Host factorisation used for the (separately timed) setup step.  SuperLU with a
 # symmetric-pattern ordering: the saddle-point matrices have symmetric structure,
@@ -136,7 +140,7 @@ def _lu_pool():
     want = os.environ.get('OCB_LU_WORKERS')
     if want is None:
         world = int(os.environ.get('WORLD_SIZE', '1'))
-        want = max(1, min(8, (os.cpu_count() or 1)//max(world, 1)))
+        want = max(1, min(14, (os.cpu_count() or 1) - 2)//max(world, 1))
     want = int(want)
     if want <= 1:
         return None
@@ -154,70 +158,110 @@ def _csc_args(mat, opts):
     return (m.data, m.indices, m.indptr, m.shape, opts)
 
 
+_SMEM_OPTIN = dict()
+
+
+def smem_optin():
+    """Opt-in shared memory per block of the current device (the packer sizes the ring)."""
+    d = torch.cuda.current_device()
+    if d not in _SMEM_OPTIN:
+        _SMEM_OPTIN[d] = int(torch.cuda.get_device_properties(d).shared_memory_per_block_optin)
+    return _SMEM_OPTIN[d]
+
+
+class FactorJob(object):
+    """Several host factorisations in flight (worker processes: SuperLU + analysis +
+    packing); ``result()`` uploads the images and returns the ``LU`` handles."""
+
+    def __init__(self, mats, lu_options=None):
+        from . import _lu_worker
+        require_cuda()
+        opts = dict(LU_OPTIONS if lu_options is None else lu_options)
+        t0 = time.perf_counter()
+        so = smem_optin()
+        args = [_csc_args(m, opts) + (so,) for m in mats]
+        self.n = len(mats)
+        pool = _lu_pool()
+        self._done = None
+        if pool is None:
+            self._sync = [_lu_worker.factor_image(a) for a in args]
+            self._async = None
+        else:
+            self._sync = None
+            self._async = [pool.apply_async(_lu_worker.factor_image_to_shm, (a,)) for a in args]
+        STATS['lu_submit_s'] += time.perf_counter() - t0
+        STATS['n_factor'] += self.n
+
+    def result(self):
+        if self._done is not None:
+            return self._done
+        out = []
+        if self._async is None:
+            for img, tf, tp in self._sync:
+                STATS['lu_factor_s'] += tf
+                STATS['lu_worker_pack_s'] += tp
+                out.append(LU(None, image=img))
+        else:
+            from multiprocessing import shared_memory
+            for ar in self._async:
+                t0 = time.perf_counter()
+                name, nbytes, tf, tp = ar.get()
+                STATS['lu_wait_s'] += time.perf_counter() - t0
+                STATS['lu_factor_s'] += tf
+                STATS['lu_worker_pack_s'] += tp
+                shm = shared_memory.SharedMemory(name=name)
+                try:
+                    img = np.frombuffer(shm.buf, dtype=np.uint8, count=nbytes)
+                    out.append(LU(None, image=img))           # uploads synchronously
+                    del img
+                finally:
+                    shm.close()
+                    shm.unlink()
+        self._sync = self._async = None
+        self._done = out
+        return out
+
+
 def factorize_many(mats, lu_options=None):
     """Factorise several matrices (the shifts of one ADI) on the host, in parallel worker
-    processes when available, then analyse + upload each: the separately timed setup."""
-    from . import _lu_worker
-    require_cuda()
-    opts = dict(LU_OPTIONS if lu_options is None else lu_options)
-    t0 = time.perf_counter()
-    args = [_csc_args(m, opts) for m in mats]
-    pool = _lu_pool() if len(mats) > 1 else None
-    if pool is None:
-        arrs = [_lu_worker.factor_arrays(a) for a in args]
-        STATS['lu_factor_s'] += time.perf_counter() - t0
-        STATS['n_factor'] += len(mats)
-        return [LU(None, arrays=a, n=m.shape[0]) for a, m in zip(arrs, mats)]
-    from multiprocessing import shared_memory
-    res = pool.map(_lu_worker.factor_to_shm, args)
-    STATS['lu_factor_s'] += time.perf_counter() - t0
-    STATS['n_factor'] += len(mats)
-    out = []
-    for (name, layout), m in zip(res, mats):
-        shm = shared_memory.SharedMemory(name=name)
-        try:
-            arrs = [np.frombuffer(shm.buf, dtype=np.dtype(d), count=c, offset=o)
-                    for d, c, o in layout]
-            out.append(LU(None, arrays=arrs, n=m.shape[0]))   # uploads synchronously
-            del arrs
-        finally:
-            shm.close()
-            shm.unlink()
-    return out
+    processes when available, then upload each: the separately timed setup."""
+    return FactorJob(mats, lu_options).result()
 
 
 class LU(object):
     """Device-resident LU factorisation ``Pr A Pc = L U`` (handle of the C ABI)."""
 
-    def __init__(self, mat, lu_options=None, arrays=None, n=None):
+    def __init__(self, mat, lu_options=None, image=None):
         lib = require_cuda()
-        if arrays is None:
+        if image is None:
             from . import _lu_worker
             opts = dict(LU_OPTIONS if lu_options is None else lu_options)
-            t0 = time.perf_counter()
-            arrays = _lu_worker.factor_arrays(_csc_args(mat, opts))
-            STATS['lu_factor_s'] += time.perf_counter() - t0
+            image, tf, tp = _lu_worker.factor_image(_csc_args(mat, opts) + (smem_optin(),))
+            STATS['lu_factor_s'] += tf
+            STATS['lu_worker_pack_s'] += tp
             STATS['n_factor'] += 1
-            n = mat.shape[0]
         t1 = time.perf_counter()
-        self.n = n
-        arrs = arrays
         h = C.c_void_p()
-        _cabi.check(lib.ocb_lu_create(C.byref(h), n, *[a.ctypes.data for a in arrs],
-                                      stream_ptr()), 'ocb_lu_create')
+        # the device image lives in a torch buffer: the caching allocator makes creating and
+        # dropping a factorisation free of cudaMalloc / cudaFree (both synchronise the device)
+        self.arena = torch.empty(int(image.nbytes), dtype=torch.uint8, device=cur_device())
+        _cabi.check(lib.ocb_lu_create_from_image(C.byref(h), image.ctypes.data, image.nbytes,
+                                                 ptr(self.arena), stream_ptr()),
+                    'ocb_lu_create_from_image')
         self.handle = h
         self._lib = lib
         info = (C.c_int64*8)()
         _cabi.check(lib.ocb_lu_info(h, info), 'ocb_lu_info')
         st8 = (C.c_int64*8)()
         _cabi.check(lib.ocb_lu_stats(h, st8), 'ocb_lu_stats')
+        self.n = int(info[0])
         self.info = dict(n=info[0], nnzL=info[1], nnzU=info[2], levelsL=info[3],
                          levelsU=info[4], device_bytes=info[5], stream_kp=info[6],
                          stream_batches=info[7], n_ext=st8[0], supernodes=st8[1],
                          max_supernode=st8[2], segments=st8[3], program_rows=st8[4],
                          program_entries=st8[5], stage_bytes=st8[6], stages=st8[7])
         STATS['lu_analyse_upload_s'] += time.perf_counter() - t1
-        STATS['h2d_bytes'] += sum(a.nbytes for a in arrs)
+        STATS['h2d_bytes'] += image.nbytes
 
     def __del__(self):
         try:

@@ -66,24 +66,58 @@ class StepSetup(object):
         self.fac = pru.ShiftedFactors(sps.csr_matrix(ft_mat), ctx.MT, ctx.J, ctx.shifts,
                                       Mt_dev=ctx.Mt_dev)
         at_mat = ctx.MT + cts*(ctx.AT + NT)
-        self.at_lu = dv.LU(dv.sadpnt_matrix(at_mat, ctx.J))
+        self._at_job = dv.FactorJob([dv.sadpnt_matrix(at_mat, ctx.J)])
         self.ftilde = dv.to_dev(np.asarray(rhsvtd) + ctx.rhsv)
         self.fl1 = dv.to_dev(np.dot(ctx.mcmatT, ctx.ystarvec(t)))
         sq = np.sqrt(cts)
         self.Bd = sq*ctx.tb
         self.Vt_b = dv.DeviceCSR(sq*ctx.tb_host.T)
+        self.at_lu = None
+
+    def finish(self):
+        """Wait for the background factorisations and upload them (still setup, not step)."""
+        if self.at_lu is None:
+            self.at_lu = self._at_job.result()[0]
+            self.fac.lus
+        return self
 
 
-def run_step(ctx, st, info=None):
+class _Phases(object):
+    """Optional CUDA-event phase timer (bench.py --phases): name -> summed milliseconds."""
+
+    def __init__(self):
+        self.ev, self.ms = [], {}
+
+    def mark(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.ev.append((name, e))
+
+    def collect(self):
+        torch.cuda.synchronize()
+        for (_, a), (name, b) in zip(self.ev, self.ev[1:]):
+            if name != 'start':
+                self.ms[name] = self.ms.get(name, 0.0) + a.elapsed_time(b)
+        self.ev = []
+        return self.ms
+
+
+def run_step(ctx, st, info=None, phases=None):
     """Device part of one backward step; updates ctx.Zc, ctx.mtxtb, ctx.wc in place."""
     cts = st.cts
+    st.finish()
+    mark = phases.mark if phases is not None else (lambda name: None)
+    mark('start')
     w_mat = torch.cat([ctx.Mt_dev.matmul(ctx.Zc), np.sqrt(cts)*ctx.tct], dim=1).contiguous()
+    mark('rhs')
     Zp, ninfo = pru.newtonadi_dev(st.fac, st.Bd, st.Vt_b, w_mat, ctx.Zc, ctx.nwtn_adi_dict)
+    mark('newton_adi')
     if ctx.maxc is not None or ctx.thresh is not None:
         Zc, cinfo = dv.compress(Zp, thresh=ctx.thresh, k=ctx.maxc)
         Zc = Zc.contiguous()
     else:
         Zc, cinfo = Zp.contiguous(), {}
+    mark('compress')
     # feed-forward (solve_dae_ric.py:173-194); the SMW gain is the PREVIOUS step's mtxtb
     cnsmtxtb = ctx.mtxtb
     mtxft = dv.feedback(ctx.Mt_dev, Zc, st.ftilde)
@@ -92,6 +126,7 @@ def run_step(ctx, st, info=None):
     wc = st.at_lu.smw_solve(rhswc, ctx.NV, Ufb=(cts*cnsmtxtb).contiguous(), Vt=ctx.tbT,
                             nrows_out=ctx.NV)
     ctx.Zc, ctx.mtxtb, ctx.wc = Zc, mtxtb, wc
+    mark('feedforward')
     if info is not None:
         info.append(dict(t=st.t, tau=cts, adi_steps=ninfo['adi_steps'],
                          nwtn_upd_fnorms=ninfo['nwtn_upd_fnorms'], zp_cols=Zp.shape[1],
@@ -120,4 +155,6 @@ def prepare_steps(ctx, kw, nsteps):
         t = tm[tk]
         nmattd, rhsvtd = kw['get_tdpart'](time=t, **kw['gttdprtargs'])
         out.append(StepSetup(ctx, t, tm[tk+1]-t, nmattd, rhsvtd))
+    for st in out:          # all factorisations were submitted above and run concurrently
+        st.finish()
     return out

@@ -85,11 +85,16 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
                       get_datastr=None, gtdtstrargs=None,
                       check_c_consist=True,
                       lau=None, pru=None, store=None, verbose=False,
-                      stepinfo=None, step_callback=None):
+                      stepinfo=None, step_callback=None, lookahead=True):
     """Same keyword signature as the reference's ``solve_flow_daeric`` plus
     ``lau``/``pru`` (backend modules), ``store`` and ``stepinfo`` (optional list
     that receives per-step diagnostics).  Returns the ``feedbackthroughdict``
-    ``{t: dict(w=..., mtxtb=...)}`` of store keys."""
+    ``{t: dict(w=..., mtxtb=...)}`` of store keys.
+
+    ``lookahead``: the coefficient matrices of a time step depend on ``t`` only, not on the
+    Riccati solution, so when the backend offers ``pru.factors_async`` / ``lau.sadlu_async``
+    the sparse LU setup of step ``k-1`` is started (host worker processes) before the
+    device work of step ``k``; the numbers are the same with or without it."""
     if lau is None or pru is None:
         from . import lin_alg_utils as _lau, proj_ric_utils as _pru
         lau, pru = lau or _lau, pru or _pru
@@ -126,6 +131,25 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         store.save(wc, curnwtnsdict[tE]['w'])
         store.save(mtxtb, curnwtnsdict[tE]['mtxtb'])
 
+    can_prefetch = lookahead and hasattr(pru, 'factors_async') and hasattr(lau, 'sadlu_async')
+
+    def prepare(tk):
+        """Everything of step tk that depends on t only (incl. background factorisations)."""
+        t = tmesh[tk]
+        cts = tmesh[tk+1] - t
+        nmattd, rhsvtd = get_tdpart(time=t, **gttdprtargs)
+        NT = nmattd.T
+        ft_mat = -(0.5*MT + cts*(AT + NT))
+        at_mat = MT + cts*(AT + NT)
+        pre = dict(nmattd=nmattd, rhsvtd=rhsvtd, NT=NT, ft_mat=ft_mat, at_mat=at_mat,
+                   fac=None, sadlu=None)
+        if can_prefetch:
+            pre['fac'] = pru.factors_async(mmat=MT, amat=ft_mat, jmat=jmat, transposed=True,
+                                           nwtn_adi_dict=nwtn_adi_dict)
+            pre['sadlu'] = lau.sadlu_async(amat=at_mat, jmat=jmat)
+        return pre
+
+    nxt = None
     for tk in range(len(tmesh)-2, -1, -1):
         t = tmesh[tk]
         cts = tmesh[tk+1] - t
@@ -133,8 +157,9 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
             print('Time is {0}, timestep is {1}'.format(t, cts))
         gtdtstrargs.update(time=t)
         key = get_datastr(**gtdtstrargs)
-        nmattd, rhsvtd = get_tdpart(time=t, **gttdprtargs)
-        NT = nmattd.T
+        pre = nxt if nxt is not None else prepare(tk)
+        nxt = prepare(tk-1) if (can_prefetch and tk > 0) else None
+        nmattd, rhsvtd, NT = pre['nmattd'], pre['rhsvtd'], pre['NT']
 
         cnsw, cnsmtxtb = None, None
         if curnwtnsdict is not None:
@@ -148,14 +173,15 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         try:
             Zc = store.load(key + '__Z')
         except IOError:
-            ft_mat = -(0.5*MT + cts*(AT + NT))
+            ft_mat = pre['ft_mat']
             w_mat = np.hstack([MT @ Zc, np.sqrt(cts)*tct_mat])
             oldfb = np.sqrt(cts)*cnsmtxtb if cnsmtxtb is not None else None
+            xkw = dict(_factors=pre['fac']) if pre['fac'] is not None else {}
             nres = pru.proj_alg_ric_newtonadi(mmat=MT, amat=ft_mat, transposed=True,
                                               mtxoldb=oldfb, jmat=jmat,
                                               bmat=np.sqrt(cts)*tb_mat,
                                               wmat=w_mat, z0=Zc,
-                                              nwtn_adi_dict=nwtn_adi_dict)
+                                              nwtn_adi_dict=nwtn_adi_dict, **xkw)
             Zp = nres['zfac']
             info.update(nwtn_upd_fnorms=nres.get('nwtn_upd_fnorms'),
                         adi_steps=nres.get('adi_steps'), zp_cols=Zp.shape[1])
@@ -166,7 +192,7 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
             store.save(Zp if save_full_z else Zc, key + '__Z')
         info.update(zc_cols=Zc.shape[1])
 
-        at_mat = MT + cts*(AT + NT)
+        at_mat = pre['at_mat']
         ftilde = rhsvtd + rhsv
         if cnsw is not None:
             ftilde = rhsvtd + rhsv + cnsw
@@ -177,9 +203,10 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         fl1 = np.dot(mcmat.T, ystarvec(t))
         rhswc = MT @ wc + cts*(fl1 - mtxft)
         mtxtb = -pru.get_mTzzTtb(MT, Zc, tb_mat)
+        xkw = dict(sadlu=pre['sadlu']) if pre['sadlu'] is not None else {}
         wc = lau.solve_sadpnt_smw(amat=at_mat, jmat=jmat,
                                   umat=cts*cnsmtxtb, vmat=tb_mat.T,
-                                  rhsv=rhswc)[:NV]
+                                  rhsv=rhswc, **xkw)[:NV]
 
         if curnwtnsdict is not None:
             cnsw = cnsw + wc if cnsw is not None else wc

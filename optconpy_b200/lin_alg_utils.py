@@ -17,7 +17,7 @@ from . import device as dv
 __all__ = ['mm_dnssps', 'app_luinv_to_spmat', 'apply_massinv', 'apply_sqrt_fromright',
            'apply_invsqrt_fromright', 'get_Sinv_smw', 'app_smw_inv', 'solve_sadpnt_smw',
            'app_prj_via_sadpnt', 'comp_sqfnrm_factrd_diff', 'comp_sqfnrm_factrd_sum',
-           'comp_sqfnrm_factrd_lyap_res', 'SadLU']
+           'comp_sqfnrm_factrd_lyap_res', 'SadLU', 'sadlu_async']
 
 
 def _dense(a):
@@ -31,15 +31,32 @@ class SadLU(object):
     """Callable LU handle (what ``spsla.factorized`` returns in the reference):
     ``alu(rhs)`` solves on the device."""
 
-    def __init__(self, mat):
-        self.lu = dv.LU(mat)
+    def __init__(self, mat, background=False):
         self.shape = mat.shape
+        self._lu = None
+        # background=True: the factorisation runs in a worker process, uploaded on first use
+        self._job = dv.FactorJob([mat]) if background else None
+        if not background:
+            self._lu = dv.LU(mat)
+
+    @property
+    def lu(self):
+        if self._lu is None:
+            self._lu = self._job.result()[0]
+        return self._lu
 
     def __call__(self, rhs):
         rhs = np.asarray(rhs, dtype=np.float64)
         one_d = rhs.ndim == 1
         x = dv.to_host(self.lu.solve(dv.to_dev(rhs)))
         return x[:, 0] if one_d else x
+
+
+def sadlu_async(amat=None, jmat=None, jmatT=None):
+    """Start the factorisation of ``[[A, J^T], [J, 0]]`` in the background; pass the result
+    to ``solve_sadpnt_smw(..., sadlu=...)``.  Extension of the reference interface."""
+    dv.require_cuda()
+    return SadLU(dv.sadpnt_matrix(amat, jmat, jmatT), background=True)
 
 
 def mm_dnssps(A, v):

@@ -22,7 +22,7 @@ import torch
 from . import device as dv
 
 __all__ = ['solve_proj_lyap_stein', 'proj_alg_ric_newtonadi', 'compress_Zsvd',
-           'get_mTzzTtb', 'comp_proj_lyap_res_norm']
+           'get_mTzzTtb', 'comp_proj_lyap_res_norm', 'factors_async']
 
 DEFAULT_SHIFTS = [-30.0, -20.0, -10.0, -5.0, -3.0, -1.0]
 
@@ -35,15 +35,41 @@ def _dense(a):
 
 
 class ShiftedFactors(object):
-    """Per-shift LU handles of ``[[At + mu Mt, J^T], [J, 0]]`` — the setup step that
+    """Per-shift LU handles of ``[[At + mu Mt, J^T], [J, 0]]`` - the setup step that
     ``north_star`` times separately.  Reused across the Newton steps of one
-    Riccati solve (the low-rank closed-loop part enters through SMW only)."""
+    Riccati solve (the low-rank closed-loop part enters through SMW only).
+
+    Construction only SUBMITS the host factorisations (worker processes); the handles are
+    uploaded on first use of ``.lus``.  Creating the object early therefore overlaps the
+    setup of the next time step with the device work of the current one
+    (``factors_async`` / ``dre_stepper`` look-ahead)."""
 
     def __init__(self, At, Mt, jmat, ms, Mt_dev=None):
         self.ms = [float(m) for m in ms]
         self.NV, self.NP = At.shape[0], jmat.shape[0]
-        self.lus = dv.factorize_many([dv.sadpnt_matrix(At + mu*Mt, jmat) for mu in self.ms])
-        self.Mt_dev = dv.DeviceCSR(Mt) if Mt_dev is None else Mt_dev
+        self._job = dv.FactorJob([dv.sadpnt_matrix(At + mu*Mt, jmat) for mu in self.ms])
+        self._Mt, self._Mt_dev = Mt, Mt_dev
+
+    @property
+    def lus(self):
+        return self._job.result()
+
+    @property
+    def Mt_dev(self):
+        if self._Mt_dev is None:
+            self._Mt_dev = dv.DeviceCSR(self._Mt)
+        return self._Mt_dev
+
+
+def factors_async(mmat=None, amat=None, jmat=None, nwtn_adi_dict=None, transposed=False, **kw):
+    """Start the per-shift factorisations of a later ``proj_alg_ric_newtonadi`` /
+    ``solve_proj_lyap_stein`` call (same ``mmat, amat, jmat, transposed``) in the background;
+    hand the result to that call as ``_factors=``.  Extension of the reference interface:
+    callers that do not use it get the same numbers, only later."""
+    dv.require_cuda()
+    At, Mt = _transposed_pair(amat, mmat, transposed)
+    ms = (nwtn_adi_dict or {}).get('ms', DEFAULT_SHIFTS)
+    return ShiftedFactors(At, Mt, jmat, ms)
 
 
 def _stein_dev(fac, W, adi_dict, Ufb=None, Vt=None):
@@ -70,7 +96,9 @@ def solve_proj_lyap_stein(amat=None, jmat=None, wmat=None, mmat=None,
     if nwtn_adi_dict is not None:
         adi_dict = nwtn_adi_dict
     At, Mt = _transposed_pair(amat, mmat, transposed)
-    fac = ShiftedFactors(At, Mt, jmat, adi_dict.get('ms', DEFAULT_SHIFTS))
+    fac = kw.get('_factors')
+    if fac is None:
+        fac = ShiftedFactors(At, Mt, jmat, adi_dict.get('ms', DEFAULT_SHIFTS))
     W = dv.to_dev(_dense(wmat))
     Ufb = Vt = None
     if umat is not None and vmat is not None:
