@@ -30,18 +30,33 @@ def factor_arrays(args):
             np.ascontiguousarray(slu.perm_c, dtype=np.int32)]
 
 
+class _CImage(object):
+    """Device image in a C buffer (``ocb_lu_pack_host``); ``view`` is a uint8 numpy view,
+    ``free()`` releases it."""
+
+    def __init__(self, arrs, n, smem_optin):
+        from optconpy_b200 import _cabi
+        self._lib = _cabi.load()
+        img, nbytes = C.c_void_p(), C.c_int64(0)
+        _cabi.check(self._lib.ocb_lu_pack_host(n, *[a.ctypes.data for a in arrs], int(smem_optin),
+                                               C.byref(img), C.byref(nbytes)), 'ocb_lu_pack_host')
+        self._ptr = img
+        self.view = np.ctypeslib.as_array(C.cast(img, C.POINTER(C.c_uint8)), shape=(nbytes.value,))
+
+    def free(self):
+        if self._ptr is not None:
+            self.view = None
+            self._lib.ocb_host_free(self._ptr)
+            self._ptr = None
+
+
 def pack_image(arrs, n, smem_optin):
     """Host half of ``ocb_lu_create``: returns the device image as a uint8 array."""
-    from optconpy_b200 import _cabi
-    lib = _cabi.load()
-    img, nbytes = C.c_void_p(), C.c_int64(0)
-    _cabi.check(lib.ocb_lu_pack_host(n, *[a.ctypes.data for a in arrs], int(smem_optin),
-                                     C.byref(img), C.byref(nbytes)), 'ocb_lu_pack_host')
+    ci = _CImage(arrs, n, smem_optin)
     try:
-        buf = np.ctypeslib.as_array(C.cast(img, C.POINTER(C.c_uint8)), shape=(nbytes.value,)).copy()
+        return ci.view.copy()
     finally:
-        lib.ocb_host_free(img)
-    return buf
+        ci.free()
 
 
 def factor_image(args):
@@ -59,9 +74,16 @@ def factor_image_to_shm(args):
     shared-memory block (no pickling of ~15 MB through a pipe).
     Returns (name, nbytes, seconds factor, seconds analyse+pack)."""
     from multiprocessing import shared_memory
-    img, tf, tp = factor_image(args)
-    shm = shared_memory.SharedMemory(create=True, size=max(img.nbytes, 64))
-    np.frombuffer(shm.buf, dtype=np.uint8, count=img.nbytes)[:] = img
+    t0 = time.perf_counter()
+    arrs = factor_arrays(args)
+    t1 = time.perf_counter()
+    ci = _CImage(arrs, args[3][0], args[5])
+    try:
+        nbytes = ci.view.nbytes
+        shm = shared_memory.SharedMemory(create=True, size=max(nbytes, 64))
+        np.frombuffer(shm.buf, dtype=np.uint8, count=nbytes)[:] = ci.view
+    finally:
+        ci.free()
     name = shm.name
     shm.close()
-    return name, img.nbytes, tf, tp
+    return name, nbytes, t1 - t0, time.perf_counter() - t1

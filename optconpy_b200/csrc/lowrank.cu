@@ -25,6 +25,25 @@ int sym_eig_impl(double* G, int64_t ldg, int64_t k, double* lam, double* V, int6
                  int32_t* h_sweeps, cudaStream_t st);
 int smw_core_inv(const double* C, int64_t ldc, int m, double* Sinv, int* flag, cudaStream_t st);
 
+// one side stream + a few events per process (SMW preparation overlaps the ADI chain)
+struct SideStream {
+    static constexpr int MAXEV = 34;
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev[MAXEV];
+};
+static SideStream* side_stream() {
+    static SideStream* p = nullptr;
+    static bool failed = false;
+    if (!p && !failed) {
+        SideStream* q = new SideStream();
+        bool ok = cudaStreamCreateWithFlags(&q->s, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; ok && i < SideStream::MAXEV; ++i)
+            ok = cudaEventCreateWithFlags(&q->ev[i], cudaEventDisableTiming) == cudaSuccess;
+        if (ok) p = q; else failed = true;
+    }
+    return p;
+}
+
 // pinned host scratch for the few scalars that steer host-side loops
 static double* pinned_scratch() {
     static double* p = nullptr;
@@ -391,7 +410,7 @@ int64_t ocb_adi_ws_bytes(int64_t n_sad, int64_t k, int64_t m, int64_t nshifts, o
     c.take<int>(8);                              // flag
     c.take<double>(nshifts * n_sad * std::max<int64_t>(m, 1));
     c.take<double>(nshifts * m * m + 1);
-    c.take<double>(m * m + 1);
+    c.take<double>(nshifts * m * m + 1);
     c.take<double>(m * k + 1);
     c.take<double>(m * k + 1);
     c.take<char>(lws);
@@ -428,7 +447,7 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
     int* flag = c.take<int>(8);
     double* AiU = c.take<double>(nshifts * n_sad * std::max<int64_t>(m, 1));
     double* Sinv = c.take<double>(nshifts * m * m + 1);
-    double* core = c.take<double>(m * m + 1);
+    double* core = c.take<double>(nshifts * m * m + 1);
     double* small = c.take<double>(m * k + 1);
     double* S2 = c.take<double>(m * k + 1);
     void* lws = c.take<char>(lws_bytes);
@@ -437,6 +456,25 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
     OCB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 8, st));
     std::vector<char> prepared(nshifts, 0);
     (void)T;
+    // The Sherman-Morrison-Woodbury pieces of the shifts (A_i^-1 U, 8 columns each) do not
+    // depend on the iteration: they are all launched up front on a side stream, so that they
+    // fill the SMs the narrow ADI solves leave idle; the main stream waits for shift i's
+    // event right before its first use.
+    SideStream* side = nullptr;
+    if (m > 0 && lws_bytes == 0 && nshifts <= SideStream::MAXEV - 1) {
+        side = side_stream();
+        if (side) {
+            OCB_CUDA(cudaEventRecord(side->ev[SideStream::MAXEV - 1], st));
+            OCB_CUDA(cudaStreamWaitEvent(side->s, side->ev[SideStream::MAXEV - 1], 0));
+            for (int64_t i = 0; i < nshifts; ++i) {
+                int rc = smw_prepare(lus[i], NV, d_Ufb, ldu, (int)m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals,
+                                     AiU + i * NV * m, NV, core + i * m * m, Sinv + i * m * m, flag, lws,
+                                     lws_bytes, side->s);
+                if (rc) return rc;
+                OCB_CUDA(cudaEventRecord(side->ev[i], side->s));
+            }
+        }
+    }
 
     double z_nsq = 0.0;
     int64_t step = 0;
@@ -451,9 +489,14 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
         const ocb_lu* lu = lus[i];
         int rc;
         if (m > 0 && !prepared[i]) {
-            rc = smw_prepare(lu, NV, d_Ufb, ldu, (int)m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals,
-                             AiU + i * NV * m, NV, core, Sinv + i * m * m, flag, lws, lws_bytes, st);
-            if (rc) return rc;
+            if (side) {
+                OCB_CUDA(cudaStreamWaitEvent(st, side->ev[i], 0));
+            } else {
+                rc = smw_prepare(lu, NV, d_Ufb, ldu, (int)m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals,
+                                 AiU + i * NV * m, NV, core + i * m * m, Sinv + i * m * m, flag, lws,
+                                 lws_bytes, st);
+                if (rc) return rc;
+            }
             prepared[i] = 1;
         }
         const double* Vprev = step > 0 ? d_Z + (step - 1) * k : nullptr;
@@ -497,6 +540,8 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
         *h_steps = step;
         if (!(rel > reltol)) break;
     }
+    if (side)   // the workspace may be reused by the caller: order the main stream after all side work
+        OCB_CUDA(cudaStreamWaitEvent(st, side->ev[nshifts - 1], 0));
     return OCB_OK;
 }
 

@@ -7,6 +7,8 @@
 #include <numeric>
 #include <string.h>
 #include <stdlib.h>
+#include <chrono>
+#include <stdio.h>
 
 namespace ocb {
 
@@ -135,26 +137,37 @@ void invert_block(const Tri& T, int32_t r0, int32_t r1, std::vector<double>* Dbu
             const int32_t c = T.ci[p];
             if (c >= r0 && c < r1) D[(size_t)(i - r0) * w + (c - r0)] = T.va[p];
         }
+    // row-oriented triangular inversion (unit-stride inner loops):
+    //   lower, unit diagonal:  X[i,:] = e_i - sum_{k<i} D[i,k] X[k,:]
+    //   upper:                 X[i,:] = (e_i - sum_{k>i} D[i,k] X[k,:]) / D[i,i]
     if (!T.upper) {
-        for (int j = 0; j < w; ++j) {
-            X[(size_t)j * w + j] = 1.0;
-            for (int i = j + 1; i < w; ++i) {
-                double s = 0.0;
-                for (int k = j; k < i; ++k) s += D[(size_t)i * w + k] * X[(size_t)k * w + j];
-                X[(size_t)i * w + j] = -s;
+        for (int i = 0; i < w; ++i) {
+            double* xi = &X[(size_t)i * w];
+            xi[i] = 1.0;
+            for (int k = 0; k < i; ++k) {
+                const double d = D[(size_t)i * w + k];
+                if (d == 0.0) continue;
+                const double* xk = &X[(size_t)k * w];
+                for (int j = 0; j <= k; ++j) xi[j] -= d * xk[j];
             }
         }
     } else {
-        for (int j = w - 1; j >= 0; --j) {
-            X[(size_t)j * w + j] = 1.0 / D[(size_t)j * w + j];
-            for (int i = j - 1; i >= 0; --i) {
-                double s = 0.0;
-                for (int k = i + 1; k <= j; ++k) s += D[(size_t)i * w + k] * X[(size_t)k * w + j];
-                X[(size_t)i * w + j] = -s / D[(size_t)i * w + i];
+        for (int i = w - 1; i >= 0; --i) {
+            double* xi = &X[(size_t)i * w];
+            xi[i] = 1.0;
+            for (int k = i + 1; k < w; ++k) {
+                const double d = D[(size_t)i * w + k];
+                if (d == 0.0) continue;
+                const double* xk = &X[(size_t)k * w];
+                for (int j = k; j < w; ++j) xi[j] -= d * xk[j];
             }
+            const double inv = 1.0 / D[(size_t)i * w + i];
+            for (int j = i; j < w; ++j) xi[j] *= inv;
         }
     }
 }
+
+static double g_inv_ms = 0.0;
 
 struct RowRef {     // a row of the program before it is laid out
     int32_t block;  // supernode index
@@ -188,12 +201,14 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
         std::vector<RowRef>& rows = lev[s];
         if (rows.empty()) continue;
         inv.clear();
+        const auto ti0 = std::chrono::steady_clock::now();
         for (const RowRef& rr : rows)
             if (rr.kind == 1 && rr.k == 0) {
                 invert_block(T, starts[rr.block], starts[rr.block + 1], &D, &X);
                 inv_slot[rr.block] = (int32_t)inv.size();
                 inv.push_back(X);
             }
+        g_inv_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ti0).count();
         std::stable_sort(rows.begin(), rows.end(), [](const RowRef& a, const RowRef& b) {
             if (a.len != b.len) return a.len > b.len;
             return a.block < b.block;
@@ -244,7 +259,7 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                 const int32_t i = r0 + rr.k;
                 int e = 0;   // entry counter of this row
                 auto put = [&](int32_t c, double v) {
-                    const size_t pos = e0 + (size_t)(e / G) * 32 + (size_t)rl * G + (e % G);
+                    const size_t pos = e0 + ((size_t)(e >> g) << 5) + ((size_t)rl << g) + (size_t)(e & (G - 1));
                     P->col[pos] = c;
                     P->val[pos] = v;
                     ++e;
@@ -313,6 +328,12 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
             return OCB_ERR_ARG;
         }
     }
+    const bool timing = getenv("OCB_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t0 = tnow();
     std::vector<int32_t> starts;
     find_supernodes(n, Urp, Uci, &starts);
     P->nsuper = (int32_t)starts.size() - 1;
@@ -323,19 +344,27 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
     int rc = plan_factor(n, TL, starts, &planL, &P->nsub_L, &ymax);
     if (rc == OCB_OK) rc = plan_factor(n, TU, starts, &planU, &P->nsub_U, &ymax);
     if (rc != OCB_OK) return rc;
+    const auto t1 = tnow();
     P->ymax = ymax;
     P->n_ext = n + 2 * ymax;
-    const int64_t cap = (int64_t)Lrp[n] + Urp[n] + 4 * n;
+    const int64_t cap = ((int64_t)Lrp[n] + Urp[n]) * 3 / 2 + 64 * n;   // SELL padding included
     P->col.reserve(cap);
     P->val.reserve(cap);
     for (int64_t i = 0; i < n; ++i) {
         for (int32_t p = Lrp[i]; p < Lrp[i + 1]; ++p) P->nnzL += (Lci[p] != i);
     }
     P->nnzU = Urp[n];
+    const auto t2 = tnow();
     rc = emit_factor(n, TL, starts, planL, P->nsub_L, ymax, max_lanes, P);
+    const auto t3 = tnow();
     P->nsub_L = (int32_t)P->nsub();
     if (rc == OCB_OK) rc = emit_factor(n, TU, starts, planU, P->nsub_U, ymax, max_lanes, P);
     P->nsub_U = (int32_t)P->nsub() - P->nsub_L;
+    if (timing) {
+        fprintf(stderr, "lu_program: supernodes+plan %.1f ms, reserve %.1f ms, emit L %.1f ms, emit U %.1f ms (block inverses %.1f ms)\n",
+                ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, tnow()), g_inv_ms);
+        g_inv_ms = 0.0;
+    }
     return rc;
 }
 

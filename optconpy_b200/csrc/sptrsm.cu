@@ -541,7 +541,7 @@ enum { M_MAGIC = 0, M_TOTAL, M_N, M_NEXT, M_NNZL, M_NNZU, M_NSUBL, M_NSUBU, M_NS
 
 // choose ring geometry + panel placement and pack the image
 static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t* h_perm_c,
-                      int max_smem_optin, std::vector<unsigned char>* img_out) {
+                      int max_smem_optin, unsigned char** img_out, int64_t* bytes_out) {
     const int64_t smem_cap = (int64_t)max_smem_optin - 1024 - 192;
     const int64_t xe1 = P.n_ext * 8;   // bytes of a one-column panel
     int kp_smem = 0, nst = 3, cl = 4;
@@ -607,9 +607,14 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         o = align_up(o + std::max<int64_t>(off[r].back(), 16), 256);
     }
     const int64_t total = o;
-    std::vector<unsigned char>& img = *img_out;
-    img.assign((size_t)total, 0);
-    int64_t* meta = (int64_t*)img.data();
+    unsigned char* img = (unsigned char*)calloc((size_t)total, 1);   // zero pages on demand
+    if (!img) {
+        set_error("lu_pack_host: out of memory");
+        return OCB_ERR_CAPACITY;
+    }
+    *img_out = img;
+    *bytes_out = total;
+    int64_t* meta = (int64_t*)img;
     meta[M_MAGIC] = IMG_MAGIC; meta[M_TOTAL] = total; meta[M_N] = P.n; meta[M_NEXT] = P.n_ext;
     meta[M_NNZL] = P.nnzL; meta[M_NNZU] = P.nnzU; meta[M_NSUBL] = P.nsub_L; meta[M_NSUBU] = P.nsub_U;
     meta[M_NSUPER] = P.nsuper; meta[M_MAXW] = P.max_w; meta[M_NSLICE] = (int64_t)P.slices.size();
@@ -621,13 +626,13 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         meta[M_NBATCH + r] = (int64_t)batches[r].size();
     }
     if (P.n > 0) {
-        memcpy(img.data() + o_pr, h_perm_r, (size_t)P.n * 4);
-        memcpy(img.data() + o_pc, h_perm_c, (size_t)P.n * 4);
+        memcpy(img + o_pr, h_perm_r, (size_t)P.n * 4);
+        memcpy(img + o_pc, h_perm_c, (size_t)P.n * 4);
     }
     for (int r = 0; r < cl; ++r) {
-        memcpy(img.data() + o_bo[r], off[r].data(), off[r].size() * 8);
+        memcpy(img + o_bo[r], off[r].data(), off[r].size() * 8);
         for (size_t b = 0; b < batches[r].size(); ++b)
-            write_record(P, batches[r][b], cl, img.data() + o_st[r] + off[r][b]);
+            write_record(P, batches[r][b], cl, img + o_st[r] + off[r][b]);
     }
     return OCB_OK;
 }
@@ -849,18 +854,7 @@ int ocb_lu_pack_host(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_co
     int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals,
                                    ocb::trsm_threads(), &P);
     if (rc != OCB_OK) return rc;
-    std::vector<unsigned char> img;
-    rc = ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, &img);
-    if (rc != OCB_OK) return rc;
-    unsigned char* buf = (unsigned char*)malloc(img.size());
-    if (!buf) {
-        ocb::set_error("lu_pack_host: out of memory");
-        return OCB_ERR_CAPACITY;
-    }
-    memcpy(buf, img.data(), img.size());
-    *out_image = buf;
-    *out_bytes = (int64_t)img.size();
-    return OCB_OK;
+    return ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, out_image, out_bytes);
 }
 
 void ocb_host_free(void* p) { free(p); }

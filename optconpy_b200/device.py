@@ -309,6 +309,51 @@ class LU(object):
         return out
 
 
+class SaddleAssembler(object):
+    """``[[A, J^T], [J, 0]]`` in CSC for many A of ONE sparsity pattern (the shifted
+    matrices ``At + mu Mt`` of an ADI, every time step): the block matrix is assembled once
+    with ``bmat``; afterwards only the values of the (1,1) block are scattered into a copy
+    of the CSC data array (``sps.bmat`` costs ~2 ms per matrix, this ~0.2 ms)."""
+
+    def __init__(self, apattern, jmat, jmatT=None):
+        P = sps.csr_matrix(apattern, dtype=np.float64, copy=True)
+        P.sum_duplicates()
+        P.sort_indices()
+        self.indptr, self.indices = P.indptr.copy(), P.indices.copy()
+        tag = sps.csr_matrix((np.arange(1, P.nnz+1, dtype=np.float64), self.indices, self.indptr),
+                             shape=P.shape)
+        NV = P.shape[0]
+        K = sadpnt_matrix(tag, jmat, jmatT)
+        K.sort_indices()
+        # entries of the (1,1) block carry their CSR position + 1 as value
+        cols = np.repeat(np.arange(K.shape[1]), np.diff(K.indptr))
+        in_a = (K.indices < NV) & (cols < NV)
+        self.pos = np.flatnonzero(in_a)
+        self.src = np.rint(K.data[self.pos]).astype(np.int64) - 1
+        base = sadpnt_matrix(sps.csr_matrix(P.shape), jmat, jmatT)
+        self.K = K
+        self.base_data = np.zeros_like(K.data)
+        # J / J^T values: assemble once with a zero (1,1) block on the same pattern
+        Kj = K.copy()
+        Kj.data[self.pos] = 0.0
+        tagged = K.data.copy()
+        tagged[self.pos] = 0.0
+        self.base_data = tagged
+        del base, Kj
+
+    def matches(self, amat):
+        return (sps.isspmatrix_csr(amat) and amat.has_sorted_indices
+                and amat.nnz == len(self.indices)
+                and np.array_equal(amat.indptr, self.indptr)
+                and np.array_equal(amat.indices, self.indices))
+
+    def assemble(self, adata):
+        """CSC saddle-point matrix whose (1,1) block has the CSR values ``adata``."""
+        data = self.base_data.copy()
+        data[self.pos] = adata[self.src]
+        return sps.csc_matrix((data, self.K.indices, self.K.indptr), shape=self.K.shape)
+
+
 def sadpnt_matrix(amat, jmat, jmatT=None):
     """``[[A, J^T], [J, 0]]`` (host, CSC) — the coefficient of every saddle-point solve."""
     nnpp = jmat.shape[0]

@@ -85,16 +85,17 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
                       get_datastr=None, gtdtstrargs=None,
                       check_c_consist=True,
                       lau=None, pru=None, store=None, verbose=False,
-                      stepinfo=None, step_callback=None, lookahead=True):
+                      stepinfo=None, step_callback=None, lookahead=2):
     """Same keyword signature as the reference's ``solve_flow_daeric`` plus
     ``lau``/``pru`` (backend modules), ``store`` and ``stepinfo`` (optional list
     that receives per-step diagnostics).  Returns the ``feedbackthroughdict``
     ``{t: dict(w=..., mtxtb=...)}`` of store keys.
 
-    ``lookahead``: the coefficient matrices of a time step depend on ``t`` only, not on the
-    Riccati solution, so when the backend offers ``pru.factors_async`` / ``lau.sadlu_async``
-    the sparse LU setup of step ``k-1`` is started (host worker processes) before the
-    device work of step ``k``; the numbers are the same with or without it."""
+    ``lookahead`` (number of steps, 0 = off): the coefficient matrices of a time step depend
+    on ``t`` only, not on the Riccati solution, so when the backend offers
+    ``pru.factors_async`` / ``lau.sadlu_async`` the sparse LU setup of the next
+    ``lookahead`` steps is started (host worker processes) before the device work of step
+    ``k``; the numbers are the same with or without it."""
     if lau is None or pru is None:
         from . import lin_alg_utils as _lau, proj_ric_utils as _pru
         lau, pru = lau or _lau, pru or _pru
@@ -131,7 +132,7 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         store.save(wc, curnwtnsdict[tE]['w'])
         store.save(mtxtb, curnwtnsdict[tE]['mtxtb'])
 
-    can_prefetch = lookahead and hasattr(pru, 'factors_async') and hasattr(lau, 'sadlu_async')
+    can_prefetch = bool(lookahead) and hasattr(pru, 'factors_async') and hasattr(lau, 'sadlu_async')
 
     def prepare(tk):
         """Everything of step tk that depends on t only (incl. background factorisations)."""
@@ -149,7 +150,14 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
             pre['sadlu'] = lau.sadlu_async(amat=at_mat, jmat=jmat)
         return pre
 
-    nxt = None
+    # the preparation of step k-1 runs in a helper thread while this thread drives the device
+    # work of step k (the C library and numpy/scipy release the GIL)
+    pool = None
+    if can_prefetch:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=1)
+    depth = int(lookahead) if can_prefetch else 0
+    ahead = {}
     for tk in range(len(tmesh)-2, -1, -1):
         t = tmesh[tk]
         cts = tmesh[tk+1] - t
@@ -157,8 +165,10 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
             print('Time is {0}, timestep is {1}'.format(t, cts))
         gtdtstrargs.update(time=t)
         key = get_datastr(**gtdtstrargs)
-        pre = nxt if nxt is not None else prepare(tk)
-        nxt = prepare(tk-1) if (can_prefetch and tk > 0) else None
+        for tj in range(tk-1, max(tk-1-depth, -1), -1):
+            if tj not in ahead:
+                ahead[tj] = pool.submit(prepare, tj)
+        pre = ahead.pop(tk).result() if tk in ahead else prepare(tk)
         nmattd, rhsvtd, NT = pre['nmattd'], pre['rhsvtd'], pre['NT']
 
         cnsw, cnsmtxtb = None, None
@@ -221,4 +231,6 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
             stepinfo.append(info)
         if step_callback is not None:
             step_callback(tk)
+    if pool is not None:
+        pool.shutdown(wait=True)
     return fbdict

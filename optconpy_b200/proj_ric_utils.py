@@ -47,7 +47,7 @@ class ShiftedFactors(object):
     def __init__(self, At, Mt, jmat, ms, Mt_dev=None):
         self.ms = [float(m) for m in ms]
         self.NV, self.NP = At.shape[0], jmat.shape[0]
-        self._job = dv.FactorJob([dv.sadpnt_matrix(At + mu*Mt, jmat) for mu in self.ms])
+        self._job = dv.FactorJob(_shifted_saddle_matrices(At, Mt, jmat, self.ms))
         self._Mt, self._Mt_dev = Mt, Mt_dev
 
     @property
@@ -59,6 +59,48 @@ class ShiftedFactors(object):
         if self._Mt_dev is None:
             self._Mt_dev = dv.DeviceCSR(self._Mt)
         return self._Mt_dev
+
+
+_ASM = dict()
+
+
+def _same_pattern(a, indptr, indices):
+    return (a.nnz == len(indices) and np.array_equal(a.indptr, indptr)
+            and np.array_equal(a.indices, indices))
+
+
+def _shifted_saddle_matrices(At, Mt, jmat, ms):
+    """``[[At + mu Mt, J^T], [J, 0]]`` for every shift.  The block structure is assembled
+    once per (pattern of At, pattern of Mt, J) on the union pattern and cached; per shift and
+    per time step only values are scattered (``sps.bmat`` + a sparse add per matrix otherwise)."""
+    At, Mt = sps.csr_matrix(At), sps.csr_matrix(Mt)
+    for m_ in (At, Mt):
+        m_.sum_duplicates()
+        if not m_.has_sorted_indices:
+            m_.sort_indices()
+    c = _ASM.get('asm')
+    if not (c is not None and c['jmat'] is jmat and _same_pattern(At, c['a_ip'], c['a_ix'])
+            and _same_pattern(Mt, c['m_ip'], c['m_ix'])):
+        ncol = At.shape[1]
+        P = sps.csr_matrix((np.ones(At.nnz), At.indices, At.indptr), shape=At.shape) \
+            + sps.csr_matrix((np.ones(Mt.nnz), Mt.indices, Mt.indptr), shape=Mt.shape)
+        P.sort_indices()
+        rows = lambda m_: np.repeat(np.arange(m_.shape[0], dtype=np.int64), np.diff(m_.indptr))
+        keyP = rows(P)*ncol + P.indices
+        c = dict(jmat=jmat, a_ip=At.indptr.copy(), a_ix=At.indices.copy(),
+                 m_ip=Mt.indptr.copy(), m_ix=Mt.indices.copy(), nnz=P.nnz,
+                 posA=np.searchsorted(keyP, rows(At)*ncol + At.indices),
+                 posM=np.searchsorted(keyP, rows(Mt)*ncol + Mt.indices),
+                 asm=dv.SaddleAssembler(P, jmat))
+        _ASM['asm'] = c
+    out = []
+    base = np.zeros(c['nnz'])
+    base[c['posA']] = At.data
+    for mu in ms:
+        d = base.copy()
+        d[c['posM']] += mu*Mt.data
+        out.append(c['asm'].assemble(d))
+    return out
 
 
 def factors_async(mmat=None, amat=None, jmat=None, nwtn_adi_dict=None, transposed=False, **kw):
