@@ -33,6 +33,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# fewer cudaMalloc/cudaFree (device-synchronising) calls when block sizes vary between steps
+os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')
+
 import numpy as np  # noqa: E402
 
 METRIC = 'dre_backward_steps_per_s'
@@ -50,47 +53,80 @@ def _config(N):
 
 
 class ClockSampler(object):
-    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,' \
-        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
-        'clocks_event_reasons.sw_power_cap'
+    """SM clock + throttle reasons DURING the timed region.  In-process NVML polling thread
+    (a separate ``nvidia-smi -lms`` process was seen to stall driver calls of the benchmark
+    itself for 100+ ms on some boxes); falls back to one nvidia-smi query per sample."""
+    REASONS = dict(hw_slowdown=0x8, sw_thermal_slowdown=0x20, hw_thermal_slowdown=0x40,
+                   sw_power_cap=0x4)
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, period=0.25):
+        self.index, self.period = index, period
+        self.sm, self.smax, self.reasons = [], [], set()
+        self._stop = threading.Event()
+        self.collecting = False
+        self.nvml = None
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '200'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if vis:
+                ids = [v for v in vis.split(',') if v.strip() != '']
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
         except Exception:
-            self.proc = None
+            self.nvml = None
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+            rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            return float(sm), float(mx), [k for k, bit in self.REASONS.items() if rs & bit]
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index),
+                              '--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+                              'clocks_event_reasons.hw_thermal_slowdown,'
+                              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap',
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                             timeout=10).stdout.strip().split(',')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        return float(out[0]), float(out[1]), [nm for nm, v in zip(names, out[2:6])
+                                              if v.strip().lower().startswith('active')]
+
+    def _run(self):
+        while not self._stop.is_set():
+            if self.collecting:
+                try:
+                    sm, mx, rs = self._sample()
+                    self.sm.append(sm)
+                    self.smax.append(mx)
+                    self.reasons.update(rs)
+                except Exception:
+                    pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        self.collecting = True
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
-            f = [x.strip() for x in r.split(',')]
-            if len(f) < 6:
-                continue
+        self.collecting = False
+        self._stop.set()
+        if not self.sm:
             try:
-                sm.append(float(f[0]))
-                smax.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(nm)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None,
-                    sm_max_mhz=float(max(smax)) if smax else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                sm, mx, rs = self._sample()
+                self.sm.append(sm)
+                self.smax.append(mx)
+                self.reasons.update(rs)
+            except Exception:
+                return dict(sm_mhz=None, sm_max_mhz=None, reasons=['clock query unavailable'])
+        return dict(sm_mhz=float(np.median(self.sm)), sm_max_mhz=float(max(self.smax)),
+                    reasons=sorted(self.reasons), samples=len(self.sm),
+                    source='nvml' if self.nvml is not None else 'nvidia-smi')
 
 
 def _measured_peak():
@@ -216,10 +252,12 @@ def main():
     setup_s = time.perf_counter() - t0
     setup_stats = dict(dv.STATS)
     info = []
+    sampler = ClockSampler(local)          # thread + NVML initialised before the warm-up
     for st in setups[:W]:
         dd.run_step(ctx, st, info)
-    sampler = ClockSampler(local)
     barrier()
+    if not os.environ.get('OCB_BENCH_NO_CLOCKS'):
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lib.ocb_prof_enable(1)
     n0 = dv.launch_count()
@@ -289,7 +327,9 @@ def main():
                 import pstats
                 prof = cProfile.Profile()
                 prof.enable()
-            ds.solve_flow_daeric(lau=glau, pru=gpru, store=ds.NpyStore(), step_callback=cb, **kw2)
+            stimes = {}
+            ds.solve_flow_daeric(lau=glau, pru=gpru, store=ds.NpyStore(), step_callback=cb,
+                                 timing=stimes, **kw2)
             if args.phases:
                 prof.disable()
                 pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(45)
@@ -307,6 +347,8 @@ def main():
                        host_setup_per_step={k: (v/S) for k, v in dv.STATS.items()
                                             if k.startswith('lu_') or k == 'n_factor'},
                        lu_workers=dv._POOL['workers'],
+                       main_thread_phase_s_per_step=dict({k: v/S for k, v in dv.PHASE.items()},
+                                                         **{k: v/S for k, v in stimes.items()}),
                        note='LU setup of step k-1 runs in worker processes while the GPU works '
                             'on step k (dre_stepper look-ahead); lu_wait_s is what the main '
                             'process still blocks on')

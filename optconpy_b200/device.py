@@ -18,9 +18,27 @@ from . import _cabi
 STATS = dict(lu_factor_s=0.0,          # SuperLU seconds summed over the workers
              lu_worker_pack_s=0.0,     # host analysis + packing seconds summed over the workers
              lu_submit_s=0.0,          # main process: building + sending the CSC arguments
-             lu_wait_s=0.0,            # main process: blocked on a worker result
+             lu_wait_s=0.0,            # main thread: blocked until the factors are on the device
+             lu_collect_wait_s=0.0,    # collecting thread: blocked on a worker result
              lu_analyse_upload_s=0.0,  # main process: image upload + handle creation
              n_factor=0, h2d_bytes=0, d2h_bytes=0)
+
+# wall seconds of the main thread per phase of the host API (diagnostics, bench.py e2e)
+PHASE = dict()
+
+
+class phase(object):
+    """``with phase('name'):`` adds the wall time of the block to PHASE['name']."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.t0 = time.perf_counter()
+
+    def __exit__(self, *a):
+        PHASE[self.name] = PHASE.get(self.name, 0.0) + time.perf_counter() - self.t0
+        return False
 
 # Host factorisation used for the (separately timed) setup step.  SuperLU with a
 # symmetric-pattern ordering: the saddle-point matrices have symmetric structure,
@@ -49,6 +67,7 @@ def cur_device():
 def reset_stats():
     for k in STATS:
         STATS[k] = 0 if isinstance(STATS[k], int) else 0.0
+    PHASE.clear()
 
 
 def to_dev(arr):
@@ -83,8 +102,16 @@ class Workspace(object):
     def get(self, nbytes):
         nbytes = int(max(nbytes, 256))
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != cur_device():
-            self.buf = torch.empty(int(nbytes*1.25) + 1024, dtype=torch.uint8,
+            import os
+            t0 = time.perf_counter()
+            self.buf = None
+            self.buf = torch.empty(int(nbytes*1.5) + 1024, dtype=torch.uint8,
                                    device=cur_device())
+            if os.environ.get('OCB_DEBUG_WS'):
+                torch.cuda.synchronize()
+                import sys
+                sys.stderr.write('workspace grow to %.1f MB took %.1f ms\n'
+                                 % (self.buf.numel()/1e6, 1e3*(time.perf_counter() - t0)))
         return self.buf
 
 
@@ -169,6 +196,22 @@ def smem_optin():
     return _SMEM_OPTIN[d]
 
 
+_UPLOADER = dict(pool=None)
+
+
+def _uploader_init(device_index):
+    torch.cuda.set_device(device_index)
+    torch.cuda.set_stream(torch.cuda.Stream())      # thread-local: uploads leave the compute stream alone
+
+
+def _uploader():
+    if _UPLOADER['pool'] is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _UPLOADER['pool'] = ThreadPoolExecutor(max_workers=1, initializer=_uploader_init,
+                                               initargs=(torch.cuda.current_device(),))
+    return _UPLOADER['pool']
+
+
 class FactorJob(object):
     """Several host factorisations in flight (worker processes: SuperLU + analysis +
     packing); ``result()`` uploads the images and returns the ``LU`` handles."""
@@ -183,6 +226,7 @@ class FactorJob(object):
         self.n = len(mats)
         pool = _lu_pool()
         self._done = None
+        self._future = None
         if pool is None:
             self._sync = [_lu_worker.factor_image(a) for a in args]
             self._async = None
@@ -192,7 +236,26 @@ class FactorJob(object):
         STATS['lu_submit_s'] += time.perf_counter() - t0
         STATS['n_factor'] += self.n
 
+    def start_upload(self):
+        """Collect the worker results and upload the images from a helper thread on its own
+        CUDA stream (copy engine), so that the main thread does not spend its time in
+        pageable host-to-device copies; ``result()`` then only joins."""
+        import os
+        if self._future is None and self._done is None and not os.environ.get('OCB_NO_UPLOAD_THREAD'):
+            self._future = _uploader().submit(self._collect)
+        return self
+
     def result(self):
+        if self._done is not None:
+            return self._done
+        if self._future is not None:
+            t0 = time.perf_counter()
+            out = self._future.result()
+            STATS['lu_wait_s'] += time.perf_counter() - t0
+            return out
+        return self._collect()
+
+    def _collect(self):
         if self._done is not None:
             return self._done
         out = []
@@ -206,7 +269,7 @@ class FactorJob(object):
             for ar in self._async:
                 t0 = time.perf_counter()
                 name, nbytes, tf, tp = ar.get()
-                STATS['lu_wait_s'] += time.perf_counter() - t0
+                STATS['lu_collect_wait_s'] += time.perf_counter() - t0
                 STATS['lu_factor_s'] += tf
                 STATS['lu_worker_pack_s'] += tp
                 shm = shared_memory.SharedMemory(name=name)
@@ -284,6 +347,7 @@ class LU(object):
         nrows_out = self.n if nrows_out is None else nrows_out
         if out is None:
             out = torch.empty((nrows_out, k), dtype=torch.float64, device=B.device)
+        self.arena.record_stream(torch.cuda.current_stream())
         wsb = lib.ocb_lu_solve_ws_bytes(self.handle, k)
         ws = workspace('lu', wsb) if wsb > 0 else None
         _cabi.check(lib.ocb_lu_solve(self.handle, ptr(B), B.stride(0), B.shape[0],
@@ -298,6 +362,7 @@ class LU(object):
         k = B.shape[1]
         nrows_out = self.n if nrows_out is None else nrows_out
         m = 0 if Ufb is None else Ufb.shape[1]
+        self.arena.record_stream(torch.cuda.current_stream())
         out = torch.empty((nrows_out, k), dtype=torch.float64, device=B.device)
         wsb = lib.ocb_smw_solve_ws_bytes(self.handle, k, m)
         ws = workspace('smw', wsb)
@@ -449,12 +514,19 @@ def adi_run(lus, shifts, NV, NP, Mt, W, maxsteps, reltol, Ufb=None, Vt=None):
     k = W.shape[1]
     m = 0 if Ufb is None else Ufb.shape[1]
     nsh = len(shifts)
-    free, _ = torch.cuda.mem_get_info()
     steps_cap = int(maxsteps)
     need = NV*k*steps_cap*8
-    if need > 0.6*free:
-        steps_cap = max(1, int(0.6*free // (NV*k*8)))
-    Z = torch.empty((NV, k*steps_cap), dtype=torch.float64, device=W.device)
+    if need > (4 << 30):            # only then is the driver asked (the query is not free)
+        free, _ = torch.cuda.mem_get_info()
+        if need > 0.6*free:
+            steps_cap = max(1, int(0.6*free // (NV*k*8)))
+    # the iteration writes into a persistent, monotonically growing buffer (a fresh
+    # 0.4 GB torch.empty per call made the caching allocator cudaMalloc/cudaFree, i.e.
+    # synchronise, whenever the block width changed); the used part is copied out compactly
+    zbuf = workspace('adi_Z', NV*k*steps_cap*8)
+    Z = zbuf[:NV*k*steps_cap*8].view(torch.float64).view(NV, k*steps_cap)
+    for lu in lus:
+        lu.arena.record_stream(torch.cuda.current_stream())
     harr = (C.c_void_p*nsh)(*[lu.handle.value for lu in lus])
     sarr = (C.c_double*nsh)(*[float(s) for s in shifts])
     rel = (C.c_double*int(maxsteps))()
@@ -468,7 +540,7 @@ def adi_run(lus, shifts, NV, NP, Mt, W, maxsteps, reltol, Ufb=None, Vt=None):
         int(min(maxsteps, steps_cap)), float(reltol), ptr(Z), Z.stride(0), Z.shape[1],
         rel, C.byref(nst), ptr(ws), wsb, stream_ptr()), 'ocb_adi_run')
     steps = int(nst.value)
-    return Z[:, :steps*k], [rel[i] for i in range(steps)]
+    return Z[:, :steps*k].contiguous(), [rel[i] for i in range(steps)]
 
 
 def launch_count():

@@ -45,6 +45,10 @@ class DreContext(object):
         self.tct = dv.to_dev(tct)
         self.tb = dv.to_dev(tb)                                  # dense NV x m
         self.tbT = dv.DeviceCSR(self.tb_host.T)                  # m x NV, SMW "V" factor
+        # size the ADI factor buffer for the widest block the recursion can produce, so that no
+        # time step pays for growing it (a 0.5 GB cudaMalloc takes 30-700 ms on a shared box)
+        kmax = (comprz_maxc if comprz_maxc is not None else 64) + self.tct.shape[1] + self.tb.shape[1]
+        dv.workspace('adi_Z', self.NV*kmax*int(self.nwtn_adi_dict['adi_max_steps'])*8)
         mlu = dv.LU(sps.csc_matrix(mmat))
         self.Zc = np.sqrt(gamma)*mlu.solve(self.tct)
         self.mtxtb = dv.feedback(self.Mt_dev, self.Zc, self.tb, alpha=-1.0)
@@ -66,7 +70,7 @@ class StepSetup(object):
         self.fac = pru.ShiftedFactors(sps.csr_matrix(ft_mat), ctx.MT, ctx.J, ctx.shifts,
                                       Mt_dev=ctx.Mt_dev)
         at_mat = ctx.MT + cts*(ctx.AT + NT)
-        self._at_job = dv.FactorJob([dv.sadpnt_matrix(at_mat, ctx.J)])
+        self._at_job = dv.FactorJob([dv.sadpnt_matrix(at_mat, ctx.J)]).start_upload()
         self.ftilde = dv.to_dev(np.asarray(rhsvtd) + ctx.rhsv)
         self.fl1 = dv.to_dev(np.dot(ctx.mcmatT, ctx.ystarvec(t)))
         sq = np.sqrt(cts)

@@ -85,7 +85,7 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
                       get_datastr=None, gtdtstrargs=None,
                       check_c_consist=True,
                       lau=None, pru=None, store=None, verbose=False,
-                      stepinfo=None, step_callback=None, lookahead=2):
+                      stepinfo=None, step_callback=None, lookahead=2, timing=None):
     """Same keyword signature as the reference's ``solve_flow_daeric`` plus
     ``lau``/``pru`` (backend modules), ``store`` and ``stepinfo`` (optional list
     that receives per-step diagnostics).  Returns the ``feedbackthroughdict``
@@ -100,6 +100,21 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         from . import lin_alg_utils as _lau, proj_ric_utils as _pru
         lau, pru = lau or _lau, pru or _pru
     store = NpyStore() if store is None else store
+    if timing is not None:      # wall seconds of this thread: waiting for look-ahead, storage
+        import time as _time
+
+        class _TimedStore(object):
+            def __init__(self, inner):
+                self.inner = inner
+
+            def save(self, arr, fstring):
+                t0 = _time.perf_counter()
+                self.inner.save(arr, fstring)
+                timing['store_s'] = timing.get('store_s', 0.0) + _time.perf_counter() - t0
+
+            def load(self, fstring):
+                return self.inner.load(fstring)
+        store = _TimedStore(store)
     get_datastr = default_datastr if get_datastr is None else get_datastr
     gtdtstrargs = {} if gtdtstrargs is None else gtdtstrargs
     gttdprtargs = {} if gttdprtargs is None else gttdprtargs
@@ -168,7 +183,11 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         for tj in range(tk-1, max(tk-1-depth, -1), -1):
             if tj not in ahead:
                 ahead[tj] = pool.submit(prepare, tj)
+        if timing is not None:
+            _t0 = _time.perf_counter()
         pre = ahead.pop(tk).result() if tk in ahead else prepare(tk)
+        if timing is not None:
+            timing['prepare_wait_s'] = timing.get('prepare_wait_s', 0.0) + _time.perf_counter() - _t0
         nmattd, rhsvtd, NT = pre['nmattd'], pre['rhsvtd'], pre['NT']
 
         cnsw, cnsmtxtb = None, None

@@ -35,7 +35,7 @@ class SadLU(object):
         self.shape = mat.shape
         self._lu = None
         # background=True: the factorisation runs in a worker process, uploaded on first use
-        self._job = dv.FactorJob([mat]) if background else None
+        self._job = dv.FactorJob([mat]).start_upload() if background else None
         if not background:
             self._lu = dv.LU(mat)
 
@@ -129,16 +129,19 @@ def solve_sadpnt_smw(amat=None, jmat=None, rhsv=None, jmatT=None,
     dv.require_cuda()
     NV, nnpp = amat.shape[0], jmat.shape[0]
     rv = _dense(rhsv)
-    alu = sadlu if sadlu is not None else SadLU(dv.sadpnt_matrix(amat, jmat, jmatT))
-    rhs = rv if rhsp is None else np.vstack([rv, _dense(rhsp)])
-    B = dv.to_dev(rhs)
-    if umat is not None:
-        Ufb = dv.to_dev(_dense(umat))
-        Vt = dv.DeviceCSR(sps.csr_matrix(vmat))
-        sol = alu.lu.smw_solve(B, NV, Ufb=Ufb, Vt=Vt)
-    else:
-        sol = alu.lu.solve(B)
-    sol = dv.to_host(sol)
+    with dv.phase('sadpnt_factor_wait_upload'):
+        alu = sadlu if sadlu is not None else SadLU(dv.sadpnt_matrix(amat, jmat, jmatT))
+        alu.lu
+    with dv.phase('sadpnt_solve'):
+        rhs = rv if rhsp is None else np.vstack([rv, _dense(rhsp)])
+        B = dv.to_dev(rhs)
+        if umat is not None:
+            Ufb = dv.to_dev(_dense(umat))
+            Vt = dv.DeviceCSR(sps.csr_matrix(vmat))
+            sol = alu.lu.smw_solve(B, NV, Ufb=Ufb, Vt=Vt)
+        else:
+            sol = alu.lu.solve(B)
+        sol = dv.to_host(sol)
     if return_alu:
         return sol, alu
     return sol

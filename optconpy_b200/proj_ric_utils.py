@@ -26,6 +26,11 @@ __all__ = ['solve_proj_lyap_stein', 'proj_alg_ric_newtonadi', 'compress_Zsvd',
 
 DEFAULT_SHIFTS = [-30.0, -20.0, -10.0, -5.0, -3.0, -1.0]
 
+# the last factor handed back to the caller (host array, device tensor): compress_Zsvd of that
+# very array object skips the re-upload.  Callers must not modify the array in between - the
+# reference never does (solve_dae_ric.py:159-162 passes it straight on).
+_LAST = dict()
+
 
 def _dense(a):
     if sps.issparse(a):
@@ -47,7 +52,7 @@ class ShiftedFactors(object):
     def __init__(self, At, Mt, jmat, ms, Mt_dev=None):
         self.ms = [float(m) for m in ms]
         self.NV, self.NP = At.shape[0], jmat.shape[0]
-        self._job = dv.FactorJob(_shifted_saddle_matrices(At, Mt, jmat, self.ms))
+        self._job = dv.FactorJob(_shifted_saddle_matrices(At, Mt, jmat, self.ms)).start_upload()
         self._Mt, self._Mt_dev = Mt, Mt_dev
 
     @property
@@ -151,12 +156,27 @@ def solve_proj_lyap_stein(amat=None, jmat=None, wmat=None, mmat=None,
     return dict(zfac=dv.to_host(Z), adi_rel_newZ_norms=rel)
 
 
+_CSR_CACHE = dict()
+
+
+def _cached_csr(mat):
+    """DeviceCSR of a host matrix the caller passes again and again (``MT`` in every
+    feedback product): keyed by object identity, validated by the value checksum."""
+    c = _CSR_CACHE.get('m')
+    sig = (id(mat), mat.shape, mat.nnz, float(mat.data.sum()) if mat.nnz else 0.0)
+    if c is None or c[0] != sig:
+        c = (sig, dv.DeviceCSR(mat))
+        _CSR_CACHE['m'] = c
+    return c[1]
+
+
 def get_mTzzTtb(MT, Z, tB, output=None):
     """``M^T (Z (Z^T tB))`` -> dense ndarray (NV, m)."""
     dv.require_cuda()
-    Mt = MT if isinstance(MT, dv.DeviceCSR) else dv.DeviceCSR(MT)
-    out = dv.feedback(Mt, dv.to_dev(Z), dv.to_dev(_dense(tB)))
-    return dv.to_host(out)
+    with dv.phase('feedback'):
+        Mt = MT if isinstance(MT, dv.DeviceCSR) else _cached_csr(MT)
+        out = dv.feedback(Mt, dv.to_dev(Z), dv.to_dev(_dense(tB)))
+        return dv.to_host(out)
 
 
 def _probe_vec(n, nwtn_adi_dict):
@@ -232,15 +252,24 @@ def proj_alg_ric_newtonadi(mmat=None, amat=None, jmat=None,
     fac = kw.get('_factors')
     if fac is None:
         fac = ShiftedFactors(At, Mt, jmat, nwtn_adi_dict.get('ms', DEFAULT_SHIFTS))
-    Bd = dv.to_dev(_dense(bmat))
-    Vt_b = dv.DeviceCSR(sps.csr_matrix(bmat).T)
-    W = dv.to_dev(_dense(wmat))
-    z0d = None if z0 is None else dv.to_dev(z0)
-    old = None if mtxoldb is None else dv.to_dev(_dense(mtxoldb))
-    Z, info = newtonadi_dev(fac, Bd, Vt_b, W, z0d, nwtn_adi_dict, mtxoldb=old)
+    with dv.phase('ric_upload_inputs'):
+        Bd = dv.to_dev(_dense(bmat))
+        Vt_b = dv.DeviceCSR(sps.csr_matrix(bmat).T)
+        W = dv.to_dev(_dense(wmat))
+        z0d = None if z0 is None else dv.to_dev(z0)
+        old = None if mtxoldb is None else dv.to_dev(_dense(mtxoldb))
+    with dv.phase('ric_factor_wait_upload'):
+        fac.lus
+        fac.Mt_dev
+    with dv.phase('ric_newton_adi_device'):
+        Z, info = newtonadi_dev(fac, Bd, Vt_b, W, z0d, nwtn_adi_dict, mtxoldb=old)
+        torch.cuda.current_stream().synchronize()
     if kw.get('_return_device'):
         return dict(zfac=Z, **info)
-    return dict(zfac=dv.to_host(Z), **info)
+    with dv.phase('ric_d2h_factor'):
+        zh = dv.to_host(Z)
+    _LAST['host'], _LAST['dev'] = zh, Z
+    return dict(zfac=zh, **info)
 
 
 def compress_Zsvd(Z, k=None, thresh=None, shplot=False):
@@ -248,11 +277,18 @@ def compress_Zsvd(Z, k=None, thresh=None, shplot=False):
     rank-revealing Cholesky of the Gram matrix, Jacobi eigen-solver and the two
     tall products, all on the device."""
     dv.require_cuda()
-    Zd = Z if isinstance(Z, torch.Tensor) else dv.to_dev(Z)
-    Zc, info = dv.compress(Zd, thresh=thresh, k=k)
-    if isinstance(Z, torch.Tensor):
-        return Zc
-    return dv.to_host(Zc)
+    with dv.phase('compress'):
+        if isinstance(Z, torch.Tensor):
+            Zd = Z
+        elif Z is _LAST.get('host'):
+            Zd = _LAST['dev']          # the factor this module just returned: still in HBM
+        else:
+            Zd = dv.to_dev(Z)
+        _LAST.clear()
+        Zc, info = dv.compress(Zd, thresh=thresh, k=k)
+        if isinstance(Z, torch.Tensor):
+            return Zc
+        return dv.to_host(Zc)
 
 
 def comp_proj_lyap_res_norm(Z, amat=None, mmat=None, wmat=None, jmat=None,
