@@ -149,7 +149,7 @@ def _ncu_traffic():
     return None
 
 
-def run_reference(args):
+def run_reference(args, out_stream):
     """The reference's CPU implementation of the path: the scipy/SuperLU oracle (the
     reference's own sadptprj_riclyap_adi is absent), all host threads it can use
     (SuperLU solves are serial; numpy parts use the BLAS threads)."""
@@ -182,7 +182,8 @@ def run_reference(args):
     done = len(stamps) - 1
     timed = done - args.warmup
     if timed <= 0:
-        print(json.dumps(dict(impl='reference', unavailable='no timed step finished in budget')))
+        out_stream.write(json.dumps(dict(impl='reference', unavailable='no timed step finished in budget')) + '\n')
+        out_stream.flush()
         return
     el = stamps[-1] - stamps[args.warmup]
     val = timed/el
@@ -199,10 +200,21 @@ def run_reference(args):
                                       'dense parts use the BLAS threads'),
                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
-    print(json.dumps(out))
+    out_stream.write(json.dumps(out) + '\n')
+    out_stream.flush()
+
+
+def _quiet_stdout():
+    """Library chatter (NCCL's version banner, ...) must not share stdout with the ONE JSON
+    line: route fd 1 to stderr for the run and return a file on the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, 'w')
 
 
 def main():
+    out_stream = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=8)
@@ -215,7 +227,7 @@ def main():
     ap.add_argument('--phases', action='store_true', help='extra untimed pass with per-phase CUDA events + cProfile of the e2e loop (diagnostics on stderr)')
     args = ap.parse_args()
     if args.impl == 'reference':
-        return run_reference(args)
+        return run_reference(args, out_stream)
 
     import torch
     import torch.distributed as dist
@@ -392,7 +404,8 @@ def main():
                    steps_info=[dict(tau=float(i['tau']), adi_steps=i['adi_steps'],
                                     zp_cols=i['zp_cols'], zc_cols=i['zc_cols']) for i in info[W:]])
         out.pop('rhs_columns_per_s')
-        print(json.dumps(out))
+        out_stream.write(json.dumps(out) + '\n')
+        out_stream.flush()
     if world > 1:
         dist.destroy_process_group()
 

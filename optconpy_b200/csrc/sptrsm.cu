@@ -149,6 +149,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         "r"(parity)
         : "memory");
 }
+// remote store whose completion is counted (8 bytes) on an mbarrier of the destination CTA:
+// data and signal travel together, no fence on the sender
+__device__ __forceinline__ void st_async_f64(uint32_t addr, double v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(addr),
+                 "l"(__double_as_longlong(v)), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -211,7 +218,9 @@ __global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(cons
             mbar_init(full + s, 1);
             mbar_init(empty + s, nwarps);
         }
-        mbar_init(lvlbar, CL);
+        mbar_init(lvlbar, 1);       // level barriers (parity of the sub-level): 1 arrival + tx bytes
+        mbar_init(lvlbar + 1, 1);
+        mbar_init(lvlbar + 2, CL);  // start barrier (panel copies loaded everywhere)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -251,8 +260,12 @@ __global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(cons
     if (CL == 1) {
         asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
     } else {   // nobody may write results into a panel copy that is still being loaded
-        cluster_level_barrier<CL>(lvlbar, lvl_phase, ncons, tid);
+        cluster_level_barrier<CL>(lvlbar + 2, lvl_phase, ncons, tid);
     }
+    uint32_t lvl_idx = 0;          // sub-level counter: barrier lvlbar[lvl_idx & 1], phase (lvl_idx >> 1) & 1
+    uint32_t barbase[CL];          // the two level barriers of every rank (cluster addresses)
+#pragma unroll
+    for (int r = 0; r < CL; ++r) barbase[r] = CL > 1 ? mapa_u32(smem_u32(lvlbar), r) : 0;
     if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[trace_n++] = clock64();
     for (int b = 0; b < nbatch; ++b) {
         const int s = b % S;
@@ -355,19 +368,40 @@ __global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(cons
 #pragma unroll
                         for (int c = 0; c < KP; ++c) xd[c] = res[c];
                     } else {
+                        // every rank gets the result; each 8-byte store is counted on the level
+                        // barrier of its destination, which expects rows * KP * 8 bytes
                         const uint32_t o = (uint32_t)di * (KP * 8);
+                        const uint32_t bo = (lvl_idx & 1) * 8;
 #pragma unroll
                         for (int r = 0; r < CL; ++r)
 #pragma unroll
-                            for (int c = 0; c < KP; ++c) st_cluster_f64(xbase[r] + o + c * 8, res[c]);
+                            for (int c = 0; c < KP; ++c)
+                                st_async_f64(xbase[r] + o + c * 8, res[c], barbase[r] + bo);
                     }
                 }
             }
             if (pd.z) {
                 if (CL == 1) {
                     asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
-                } else {   // cluster-wide sub-level barrier among the consumer warps
-                    cluster_level_barrier<CL>(lvlbar, lvl_phase, ncons, tid);
+                } else {
+                    // cluster-wide sub-level barrier: the barrier of this CTA completes when all
+                    // pd.w rows of the sub-level (computed by whichever rank) have landed here
+                    // (pd.w: rows of the sub-level | ranks without a row << 24).  A rank without
+                    // rows sends an 8-byte TOKEN instead, so that every rank contributes to every
+                    // barrier: nobody can run more than one sub-level ahead of anybody else, which
+                    // is what makes two alternating barriers (and the y scratch parity) safe.
+                    uint64_t* bar = lvlbar + (lvl_idx & 1);
+                    if (tid == 0) {
+                        if (pd.x == pd.y) {
+                            const uint32_t bo = (lvl_idx & 1) * 8;
+#pragma unroll
+                            for (int r = 0; r < CL; ++r)
+                                st_async_f64(xbase[r] + (uint32_t)a.n_ext * (KP * 8), 0.0, barbase[r] + bo);
+                        }
+                        mbar_expect_tx(bar, (uint32_t)(pd.w & 0xffffff) * (KP * 8) + (uint32_t)(pd.w >> 24) * 8);
+                    }
+                    mbar_wait_cluster(bar, (lvl_idx >> 1) & 1);
+                    ++lvl_idx;
                 }
                 if (a.trace && blockIdx.x == 0 && tid == 0 && trace_n < 4000) a.trace[trace_n++] = clock64();
             }
@@ -402,6 +436,7 @@ static int64_t record_bytes(int64_t npiece, int64_t nslice, int64_t nrows, int64
 
 struct Piece {   // slices [s0, s1) of one sub-level placed in a batch
     int32_t s0, s1, barrier;
+    int32_t rows_total;   // rows of the whole sub-level over all ranks (level barrier byte count)
 };
 
 static inline int slice_rows(const Slice& sl) { return sl.glog_nrows >> 8; }
@@ -424,9 +459,14 @@ static bool plan_batches(const LuProgram& P, int64_t cap, int rank, int cl,
     for (int64_t sb = 0; sb < P.nsub(); ++sb) {
         int32_t s = P.sub_ptr[sb] + rank;
         const int32_t send = P.sub_ptr[sb + 1];
+        int32_t rows_total = 0;
+        for (int32_t q = P.sub_ptr[sb]; q < send; ++q) rows_total += slice_rows(P.slices[q]);
+        const int32_t nslices_sub = send - P.sub_ptr[sb];
+        const int32_t n_empty = std::max(0, cl - nslices_sub);   // ranks r >= nslices_sub own no slice
+        rows_total |= n_empty << 24;
         if (s >= send) {   // nothing for this rank: it still takes part in the barrier
             if (record_bytes((int64_t)cur.size() + 1, nsl, rows, ent) > cap) flush();
-            cur.push_back(Piece{s, s, 1});
+            cur.push_back(Piece{s, s, 1, rows_total});
             continue;
         }
         while (s < send) {
@@ -445,7 +485,7 @@ static bool plan_batches(const LuProgram& P, int64_t cap, int rank, int cl,
                 flush();
                 continue;
             }
-            cur.push_back(Piece{s, s2, (s2 >= send) ? 1 : 0});
+            cur.push_back(Piece{s, s2, (s2 >= send) ? 1 : 0, rows_total});
             nsl = n2;
             rows = r2;
             ent = e2;
@@ -512,7 +552,7 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl
         piece[4 * pi + 0] = ls;
         piece[4 * pi + 1] = ls + cnt;
         piece[4 * pi + 2] = p.barrier;
-        piece[4 * pi + 3] = 0;
+        piece[4 * pi + 3] = p.barrier ? p.rows_total : 0;
         for (int32_t s = p.s0; s < p.s1; s += cl, ++ls) {
             const Slice& sl = P.slices[s];
             const int nr = slice_rows(sl), ne = sl.trips * 32;
@@ -543,7 +583,7 @@ enum { M_MAGIC = 0, M_TOTAL, M_N, M_NEXT, M_NNZL, M_NNZU, M_NSUBL, M_NSUBU, M_NS
 static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t* h_perm_c,
                       int max_smem_optin, unsigned char** img_out, int64_t* bytes_out) {
     const int64_t smem_cap = (int64_t)max_smem_optin - 1024 - 192;
-    const int64_t xe1 = P.n_ext * 8;   // bytes of a one-column panel
+    const int64_t xe1 = (P.n_ext + 1) * 8;   // bytes of a one-column panel (+ the token slot)
     int kp_smem = 0, nst = 3, cl = 4;
     int64_t cap = 0;
     const char* env = getenv("OCB_SPTRSM_FORCE_GLOBAL");
@@ -678,7 +718,7 @@ static int upload_image(ocb_lu* lu, const unsigned char* img, int64_t bytes, voi
 template <int KP, bool XG, int CL>
 static int launch_stream(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 192 +
-                        (XG ? 0 : (size_t)lu->n_ext * KP * sizeof(double));
+                        (XG ? 0 : (size_t)(lu->n_ext + 1) * KP * sizeof(double));
     OCB_CUDA(cudaFuncSetAttribute(sptrsm_stream_kernel<KP, XG, CL>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned npanels = (unsigned)((a.k + KP - 1) / KP);
@@ -707,7 +747,7 @@ static int max_clusters(const ocb_lu* lu) {
     static int cache[9] = {0};
     const int slot = KP;   // per (KP, CL) instantiation; shared memory is the same for one problem size
     if (cache[slot] > 0) return cache[slot];
-    const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 192 + (size_t)lu->n_ext * KP * sizeof(double);
+    const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 192 + (size_t)(lu->n_ext + 1) * KP * sizeof(double);
     cudaFuncSetAttribute(sptrsm_stream_kernel<KP, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
     cudaLaunchConfig_t cfg;

@@ -167,7 +167,7 @@ def _lu_pool():
     want = os.environ.get('OCB_LU_WORKERS')
     if want is None:
         world = int(os.environ.get('WORLD_SIZE', '1'))
-        want = max(1, min(14, (os.cpu_count() or 1) - 2)//max(world, 1))
+        want = max(2, min(14, (os.cpu_count() or 1) - 2)//max(world, 1))
     want = int(want)
     if want <= 1:
         return None
@@ -540,7 +540,9 @@ def adi_run(lus, shifts, NV, NP, Mt, W, maxsteps, reltol, Ufb=None, Vt=None):
         int(min(maxsteps, steps_cap)), float(reltol), ptr(Z), Z.stride(0), Z.shape[1],
         rel, C.byref(nst), ptr(ws), wsb, stream_ptr()), 'ocb_adi_run')
     steps = int(nst.value)
-    return Z[:, :steps*k].contiguous(), [rel[i] for i in range(steps)]
+    # clone, not contiguous(): when the iteration used the whole buffer the slice IS contiguous
+    # and contiguous() would hand out a view of the workspace that the next call overwrites
+    return Z[:, :steps*k].clone(memory_format=torch.contiguous_format), [rel[i] for i in range(steps)]
 
 
 def launch_count():

@@ -201,3 +201,39 @@ def test_device_resident_loop_matches_host_api(mods):
     assert _relerr(dv.to_host(ctx.mtxtb), sg[fg[t0]['mtxtb']]) < 1e-10
     assert _relerr(dv.to_host(ctx.wc), sg[fg[t0]['w']]) < 1e-10
     assert _zzt_relerr(dv.to_host(ctx.Zc), sg[fg[t0]['mtxtb'].replace('__mtxtb', '__Z')]) < 1e-10
+
+
+def test_steady_state_branch_parity(mods):
+    """Config 3 (cyl_wake_cont.py params on the synthetic channel, coarse): the steady-state
+    branch optcont_main.py:488-514 - Newton-ADI from z0=None with the built-in shift list,
+    gain and feed-forward - CUDA modules against the oracle."""
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import scenarios as sc
+    prob, cs, kw = sc.config3(olau, nx=22, ny=8, nu=2e-2)
+    kw['nwtn_adi_dict'] = dict(kw['nwtn_adi_dict'], adi_max_steps=120, nwtn_max_steps=8)
+    ro = sc.steady_state_feedback(prob, cs, lau=olau, pru=opru, **kw)
+    rg = sc.steady_state_feedback(prob, cs, lau=glau, pru=gpru, **kw)
+    assert rg['info']['adi_steps'] == ro['info']['adi_steps']
+    assert _zzt_relerr(rg['Z'], ro['Z']) < TOL_FACTOR
+    assert _relerr(rg['mtxtb'], ro['mtxtb']) < TOL_FACTOR
+    assert _relerr(rg['w'], ro['w']) < TOL_TRAJ
+    # compressed variant (optcont_main.py:497-500)
+    rgc = sc.steady_state_feedback(prob, cs, lau=glau, pru=gpru, compress=(5e-5, 100), **kw)
+    roc = sc.steady_state_feedback(prob, cs, lau=olau, pru=opru, compress=(5e-5, 100), **kw)
+    assert rgc['Z'].shape == roc['Z'].shape
+    assert _relerr(rgc['mtxtb'], roc['mtxtb']) < 1e-7     # truncation at 5e-5 bounds the agreement
+
+
+def test_lookahead_does_not_change_results(mods):
+    """The background LU setup of later steps (dre_stepper look-ahead) is numerically inert."""
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import scenarios as sc, dre_stepper as ds
+    prob, cs, kw = sc.config1(glau, Nts=3)
+    s0, s2 = ds.MemStore(), ds.MemStore()
+    f0 = ds.solve_flow_daeric(lau=glau, pru=gpru, store=s0, lookahead=0,
+                              **dict(kw, gtdtstrargs=dict(kw['gtdtstrargs'])))
+    f2 = ds.solve_flow_daeric(lau=glau, pru=gpru, store=s2, lookahead=2,
+                              **dict(kw, gtdtstrargs=dict(kw['gtdtstrargs'])))
+    for t in f0:
+        assert np.array_equal(s0[f0[t]['mtxtb']], s2[f2[t]['mtxtb']])
+        assert np.array_equal(s0[f0[t]['w']], s2[f2[t]['w']])
