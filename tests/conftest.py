@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# small dense problems: a full-width BLAS thread pool only thrashes (the CPU suite ran 3x
+# slower with 8-16 threads than with 2-4)
+os.environ.setdefault('OMP_NUM_THREADS', '4')
+os.environ.setdefault('OPENBLAS_NUM_THREADS', '4')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -22,3 +27,14 @@ def cav10():
 def cav6():
     from optconpy_b200 import problems as pb
     return pb.drivcav_problem(6, 1e-2)
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _limit_blas_threads():
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:
+        yield
+        return
+    with threadpool_limits(limits=4):
+        yield
