@@ -204,6 +204,55 @@ def run_reference(args, out_stream):
     out_stream.flush()
 
 
+def run_sweep(meshes, ks, reps, rank, world, peak_gbs):
+    """Second half of the BASELINE metric: multi-RHS saddle-point solves/s on synthetic Oseen
+    saddle-point matrices (at the sizes that fit the run time): one
+    application of ``[[F^T + mu M^T, J^T], [J, 0]]^-1`` to an n x k block, inputs resident.
+    With N ranks the k columns are sharded (no collective); times are the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from optconpy_b200 import problems as pb, device as dv, parallel as par
+    out = []
+    for N in meshes:
+        prob = pb.drivcav_problem(N, 5e-3)
+        M, A, J = prob['M'], prob['A'], prob['J']
+        Nc = pb.convection_matrix(prob, pb.analytic_vortex)
+        K = dv.sadpnt_matrix(-(0.5*M.T + 2e-3*(A.T + Nc.T)) - 1.0*M.T, J)
+        t0 = time.perf_counter()
+        lu = dv.LU(K, wide=True)
+        tsetup = time.perf_counter() - t0
+        n = K.shape[0]
+        for k in ks:
+            c0, c1 = par.column_slice(k, rank, world)
+            kl = max(c1 - c0, 1)
+            B = torch.randn((n, kl), dtype=torch.float64, device='cuda')
+            X = lu.solve(B)
+            res = float(torch.linalg.norm(dv.DeviceCSR(K).matmul(X) - B)/torch.linalg.norm(B))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                lu.solve(B, out=X)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)/reps
+            t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            i = lu.info
+            ab = 12*(i['nnzL'] + i['nnzU']) + 16*(n + 1) + 32*n*k
+            fl = 2.0*(i['nnzL'] + i['nnzU'])*k
+            out.append(dict(mesh_N=N, n=n, k=k, nnz_LU=int(i['nnzL'] + i['nnzU']),
+                            sublevels=int(i['levelsL'] + i['levelsU']), ms_per_solve=ms,
+                            solves_per_s=1e3/ms, rhs_columns_per_s=1e3*k/ms,
+                            alg_GBs=ab/ms/1e6, frac_hbm=ab/ms/1e6/peak_gbs,
+                            fp64_TFs=fl/ms/1e9, residual=res, setup_s=tsetup,
+                            executor='wide' if (i['stream_kp'] == 0 or k//world >= 640) else 'cluster'))
+        del lu
+    return out
+
+
 def _quiet_stdout():
     """Library chatter (NCCL's version banner, ...) must not share stdout with the ONE JSON
     line: route fd 1 to stderr for the run and return a file on the real stdout."""
@@ -224,6 +273,8 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=2)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--sweep-meshes', default='50', help='comma list of cavity meshes for the saddle-solve sweep ("" = skip)')
+    ap.add_argument('--sweep-k', default='64,256,1024')
     ap.add_argument('--phases', action='store_true', help='extra untimed pass with per-phase CUDA events + cProfile of the e2e loop (diagnostics on stderr)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -386,6 +437,11 @@ def main():
                           'lu.solve); the terminal-value solve is included' % nc,
                    seconds=el, saddle_solves=sum(i['solves'] for i in gsame))
 
+    sweep = None
+    if args.sweep_meshes:
+        sweep = run_sweep([int(v) for v in args.sweep_meshes.split(',')],
+                          [int(v) for v in args.sweep_k.split(',')], 5, rank, world, peak)
+
     if rank == 0:
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W,
                    ms_per_step=ms_max/K, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -399,6 +455,7 @@ def main():
                                    'value, included in e2e; lu_factor_s / lu_worker_pack_s are '
                                    'summed over the workers'),
                    saddle_solves_per_s=solves/(ms_max*1e-3),
+                   saddle_sweep=sweep,
                    rhs_columns_per_s=sum(sum(a)*0 for a in []) or None,
                    step_ms=step_ms,
                    steps_info=[dict(tau=float(i['tau']), adi_steps=i['adi_steps'],

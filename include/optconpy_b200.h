@@ -66,14 +66,16 @@ int ocb_lu_destroy(ocb_lu* lu);
 /* The same in two halves, so that the analysis can run where the host LU ran (a worker
  * process without a CUDA context): ocb_lu_pack_host builds the self-describing device image
  * (malloc'ed; release with ocb_host_free) for a GPU with max_smem_optin bytes of opt-in shared
- * memory per block; ocb_lu_create_from_image uploads it with one copy into d_arena (bytes long,
+ * memory per block (flags bit 0: also include the flat program of the wide, all-columns-at-once
+ * executor that ocb_lu_solve uses for k >= 640 right-hand sides; it is always included when
+ * the column panel does not fit shared memory); ocb_lu_create_from_image uploads it with one copy into d_arena (bytes long,
  * 256-byte aligned, owned by the caller and kept alive until ocb_lu_destroy; NULL: the library
  * allocates and frees its own). */
 int ocb_lu_pack_host(int64_t n,
                      const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
                      const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
                      const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin,
-                     unsigned char** out_image, int64_t* out_bytes);
+                     int64_t flags, unsigned char** out_image, int64_t* out_bytes);
 void ocb_host_free(void* p);
 int ocb_lu_create_from_image(ocb_lu** out, const unsigned char* h_image, int64_t bytes,
                              void* d_arena, void* stream);
@@ -111,8 +113,8 @@ int ocb_lu_program_info(const ocb_lu_program* prog, int64_t* info12);
 int ocb_lu_program_export(const ocb_lu_program* prog, int32_t* h_sub_ptr, int32_t* h_slice4,
                           int32_t* h_dst, int32_t* h_init, double* h_scale,
                           int32_t* h_col, double* h_val);
-/* bytes of device workspace ocb_lu_solve needs for k right-hand sides (0 if the
- * column panel fits shared memory) */
+/* bytes of device workspace ocb_lu_solve needs for k right-hand sides (0 when the column-panel
+ * kernel is used; n_ext x roundup(k) doubles for the wide executor) */
 int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k);
 /* X[0:nrows_x, 0:k] = (A^-1 [B[0:nrows_b, 0:k]; 0])[0:nrows_x].  B and X may alias. */
 int ocb_lu_solve(const ocb_lu* lu, const double* d_B, int64_t ldb, int64_t nrows_b,

@@ -18,7 +18,7 @@ PROTOTYPES = {
                            C.c_double, C.c_double, vp]),
     'ocb_lu_create': (C.c_int, [C.POINTER(vp), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     'ocb_lu_destroy': (C.c_int, [vp]),
-    'ocb_lu_pack_host': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i64,
+    'ocb_lu_pack_host': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64,
                                    C.POINTER(vp), C.POINTER(i64)]),
     'ocb_host_free': (None, [vp]),
     'ocb_lu_create_from_image': (C.c_int, [C.POINTER(vp), vp, i64, vp, vp]),

@@ -34,12 +34,13 @@ class _CImage(object):
     """Device image in a C buffer (``ocb_lu_pack_host``); ``view`` is a uint8 numpy view,
     ``free()`` releases it."""
 
-    def __init__(self, arrs, n, smem_optin):
+    def __init__(self, arrs, n, smem_optin, flags=0):
         from optconpy_b200 import _cabi
         self._lib = _cabi.load()
         img, nbytes = C.c_void_p(), C.c_int64(0)
         _cabi.check(self._lib.ocb_lu_pack_host(n, *[a.ctypes.data for a in arrs], int(smem_optin),
-                                               C.byref(img), C.byref(nbytes)), 'ocb_lu_pack_host')
+                                               int(flags), C.byref(img), C.byref(nbytes)),
+                    'ocb_lu_pack_host')
         self._ptr = img
         self.view = np.ctypeslib.as_array(C.cast(img, C.POINTER(C.c_uint8)), shape=(nbytes.value,))
 
@@ -50,9 +51,9 @@ class _CImage(object):
             self._ptr = None
 
 
-def pack_image(arrs, n, smem_optin):
+def pack_image(arrs, n, smem_optin, flags=0):
     """Host half of ``ocb_lu_create``: returns the device image as a uint8 array."""
-    ci = _CImage(arrs, n, smem_optin)
+    ci = _CImage(arrs, n, smem_optin, flags)
     try:
         return ci.view.copy()
     finally:
@@ -65,7 +66,7 @@ def factor_image(args):
     t0 = time.perf_counter()
     arrs = factor_arrays(args)
     t1 = time.perf_counter()
-    img = pack_image(arrs, args[3][0], args[5])
+    img = pack_image(arrs, args[3][0], args[5], args[6] if len(args) > 6 else 0)
     return img, t1 - t0, time.perf_counter() - t1
 
 
@@ -77,7 +78,7 @@ def factor_image_to_shm(args):
     t0 = time.perf_counter()
     arrs = factor_arrays(args)
     t1 = time.perf_counter()
-    ci = _CImage(arrs, args[3][0], args[5])
+    ci = _CImage(arrs, args[3][0], args[5], args[6] if len(args) > 6 else 0)
     try:
         nbytes = ci.view.nbytes
         shm = shared_memory.SharedMemory(create=True, size=max(nbytes, 64))

@@ -40,8 +40,15 @@ struct ocb_lu {
     int nbatch[8] = {0};
     int64_t bytes = 0;
     int stage_bytes = 0, nstages = 0;
-    int kp_smem_max = 0;              // widest panel that fits shared memory next to the ring (0: global slab)
+    int kp_smem_max = 0;              // widest panel that fits shared memory next to the ring (0: none)
     int max_smem_optin = 0;
+    // flat program for the wide (all columns at once, one launch per sub-level) executor
+    bool has_flat = false;
+    const int4* f_slices = nullptr;
+    const int32_t *f_rowslice = nullptr, *f_dst = nullptr, *f_init = nullptr, *f_col = nullptr;
+    const double *f_scale = nullptr, *f_val = nullptr;
+    std::vector<int32_t> sub_row;     // host: first program row of every sub-level (nsub + 1)
+    std::vector<int32_t> sub_maxlen;  // host: longest (padded) row of every sub-level
 };
 
 namespace ocb {
@@ -56,7 +63,6 @@ static int trsm_threads() {
     }
     return t;
 }
-constexpr int KP_GLOBAL = 8;          // panel width when xe lives in a global slab
 
 struct SolveArgs {
     const int32_t *perm_r, *perm_c;
@@ -184,14 +190,13 @@ __device__ __forceinline__ void issue_batch(unsigned char* dst, const unsigned c
         bulk_g2s(dst + o, src + o, min(chunk, bytes - o), bar);
 }
 
-// XG = false: xe panel in shared memory;  XG = true: per-CTA slab in global memory (large n)
 // CL > 1: a thread-block CLUSTER of CL CTAs owns one column panel.  The slices of every
 // sub-level are dealt to the CL ranks, so each CTA streams and gathers only 1/CL of the
 // program; every CTA keeps a full copy of the panel xe in its shared memory, results are
 // written to all CL copies through distributed shared memory (st.shared::cluster) and the
 // sub-level barrier is an mbarrier in every CTA that all consumer warps of the cluster
 // arrive on (release/acquire at cluster scope).
-template <int KP, bool XG, int CL>
+template <int KP, int CL>
 __global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(const SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [ring: nstages * stage_bytes][mbarriers full/empty/level: 192 bytes][xe panel: n_ext*KP doubles]
@@ -201,8 +206,7 @@ __global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(cons
     uint64_t* lvlbar = full + 16;
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
     const int64_t panel = (int64_t)blockIdx.x / CL;
-    double* x = XG ? a.ws + (size_t)panel * a.n_ext * KP
-                   : (double*)(smem_raw + (size_t)a.nstages * a.stage_bytes + 192);
+    double* x = (double*)(smem_raw + (size_t)a.nstages * a.stage_bytes + 192);
     const int tid = threadIdx.x;
     // the last warp is the PRODUCER (feeds the ring with TMA bulk copies, runs ahead of the
     // consumers); all other warps are consumers and synchronise among themselves only
@@ -574,14 +578,16 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl
 // Self-describing host image of a factorisation: [meta int64[32]] perm_r | perm_c | batch
 // offsets | batch stream.  Built without any CUDA call (worker processes build it next to the
 // host LU); ocb_lu_create_from_image uploads it with one allocation and one copy.
-constexpr int64_t IMG_MAGIC = 0x4f43424c55303032LL;   // "OCBLU002"
+constexpr int64_t IMG_MAGIC = 0x4f43424c55303033LL;   // "OCBLU003"
 enum { M_MAGIC = 0, M_TOTAL, M_N, M_NEXT, M_NNZL, M_NNZU, M_NSUBL, M_NSUBU, M_NSUPER, M_MAXW, M_NSLICE,
-       M_NROWS, M_NENT, M_OPR, M_OPC, M_CL, M_STAGEB, M_NSTAGES, M_KPSMEM,
-       M_OBO = 24, M_OST = 32, M_NBATCH = 40, M_COUNT = 48 };   // OBO/OST/NBATCH: one slot per cluster rank
+       M_NROWS, M_NENT, M_OPR, M_OPC, M_CL, M_STAGEB, M_NSTAGES, M_KPSMEM, M_FLAT, M_NSUB,
+       M_OBO = 24, M_OST = 32, M_NBATCH = 40,                  // one slot per cluster rank
+       M_F_SLICE = 48, M_F_ROWSLICE, M_F_DST, M_F_INIT, M_F_SCALE, M_F_COL, M_F_VAL, M_F_SUBROW,
+       M_COUNT = 64 };
 
 // choose ring geometry + panel placement and pack the image
 static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t* h_perm_c,
-                      int max_smem_optin, unsigned char** img_out, int64_t* bytes_out) {
+                      int max_smem_optin, int flags, unsigned char** img_out, int64_t* bytes_out) {
     const int64_t smem_cap = (int64_t)max_smem_optin - 1024 - 192;
     const int64_t xe1 = (P.n_ext + 1) * 8;   // bytes of a one-column panel (+ the token slot)
     int kp_smem = 0, nst = 3, cl = 4;
@@ -611,19 +617,11 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         cap = std::min<int64_t>(left / nst, want) & ~(int64_t)15;
         if (plan_all(cap, cl)) kp_smem = kps[ki];
     }
-    if (kp_smem == 0) {   // panel in a global slab: one CTA per panel, the ring gets the shared memory
-        cl = 1;
-        nst = 3;
-        cap = std::min<int64_t>(smem_cap / 3, 64 * 1024) & ~(int64_t)15;
-        if (!plan_all(cap, 1)) {
-            nst = 2;
-            cap = (smem_cap / 2) & ~(int64_t)15;
-            if (!plan_all(cap, 1)) {
-                set_error("lu_create: a factor row does not fit the shared-memory ring");
-                return OCB_ERR_CAPACITY;
-            }
-        }
+    if (kp_smem == 0) {   // the panel does not fit shared memory: only the wide executor applies
+        cl = 0;
+        for (int r = 0; r < 8; ++r) batches[r].clear();
     }
+    const bool want_flat = (flags & 1) || kp_smem == 0;
     std::vector<int64_t> off[8];
     int64_t maxb = 16;
     for (int r = 0; r < cl; ++r) {
@@ -645,6 +643,16 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
     for (int r = 0; r < cl; ++r) {
         o_st[r] = o;
         o = align_up(o + std::max<int64_t>(off[r].back(), 16), 256);
+    }
+    // flat program (wide executor): slices | row -> slice | dst | init | scale | col | val | sub rows
+    const int64_t nsl = (int64_t)P.slices.size(), nr = P.nrows(), ne = P.nent(), nsub = P.nsub();
+    int64_t o_f[8] = {0};
+    if (want_flat) {
+        const int64_t sz[8] = {nsl * 16, nr * 4, nr * 4, nr * 4, nr * 8, ne * 4, ne * 8, 2 * (nsub + 1) * 4};
+        for (int i = 0; i < 8; ++i) {
+            o_f[i] = o;
+            o = align_up(o + std::max<int64_t>(sz[i], 16), 256);
+        }
     }
     const int64_t total = o;
     unsigned char* img = (unsigned char*)calloc((size_t)total, 1);   // zero pages on demand
@@ -673,6 +681,29 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         memcpy(img + o_bo[r], off[r].data(), off[r].size() * 8);
         for (size_t b = 0; b < batches[r].size(); ++b)
             write_record(P, batches[r][b], cl, img + o_st[r] + off[r][b]);
+    }
+    meta[M_FLAT] = want_flat ? 1 : 0;
+    meta[M_NSUB] = nsub;
+    if (want_flat) {
+        for (int i = 0; i < 8; ++i) meta[M_F_SLICE + i] = o_f[i];
+        memcpy(img + o_f[0], P.slices.data(), (size_t)nsl * 16);
+        int32_t* rowslice = (int32_t*)(img + o_f[1]);
+        for (int64_t sidx = 0; sidx < nsl; ++sidx)
+            for (int r = 0; r < slice_rows(P.slices[sidx]); ++r) rowslice[P.slices[sidx].q0 + r] = (int32_t)sidx;
+        memcpy(img + o_f[2], P.dst.data(), (size_t)nr * 4);
+        memcpy(img + o_f[3], P.init.data(), (size_t)nr * 4);
+        memcpy(img + o_f[4], P.scale.data(), (size_t)nr * 8);
+        memcpy(img + o_f[5], P.col.data(), (size_t)ne * 4);
+        memcpy(img + o_f[6], P.val.data(), (size_t)ne * 8);
+        int32_t* subrow = (int32_t*)(img + o_f[7]);
+        for (int64_t sb = 0; sb < nsub; ++sb)
+            subrow[sb] = P.sub_ptr[sb] < nsl ? P.slices[P.sub_ptr[sb]].q0 : (int32_t)nr;
+        subrow[nsub] = (int32_t)nr;
+        int32_t* submax = subrow + nsub + 1;   // the first slice of a sub-level holds its longest row
+        for (int64_t sb = 0; sb < nsub; ++sb) {
+            const Slice& f = P.slices[P.sub_ptr[sb]];
+            submax[sb] = P.sub_ptr[sb] < nsl ? (f.trips << (f.glog_nrows & 255)) : 0;
+        }
     }
     return OCB_OK;
 }
@@ -712,17 +743,30 @@ static int upload_image(ocb_lu* lu, const unsigned char* img, int64_t bytes, voi
     lu->stage_bytes = (int)meta[M_STAGEB];
     lu->nstages = (int)meta[M_NSTAGES];
     lu->kp_smem_max = (int)meta[M_KPSMEM];
+    lu->has_flat = meta[M_FLAT] != 0;
+    if (lu->has_flat) {
+        lu->f_slices = (const int4*)(lu->arena + meta[M_F_SLICE]);
+        lu->f_rowslice = (const int32_t*)(lu->arena + meta[M_F_ROWSLICE]);
+        lu->f_dst = (const int32_t*)(lu->arena + meta[M_F_DST]);
+        lu->f_init = (const int32_t*)(lu->arena + meta[M_F_INIT]);
+        lu->f_scale = (const double*)(lu->arena + meta[M_F_SCALE]);
+        lu->f_col = (const int32_t*)(lu->arena + meta[M_F_COL]);
+        lu->f_val = (const double*)(lu->arena + meta[M_F_VAL]);
+        const int32_t* sr = (const int32_t*)(img + meta[M_F_SUBROW]);
+        lu->sub_row.assign(sr, sr + meta[M_NSUB] + 1);
+        lu->sub_maxlen.assign(sr + meta[M_NSUB] + 1, sr + 2 * meta[M_NSUB] + 1);
+    }
     return OCB_OK;
 }
 
-template <int KP, bool XG, int CL>
+template <int KP, int CL>
 static int launch_stream(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 192 +
-                        (XG ? 0 : (size_t)(lu->n_ext + 1) * KP * sizeof(double));
-    OCB_CUDA(cudaFuncSetAttribute(sptrsm_stream_kernel<KP, XG, CL>,
+                        (size_t)(lu->n_ext + 1) * KP * sizeof(double);
+    OCB_CUDA(cudaFuncSetAttribute(sptrsm_stream_kernel<KP, CL>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned npanels = (unsigned)((a.k + KP - 1) / KP);
-    const unsigned threads = (XG ? std::min(512, trsm_threads()) : trsm_threads()) + 32;
+    const unsigned threads = trsm_threads() + 32;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(npanels * CL, 1, 1);
@@ -736,7 +780,7 @@ static int launch_stream(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CL > 1 ? 1 : 0;
-    OCB_CUDA(cudaLaunchKernelEx(&cfg, sptrsm_stream_kernel<KP, XG, CL>, a));
+    OCB_CUDA(cudaLaunchKernelEx(&cfg, sptrsm_stream_kernel<KP, CL>, a));
     g_launches.fetch_add(1);
     return OCB_OK;
 }
@@ -748,7 +792,7 @@ static int max_clusters(const ocb_lu* lu) {
     const int slot = KP;   // per (KP, CL) instantiation; shared memory is the same for one problem size
     if (cache[slot] > 0) return cache[slot];
     const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 192 + (size_t)(lu->n_ext + 1) * KP * sizeof(double);
-    cudaFuncSetAttribute(sptrsm_stream_kernel<KP, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(sptrsm_stream_kernel<KP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -763,7 +807,7 @@ static int max_clusters(const ocb_lu* lu) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, sptrsm_stream_kernel<KP, false, CL>, &cfg) != cudaSuccess || nc <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&nc, sptrsm_stream_kernel<KP, CL>, &cfg) != cudaSuccess || nc <= 0) {
         cudaGetLastError();
         nc = sm_count() / CL;
     }
@@ -782,8 +826,166 @@ static int launch_cluster(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st)
         const int cap1 = CL > 1 ? max_clusters<1, CL>(lu) : sm_count();
         if (a.k > cap1) kp = 2;
     }
-    if (kp == 2) return launch_stream<2, false, CL>(lu, a, st);
-    return launch_stream<1, false, CL>(lu, a, st);
+    if (kp == 2) return launch_stream<2, CL>(lu, a, st);
+    return launch_stream<1, CL>(lu, a, st);
+}
+
+// ---------------------------------------------------------------------------------
+// wide executor: ALL right-hand sides at once, one launch per sub-level
+// ---------------------------------------------------------------------------------
+// For factors whose panel does not fit shared memory (n_ext > ~27 000) and for very wide
+// blocks (k >= OCB_WIDE_MIN_K = 640, image built with the flat program) the column-panel kernel
+// above would stream the whole program once per panel.  Here the program is read ONCE per
+// solve: the extended block xe (n_ext x ldx, row-major, in the caller's workspace) stays in
+// HBM/L2, every sub-level is one kernel launch (the launch boundary is the barrier), and a warp
+// owns one program row and 32*T consecutive COLUMNS: lane = column, so the gathers
+// xe[col[p], c0 + lane] are 256-byte coalesced rows, col/val are warp-uniform (broadcast)
+// loads, and there is no reduction at all.
+struct WideArgs {
+    const int4* slices;
+    const int32_t *rowslice, *dst, *init, *col;
+    const double *scale, *val;
+    double* xe;
+    int64_t ldx;
+    int ntile;   // column tiles of 32*T per row
+};
+
+static int wide_min_k() {
+    static int v = -1;
+    if (v < 0) {
+        const char* env = getenv("OCB_WIDE_MIN_K");
+        v = env ? atoi(env) : 640;
+        if (v < 1) v = 1;
+    }
+    return v;
+}
+static bool use_wide(const ocb_lu* lu, int64_t k) {
+    return lu->has_flat && (lu->kp_smem_max == 0 || k >= wide_min_k());
+}
+static int wide_tiles(int64_t k) { return k <= 32 ? 1 : (k <= 64 ? 2 : 4); }
+static int64_t wide_ldx(int64_t k) {
+    const int64_t w = 32 * wide_tiles(k);
+    return (k + w - 1) / w * w;
+}
+
+__global__ void __launch_bounds__(256) wide_load_kernel(const SolveArgs a, double* xe, int64_t ldx) {
+    // xe[perm_r[i], :] = [b[i, :], 0...]; rows >= nrows_b are zero
+    const int64_t total = a.n * ldx;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / ldx, c = e - i * ldx;
+        double v = 0.0;
+        if (i < a.nrows_b && c < a.k) v = a.B[i * a.ldb + c];
+        xe[(int64_t)__ldg(a.perm_r + i) * ldx + c] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) wide_store_kernel(const SolveArgs a, const double* xe, int64_t ldx) {
+    const int64_t total = a.nrows_x * a.k;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = e / a.k, c = e - j * a.k;
+        a.X[j * a.ldx + c] = xe[(int64_t)__ldg(a.perm_c + j) * ldx + c];
+    }
+}
+
+// One CTA = 8 warps = (8 >> wlog) program rows x one tile of 32*T columns; the 2^wlog warps of a
+// row take alternating chunks of UNR entries (a long row would otherwise be one serial chain
+// of L2-latency-bound gathers) and their partial sums are combined through shared memory.
+template <int T>
+__global__ void __launch_bounds__(256) wide_level_kernel(const WideArgs a, int q0, int q1, int wlog) {
+    __shared__ double red[8][T][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpr = 1 << wlog, rows_per_cta = 8 >> wlog;
+    const int rowgroup = blockIdx.x / a.ntile, tile = blockIdx.x - rowgroup * a.ntile;
+    const int row = q0 + rowgroup * rows_per_cta + (warp >> wlog);
+    const int wr = warp & (wpr - 1);
+    const bool valid = row < q1;
+    const int64_t c0 = (int64_t)tile * (32 * T) + lane;
+    const double* xc = a.xe + c0;
+    double acc[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = 0.0;
+    if (valid) {
+        const int4 sl = __ldg(a.slices + __ldg(a.rowslice + row));
+        const int gl = sl.z & 255, G = 1 << gl;
+        const int r = row - sl.w;
+        const int32_t* cp = a.col + sl.x + (r << gl);
+        const double* vp = a.val + sl.x + (r << gl);
+        const int nent = sl.y << gl;   // padded entries of this row (zero padding multiplies xe[0])
+        constexpr int UNR = 8;
+        for (int e0 = wr * UNR; e0 < nent; e0 += wpr * UNR) {
+            int j[UNR];
+            double v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int e = e0 + u;
+                const bool ok = e < nent;
+                const int p = ((e >> gl) << 5) + (e & (G - 1));
+                j[u] = ok ? __ldg(cp + p) : 0;
+                v[u] = ok ? __ldg(vp + p) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const double* xr = xc + (int64_t)j[u] * a.ldx;
+#pragma unroll
+                for (int t = 0; t < T; ++t) acc[t] = fma(v[u], xr[32 * t], acc[t]);
+            }
+        }
+    }
+    if (wlog > 0) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) red[warp][t][lane] = acc[t];
+        __syncthreads();
+        if (wr == 0) {
+            for (int w2 = 1; w2 < wpr; ++w2)
+#pragma unroll
+                for (int t = 0; t < T; ++t) acc[t] += red[warp + w2][t][lane];
+        }
+    }
+    if (valid && wr == 0) {
+        const int i0 = __ldg(a.init + row);
+        const double sc = __ldg(a.scale + row);
+        double* xd = a.xe + (int64_t)__ldg(a.dst + row) * a.ldx + c0;
+        if (i0 >= 0) {
+            const double* xi = xc + (int64_t)i0 * a.ldx;
+#pragma unroll
+            for (int t = 0; t < T; ++t) xd[32 * t] = (xi[32 * t] - acc[t]) * sc;
+        } else {
+#pragma unroll
+            for (int t = 0; t < T; ++t) xd[32 * t] = -acc[t] * sc;
+        }
+    }
+}
+
+static int wide_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
+    const int T = wide_tiles(a.k);
+    const int64_t ldx = wide_ldx(a.k);
+    double* xe = a.ws;
+    const unsigned lblocks = (unsigned)std::min<int64_t>((a.n * ldx + 255) / 256, 148 * 16);
+    wide_load_kernel<<<lblocks, 256, 0, st>>>(a, xe, ldx);
+    OCB_LAUNCH_CHECK();
+    WideArgs w;
+    w.slices = lu->f_slices; w.rowslice = lu->f_rowslice; w.dst = lu->f_dst; w.init = lu->f_init;
+    w.col = lu->f_col; w.scale = lu->f_scale; w.val = lu->f_val;
+    w.xe = xe; w.ldx = ldx;
+    w.ntile = (int)(ldx / (32 * T));
+    const int nsub = (int)lu->sub_row.size() - 1;
+    for (int sb = 0; sb < nsub; ++sb) {
+        const int q0 = lu->sub_row[sb], q1 = lu->sub_row[sb + 1];
+        if (q1 <= q0) continue;
+        // warps per row from the longest row of the sub-level (rows are sorted by length)
+        const int maxlen = lu->sub_maxlen[sb];
+        const int wlog = maxlen > 256 ? 3 : (maxlen > 96 ? 2 : (maxlen > 32 ? 1 : 0));
+        const int rows_per_cta = 8 >> wlog;
+        const unsigned blocks = (unsigned)(((q1 - q0) + rows_per_cta - 1) / rows_per_cta) * (unsigned)w.ntile;
+        if (T == 1) wide_level_kernel<1><<<blocks, 256, 0, st>>>(w, q0, q1, wlog);
+        else if (T == 2) wide_level_kernel<2><<<blocks, 256, 0, st>>>(w, q0, q1, wlog);
+        else wide_level_kernel<4><<<blocks, 256, 0, st>>>(w, q0, q1, wlog);
+        OCB_LAUNCH_CHECK();
+    }
+    const unsigned sblocks = (unsigned)std::min<int64_t>((a.nrows_x * a.k + 255) / 256, 148 * 16);
+    wide_store_kernel<<<std::max(1u, sblocks), 256, 0, st>>>(a, xe, ldx);
+    OCB_LAUNCH_CHECK();
+    return OCB_OK;
 }
 
 // optional per-launch timing of the solve kernel (bench.py roofline): CUDA events on the
@@ -843,13 +1045,13 @@ static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int
         a.trace = trace_on ? trace_buf : nullptr;
         g_trace_buf = trace_buf;
     }
-    if (lu->kp_smem_max == 0) {
+    if (use_wide(lu, k)) {
         const int64_t need = ocb_lu_solve_ws_bytes(lu, k);
         if (ws == nullptr || ws_bytes < need) {
             set_error("lu_solve: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
             return OCB_ERR_CAPACITY;
         }
-        return launch_stream<KP_GLOBAL, true, 1>(lu, a, st);
+        return wide_solve(lu, a, st);
     }
     switch (lu->cl) {
         case 8: return launch_cluster<8>(lu, a, st);
@@ -885,7 +1087,7 @@ extern "C" {
 
 int ocb_lu_pack_host(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
                      const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
-                     const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin,
+                     const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin, int64_t flags,
                      unsigned char** out_image, int64_t* out_bytes) {
     OCB_ARG(n >= 0 && out_image && out_bytes, "lu_pack_host");
     OCB_ARG(h_L_rowptr && h_U_rowptr && h_perm_r && h_perm_c, "lu_pack_host: null pointer");
@@ -894,7 +1096,7 @@ int ocb_lu_pack_host(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_co
     int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals,
                                    ocb::trsm_threads(), &P);
     if (rc != OCB_OK) return rc;
-    return ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, out_image, out_bytes);
+    return ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, (int)flags, out_image, out_bytes);
 }
 
 void ocb_host_free(void* p) { free(p); }
@@ -931,7 +1133,7 @@ int ocb_lu_create(ocb_lu** out, int64_t n, const int32_t* h_L_rowptr, const int3
     unsigned char* img = nullptr;
     int64_t bytes = 0;
     int rc = ocb_lu_pack_host(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals, h_perm_r,
-                              h_perm_c, optin, &img, &bytes);
+                              h_perm_c, optin, 0, &img, &bytes);
     if (rc != OCB_OK) return rc;
     rc = ocb_lu_create_from_image(out, img, bytes, nullptr, stream);
     free(img);
@@ -1005,9 +1207,8 @@ int ocb_lu_stats(const ocb_lu* lu, int64_t* info8) {
 }
 
 int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k) {
-    if (!lu || lu->kp_smem_max > 0) return 0;
-    const int kp = ocb::KP_GLOBAL;
-    return ((k + kp - 1) / kp) * lu->n_ext * kp * (int64_t)sizeof(double);
+    if (!lu || !ocb::use_wide(lu, k)) return 0;
+    return lu->n_ext * ocb::wide_ldx(k) * (int64_t)sizeof(double);
 }
 
 int ocb_lu_solve(const ocb_lu* lu, const double* d_B, int64_t ldb, int64_t nrows_b, double* d_X,

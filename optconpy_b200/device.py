@@ -85,8 +85,18 @@ def to_dev(arr):
 
 
 def to_host(t):
-    STATS['d2h_bytes'] += t.numel()*t.element_size()
-    return t.cpu().numpy()
+    """device tensor -> fresh numpy array.  Large blocks go through a pinned buffer of torch's
+    caching host allocator (a pageable ``.cpu()`` of the 45 MB ADI factor ran at ~2 GB/s); the
+    returned array owns that buffer, which goes back to the cache when the array dies."""
+    nbytes = t.numel()*t.element_size()
+    STATS['d2h_bytes'] += nbytes
+    if nbytes < (1 << 20):
+        return t.cpu().numpy()
+    tc = t if t.is_contiguous() else t.contiguous()
+    host = torch.empty(tc.shape, dtype=tc.dtype, pin_memory=True)
+    host.copy_(tc, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
 
 
 def ptr(t):
@@ -216,13 +226,13 @@ class FactorJob(object):
     """Several host factorisations in flight (worker processes: SuperLU + analysis +
     packing); ``result()`` uploads the images and returns the ``LU`` handles."""
 
-    def __init__(self, mats, lu_options=None):
+    def __init__(self, mats, lu_options=None, wide=False):
         from . import _lu_worker
         require_cuda()
         opts = dict(LU_OPTIONS if lu_options is None else lu_options)
         t0 = time.perf_counter()
         so = smem_optin()
-        args = [_csc_args(m, opts) + (so,) for m in mats]
+        args = [_csc_args(m, opts) + (so, 1 if wide else 0) for m in mats]
         self.n = len(mats)
         pool = _lu_pool()
         self._done = None
@@ -294,12 +304,14 @@ def factorize_many(mats, lu_options=None):
 class LU(object):
     """Device-resident LU factorisation ``Pr A Pc = L U`` (handle of the C ABI)."""
 
-    def __init__(self, mat, lu_options=None, image=None):
+    def __init__(self, mat, lu_options=None, image=None, wide=False):
+        """``wide=True`` also uploads the flat program, so that blocks of >= 640 right-hand
+        sides go through the all-columns-at-once executor (factor read once per solve)."""
         lib = require_cuda()
         if image is None:
             from . import _lu_worker
             opts = dict(LU_OPTIONS if lu_options is None else lu_options)
-            image, tf, tp = _lu_worker.factor_image(_csc_args(mat, opts) + (smem_optin(),))
+            image, tf, tp = _lu_worker.factor_image(_csc_args(mat, opts) + (smem_optin(), 1 if wide else 0))
             STATS['lu_factor_s'] += tf
             STATS['lu_worker_pack_s'] += tp
             STATS['n_factor'] += 1

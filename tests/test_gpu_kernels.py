@@ -83,8 +83,29 @@ def test_lu_solve_partial_rows(dv, sad, cav10):
     assert _relerr(dv.to_host(Rd), ref) < 1e-11
 
 
+def test_lu_solve_wide_executor_small_n(dv, sad):
+    """Image with the flat program: blocks of >= 640 columns go through the all-columns
+    executor, narrower ones through the cluster kernel; both agree with SuperLU."""
+    rng = np.random.default_rng(21)
+    n = sad.shape[0]
+    lu = dv.LU(sad, wide=True)
+    ref_lu = spsla.splu(sad)
+    lib = dv.require_cuda()
+    for k in (7, 200, 641):
+        B = rng.standard_normal((n, k))
+        assert (lib.ocb_lu_solve_ws_bytes(lu.handle, k) > 0) == (k >= 640)
+        X = dv.to_host(lu.solve(dv.to_dev(B)))
+        assert _relerr(X, ref_lu.solve(B)) < 1e-11
+    # partial rows in / out through the wide path
+    NV = n - 100
+    R = rng.standard_normal((NV, 700))
+    full = np.vstack([R, np.zeros((n - NV, 700))])
+    X = dv.to_host(lu.solve(dv.to_dev(R), nrows_out=NV))
+    assert X.shape == (NV, 700) and _relerr(X, ref_lu.solve(full)[:NV]) < 1e-11
+
+
 def test_lu_solve_global_panel_path(dv):
-    """n large enough that the column panel does not fit shared memory."""
+    """n large enough that the column panel does not fit shared memory: wide executor."""
     from optconpy_b200 import problems as pb
     p = pb.drivcav_problem(64, 1e-2)
     S = dv.sadpnt_matrix(p['M'] + 0.01*p['A'], p['J'])
