@@ -354,11 +354,14 @@ class LU(object):
     def solve(self, B, nrows_out=None, out=None):
         """``(A^-1 [B; 0])[:nrows_out]`` for a device block B (rows <= n)."""
         lib = self._lib
-        assert B.dtype == torch.float64 and B.dim() == 2 and B.stride(1) == 1
+        assert B.dtype == torch.float64 and B.dim() == 2
         k = B.shape[1]
         nrows_out = self.n if nrows_out is None else nrows_out
         if out is None:
             out = torch.empty((nrows_out, k), dtype=torch.float64, device=B.device)
+        if k == 0:
+            return out
+        assert B.stride(1) == 1
         self.arena.record_stream(torch.cuda.current_stream())
         wsb = lib.ocb_lu_solve_ws_bytes(self.handle, k)
         ws = workspace('lu', wsb) if wsb > 0 else None

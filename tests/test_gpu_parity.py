@@ -237,3 +237,58 @@ def test_lookahead_does_not_change_results(mods):
     for t in f0:
         assert np.array_equal(s0[f0[t]['mtxtb']], s2[f2[t]['mtxtb']])
         assert np.array_equal(s0[f0[t]['w']], s2[f2[t]['w']])
+
+
+def test_edge_cases(mods, cav10):
+    """Ragged / degenerate inputs through the reference-facing functions."""
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import device as dv
+    M, A, J = cav10['M'], cav10['A'], cav10['J']
+    NV = cav10['NV']
+    rng = np.random.default_rng(7)
+    # a single right-hand side, given as an (NV,1) column and as a sparse column
+    r1 = rng.standard_normal((NV, 1))
+    assert _relerr(glau.apply_massinv(M, r1), olau.apply_massinv(M, r1)) < 1e-12
+    rs = sps.csr_matrix(r1)
+    assert _relerr(glau.apply_massinv(M, rs), olau.apply_massinv(M, rs)) < 1e-12
+    # compress: no truncation requested, k larger than the column count, rank-deficient input
+    Z = rng.standard_normal((NV, 6))
+    Zd = np.hstack([Z, Z[:, :3] @ rng.standard_normal((3, 4))])          # rank 6, 10 columns
+    for kw in (dict(), dict(k=50), dict(thresh=1e-8), dict(k=4), dict(k=4, thresh=1e-8)):
+        a, b = gpru.compress_Zsvd(Zd, **kw), opru.compress_Zsvd(Zd, **kw)
+        kept = min(a.shape[1], b.shape[1])
+        if 'thresh' in kw or 'k' in kw and kw['k'] < 6:
+            assert a.shape == b.shape, (kw, a.shape, b.shape)
+        # the GPU path drops numerically-zero directions even without a threshold
+        assert kept >= min(6, kw.get('k', 6))
+        assert _zzt_relerr(a, b) < 1e-9
+    # one column in, one column out
+    z1 = rng.standard_normal((NV, 1))
+    a, b = gpru.compress_Zsvd(z1, thresh=1e-10), opru.compress_Zsvd(z1, thresh=1e-10)
+    assert a.shape == b.shape == (NV, 1) and _zzt_relerr(a, b) < 1e-12
+    # feedback product with a dense 1-column and a sparse multi-column tB
+    tbs = sps.random(NV, 3, density=0.05, random_state=3, format='csr')
+    assert _relerr(gpru.get_mTzzTtb(M.T, Z, tbs), opru.get_mTzzTtb(M.T, Z, tbs)) < 1e-11
+    assert _relerr(gpru.get_mTzzTtb(M.T, Z, r1), opru.get_mTzzTtb(M.T, Z, r1)) < 1e-11
+    # zero right-hand sides are legal
+    lu = dv.LU(dv.sadpnt_matrix(M + 0.1*A, J))
+    X = lu.solve(dv.to_dev(np.zeros((lu.n, 3))))
+    assert float(X.abs().max()) == 0.0
+    assert lu.solve(dv.to_dev(np.zeros((lu.n, 0)))).shape == (lu.n, 0)
+
+
+def test_mtxoldb_and_nonconvergence_are_not_errors(mods, lyap_setup, cav10):
+    """``mtxoldb`` (outer Newton carry, solve_dae_ric.py:150-155) and hitting ``*_max_steps``
+    (non-convergence returns the last iterate)."""
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import problems as pb
+    M, F, J, _ = lyap_setup
+    cs = pb.control_setup(cav10, olau, alphau=1e-4)
+    d = dict(adi_max_steps=12, adi_newZ_reltol=1e-14, nwtn_max_steps=2, nwtn_upd_reltol=1e-14,
+             nwtn_upd_abstol=1e-16, full_upd_norm_check=False, ms=[-5.0, -2.0, -1.0])
+    old = 1e-3*np.random.default_rng(2).standard_normal((cav10['NV'], 8))
+    kw = dict(mmat=M.T, amat=F.T, transposed=True, jmat=J, bmat=cs['tb_mat'], wmat=cs['trct_mat'],
+              z0=None, mtxoldb=old, nwtn_adi_dict=d)
+    ref, got = opru.proj_alg_ric_newtonadi(**kw), gpru.proj_alg_ric_newtonadi(**kw)
+    assert got['adi_steps'] == ref['adi_steps'] == [12, 12]
+    assert _zzt_relerr(got['zfac'], ref['zfac']) < TOL_FACTOR
