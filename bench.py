@@ -33,8 +33,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# fewer cudaMalloc/cudaFree (device-synchronising) calls when block sizes vary between steps
-os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')
+# every kernel is loaded when its module is opened, not at its first launch (a first launch of
+# a new template instance in the middle of the timed loop cost 50-150 ms on a cold box); must be
+# set before the CUDA context exists
+os.environ.setdefault('CUDA_MODULE_LOADING', 'EAGER')
 
 import numpy as np  # noqa: E402
 
@@ -327,8 +329,11 @@ def main():
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K+1)]
     e0.record()
     step_ev[0].record()
+    step_ph = []
     for i, st in enumerate(setups[W:]):
-        dd.run_step(ctx, st, info)
+        ph_i = dd._Phases()
+        dd.run_step(ctx, st, info, phases=ph_i)
+        step_ph.append(ph_i)
         step_ev[i+1].record()
     e1.record()
     barrier()
@@ -339,6 +344,7 @@ def main():
     lib.ocb_prof_enable(0)
     ms = e0.elapsed_time(e1)
     step_ms = [step_ev[i].elapsed_time(step_ev[i+1]) for i in range(K)]
+    step_phases = [{k: round(v, 2) for k, v in p.collect().items()} for p in step_ph]
     tmax = torch.tensor([ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -457,7 +463,7 @@ def main():
                    saddle_solves_per_s=solves/(ms_max*1e-3),
                    saddle_sweep=sweep,
                    rhs_columns_per_s=sum(sum(a)*0 for a in []) or None,
-                   step_ms=step_ms,
+                   step_ms=step_ms, step_phase_ms=step_phases,
                    steps_info=[dict(tau=float(i['tau']), adi_steps=i['adi_steps'],
                                     zp_cols=i['zp_cols'], zc_cols=i['zc_cols']) for i in info[W:]])
         out.pop('rhs_columns_per_s')

@@ -70,10 +70,25 @@ def factor_image(args):
     return img, t1 - t0, time.perf_counter() - t1
 
 
-def factor_image_to_shm(args):
-    """Pool entry point: factorise, analyse, pack and hand the image back through one POSIX
-    shared-memory block (no pickling of ~15 MB through a pipe).
-    Returns (name, nbytes, seconds factor, seconds analyse+pack)."""
+_ATTACHED = dict()
+
+
+def _attach(name):
+    """Attach (once per worker) to a pinned segment of the main process's pool."""
+    seg = _ATTACHED.get(name)
+    if seg is None:
+        from multiprocessing import shared_memory
+        seg = shared_memory.SharedMemory(name=name)   # spawned workers share the parent's resource tracker
+        _ATTACHED[name] = seg
+    return seg
+
+
+def factor_image_to_shm(args, slot=None):
+    """Pool entry point: factorise, analyse, pack and hand the image back through POSIX shared
+    memory (no pickling of ~15 MB through a pipe).  ``slot = (name, capacity)`` is a segment of
+    the main process's page-locked pool: if the image fits it is written there (the upload is
+    then a plain DMA); otherwise a fresh segment is created.
+    Returns (name or None if the slot was used, nbytes, seconds factor, seconds analyse+pack)."""
     from multiprocessing import shared_memory
     t0 = time.perf_counter()
     arrs = factor_arrays(args)
@@ -81,6 +96,10 @@ def factor_image_to_shm(args):
     ci = _CImage(arrs, args[3][0], args[5], args[6] if len(args) > 6 else 0)
     try:
         nbytes = ci.view.nbytes
+        if slot is not None and nbytes <= slot[1]:
+            seg = _attach(slot[0])
+            np.frombuffer(seg.buf, dtype=np.uint8, count=nbytes)[:] = ci.view
+            return None, nbytes, t1 - t0, time.perf_counter() - t1
         shm = shared_memory.SharedMemory(create=True, size=max(nbytes, 64))
         np.frombuffer(shm.buf, dtype=np.uint8, count=nbytes)[:] = ci.view
     finally:

@@ -69,12 +69,12 @@ constexpr int CH_THREADS = 512, CH_WARPS = 16;
 
 // sum over rows of Z[i][j] * Z[i][p] for 32 columns j per CTA (p < 0: Z[i][j]^2).
 // 16 warps stride the rows; fixed-order shared-memory reduction => deterministic.
-__device__ __forceinline__ double col_dot_block(const double* __restrict__ Z, int64_t ldz, int64_t n,
-                                                int64_t K, int64_t j, int p, double (*red)[33]) {
+__device__ __forceinline__ double col_dot_block(const double* __restrict__ Z, int64_t ldz, int64_t i_begin,
+                                                int64_t n, int64_t K, int64_t j, int p, double (*red)[33]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc = 0.0;
     if (j < K) {
-        int64_t i = warp;
+        int64_t i = i_begin + warp;
         // 4 independent row streams per warp for memory-level parallelism
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         for (; i + 3 * CH_WARPS < n; i += 4 * CH_WARPS) {
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(CH_THREADS) chol_colsq_kernel(const double* __
                                                                int64_t n, int64_t K, double* __restrict__ d) {
     __shared__ double red[CH_WARPS][33];
     const int64_t j = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
-    const double s = col_dot_block(Z, ldz, n, K, j, -1, red);
+    const double s = col_dot_block(Z, ldz, 0, n, K, j, -1, red);
     if (threadIdx.x < 32 && j < K) d[j] = s;
 }
 
@@ -143,29 +143,47 @@ __global__ void __launch_bounds__(1024) chol_pick_kernel(const double* __restric
 }
 
 // column t of the Cholesky factor: Rt[j][t] = (z_j . z_p - sum_{s<t} Rt[p][s] Rt[j][s]) / sqrt(dp)
+// Pass 1 (grid: column blocks x CH_SPLIT row chunks, so that all SMs stream Z): partial dot
+// products z_j . z_p of one row chunk.  Pass 2: ordered sum of the chunks (deterministic),
+// subtraction of the previous factor columns, diagonal downdate.
+constexpr int CH_SPLIT = 4;
+
 __global__ void __launch_bounds__(CH_THREADS) chol_col_kernel(const double* __restrict__ Z, int64_t ldz,
-                                                             int64_t n, int64_t K, int t,
-                                                             double* __restrict__ Rt, int64_t ldr,
-                                                             double* __restrict__ d,
+                                                             int64_t n, int64_t K,
+                                                             double* __restrict__ gpart,
                                                              const CholState* __restrict__ st) {
     __shared__ double red[CH_WARPS][33];
+    if (st->done) return;
+    const int p = st->piv;
+    const int64_t chunk = (n + CH_SPLIT - 1) / CH_SPLIT;
+    const int64_t i0 = (int64_t)blockIdx.y * chunk, i1 = i0 + chunk < n ? i0 + chunk : n;
+    const int64_t j = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    const double g = col_dot_block(Z, ldz, i0, i1, K, j, p, red);  // contains a __syncthreads
+    if (threadIdx.x < 32 && j < K) gpart[(int64_t)blockIdx.y * K + j] = g;
+}
+
+__global__ void __launch_bounds__(256) chol_col_finish_kernel(const double* __restrict__ gpart, int64_t K,
+                                                             int t, double* __restrict__ Rt, int64_t ldr,
+                                                             double* __restrict__ d,
+                                                             const CholState* __restrict__ st) {
     __shared__ double rp[1024];
     if (st->done) return;
     const int p = st->piv;
     const double dp = st->dp;
-    for (int s = threadIdx.x; s < t; s += CH_THREADS) rp[s] = Rt[(int64_t)p * ldr + s];
-    const int64_t j = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
-    const double g = col_dot_block(Z, ldz, n, K, j, p, red);  // contains a __syncthreads
-    if (threadIdx.x < 32 && j < K) {
-        const double* rj = Rt + j * ldr;
-        double s0 = 0.0, s1 = 0.0;
-        int s = 0;
-        for (; s + 1 < t; s += 2) { s0 = fma(rp[s], rj[s], s0); s1 = fma(rp[s + 1], rj[s + 1], s1); }
-        if (s < t) s0 = fma(rp[s], rj[s], s0);
-        const double row = (g - (s0 + s1)) / sqrt(dp);
-        Rt[j * ldr + t] = row;
-        d[j] = (j == p) ? -1.0 : d[j] - row * row;
-    }
+    for (int s = threadIdx.x; s < t; s += blockDim.x) rp[s] = Rt[(int64_t)p * ldr + s];
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    double g = 0.0;
+    for (int c = 0; c < CH_SPLIT; ++c) g += gpart[(int64_t)c * K + j];
+    const double* rj = Rt + j * ldr;
+    double s0 = 0.0, s1 = 0.0;
+    int s = 0;
+    for (; s + 1 < t; s += 2) { s0 = fma(rp[s], rj[s], s0); s1 = fma(rp[s + 1], rj[s + 1], s1); }
+    if (s < t) s0 = fma(rp[s], rj[s], s0);
+    const double row = (g - (s0 + s1)) / sqrt(dp);
+    Rt[j * ldr + t] = row;
+    d[j] = (j == p) ? -1.0 : d[j] - row * row;
 }
 
 __global__ void scale_cols_kernel(const double* __restrict__ U, int64_t ldu, int r, int kk,
@@ -177,7 +195,7 @@ __global__ void scale_cols_kernel(const double* __restrict__ U, int64_t ldu, int
 }
 
 struct CompressWs {
-    double *d, *Rt, *S, *U, *lam, *Us, *T, *gws;
+    double *d, *Rt, *S, *U, *lam, *Us, *T, *gws, *gpart;
     CholState* st;
     int64_t gws_bytes;
 };
@@ -187,6 +205,7 @@ static int64_t compress_carve(void* ws, int64_t bytes, int64_t n, int64_t K, int
     CompressWs w;
     w.st = c.take<CholState>(1);
     w.d = c.take<double>(K);
+    w.gpart = c.take<double>(K * CH_SPLIT);
     w.Rt = c.take<double>(K * rmax);
     w.S = c.take<double>(rmax * rmax);
     w.U = c.take<double>(rmax * rmax);
@@ -238,7 +257,10 @@ int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K, double th
         for (; t < batch_end; ++t) {
             chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
             OCB_LAUNCH_CHECK();
-            chol_col_kernel<<<cblocks, CH_THREADS, 0, st>>>(d_Z, ldz, n, K, t, w.Rt, rmax, w.d, w.st);
+            chol_col_kernel<<<dim3(cblocks, CH_SPLIT), CH_THREADS, 0, st>>>(d_Z, ldz, n, K, w.gpart, w.st);
+            OCB_LAUNCH_CHECK();
+            chol_col_finish_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(w.gpart, K, t, w.Rt, rmax,
+                                                                                w.d, w.st);
             OCB_LAUNCH_CHECK();
         }
         if (t >= rmax) {  // closes the factorisation at rank rmax if the rule never fired

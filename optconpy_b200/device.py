@@ -206,6 +206,67 @@ def smem_optin():
     return _SMEM_OPTIN[d]
 
 
+class _PinnedShmPool(object):
+    """Page-locked POSIX shared-memory segments that the LU worker processes write their
+    device images into: the host-to-device copy is then a DMA from pinned memory instead of a
+    driver-staged pageable copy (1.9 GB/s measured under load, and it serialises other CUDA
+    calls of the process).  Created lazily once the image size is known."""
+
+    def __init__(self, nseg, seg_bytes):
+        from multiprocessing import shared_memory
+        import threading
+        self.seg_bytes = int(seg_bytes)
+        self.segs, self.free = [], []
+        self.lock = threading.Lock()
+        rt = torch.cuda.cudart()
+        for i in range(nseg):
+            shm = shared_memory.SharedMemory(create=True, size=self.seg_bytes)
+            addr = C.addressof(C.c_char.from_buffer(shm.buf))
+            pinned = int(rt.cudaHostRegister(addr, self.seg_bytes, 0)) == 0
+            self.segs.append((shm, addr, pinned))
+            self.free.append(i)
+
+    def acquire(self):
+        with self.lock:
+            return self.free.pop() if self.free else None
+
+    def release(self, i):
+        with self.lock:
+            self.free.append(i)
+
+    def close(self):
+        rt = torch.cuda.cudart()
+        for shm, addr, pinned in self.segs:
+            try:
+                if pinned:
+                    rt.cudaHostUnregister(addr)
+                shm.close()
+                shm.unlink()
+            except Exception:
+                pass
+        self.segs, self.free = [], []
+
+
+_SHM = dict(pool=None, disabled=False)
+
+
+def _shm_pool(image_bytes=None):
+    """The pinned pool (created after the first image told us the size), or None."""
+    import os
+    if _SHM['disabled'] or os.environ.get('OCB_NO_PINNED_POOL'):
+        return None
+    if _SHM['pool'] is None and image_bytes is not None:
+        try:
+            nseg = int(os.environ.get('OCB_PINNED_POOL_SEGMENTS', '28'))
+            _SHM['pool'] = _PinnedShmPool(nseg, int(image_bytes*1.3) + (1 << 20))
+            import atexit
+            atexit.register(_SHM['pool'].close)
+        except Exception:
+            _SHM['disabled'] = True
+            return None
+    return _SHM['pool']
+
+
 _UPLOADER = dict(pool=None)
 
 
@@ -242,7 +303,13 @@ class FactorJob(object):
             self._async = None
         else:
             self._sync = None
-            self._async = [pool.apply_async(_lu_worker.factor_image_to_shm, (a,)) for a in args]
+            self._async, self._slots = [], []
+            shp = _shm_pool()
+            for a in args:
+                i = shp.acquire() if shp is not None else None
+                slot = None if i is None else (shp.segs[i][0].name, shp.seg_bytes)
+                self._slots.append(i)
+                self._async.append(pool.apply_async(_lu_worker.factor_image_to_shm, (a, slot)))
         STATS['lu_submit_s'] += time.perf_counter() - t0
         STATS['n_factor'] += self.n
 
@@ -276,12 +343,23 @@ class FactorJob(object):
                 out.append(LU(None, image=img))
         else:
             from multiprocessing import shared_memory
-            for ar in self._async:
+            for ar, slot in zip(self._async, self._slots):
                 t0 = time.perf_counter()
                 name, nbytes, tf, tp = ar.get()
                 STATS['lu_collect_wait_s'] += time.perf_counter() - t0
                 STATS['lu_factor_s'] += tf
                 STATS['lu_worker_pack_s'] += tp
+                shp = _shm_pool(nbytes)
+                if name is None:                  # the worker wrote into our pinned segment
+                    img = np.frombuffer(shp.segs[slot][0].buf, dtype=np.uint8, count=nbytes)
+                    try:
+                        out.append(LU(None, image=img))       # DMA from page-locked memory
+                    finally:
+                        del img
+                        shp.release(slot)
+                    continue
+                if slot is not None:
+                    shp.release(slot)
                 shm = shared_memory.SharedMemory(name=name)
                 try:
                     img = np.frombuffer(shm.buf, dtype=np.uint8, count=nbytes)

@@ -49,6 +49,7 @@ class DreContext(object):
         # time step pays for growing it (a 0.5 GB cudaMalloc takes 30-700 ms on a shared box)
         kmax = (comprz_maxc if comprz_maxc is not None else 64) + self.tct.shape[1] + self.tb.shape[1]
         dv.workspace('adi_Z', self.NV*kmax*int(self.nwtn_adi_dict['adi_max_steps'])*8)
+        dv.workspace('compress', dv.require_cuda().ocb_compress_ws_bytes(self.NV, kmax*48, 1024))
         mlu = dv.LU(sps.csc_matrix(mmat))
         self.Zc = np.sqrt(gamma)*mlu.solve(self.tct)
         self.mtxtb = dv.feedback(self.Mt_dev, self.Zc, self.tb, alpha=-1.0)
