@@ -80,6 +80,11 @@ class ClockSampler(object):
             self.nvml = pynvml
         except Exception:
             self.nvml = None
+        try:
+            self._sample()      # NVML's first query of a kind takes 10-130 ms: pay it here, not
+            self._sample()      # in the timed region (later queries take microseconds)
+        except Exception:
+            pass
         self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
 

@@ -126,6 +126,19 @@ class Workspace(object):
 
 
 _WS = dict()
+_POOL_RESERVED = dict(bytes=0)
+
+
+def reserve_pool(nbytes):
+    """Make torch's caching allocator hold ``nbytes`` of free device memory (allocate once,
+    release to the cache): the blocks whose size changes from call to call - the ADI factor
+    grows with the block width every time step - are then carved out of that cached block
+    instead of triggering a cudaMalloc (20-100 ms on a busy box, and it synchronises)."""
+    nbytes = int(nbytes)
+    if nbytes > _POOL_RESERVED['bytes']:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=cur_device())
+        del t
+        _POOL_RESERVED['bytes'] = nbytes
 
 
 def workspace(name, nbytes):
@@ -193,6 +206,25 @@ def _csc_args(mat, opts):
     m = sps.csc_matrix(mat, dtype=np.float64)
     m.sum_duplicates()
     return (m.data, m.indices, m.indptr, m.shape, opts)
+
+
+# fill-reducing orderings by sparsity pattern: the first factorisation of a pattern runs
+# SuperLU's minimum-degree ordering, all later ones (other shifts, other time steps) reuse it
+_ORDER = dict()
+
+
+def _pattern_key(a):
+    import zlib
+    return (a[3], len(a[1]), zlib.crc32(a[1].tobytes()), zlib.crc32(a[2].tobytes()))
+
+
+def _with_order(a, opts):
+    """worker arguments (.., smem, flags, q) with the cached ordering of this pattern, if any"""
+    import os
+    if os.environ.get('OCB_NO_ORDER_REUSE') or opts.get('permc_spec') == 'NATURAL':
+        return a, None
+    key = _pattern_key(a)
+    return a + (_ORDER.get(key),), key
 
 
 _SMEM_OPTIN = dict()
@@ -293,7 +325,11 @@ class FactorJob(object):
         opts = dict(LU_OPTIONS if lu_options is None else lu_options)
         t0 = time.perf_counter()
         so = smem_optin()
-        args = [_csc_args(m, opts) + (so, 1 if wide else 0) for m in mats]
+        args, self._keys = [], []
+        for m in mats:
+            a, key = _with_order(_csc_args(m, opts) + (so, 1 if wide else 0), opts)
+            args.append(a)
+            self._keys.append(key)
         self.n = len(mats)
         pool = _lu_pool()
         self._done = None
@@ -337,15 +373,19 @@ class FactorJob(object):
             return self._done
         out = []
         if self._async is None:
-            for img, tf, tp in self._sync:
+            for (img, tf, tp, order), key in zip(self._sync, self._keys):
                 STATS['lu_factor_s'] += tf
                 STATS['lu_worker_pack_s'] += tp
+                if order is not None and key is not None:
+                    _ORDER.setdefault(key, order)
                 out.append(LU(None, image=img))
         else:
             from multiprocessing import shared_memory
-            for ar, slot in zip(self._async, self._slots):
+            for ar, slot, key in zip(self._async, self._slots, self._keys):
                 t0 = time.perf_counter()
-                name, nbytes, tf, tp = ar.get()
+                name, nbytes, tf, tp, order = ar.get()
+                if order is not None and key is not None:
+                    _ORDER.setdefault(key, order)
                 STATS['lu_collect_wait_s'] += time.perf_counter() - t0
                 STATS['lu_factor_s'] += tf
                 STATS['lu_worker_pack_s'] += tp
@@ -389,7 +429,10 @@ class LU(object):
         if image is None:
             from . import _lu_worker
             opts = dict(LU_OPTIONS if lu_options is None else lu_options)
-            image, tf, tp = _lu_worker.factor_image(_csc_args(mat, opts) + (smem_optin(), 1 if wide else 0))
+            a, key = _with_order(_csc_args(mat, opts) + (smem_optin(), 1 if wide else 0), opts)
+            image, tf, tp, order = _lu_worker.factor_image(a)
+            if order is not None and key is not None:
+                _ORDER.setdefault(key, order)
             STATS['lu_factor_s'] += tf
             STATS['lu_worker_pack_s'] += tp
             STATS['n_factor'] += 1
@@ -616,6 +659,7 @@ def adi_run(lus, shifts, NV, NP, Mt, W, maxsteps, reltol, Ufb=None, Vt=None):
     # the iteration writes into a persistent, monotonically growing buffer (a fresh
     # 0.4 GB torch.empty per call made the caching allocator cudaMalloc/cudaFree, i.e.
     # synchronise, whenever the block width changed); the used part is copied out compactly
+    reserve_pool(min(12*NV*max(k, 64)*64*8, 4 << 30))
     zbuf = workspace('adi_Z', NV*k*steps_cap*8)
     Z = zbuf[:NV*k*steps_cap*8].view(torch.float64).view(NV, k*steps_cap)
     for lu in lus:

@@ -182,3 +182,27 @@ def test_small_and_degenerate_factors():
     e = np.zeros(0)
     prog0 = _program([z, z, e, z, z, e], 0)
     assert prog0[0]['nrows'] == 0 and prog0[0]['nslice'] == 0
+
+
+def test_reused_ordering_gives_the_same_solution(cav10):
+    """Second and later factorisations of one sparsity pattern reuse the first one's ordering
+    (symmetric pre-permutation + NATURAL column order, _lu_worker.factor_arrays): the composed
+    permutations must still solve the ORIGINAL system, with no more fill than before."""
+    K = _saddle(cav10)
+    n = K.shape[0]
+    a = dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, 0)
+    arrs1, order = _lu_worker.factor_arrays(a, want_order=True)
+    assert order is not None and sorted(order.tolist()) == list(range(n))
+    K2 = _saddle(cav10, mu=-3.0, tau=0.02)                       # same pattern, other values
+    a2 = dv._csc_args(K2, dict(dv.LU_OPTIONS)) + (232448, 0, order)
+    arrs2, order2 = _lu_worker.factor_arrays(a2, want_order=True)
+    assert order2 is None
+    prog = _program(arrs2, n)
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((n, 2))
+    X = np.zeros((prog[0]['n_ext'], 2))
+    X[arrs2[6]] = B
+    _execute(prog, X, check_hazards=True)
+    got = X[arrs2[7]]
+    assert np.linalg.norm(K2 @ got - B) <= 1e-12*np.linalg.norm(B)
+    assert len(arrs2[2]) + len(arrs2[5]) <= 1.05*(len(arrs1[2]) + len(arrs1[5]))
