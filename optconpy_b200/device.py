@@ -195,7 +195,7 @@ def _lu_pool():
     want = os.environ.get('OCB_LU_WORKERS')
     if want is None:
         world = int(os.environ.get('WORLD_SIZE', '1'))
-        want = max(2, min(14, (os.cpu_count() or 1) - 2)//max(world, 1))
+        want = max(2, min(14, ((os.cpu_count() or 1) - 2)//max(world, 1)))
     want = int(want)
     if want <= 1:
         return None
