@@ -229,6 +229,18 @@ def run_sweep(meshes, ks, reps, rank, world, peak_gbs):
         lu = dv.LU(K, wide=True)
         tsetup = time.perf_counter() - t0
         n = K.shape[0]
+        # scipy/SuperLU on the host cores, same matrix: whole-block solve of 32 columns
+        # (SuperLU's triangular solves are serial; the time is linear in the column count)
+        cpu_ms_col = None
+        if rank == 0:
+            import scipy.sparse.linalg as spsla
+            slu = spsla.splu(K)
+            Bc = np.random.default_rng(0).standard_normal((n, 32))
+            slu.solve(Bc[:, :2])
+            t0 = time.perf_counter()
+            slu.solve(Bc)
+            cpu_ms_col = 1e3*(time.perf_counter() - t0)/32
+            del slu
         for k in ks:
             c0, c1 = par.column_slice(k, rank, world)
             kl = max(c1 - c0, 1)
@@ -255,6 +267,9 @@ def run_sweep(meshes, ks, reps, rank, world, peak_gbs):
                             solves_per_s=1e3/ms, rhs_columns_per_s=1e3*k/ms,
                             alg_GBs=ab/ms/1e6, frac_hbm=ab/ms/1e6/peak_gbs,
                             fp64_TFs=fl/ms/1e9, residual=res, setup_s=tsetup,
+                            cpu_scipy_ms_per_solve=None if cpu_ms_col is None else cpu_ms_col*k,
+                            cpu_scipy_rhs_columns_per_s=None if cpu_ms_col is None else 1e3/cpu_ms_col,
+                            speedup_vs_cpu=None if cpu_ms_col is None else cpu_ms_col*k/ms,
                             executor='wide' if (i['stream_kp'] == 0 or k//world >= 640) else 'cluster'))
         del lu
     return out
@@ -280,7 +295,7 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=2)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--sweep-meshes', default='50', help='comma list of cavity meshes for the saddle-solve sweep ("" = skip)')
+    ap.add_argument('--sweep-meshes', default='25,50', help='comma list of cavity meshes for the saddle-solve sweep ("" = skip)')
     ap.add_argument('--sweep-k', default='64,256,1024')
     ap.add_argument('--phases', action='store_true', help='extra untimed pass with per-phase CUDA events + cProfile of the e2e loop (diagnostics on stderr)')
     args = ap.parse_args()

@@ -21,7 +21,8 @@ import numpy as np
 import scipy.sparse as sps
 import scipy.sparse.linalg as spsla
 
-__all__ = ['eval_costfunc', 'simulate_closed_loop']
+__all__ = ['eval_costfunc', 'simulate_closed_loop', 'extract_output', 'save_output_json',
+           'load_json_dicts']
 
 
 def eval_costfunc(V=None, W=None, R=None, cmat=None, ystar=None, bmat=None, tbmat=None,
@@ -87,3 +88,35 @@ def simulate_closed_loop(mmat=None, amat=None, jmat=None, rhsv=None, tb_mat=None
         store.save(v, key_prfx + repr(float(t1)))
         veldict[t1] = key_prfx + repr(float(t1))
     return veldict
+
+
+def extract_output(dictofpaths=None, tmesh=None, c_mat=None, ystarvec=None, store=None):
+    """Output signals ``y(t) = C v(t)`` and the targets along ``tmesh`` as lists per component
+    (``dou.extract_output`` as called at ``optcont_main.py:642-645``)."""
+    ys, ystars = [], []
+    for t in tmesh:
+        y = np.asarray(c_mat @ store.load(dictofpaths[t])).ravel()
+        ys.append(y.tolist())
+        if ystarvec is not None:
+            ystars.append(np.asarray(ystarvec(t)).ravel().tolist())
+    yscomplist = [list(c) for c in zip(*ys)]
+    ystarlist = [list(c) for c in zip(*ystars)] if ystars else None
+    return yscomplist, ystarlist
+
+
+def save_output_json(ycomp, tmesh, ystar=None, fstring=None):
+    """The ``__sigout`` file of ``optcont_main.py:160-175``: one JSON object with the keys
+    ``ycomp``, ``tmesh``, ``ystar`` (what ``plot_output.plot_optcont_json`` reads)."""
+    import json
+    if fstring is None:
+        fstring = 'nonspecified_output'
+    with open(fstring, mode='w') as jsfile:
+        jsfile.write(json.dumps(dict(ycomp=ycomp, tmesh=list(tmesh), ystar=ystar)))
+    return fstring
+
+
+def load_json_dicts(StrToJs):
+    """``optcont_main.py:178-182``."""
+    import json
+    with open(StrToJs) as fjs:
+        return json.load(fjs)

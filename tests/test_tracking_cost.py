@@ -70,6 +70,19 @@ def test_feedback_lowers_the_tracking_cost():
         assert np.linalg.norm(prob['J'] @ store[vel[t]]) < 1e-10
 
 
+def test_sigout_json_roundtrip(tmp_path):
+    """``__sigout`` format of optcont_main.py:160-182 (read by plot_output.py)."""
+    c_fb, store, vel = _closed_loop_cost(olau, opru, Nts=3, feedback=False, N=6)
+    prob, cs, kw = _case(6, 3)
+    ys, ystars = tr.extract_output(dictofpaths=vel, tmesh=kw['tmesh'], c_mat=cs['c_mat'],
+                                   ystarvec=kw['ystarvec'], store=store)
+    assert len(ys) == cs['c_mat'].shape[0] and len(ys[0]) == len(kw['tmesh'])
+    f = tr.save_output_json(ys, kw['tmesh'].tolist(), ystar=ystars, fstring=str(tmp_path / 'x__sigout'))
+    js = tr.load_json_dicts(f)
+    assert sorted(js) == ['tmesh', 'ycomp', 'ystar']
+    assert np.allclose(js['ycomp'], ys) and np.allclose(js['tmesh'], kw['tmesh'])
+
+
 @pytest.mark.gpu
 def test_tracking_cost_parity_gpu_vs_oracle():
     import optconpy_b200.lin_alg_utils as glau
