@@ -172,6 +172,11 @@ int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K,
  * Blocks V_i are written side by side into d_Z (NV x ldz), block i at column i*k.
  * Stops after step i when ||V_i||_F / ||[V_1..V_i]||_F <= reltol or i == maxsteps.
  * h_relnorms (maxsteps doubles) receives the ratios; *h_steps the number of blocks. */
+/* Column-sharded runs: every rank iterates on its own slice of the right-hand-side
+ * columns; the stopping test needs the GLOBAL ||V_i||_F^2.  When a hook is set (per calling
+ * thread; NULL clears it) ocb_adi_run passes the local value through it after every step and
+ * uses what comes back - the caller all-reduces the scalar (torch.distributed / NCCL). */
+int ocb_adi_set_norm_hook(void (*hook)(double* v_nsq, void* ctx), void* ctx);
 int64_t ocb_adi_ws_bytes(int64_t n_sad, int64_t k, int64_t m, int64_t nshifts,
                          ocb_lu* const* lus);
 int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts,

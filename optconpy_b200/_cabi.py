@@ -41,6 +41,7 @@ PROTOTYPES = {
     'ocb_compress_ws_bytes': (i64, [i64, i64, i64]),
     'ocb_compress': (C.c_int, [f64p, i64, i64, i64, C.c_double, i64, C.c_double, i64,
                                f64p, i64, i64, f64p, C.POINTER(i64), vp, i64, vp]),
+    'ocb_adi_set_norm_hook': (C.c_int, [vp, vp]),
     'ocb_adi_ws_bytes': (i64, [i64, i64, i64, i64, C.POINTER(vp)]),
     'ocb_adi_run': (C.c_int, [C.POINTER(vp), C.POINTER(C.c_double), i64, i64, i64,
                               i32p, i32p, f64p, f64p, i64, i64, f64p, i64, i64,

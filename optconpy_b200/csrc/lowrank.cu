@@ -25,6 +25,12 @@ int sym_eig_impl(double* G, int64_t ldg, int64_t k, double* lam, double* V, int6
                  int32_t* h_sweeps, cudaStream_t st);
 int smw_core_inv(const double* C, int64_t ldc, int m, double* Sinv, int* flag, cudaStream_t st);
 
+// optional hook that turns the local ||V_i||_F^2 of an ADI step into the global one when the
+// right-hand-side columns are sharded over ranks (the caller all-reduces the scalar)
+typedef void (*ocb_norm_hook_t)(double* v_nsq, void* ctx);
+static thread_local ocb_norm_hook_t g_norm_hook = nullptr;
+static thread_local void* g_norm_hook_ctx = nullptr;
+
 // one side stream + a few events per process (SMW preparation overlaps the ADI chain)
 struct SideStream {
     static constexpr int MAXEV = 34;
@@ -419,6 +425,12 @@ static int smw_prepare(const ocb_lu* lu, int64_t NV, const double* Ufb, int64_t 
 
 extern "C" {
 
+int ocb_adi_set_norm_hook(void (*hook)(double*, void*), void* ctx) {
+    ocb::g_norm_hook = hook;
+    ocb::g_norm_hook_ctx = ctx;
+    return OCB_OK;
+}
+
 int64_t ocb_adi_ws_bytes(int64_t n_sad, int64_t k, int64_t m, int64_t nshifts, ocb_lu* const* lus) {
     using namespace ocb;
     int64_t lws = 0;
@@ -554,7 +566,8 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
             set_error("adi: singular Sherman-Morrison-Woodbury core at shift %lld", (long long)i);
             return OCB_ERR_SINGULAR;
         }
-        const double v_nsq = hp[0];
+        double v_nsq = hp[0];
+        if (g_norm_hook) g_norm_hook(&v_nsq, g_norm_hook_ctx);   // column-sharded run: global norm
         z_nsq += v_nsq;
         const double rel = z_nsq > 0.0 ? sqrt(v_nsq / z_nsq) : 0.0;
         h_relnorms[step] = rel;

@@ -648,7 +648,10 @@ def feedback(Mt, Z, tB, alpha=1.0):
     return out
 
 
-def adi_run(lus, shifts, NV, NP, Mt, W, maxsteps, reltol, Ufb=None, Vt=None):
+NORM_HOOK_T = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_void_p)
+
+
+def adi_run(lus, shifts, NV, NP, Mt, W, maxsteps, reltol, Ufb=None, Vt=None, norm_reduce=None):
     """The LR-ADI loop on the device.  Returns (Z device tensor NV x (steps*k),
     list of relative norms)."""
     lib = require_cuda()
@@ -675,16 +678,34 @@ def adi_run(lus, shifts, NV, NP, Mt, W, maxsteps, reltol, Ufb=None, Vt=None):
     nst = C.c_int64(0)
     wsb = lib.ocb_adi_ws_bytes(NV+NP, k, m, nsh, harr)
     ws = workspace('adi', wsb)
-    _cabi.check(lib.ocb_adi_run(
-        harr, sarr, nsh, NV, NP, ptr(Mt.rowptr), ptr(Mt.colidx), ptr(Mt.vals),
-        ptr(W), W.stride(0), k, ptr(Ufb), Ufb.stride(0) if m else 0, m,
-        ptr(Vt.rowptr) if m else 0, ptr(Vt.colidx) if m else 0, ptr(Vt.vals) if m else 0,
-        int(min(maxsteps, steps_cap)), float(reltol), ptr(Z), Z.stride(0), Z.shape[1],
-        rel, C.byref(nst), ptr(ws), wsb, stream_ptr()), 'ocb_adi_run')
+    hook = None
+    if norm_reduce is not None:
+        # column-sharded run: ``norm_reduce(local ||V_i||^2) -> global`` (an all-reduce)
+        def _hook(pv, _ctx):
+            pv[0] = float(norm_reduce(pv[0]))
+        hook = NORM_HOOK_T(_hook)
+        _cabi.check(lib.ocb_adi_set_norm_hook(C.cast(hook, C.c_void_p), None), 'set_norm_hook')
+    try:
+        rc = _adi_call(lib, harr, sarr, nsh, NV, NP, Mt, W, k, Ufb, m, Vt, maxsteps, steps_cap, reltol,
+                       Z, rel, nst, ws, wsb)
+    finally:
+        if hook is not None:
+            lib.ocb_adi_set_norm_hook(None, None)
+    _cabi.check(rc, 'ocb_adi_run')
     steps = int(nst.value)
     # clone, not contiguous(): when the iteration used the whole buffer the slice IS contiguous
     # and contiguous() would hand out a view of the workspace that the next call overwrites
     return Z[:, :steps*k].clone(memory_format=torch.contiguous_format), [rel[i] for i in range(steps)]
+
+
+def _adi_call(lib, harr, sarr, nsh, NV, NP, Mt, W, k, Ufb, m, Vt, maxsteps, steps_cap, reltol, Z, rel,
+              nst, ws, wsb):
+    return (lib.ocb_adi_run(
+        harr, sarr, nsh, NV, NP, ptr(Mt.rowptr), ptr(Mt.colidx), ptr(Mt.vals),
+        ptr(W), W.stride(0), k, ptr(Ufb), Ufb.stride(0) if m else 0, m,
+        ptr(Vt.rowptr) if m else 0, ptr(Vt.colidx) if m else 0, ptr(Vt.vals) if m else 0,
+        int(min(maxsteps, steps_cap)), float(reltol), ptr(Z), Z.stride(0), Z.shape[1],
+        rel, C.byref(nst), ptr(ws), wsb, stream_ptr()))
 
 
 def launch_count():
