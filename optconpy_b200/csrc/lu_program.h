@@ -12,8 +12,8 @@
 // sub-level are independent; a barrier separates sub-levels.  Within a sub-level the rows
 // are sorted by length and cut into SLICES of 32 >> g rows (2^g lanes per row, g from the
 // row length); a slice is the unit of work of one warp and its entries are stored
-// trip-major (sliced ELLPACK), so that the 32 lanes of a warp read 32 consecutive entries.  For the N=25 cavity factor
-// this is 143 sub-levels instead of 1784 scalar dependency levels.
+// trip-major (sliced ELLPACK), so that the 32 lanes of a warp read 32 consecutive entries.  
+// For the N=25 cavity factor this is 139-143 sub-levels instead of 1784 scalar dependency levels.
 #pragma once
 #include <stdint.h>
 #include <vector>

@@ -2,20 +2,25 @@
 //
 // Design (DESIGN.md "K1").  The host turns the factors into a GATHER PROGRAM
 // (lu_program.h): supernodes with inverted diagonal blocks, so that the whole solve is a
-// short sequence of sub-levels (143 for the N=25 cavity instead of 1784 scalar dependency
+// short sequence of sub-levels (139 for the N=25 cavity instead of 1784 scalar dependency
 // levels), every sub-level a set of independent rows
-//     xe[dst] = ((init >= 0 ? xe[init] : 0) - sum_p val[p] * xe[col[p]]) * scale.
-// The right-hand-side COLUMNS are independent: the block is cut into panels of KP columns
-// and ONE CTA owns one panel for the whole solve (row permutation, all sub-levels, column
-// permutation) - no inter-CTA synchronisation, one __syncthreads() per sub-level.  The
-// panel xe lives in shared memory (or in a per-CTA global slab when n is too large); the
-// program is consumed from a packed, 16-byte aligned BATCH STREAM that the TMA engine
-// (cp.async.bulk + mbarrier complete_tx) copies into a shared-memory ring a few batches
-// ahead of the consumers, so a sub-level only ever sees shared-memory latency.  A row is
-// reduced by 2^g lanes (g per segment, chosen on the host from the row lengths) with
-// shuffle butterflies.  For few right-hand sides the launch picks KP = 1 so that as many
-// SMs as there are columns work concurrently (latency-optimal); more columns per CTA
-// amortise the program stream when there are more columns than SMs.
+//     xe[dst] = ((init >= 0 ? xe[init] : 0) - sum_p val[p] * xe[col[p]]) * scale,
+// cut into SLICES (the unit of work of one warp, sliced-ELLPACK entry layout).
+//
+// sptrsm_stream_kernel<KP, CL> (the hot one at the reference's sizes).  The right-hand-side
+// COLUMNS are independent: the block is cut into panels of KP columns and one thread-block
+// CLUSTER of CL CTAs owns one panel for the whole solve (row permutation, all sub-levels,
+// column permutation) - no grid-wide synchronisation.  The slices of every sub-level are dealt
+// to the CL ranks; every CTA keeps a full copy of the panel xe in shared memory, streams its
+// share of the program through a shared-memory ring fed by a producer warp with TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx), and publishes every result row to all CL
+// copies with st.async, counted on the level mbarrier of the destination CTA - data and
+// barrier signal travel together.  A row is reduced by 2^g lanes (g per slice, chosen on the
+// host from the row length) with shuffle butterflies.  The launch picks KP = 1 while one wave
+// of clusters covers all columns (latency) and KP = 2 beyond.
+//
+// wide_level_kernel<T> (large n, very wide blocks): all columns at once, one launch per
+// sub-level, lane = column; the program is read once per solve.
 //
 // Algorithmic bytes per solve: 12*(nnzL+nnzU) + 16*(n+1) + 32*n*k.
 #include "common.cuh"
