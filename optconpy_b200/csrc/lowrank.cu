@@ -3,6 +3,7 @@
 //   * the LR-ADI loop with Sherman-Morrison-Woodbury corrections (K6/K7 fused update + norm)
 //   * single SMW saddle-point solves, the feedback product  Mt (Z (Z^T tB)).
 #include "common.cuh"
+#include <stdlib.h>
 #include <math.h>
 #include <vector>
 #include <algorithm>
@@ -495,7 +496,8 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
     // fill the SMs the narrow ADI solves leave idle; the main stream waits for shift i's
     // event right before its first use.
     SideStream* side = nullptr;
-    if (m > 0 && lws_bytes == 0 && nshifts <= SideStream::MAXEV - 1) {
+    static const bool no_side = getenv("OCB_NO_SIDE_STREAM") != nullptr;
+    if (m > 0 && lws_bytes == 0 && nshifts <= SideStream::MAXEV - 1 && !no_side) {
         side = side_stream();
         if (side) {
             OCB_CUDA(cudaEventRecord(side->ev[SideStream::MAXEV - 1], st));

@@ -90,7 +90,7 @@ struct SolveArgs {
 //                    off_scale, off_col, off_val, -}
 //   int32 piece[4*npiece] = {s0, s1, barrier, -}: slices [s0, s1) of one sub-level
 //   int32 slice[4*nslice] = {ebase, trips, glog | nrows << 8, q0}  (local to the record)
-//   int32 dst[nrows], int32 init[nrows], f64 scale[nrows], int32 col[nent], f64 val[nent]
+//   int32 dst[nrows], int32 init[nrows], f64 scale[nrows], uint16 col[nent], f64 val[nent]
 constexpr int HDR_INTS = 12;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(cons
         const int32_t* dst = (const int32_t*)(rec + hdr[6]);
         const int32_t* init = (const int32_t*)(rec + hdr[7]);
         const double* scale = (const double*)(rec + hdr[8]);
-        const int32_t* col = (const int32_t*)(rec + hdr[9]);
+        const uint16_t* col = (const uint16_t*)(rec + hdr[9]);
         const double* val = (const double*)(rec + hdr[10]);
         for (int pc = 0; pc < npiece; ++pc) {
             const int4 pd = piece[pc];
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(cons
                     di = dst[q];
                     sc = scale[q];
                 }
-                const int32_t* cp = col + sd.x + lane;
+                const uint16_t* cp = col + sd.x + lane;
                 const double* vp = val + sd.x + lane;
                 const int trips = sd.y;
                 // UNR trips per step, all loads of a step issued before the first use;
@@ -435,7 +435,7 @@ static int64_t record_bytes(int64_t npiece, int64_t nslice, int64_t nrows, int64
     o = a16(o + nrows * 4);
     o = a16(o + nrows * 4);
     o = a16(o + nrows * 8);
-    o = a16(o + nent * 4);
+    o = a16(o + nent * 2);   // 16-bit column indices: the panel has < 65536 rows whenever it fits shared memory
     o = a16(o + nent * 8);
     return o;
 }
@@ -537,7 +537,7 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl
     const int64_t off_scale = o;
     o = a16(o + nrows * 8);
     const int64_t off_col = o;
-    o = a16(o + nent * 4);
+    o = a16(o + nent * 2);
     const int64_t off_val = o;
     hdr[0] = (int32_t)npiece; hdr[1] = (int32_t)nsl; hdr[2] = (int32_t)nrows; hdr[3] = (int32_t)nent;
     hdr[4] = (int32_t)off_piece; hdr[5] = (int32_t)off_slice; hdr[6] = (int32_t)off_dst;
@@ -548,7 +548,7 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl
     int32_t* dst = (int32_t*)(rec + off_dst);
     int32_t* init = (int32_t*)(rec + off_init);
     double* scale = (double*)(rec + off_scale);
-    int32_t* col = (int32_t*)(rec + off_col);
+    uint16_t* col = (uint16_t*)(rec + off_col);
     double* val = (double*)(rec + off_val);
     int32_t ls = 0, r = 0, e = 0;
     for (size_t pi = 0; pi < b.size(); ++pi) {
@@ -569,7 +569,7 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl
             memcpy(dst + r, P.dst.data() + sl.q0, (size_t)nr * 4);
             memcpy(init + r, P.init.data() + sl.q0, (size_t)nr * 4);
             memcpy(scale + r, P.scale.data() + sl.q0, (size_t)nr * 8);
-            memcpy(col + e, P.col.data() + sl.ebase, (size_t)ne * 4);
+            for (int q = 0; q < ne; ++q) col[e + q] = (uint16_t)P.col[sl.ebase + q];
             memcpy(val + e, P.val.data() + sl.ebase, (size_t)ne * 8);
             r += nr;
             e += ne;
@@ -615,7 +615,7 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
     const int64_t want = (e_kb && atoi(e_kb) >= 4) ? (int64_t)atoi(e_kb) * 1024 : 40 * 1024;
     for (int ki = 0; ki < 2 && !force_global && kp_smem == 0; ++ki) {
         const int64_t left = smem_cap - xe1 * kps[ki];
-        if (left < nst * 8192) continue;
+        if (left < nst * 8192 || P.n_ext >= 65535) continue;
         cap = std::min<int64_t>(left / nst, want) & ~(int64_t)15;
         if (plan_all(cap, cl)) kp_smem = kps[ki];
     }
