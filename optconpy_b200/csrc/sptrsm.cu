@@ -592,7 +592,7 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
                       int max_smem_optin, int flags, unsigned char** img_out, int64_t* bytes_out) {
     const int64_t smem_cap = (int64_t)max_smem_optin - 1024 - 192;
     const int64_t xe1 = (P.n_ext + 1) * 8;   // bytes of a one-column panel (+ the token slot)
-    int kp_smem = 0, nst = 3, cl = 4;
+    int kp_smem = 0, nst = 2, cl = 4;   // two large stages: a bulk copy has ~0.35 us of fixed cost
     int64_t cap = 0;
     const char* env = getenv("OCB_SPTRSM_FORCE_GLOBAL");
     const bool force_global = env && env[0] == '1';
@@ -612,7 +612,7 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
     const char* e_st = getenv("OCB_RING_STAGES");
     const char* e_kb = getenv("OCB_RING_STAGE_KB");
     if (e_st && atoi(e_st) >= 2 && atoi(e_st) <= 8) nst = atoi(e_st);
-    const int64_t want = (e_kb && atoi(e_kb) >= 4) ? (int64_t)atoi(e_kb) * 1024 : 40 * 1024;
+    const int64_t want = (e_kb && atoi(e_kb) >= 4) ? (int64_t)atoi(e_kb) * 1024 : 60 * 1024;
     for (int ki = 0; ki < 2 && !force_global && kp_smem == 0; ++ki) {
         const int64_t left = smem_cap - xe1 * kps[ki];
         if (left < nst * 8192 || P.n_ext >= 65535) continue;
