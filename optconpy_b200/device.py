@@ -256,12 +256,21 @@ class _PinnedShmPool(object):
         self.segs, self.free = [], []
         self.lock = threading.Lock()
         rt = torch.cuda.cudart()
-        for i in range(nseg):
-            shm = shared_memory.SharedMemory(create=True, size=self.seg_bytes)
-            addr = C.addressof(C.c_char.from_buffer(shm.buf))
-            pinned = int(rt.cudaHostRegister(addr, self.seg_bytes, 0)) == 0
-            self.segs.append((shm, addr, pinned))
-            self.free.append(i)
+        try:
+            for i in range(nseg):
+                shm = shared_memory.SharedMemory(create=True, size=self.seg_bytes)
+                addr = C.addressof(C.c_char.from_buffer(shm.buf))
+                self.segs.append((shm, addr, False))
+                # page-locking touches (and thereby really allocates) every page of the segment:
+                # if /dev/shm cannot back it this fails here, in the parent, not as a SIGBUS in a
+                # worker that writes into it later
+                if int(rt.cudaHostRegister(addr, self.seg_bytes, 0)) != 0:
+                    raise MemoryError('cudaHostRegister failed')
+                self.segs[-1] = (shm, addr, True)
+                self.free.append(i)
+        except Exception:
+            self.close()
+            raise
 
     def acquire(self):
         with self.lock:
@@ -277,7 +286,13 @@ class _PinnedShmPool(object):
             try:
                 if pinned:
                     rt.cudaHostUnregister(addr)
+            except Exception:
+                pass
+            try:
                 shm.close()
+            except Exception:
+                pass            # exported buffer views may still exist at interpreter exit
+            try:
                 shm.unlink()
             except Exception:
                 pass
@@ -294,8 +309,16 @@ def _shm_pool(image_bytes=None):
         return None
     if _SHM['pool'] is None and image_bytes is not None:
         try:
-            nseg = int(os.environ.get('OCB_PINNED_POOL_SEGMENTS', '28'))
-            _SHM['pool'] = _PinnedShmPool(nseg, int(image_bytes*1.3) + (1 << 20))
+            world = max(int(os.environ.get('WORLD_SIZE', '1')), 1)
+            nseg = int(os.environ.get('OCB_PINNED_POOL_SEGMENTS', str(max(12, 28//world))))
+            seg_bytes = int(image_bytes*1.3) + (1 << 20)
+            try:
+                st = os.statvfs('/dev/shm')
+                if nseg*seg_bytes > 0.4*st.f_bavail*st.f_frsize:
+                    raise MemoryError('/dev/shm too small for the pinned pool')
+            except OSError:
+                pass
+            _SHM['pool'] = _PinnedShmPool(nseg, seg_bytes)
             import atexit
             atexit.register(_SHM['pool'].close)
         except Exception:
