@@ -401,7 +401,11 @@ def main():
         tmp = tempfile.mkdtemp(prefix='ocb_bench_')
         try:
             prob2, cs2, kw2 = sc.config2(glau, N=N)
-            kw2['tmesh'] = kw2['tmesh'][-(S+1):]
+            # the stepper prepares `la` steps ahead: run `la` extra (untimed) steps after the
+            # timed ones so that the look-ahead pipeline stays full during the timed region
+            # (steady state) instead of draining inside it
+            la = int(os.environ.get('OCB_LOOKAHEAD', '4'))
+            kw2['tmesh'] = kw2['tmesh'][-(S+la+1):]
             kw2['gtdtstrargs'] = dict(kw2['gtdtstrargs'], data_prfx=os.path.join(tmp, 'tdst_'))
             stamps, bytes_at = [], []
 
@@ -418,7 +422,7 @@ def main():
                 prof.enable()
             stimes = {}
             ds.solve_flow_daeric(lau=glau, pru=gpru, store=ds.NpyStore(), step_callback=cb,
-                                 timing=stimes, **kw2)
+                                 timing=stimes, lookahead=la, **kw2)
             if args.phases:
                 prof.disable()
                 pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(45)
@@ -433,11 +437,11 @@ def main():
                        d2h_bytes_per_step=int(d2h), ms_per_step=1e3*float(tm.item())/K,
                        api='optconpy_b200.dre_stepper.solve_flow_daeric(lau, pru) with scipy/numpy '
                            'inputs and .npy outputs; host LU setup inside the timed region',
-                       host_setup_per_step={k: (v/S) for k, v in dv.STATS.items()
+                       host_setup_per_step={k: (v/(S+la)) for k, v in dv.STATS.items()
                                             if k.startswith('lu_') or k == 'n_factor'},
-                       lu_workers=dv._POOL['workers'],
-                       main_thread_phase_s_per_step=dict({k: v/S for k, v in dv.PHASE.items()},
-                                                         **{k: v/S for k, v in stimes.items()}),
+                       lu_workers=dv._POOL['workers'], lookahead_steps=la,
+                       main_thread_phase_s_per_step=dict({k: v/(S+la) for k, v in dv.PHASE.items()},
+                                                         **{k: v/(S+la) for k, v in stimes.items()}),
                        note='LU setup of step k-1 runs in worker processes while the GPU works '
                             'on step k (dre_stepper look-ahead); lu_wait_s is what the main '
                             'process still blocks on')
