@@ -10,6 +10,17 @@ import scipy.sparse as sps
 import scipy.sparse.linalg as spsla
 
 
+def worker_init():
+    """Pool initializer: the factorisations are throughput work - run them at a lower priority
+    than the main process, whose threads drive the GPU and are latency sensitive (with as many
+    busy workers as cores every host-side wait of the main thread otherwise costs milliseconds)."""
+    import os
+    try:
+        os.nice(10)
+    except OSError:
+        pass
+
+
 def factor_arrays(args, want_order=False):
     """(data, indices, indptr, shape, lu_options[, smem, flags, q]) of a CSC matrix ->
     int32/FP64 CSR arrays of L and U plus the two permutations.

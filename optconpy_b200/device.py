@@ -204,7 +204,8 @@ def _lu_pool():
     if _POOL['pool'] is None or _POOL['workers'] != want:
         if _POOL['pool'] is not None:
             _POOL['pool'].terminate()
-        _POOL['pool'] = mp.get_context('spawn').Pool(want)
+        from . import _lu_worker
+        _POOL['pool'] = mp.get_context('spawn').Pool(want, initializer=_lu_worker.worker_init)
         _POOL['workers'] = want
     return _POOL['pool']
 

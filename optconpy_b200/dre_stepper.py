@@ -168,9 +168,16 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
     # the preparation of step k-1 runs in a helper thread while this thread drives the device
     # work of step k (the C library and numpy/scipy release the GIL)
     pool = None
+    old_switch = None
     if can_prefetch:
+        import sys
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max_workers=1)
+        # this thread drives the GPU with many short blocking calls; each one has to win the
+        # GIL back from the helper threads (assembly, pickling), which by default may keep it
+        # for 5 ms at a time
+        old_switch = sys.getswitchinterval()
+        sys.setswitchinterval(1e-4)
     depth = int(lookahead) if can_prefetch else 0
     ahead = {}
     for tk in range(len(tmesh)-2, -1, -1):
@@ -252,4 +259,5 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
             step_callback(tk)
     if pool is not None:
         pool.shutdown(wait=True)
+        sys.setswitchinterval(old_switch)
     return fbdict
