@@ -5,6 +5,7 @@ There is no CPU fallback: every entry point calls :func:`require_cuda` and the
 library loader raises if the extension is missing.
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -119,7 +120,6 @@ class Workspace(object):
     def get(self, nbytes):
         nbytes = int(max(nbytes, 256))
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != cur_device():
-            import os
             t0 = time.perf_counter()
             self.buf = None
             self.buf = torch.empty(int(nbytes*1.5) + 1024, dtype=torch.uint8,
@@ -193,7 +193,6 @@ def _lu_pool():
     """Process pool for the host LU setup (SuperLU holds the GIL).  OCB_LU_WORKERS=0
     keeps everything in-process."""
     import multiprocessing as mp
-    import os
     want = os.environ.get('OCB_LU_WORKERS')
     if want is None:
         world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -228,7 +227,6 @@ def _pattern_key(a):
 
 def _with_order(a, opts):
     """worker arguments (.., smem, flags, q) with the cached ordering of this pattern, if any"""
-    import os
     if os.environ.get('OCB_NO_ORDER_REUSE') or opts.get('permc_spec') == 'NATURAL':
         return a, None
     key = _pattern_key(a)
@@ -307,7 +305,6 @@ _SHM = dict(pool=None, disabled=False)
 
 def _shm_pool(image_bytes=None):
     """The pinned pool (created after the first image told us the size), or None."""
-    import os
     if _SHM['disabled'] or os.environ.get('OCB_NO_PINNED_POOL'):
         return None
     if _SHM['pool'] is None and image_bytes is not None:
@@ -384,7 +381,6 @@ class FactorJob(object):
         """Collect the worker results and upload the images from a helper thread on its own
         CUDA stream (copy engine), so that the main thread does not spend its time in
         pageable host-to-device copies; ``result()`` then only joins."""
-        import os
         if self._future is None and self._done is None and not os.environ.get('OCB_NO_UPLOAD_THREAD'):
             self._future = _uploader().submit(self._collect)
         return self
@@ -414,7 +410,10 @@ class FactorJob(object):
             from multiprocessing import shared_memory
             for ar, slot, key in zip(self._async, self._slots, self._keys):
                 t0 = time.perf_counter()
-                name, nbytes, tf, tp, order = ar.get()
+                try:
+                    name, nbytes, tf, tp, order = ar.get(timeout=float(os.environ.get('OCB_LU_TIMEOUT_S', '900')))
+                except Exception as exc:        # a dead worker would otherwise block forever
+                    raise RuntimeError('optconpy_b200: host LU worker failed or timed out: %r' % (exc,))
                 if order is not None and key is not None:
                     _ORDER.setdefault(key, order)
                 STATS['lu_collect_wait_s'] += time.perf_counter() - t0
