@@ -346,9 +346,24 @@ __global__ void __launch_bounds__(256) adi_update_kernel(const double* __restric
                                                         double* __restrict__ Vnew, int64_t ldn,
                                                         int64_t nrows, int64_t k, double a, double b,
                                                         double* __restrict__ partials,
-                                                        double* __restrict__ nrm2) {
+                                                        double* __restrict__ nrm2,
+                                                        const double* __restrict__ Sinv,
+                                                        const double* __restrict__ small) {
+    extern __shared__ double s2s[];   // fused variant: S2 = Sinv * small, recomputed per CTA
     __shared__ double red[8];
     __shared__ bool last;
+    if (MMAX > 0 && Sinv != nullptr) {
+        // same formula and summation order as smw_s2_kernel: bit-identical, one launch less
+        for (int64_t e = threadIdx.x; e < (int64_t)m * k; e += blockDim.x) {
+            const int r = (int)(e / k);
+            const int64_t c = e % k;
+            double sv = 0.0;
+            for (int l = 0; l < m; ++l) sv = fma(Sinv[r * m + l], small[(int64_t)l * k + c], sv);
+            s2s[e] = sv;
+        }
+        __syncthreads();
+        S2 = s2s;
+    }
     const int64_t total = nrows * k;
     double acc = 0.0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -387,15 +402,21 @@ __global__ void __launch_bounds__(256) adi_update_kernel(const double* __restric
 
 constexpr int UPD_MAXBLOCKS = 1024;
 
+constexpr int64_t UPD_FUSE_MAX = 4096;   // m*k doubles of shared memory for the fused S2
+
+// Sinv/small != null: S2 = Sinv*small is computed inside the update kernel (requires
+// m*k <= UPD_FUSE_MAX); otherwise S2 must hold it already.
 static int adi_update(const double* Vold, int64_t ldv, const double* Y, int64_t ldy, const double* AiU,
                       int64_t lda, int m, const double* S2, double* Vnew, int64_t ldn, int64_t nrows,
-                      int64_t k, double a, double b, double* partials, double* nrm2, cudaStream_t st) {
+                      int64_t k, double a, double b, double* partials, double* nrm2, cudaStream_t st,
+                      const double* Sinv = nullptr, const double* small = nullptr) {
     const int64_t total = nrows * k;
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(UPD_MAXBLOCKS, (total + 1023) / 1024));
+    const size_t smem = (m > 0 && Sinv) ? (size_t)m * k * sizeof(double) : 0;
     if (m > 0)
-        adi_update_kernel<1><<<blocks, 256, 0, st>>>(Vold, ldv, Y, ldy, AiU, lda, m, S2, Vnew, ldn, nrows, k, a, b, partials, nrm2);
+        adi_update_kernel<1><<<blocks, 256, smem, st>>>(Vold, ldv, Y, ldy, AiU, lda, m, S2, Vnew, ldn, nrows, k, a, b, partials, nrm2, Sinv, small);
     else
-        adi_update_kernel<0><<<blocks, 256, 0, st>>>(Vold, ldv, Y, ldy, AiU, lda, 0, S2, Vnew, ldn, nrows, k, a, b, partials, nrm2);
+        adi_update_kernel<0><<<blocks, 256, 0, st>>>(Vold, ldv, Y, ldy, AiU, lda, 0, S2, Vnew, ldn, nrows, k, a, b, partials, nrm2, nullptr, nullptr);
     OCB_LAUNCH_CHECK();
     return OCB_OK;
 }
@@ -545,11 +566,14 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
             rc = lu_solve_impl(lu, T, k, NV, Y, k, NV, k, lws, lws_bytes, st);
         }
         if (rc) return rc;
+        const bool fuse_s2 = m > 0 && m * k <= UPD_FUSE_MAX;
         if (m > 0) {
             rc = spmm_launch(m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals, Y, k, small, k, k, 1.0, 0.0, st);
             if (rc) return rc;
-            smw_s2_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, st>>>(Sinv + i * m * m, (int)m, small, k, S2);
-            OCB_LAUNCH_CHECK();
+            if (!fuse_s2) {
+                smw_s2_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, st>>>(Sinv + i * m * m, (int)m, small, k, S2);
+                OCB_LAUNCH_CHECK();
+            }
         }
         double a, b;
         if (step == 0) { a = 0.0; b = sqrt(-2.0 * h_shifts[0]); }
@@ -559,7 +583,7 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
             b = -cs * (h_shifts[i] + h_shifts[ip]);
         }
         rc = adi_update(Vprev, ldz, Y, k, AiU + i * NV * m, m, (int)m, S2, Vnew, ldz, NV, k, a, b,
-                        partials, dnorm, st);
+                        partials, dnorm, st, fuse_s2 ? Sinv + i * m * m : nullptr, fuse_s2 ? small : nullptr);
         if (rc) return rc;
         OCB_CUDA(cudaMemcpyAsync(hp, dnorm, sizeof(double), cudaMemcpyDeviceToHost, st));
         OCB_CUDA(cudaMemcpyAsync(hp + 1, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
