@@ -21,6 +21,15 @@ def worker_init():
         pass
 
 
+def order_only(args):
+    """The fill-reducing ordering of a sparsity pattern (one full SuperLU run with its
+    minimum-degree ordering; done ONCE per pattern, before any job of that pattern is queued, so
+    that every queued factorisation already takes the fast reuse path)."""
+    data, indices, indptr, shape, opts = args[:5]
+    slu = spsla.splu(sps.csc_matrix((data, indices, indptr), shape=shape), **opts)
+    return np.argsort(slu.perm_c).astype(np.int32)
+
+
 def factor_arrays(args, want_order=False):
     """(data, indices, indptr, shape, lu_options[, smem, flags, q]) of a CSC matrix ->
     int32/FP64 CSR arrays of L and U plus the two permutations.

@@ -18,6 +18,7 @@ from . import _cabi
 # Counters the bench reads (setup is timed separately, north_star).
 STATS = dict(lu_factor_s=0.0,          # SuperLU seconds summed over the workers
              lu_worker_pack_s=0.0,     # host analysis + packing seconds summed over the workers
+             lu_order_s=0.0,           # main process: one-off minimum-degree ordering per pattern
              lu_submit_s=0.0,          # main process: building + sending the CSC arguments
              lu_wait_s=0.0,            # main thread: blocked until the factors are on the device
              lu_collect_wait_s=0.0,    # collecting thread: blocked on a worker result
@@ -230,7 +231,14 @@ def _with_order(a, opts):
     if os.environ.get('OCB_NO_ORDER_REUSE') or opts.get('permc_spec') == 'NATURAL':
         return a, None
     key = _pattern_key(a)
-    return a + (_ORDER.get(key),), key
+    if key not in _ORDER:
+        # first matrix of this pattern: get the ordering NOW (one synchronous SuperLU run), so
+        # that no queued job runs the slow path or produces the larger factor
+        from . import _lu_worker
+        t0 = time.perf_counter()
+        _ORDER[key] = _lu_worker.order_only(a)
+        STATS['lu_order_s'] += time.perf_counter() - t0
+    return a + (_ORDER[key],), key
 
 
 _SMEM_OPTIN = dict()
