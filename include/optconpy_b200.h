@@ -66,7 +66,11 @@ int ocb_lu_destroy(ocb_lu* lu);
 /* The same in two halves, so that the analysis can run where the host LU ran (a worker
  * process without a CUDA context): ocb_lu_pack_host builds the self-describing device image
  * (malloc'ed; release with ocb_host_free) for a GPU with max_smem_optin bytes of opt-in shared
- * memory per block (flags bit 0: also include the flat program of the wide, all-columns-at-once
+ * memory per block (flags bit 1: TRANSPOSED layout - the factors come from an LU factorisation
+ * of A^T handed over column-wise, A = U^T L^T: the first three arrays are then the rows of the
+ * lower factor U^T, which carries the pivots, the next three the rows of the unit upper factor
+ * L^T, and h_perm_r / h_perm_c are that factorisation's perm_c / perm_r; SuperLU's compressed-
+ * column output is used as is, no transposition on the host.  flags bit 0: also include the flat program of the wide, all-columns-at-once
  * executor that ocb_lu_solve uses for k >= 640 right-hand sides; it is always included when
  * the column panel does not fit shared memory); ocb_lu_create_from_image uploads it with one copy into d_arena (bytes long,
  * 256-byte aligned, owned by the caller and kept alive until ocb_lu_destroy; NULL: the library
@@ -104,7 +108,8 @@ int ocb_debug_trace(int64_t* h_out, int64_t count);
 typedef struct ocb_lu_program ocb_lu_program;
 int ocb_lu_program_create(ocb_lu_program** out, int64_t n,
                           const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
-                          const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals);
+                          const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
+                          int64_t flags);
 int ocb_lu_program_destroy(ocb_lu_program* prog);
 /* info[0..11] = n, n_ext, ymax, sub-levels L, sub-levels U, #supernodes, widest supernode,
  *               #slices, #rows, #entries (padded), nnz(L) strictly lower, nnz(U) */

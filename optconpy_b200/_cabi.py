@@ -25,7 +25,7 @@ PROTOTYPES = {
     'ocb_lu_info': (C.c_int, [vp, C.POINTER(i64)]),
     'ocb_lu_stats': (C.c_int, [vp, C.POINTER(i64)]),
     'ocb_debug_trace': (C.c_int, [vp, i64]),
-    'ocb_lu_program_create': (C.c_int, [C.POINTER(vp), i64, vp, vp, vp, vp, vp, vp]),
+    'ocb_lu_program_create': (C.c_int, [C.POINTER(vp), i64, vp, vp, vp, vp, vp, vp, i64]),
     'ocb_lu_program_destroy': (C.c_int, [vp]),
     'ocb_lu_program_info': (C.c_int, [vp, C.POINTER(i64)]),
     'ocb_lu_program_export': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -30,40 +30,57 @@ def order_only(args):
     return np.argsort(slu.perm_c).astype(np.int32)
 
 
-def factor_arrays(args, want_order=False):
+def factor_arrays(args, want_order=False, transposed=False):
     """(data, indices, indptr, shape, lu_options[, smem, flags, q]) of a CSC matrix ->
-    int32/FP64 CSR arrays of L and U plus the two permutations.
+    int32/FP64 CSR arrays of the lower and the upper factor plus the two permutations, in the
+    layout ``ocb_lu_pack_host`` expects.
 
     ``q`` (optional, args[7]): a fill-reducing ordering obtained from an earlier factorisation
     of a matrix with the SAME sparsity pattern.  The matrix is then permuted symmetrically,
     ``B = A[q][:, q]``, and factorised with the NATURAL column order: SuperLU skips its
     minimum-degree ordering (half of its run time here) and, because the permutation is
     symmetric, pivots on the diagonal more often (25 % fewer entries in L+U on the cavity
-    matrices).  The returned permutations are composed so that they refer to ``A`` again."""
+    matrices).  The returned permutations are composed so that they refer to ``A`` again.
+
+    ``transposed=True`` (flags bit 1 of ``ocb_lu_pack_host``): factorise ``A^T`` instead.
+    SuperLU hands its factors out column-wise; the columns of ``U`` are the rows of the lower
+    factor ``U^T`` and the columns of ``L`` the rows of the upper factor ``L^T`` in
+    ``A = U^T L^T``, so no CSC->CSR conversion (19 of 80 ms per matrix) is needed.  With
+    ``Pr A^T Pc = L U``:  ``U^T L^T (Pr x) = Pc^T b``, i.e. the kernel's load permutation is this
+    factorisation's ``perm_c`` and its store permutation ``perm_r``."""
     data, indices, indptr, shape, opts = args[:5]
     q = args[7] if len(args) > 7 else None
+    n = shape[0]
     mat = sps.csc_matrix((data, indices, indptr), shape=shape)
-    if q is None:
-        slu = spsla.splu(mat, **opts)
-        perm_r, perm_c = slu.perm_r, slu.perm_c
-    else:
-        o2 = dict(opts)
+    if transposed:
+        mat = mat.T.tocsc()
+    o2 = dict(opts)
+    if q is not None:
         o2['permc_spec'] = 'NATURAL'
-        slu = spsla.splu(mat[q][:, q].tocsc(), **o2)
-        perm_r = np.empty(shape[0], dtype=np.int32)
-        perm_c = np.empty(shape[0], dtype=np.int32)
-        perm_r[q] = slu.perm_r        # xe[perm_r[i]] = b[i]   with b' = b[q]
-        perm_c[q] = slu.perm_c        # x[j] = xe[perm_c[j]]   with x[q] = y
-    L = sps.csr_matrix(slu.L)
-    U = sps.csr_matrix(slu.U)
-    L.sort_indices()
-    U.sort_indices()
-    out = [np.ascontiguousarray(L.indptr, dtype=np.int32),
-           np.ascontiguousarray(L.indices, dtype=np.int32),
-           np.ascontiguousarray(L.data, dtype=np.float64),
-           np.ascontiguousarray(U.indptr, dtype=np.int32),
-           np.ascontiguousarray(U.indices, dtype=np.int32),
-           np.ascontiguousarray(U.data, dtype=np.float64),
+        mat = mat[q][:, q].tocsc()
+    slu = spsla.splu(mat, **o2)
+    load_p, store_p = (slu.perm_c, slu.perm_r) if transposed else (slu.perm_r, slu.perm_c)
+    if q is None:
+        perm_r, perm_c = load_p, store_p
+    else:
+        perm_r = np.empty(n, dtype=np.int32)
+        perm_c = np.empty(n, dtype=np.int32)
+        perm_r[q] = load_p            # xe[perm_r[i]] = b[i]   with b' = b[q]
+        perm_c[q] = store_p           # x[j] = xe[perm_c[j]]   with x[q] = y
+    if transposed:
+        lo, up = slu.U, slu.L         # CSC columns of U / L = CSR rows of U^T / L^T
+        up.sort_indices()             # supernode detection needs sorted rows; the lower factor does not
+    else:
+        lo = sps.csr_matrix(slu.L)
+        up = sps.csr_matrix(slu.U)
+        lo.sort_indices()
+        up.sort_indices()
+    out = [np.ascontiguousarray(lo.indptr, dtype=np.int32),
+           np.ascontiguousarray(lo.indices, dtype=np.int32),
+           np.ascontiguousarray(lo.data, dtype=np.float64),
+           np.ascontiguousarray(up.indptr, dtype=np.int32),
+           np.ascontiguousarray(up.indices, dtype=np.int32),
+           np.ascontiguousarray(up.data, dtype=np.float64),
            np.ascontiguousarray(perm_r, dtype=np.int32),
            np.ascontiguousarray(perm_c, dtype=np.int32)]
     if want_order:
@@ -106,9 +123,10 @@ def factor_image(args):
     """(data, indices, indptr, shape, lu_options, smem_optin) -> (image, seconds factor,
     seconds analyse+pack)."""
     t0 = time.perf_counter()
-    arrs, order = factor_arrays(args, want_order=True)
+    flags = args[6] if len(args) > 6 else 0
+    arrs, order = factor_arrays(args, want_order=True, transposed=bool(flags & 2))
     t1 = time.perf_counter()
-    img = pack_image(arrs, args[3][0], args[5], args[6] if len(args) > 6 else 0)
+    img = pack_image(arrs, args[3][0], args[5], flags)
     return img, t1 - t0, time.perf_counter() - t1, order
 
 
@@ -134,9 +152,10 @@ def factor_image_to_shm(args, slot=None):
     ordering for later matrices of the same pattern or None)."""
     from multiprocessing import shared_memory
     t0 = time.perf_counter()
-    arrs, order = factor_arrays(args, want_order=True)
+    flags = args[6] if len(args) > 6 else 0
+    arrs, order = factor_arrays(args, want_order=True, transposed=bool(flags & 2))
     t1 = time.perf_counter()
-    ci = _CImage(arrs, args[3][0], args[5], args[6] if len(args) > 6 else 0)
+    ci = _CImage(arrs, args[3][0], args[5], flags)
     try:
         nbytes = ci.view.nbytes
         if slot is not None and nbytes <= slot[1]:

@@ -27,6 +27,7 @@ struct Tri {
     const int32_t* ci;
     const double* va;
     bool upper;
+    bool unit;   // unit diagonal (stored entries on the diagonal are ignored)
 };
 
 inline int pow2ceil(int64_t v) {
@@ -94,14 +95,14 @@ int plan_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                 dep = std::max(dep, done[c]);
                 ++noff;
             }
-            if (T.upper && !diag) {
-                set_error("U has a zero pivot in row %d", i);
+            if (!T.unit && !diag) {
+                set_error("the %s factor has a zero pivot in row %d", T.upper ? "upper" : "lower", i);
                 return OCB_ERR_SINGULAR;
             }
         }
         BlockPlan& bp = (*plan)[t];
         if (w == 1) {
-            if (!T.upper && noff == 0) continue;  // unit diagonal, nothing to subtract
+            if (T.unit && noff == 0) continue;  // unit diagonal, nothing to subtract
             bp.sA = dep + 1;
             done[r0] = bp.sA;
             top = std::max(top, bp.sA);
@@ -138,8 +139,8 @@ void invert_block(const Tri& T, int32_t r0, int32_t r1, std::vector<double>* Dbu
             if (c >= r0 && c < r1) D[(size_t)(i - r0) * w + (c - r0)] = T.va[p];
         }
     // row-oriented triangular inversion (unit-stride inner loops):
-    //   lower, unit diagonal:  X[i,:] = e_i - sum_{k<i} D[i,k] X[k,:]
-    //   upper:                 X[i,:] = (e_i - sum_{k>i} D[i,k] X[k,:]) / D[i,i]
+    //   lower:  X[i,:] = (e_i - sum_{k<i} D[i,k] X[k,:]) / D[i,i]
+    //   upper:  X[i,:] = (e_i - sum_{k>i} D[i,k] X[k,:]) / D[i,i]       (D[i,i] = 1 if unit)
     if (!T.upper) {
         for (int i = 0; i < w; ++i) {
             double* xi = &X[(size_t)i * w];
@@ -149,6 +150,10 @@ void invert_block(const Tri& T, int32_t r0, int32_t r1, std::vector<double>* Dbu
                 if (d == 0.0) continue;
                 const double* xk = &X[(size_t)k * w];
                 for (int j = 0; j <= k; ++j) xi[j] -= d * xk[j];
+            }
+            if (!T.unit) {
+                const double inv = 1.0 / D[(size_t)i * w + i];
+                for (int j = 0; j <= i; ++j) xi[j] *= inv;
             }
         }
     } else {
@@ -161,8 +166,10 @@ void invert_block(const Tri& T, int32_t r0, int32_t r1, std::vector<double>* Dbu
                 const double* xk = &X[(size_t)k * w];
                 for (int j = k; j < w; ++j) xi[j] -= d * xk[j];
             }
-            const double inv = 1.0 / D[(size_t)i * w + i];
-            for (int j = i; j < w; ++j) xi[j] *= inv;
+            if (!T.unit) {
+                const double inv = 1.0 / D[(size_t)i * w + i];
+                for (int j = i; j < w; ++j) xi[j] *= inv;
+            }
         }
     }
 }
@@ -270,7 +277,7 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                         const int32_t c = T.ci[p];
                         if (c < r0 || c >= r1) {
                             put(c, T.va[p]);
-                        } else if (c == i && T.upper) {
+                        } else if (c == i && !T.unit) {
                             dg = T.va[p];
                         }
                     }
@@ -304,7 +311,7 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
 
 int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const double* Lva,
                      const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
-                     LuProgram* P) {
+                     bool transposed, LuProgram* P) {
     *P = LuProgram();
     P->n = n;
     P->sub_ptr.push_back(0);
@@ -338,7 +345,9 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
     find_supernodes(n, Urp, Uci, &starts);
     P->nsuper = (int32_t)starts.size() - 1;
     for (size_t t = 0; t + 1 < starts.size(); ++t) P->max_w = std::max(P->max_w, starts[t + 1] - starts[t]);
-    const Tri TL{Lrp, Lci, Lva, false}, TU{Urp, Uci, Uva, true};
+    // layout 0: unit lower L, upper U with the pivots (P A Q = L U);  transposed layout: the
+    // lower factor carries the pivots and the upper one is unit (A = (L U)^T = U^T L^T)
+    const Tri TL{Lrp, Lci, Lva, false, !transposed}, TU{Urp, Uci, Uva, true, transposed};
     std::vector<BlockPlan> planL, planU;
     int64_t ymax = 0;
     int rc = plan_factor(n, TL, starts, &planL, &P->nsub_L, &ymax);
@@ -350,10 +359,10 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
     const int64_t cap = ((int64_t)Lrp[n] + Urp[n]) * 3 / 2 + 64 * n;   // SELL padding included
     P->col.reserve(cap);
     P->val.reserve(cap);
-    for (int64_t i = 0; i < n; ++i) {
-        for (int32_t p = Lrp[i]; p < Lrp[i + 1]; ++p) P->nnzL += (Lci[p] != i);
+    for (int64_t i = 0; i < n; ++i) {   // stored entries, unit diagonals not counted
+        for (int32_t p = Lrp[i]; p < Lrp[i + 1]; ++p) P->nnzL += (Lci[p] != i) || transposed;
+        for (int32_t p = Urp[i]; p < Urp[i + 1]; ++p) P->nnzU += (Uci[p] != i) || !transposed;
     }
-    P->nnzU = Urp[n];
     const auto t2 = tnow();
     rc = emit_factor(n, TL, starts, planL, P->nsub_L, ymax, max_lanes, P);
     const auto t3 = tnow();
@@ -381,11 +390,11 @@ extern "C" {
 
 int ocb_lu_program_create(ocb_lu_program** out, int64_t n, const int32_t* h_L_rowptr,
                           const int32_t* h_L_colidx, const double* h_L_vals, const int32_t* h_U_rowptr,
-                          const int32_t* h_U_colidx, const double* h_U_vals) {
+                          const int32_t* h_U_colidx, const double* h_U_vals, int64_t flags) {
     OCB_ARG(out && n >= 0 && h_L_rowptr && h_U_rowptr, "lu_program_create");
     ocb_lu_program* h = new ocb_lu_program();
     const int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx,
-                                         h_U_vals, 512, &h->P);
+                                         h_U_vals, 512, (flags & 2) != 0, &h->P);
     if (rc != OCB_OK) {
         delete h;
         return rc;

@@ -48,8 +48,11 @@ struct LuProgram {
 
 // Build the program from CSR factors (L unit lower, diagonal optional; U upper with the
 // diagonal).  Returns 0 or a negative ocb_status (message via set_error).
+// transposed = true: the factors come from an LU factorisation of A^T handed over column-wise
+// (A = U^T L^T): the LOWER factor (first three arrays, rows of U^T) carries the pivots and the
+// UPPER factor (rows of L^T) has the unit diagonal.
 int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const double* Lva,
                      const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
-                     LuProgram* out);
+                     bool transposed, LuProgram* out);
 
 }  // namespace ocb

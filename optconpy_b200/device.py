@@ -221,6 +221,12 @@ def _csc_args(mat, opts):
 _ORDER = dict()
 
 
+def _pack_flags(wide):
+    """ocb_lu_pack_host flags: bit 0 = flat program for the wide executor, bit 1 = factorise A^T
+    and take SuperLU's column-wise factors as they are (no CSC->CSR conversion on the host)."""
+    return (1 if wide else 0) | (0 if os.environ.get('OCB_NO_TRANSPOSED_LU') else 2)
+
+
 def _pattern_key(a):
     import zlib
     return (a[3], len(a[1]), zlib.crc32(a[1].tobytes()), zlib.crc32(a[2].tobytes()))
@@ -363,7 +369,7 @@ class FactorJob(object):
         so = smem_optin()
         args, self._keys = [], []
         for m in mats:
-            a, key = _with_order(_csc_args(m, opts) + (so, 1 if wide else 0), opts)
+            a, key = _with_order(_csc_args(m, opts) + (so, _pack_flags(wide)), opts)
             args.append(a)
             self._keys.append(key)
         self.n = len(mats)
@@ -467,7 +473,7 @@ class LU(object):
         if image is None:
             from . import _lu_worker
             opts = dict(LU_OPTIONS if lu_options is None else lu_options)
-            a, key = _with_order(_csc_args(mat, opts) + (smem_optin(), 1 if wide else 0), opts)
+            a, key = _with_order(_csc_args(mat, opts) + (smem_optin(), _pack_flags(wide)), opts)
             image, tf, tp, order = _lu_worker.factor_image(a)
             if order is not None and key is not None:
                 _ORDER.setdefault(key, order)

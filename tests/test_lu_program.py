@@ -15,10 +15,10 @@ import scipy.sparse.linalg as spsla
 from optconpy_b200 import _cabi, _lu_worker, device as dv, problems as pb
 
 
-def _program(arrs, n):
+def _program(arrs, n, flags=0):
     lib = _cabi.load()
     h = C.c_void_p()
-    _cabi.check(lib.ocb_lu_program_create(C.byref(h), n, *[a.ctypes.data for a in arrs[:6]]),
+    _cabi.check(lib.ocb_lu_program_create(C.byref(h), n, *[a.ctypes.data for a in arrs[:6]], flags),
                 'ocb_lu_program_create')
     info = (C.c_int64*12)()
     _cabi.check(lib.ocb_lu_program_info(h, info), 'info')
@@ -172,10 +172,10 @@ def test_small_and_degenerate_factors():
     h = C.c_void_p()
     bad = [arrs[0], arrs[1], arrs[2], Ubad.indptr.astype(np.int32), Ubad.indices.astype(np.int32),
            Ubad.data]
-    rc = lib.ocb_lu_program_create(C.byref(h), 6, *[a.ctypes.data for a in bad])
+    rc = lib.ocb_lu_program_create(C.byref(h), 6, *[a.ctypes.data for a in bad], 0)
     assert rc == -3 and b'zero pivot' in lib.ocb_last_error()
     rc = lib.ocb_lu_program_create(C.byref(h), 6, *[a.ctypes.data for a in
-                                                    (arrs[3], arrs[4], arrs[5], arrs[3], arrs[4], arrs[5])])
+                                                    (arrs[3], arrs[4], arrs[5], arrs[3], arrs[4], arrs[5])], 0)
     assert rc == -1 and b'wrong side' in lib.ocb_last_error()
     # n = 0
     z = np.zeros(1, dtype=np.int32)
@@ -206,3 +206,30 @@ def test_reused_ordering_gives_the_same_solution(cav10):
     got = X[arrs2[7]]
     assert np.linalg.norm(K2 @ got - B) <= 1e-12*np.linalg.norm(B)
     assert len(arrs2[2]) + len(arrs2[5]) <= 1.05*(len(arrs1[2]) + len(arrs1[5]))
+
+
+@pytest.mark.parametrize('reuse', [False, True])
+def test_transposed_layout(cav10, reuse):
+    """Factors of A^T taken column-wise (no CSC->CSR conversion on the host): lower factor with
+    the pivots, unit upper factor, swapped permutations - same solution of A x = b."""
+    K = _saddle(cav10)
+    n = K.shape[0]
+    a = dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, 2)
+    if reuse:
+        a = a + (_lu_worker.order_only(a),)
+    arrs = _lu_worker.factor_arrays(a, transposed=True)
+    prog = _program(arrs, n, flags=2)
+    rng = np.random.default_rng(8)
+    B = rng.standard_normal((n, 3))
+    X = np.zeros((prog[0]['n_ext'], 3))
+    X[arrs[6]] = B
+    _execute(prog, X, check_hazards=True)
+    got = X[arrs[7]]
+    ref = spsla.splu(K).solve(B)
+    assert np.linalg.norm(got - ref) <= 1e-12*np.linalg.norm(ref)
+    assert np.linalg.norm(K @ got - B) <= 1e-12*np.linalg.norm(B)
+    # same amount of work as the row-wise layout (structurally symmetric pattern)
+    a0 = a[:6] + (0,) + a[7:]
+    arrs0 = _lu_worker.factor_arrays(a0)
+    p0 = _program(arrs0, n)[0]
+    assert prog[0]['nent'] <= 1.15*p0['nent'] and prog[0]['nsub_L'] + prog[0]['nsub_U'] <= 1.3*(p0['nsub_L'] + p0['nsub_U'])
