@@ -145,7 +145,7 @@ def _attach(name):
 
 def factor_image_to_shm(args, slot=None):
     """Pool entry point: factorise, analyse, pack and hand the image back through POSIX shared
-    memory (no pickling of ~15 MB through a pipe).  ``slot = (name, capacity)`` is a segment of
+    memory (no pickling of ~10 MB through a pipe).  ``slot = (name, capacity)`` is a segment of
     the main process's page-locked pool: if the image fits it is written there (the upload is
     then a plain DMA); otherwise a fresh segment is created.
     Returns (name or None if the slot was used, nbytes, seconds factor, seconds analyse+pack,
