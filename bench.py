@@ -42,12 +42,13 @@ import numpy as np  # noqa: E402
 
 METRIC = 'dre_backward_steps_per_s'
 UNIT = 'steps/s'
-WORKLOAD = 'drivcav N=25 (NV 4802, NP 675), run_optcont.py params: nu=5e-3, Nts=128, tE=0.2, ' \
+WORKLOAD = 'drivcav N=%d (NV %d, NP %d), run_optcont.py params: nu=5e-3, Nts=128, tE=0.2, ' \
            'alphau=1e-7, gamma=1e-1, 7 ADI shifts, compress 5e-5/50; backward steps from t=tE'
 
 
 def _config(N):
-    return dict(workload=WORKLOAD, mesh_N=N, NV=2*(2*N-1)**2, NP=(N+1)**2-1,
+    return dict(workload=WORKLOAD % (N, 2*(2*N-1)**2, (N+1)**2-1), mesh_N=N, NV=2*(2*N-1)**2,
+                NP=(N+1)**2-1,
                 parallelism='independent DRE replica per GPU',
                 l2_policy='no flush: every timed step works on inputs that were never touched '
                           'before - its own 8 factor images (~75 MB, uploaded during setup) and a '
