@@ -14,7 +14,15 @@ namespace ocb {
 
 namespace {
 
-constexpr int WMAX = 512;    // widest supernode (its inverse block has w(w+1)/2 entries)
+static int wmax() {           // widest supernode (its inverse block has w(w+1)/2 entries)
+    static int v = 0;
+    if (v == 0) {
+        const char* env = getenv("OCB_SUPERNODE_WMAX");
+        v = env ? atoi(env) : 512;
+        if (v < 1 || v > 512) v = 512;
+    }
+    return v;
+}
 constexpr int YCAP = 1024;   // y-scratch rows one sub-level may use (two such regions exist)
 
 struct BlockPlan {
@@ -44,7 +52,7 @@ int find_supernodes(int64_t n, const int32_t* rp, const int32_t* ci, std::vector
     for (int64_t i = 0; i + 1 < n; ++i) {
         const int32_t a0 = rp[i], a1 = rp[i + 1], b0 = rp[i + 1], b1 = rp[i + 2];
         bool same = false;
-        if (a1 > a0 && ci[a0] == i && (a1 - a0 - 1) == (b1 - b0) && b1 > b0 && w < WMAX)
+        if (a1 > a0 && ci[a0] == i && (a1 - a0 - 1) == (b1 - b0) && b1 > b0 && w < wmax())
             same = memcmp(ci + a0 + 1, ci + b0, (size_t)(b1 - b0) * sizeof(int32_t)) == 0;
         if (same) {
             ++w;
