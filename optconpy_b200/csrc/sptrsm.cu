@@ -596,6 +596,10 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
     int64_t cap = 0;
     const char* env = getenv("OCB_SPTRSM_FORCE_GLOBAL");
     const bool force_global = env && env[0] == '1';
+    {   // cluster size: flags bits 4..7 (the caller's hint from the expected block width), else 4
+        const int hint = (flags >> 4) & 15;
+        if (hint == 1 || hint == 2 || hint == 4 || hint == 8) cl = hint;
+    }
     const char* e_cl = getenv("OCB_TRSM_CLUSTER");
     if (e_cl) {
         const int v = atoi(e_cl);

@@ -221,10 +221,14 @@ def _csc_args(mat, opts):
 _ORDER = dict()
 
 
-def _pack_flags(wide):
+def _pack_flags(wide, k_hint=None):
     """ocb_lu_pack_host flags: bit 0 = flat program for the wide executor, bit 1 = factorise A^T
-    and take SuperLU's column-wise factors as they are (no CSC->CSR conversion on the host)."""
-    return (1 if wide else 0) | (0 if os.environ.get('OCB_NO_TRANSPOSED_LU') else 2)
+    and take SuperLU's column-wise factors as they are (no CSC->CSR conversion on the host),
+    bits 4..7 = cluster size of the column-panel kernel from the expected block width
+    (measured: clusters of 4 are fastest up to 33 right-hand sides - one column per cluster fits
+    one wave -, clusters of 2 from 34 columns on)."""
+    cl = 0 if k_hint is None else (4 if k_hint <= 33 else 2)
+    return (1 if wide else 0) | (0 if os.environ.get('OCB_NO_TRANSPOSED_LU') else 2) | (cl << 4)
 
 
 def _pattern_key(a):
@@ -361,7 +365,7 @@ class FactorJob(object):
     """Several host factorisations in flight (worker processes: SuperLU + analysis +
     packing); ``result()`` uploads the images and returns the ``LU`` handles."""
 
-    def __init__(self, mats, lu_options=None, wide=False):
+    def __init__(self, mats, lu_options=None, wide=False, k_hint=None):
         from . import _lu_worker
         require_cuda()
         opts = dict(LU_OPTIONS if lu_options is None else lu_options)
@@ -369,7 +373,7 @@ class FactorJob(object):
         so = smem_optin()
         args, self._keys = [], []
         for m in mats:
-            a, key = _with_order(_csc_args(m, opts) + (so, _pack_flags(wide)), opts)
+            a, key = _with_order(_csc_args(m, opts) + (so, _pack_flags(wide, k_hint)), opts)
             args.append(a)
             self._keys.append(key)
         self.n = len(mats)

@@ -160,8 +160,10 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         pre = dict(nmattd=nmattd, rhsvtd=rhsvtd, NT=NT, ft_mat=ft_mat, at_mat=at_mat,
                    fac=None, sadlu=None)
         if can_prefetch:
+            # block width of the ADI right-hand sides of that step: [M^T Z (Z^T B), M^T Zc, C~^T]
+            khint = zc_width[0] + tct_mat.shape[1] + tb_mat.shape[1]
             pre['fac'] = pru.factors_async(mmat=MT, amat=ft_mat, jmat=jmat, transposed=True,
-                                           nwtn_adi_dict=nwtn_adi_dict)
+                                           nwtn_adi_dict=nwtn_adi_dict, k_hint=khint)
             pre['sadlu'] = lau.sadlu_async(amat=at_mat, jmat=jmat)
         return pre
 
@@ -179,6 +181,7 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         old_switch = sys.getswitchinterval()
         sys.setswitchinterval(1e-4)
     depth = int(lookahead) if can_prefetch else 0
+    zc_width = [Zc.shape[1]]        # latest factor width, read by the look-ahead thread
     ahead = {}
     for tk in range(len(tmesh)-2, -1, -1):
         t = tmesh[tk]
@@ -227,6 +230,7 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
                 Zc = Zp
             store.save(Zp if save_full_z else Zc, key + '__Z')
         info.update(zc_cols=Zc.shape[1])
+        zc_width[0] = Zc.shape[1]
 
         at_mat = pre['at_mat']
         ftilde = rhsvtd + rhsv

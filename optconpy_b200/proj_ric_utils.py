@@ -49,10 +49,13 @@ class ShiftedFactors(object):
     setup of the next time step with the device work of the current one
     (``factors_async`` / ``dre_stepper`` look-ahead)."""
 
-    def __init__(self, At, Mt, jmat, ms, Mt_dev=None):
+    def __init__(self, At, Mt, jmat, ms, Mt_dev=None, k_hint=None):
         self.ms = [float(m) for m in ms]
         self.NV, self.NP = At.shape[0], jmat.shape[0]
-        self._job = dv.FactorJob(_shifted_saddle_matrices(At, Mt, jmat, self.ms)).start_upload()
+        # k_hint: expected number of right-hand-side columns of the ADI blocks (picks the
+        # cluster size the factor images are packed for)
+        self._job = dv.FactorJob(_shifted_saddle_matrices(At, Mt, jmat, self.ms),
+                                 k_hint=k_hint).start_upload()
         self._Mt, self._Mt_dev = Mt, Mt_dev
 
     @property
@@ -108,7 +111,8 @@ def _shifted_saddle_matrices(At, Mt, jmat, ms):
     return out
 
 
-def factors_async(mmat=None, amat=None, jmat=None, nwtn_adi_dict=None, transposed=False, **kw):
+def factors_async(mmat=None, amat=None, jmat=None, nwtn_adi_dict=None, transposed=False,
+                  k_hint=None, **kw):
     """Start the per-shift factorisations of a later ``proj_alg_ric_newtonadi`` /
     ``solve_proj_lyap_stein`` call (same ``mmat, amat, jmat, transposed``) in the background;
     hand the result to that call as ``_factors=``.  Extension of the reference interface:
@@ -116,7 +120,7 @@ def factors_async(mmat=None, amat=None, jmat=None, nwtn_adi_dict=None, transpose
     dv.require_cuda()
     At, Mt = _transposed_pair(amat, mmat, transposed)
     ms = (nwtn_adi_dict or {}).get('ms', DEFAULT_SHIFTS)
-    return ShiftedFactors(At, Mt, jmat, ms)
+    return ShiftedFactors(At, Mt, jmat, ms, k_hint=k_hint)
 
 
 def _stein_dev(fac, W, adi_dict, Ufb=None, Vt=None):
@@ -145,7 +149,8 @@ def solve_proj_lyap_stein(amat=None, jmat=None, wmat=None, mmat=None,
     At, Mt = _transposed_pair(amat, mmat, transposed)
     fac = kw.get('_factors')
     if fac is None:
-        fac = ShiftedFactors(At, Mt, jmat, adi_dict.get('ms', DEFAULT_SHIFTS))
+        fac = ShiftedFactors(At, Mt, jmat, adi_dict.get('ms', DEFAULT_SHIFTS),
+                             k_hint=_dense(wmat).shape[1])
     W = dv.to_dev(_dense(wmat))
     Ufb = Vt = None
     if umat is not None and vmat is not None:
@@ -251,7 +256,8 @@ def proj_alg_ric_newtonadi(mmat=None, amat=None, jmat=None,
     At, Mt = _transposed_pair(amat, mmat, transposed)
     fac = kw.get('_factors')
     if fac is None:
-        fac = ShiftedFactors(At, Mt, jmat, nwtn_adi_dict.get('ms', DEFAULT_SHIFTS))
+        khint = _dense(wmat).shape[1] + (0 if z0 is None else sps.csr_matrix(bmat).shape[1])
+        fac = ShiftedFactors(At, Mt, jmat, nwtn_adi_dict.get('ms', DEFAULT_SHIFTS), k_hint=khint)
     with dv.phase('ric_upload_inputs'):
         Bd = dv.to_dev(_dense(bmat))
         Vt_b = dv.DeviceCSR(sps.csr_matrix(bmat).T)
