@@ -104,3 +104,48 @@ def test_column_slices_partition():
             assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
             w = [b - a for a, b in sl]
             assert max(w) - min(w) <= 1
+
+
+def test_outer_newton_carry(cav6):
+    """Outer Newton passes (optcont_main.py:577-600): ``curnwtnsdict`` names the entries that
+    accumulate w and the gain across passes (init_nwtnstps_value_dict, :200-210).  Pass 1 fills
+    them; pass 2 finds them, hands ``sqrt(tau) * cnsmtxtb`` to the Riccati solver as ``mtxoldb``
+    and adds the carried w to the right-hand side (solve_dae_ric.py:134-141,150,176-178)."""
+    cs = pb.control_setup(cav6, olau, alphau=1e-4)
+    tmesh = pb.get_tint(0.0, 0.1, 2)
+    nd = dict(sc.DEFAULT_NWTN_ADI, adi_max_steps=60, nwtn_max_steps=3)
+    kw = sc.dre_kwargs(cav6, cs, tmesh, nd, 1e-3, sc._ystar_sin(cs['NY']))
+    cnd = {t: dict(v='cns_v_t%r' % t, mtxtb='cns_mtxtb_t%r' % t, w='cns_w_t%r' % t) for t in tmesh}
+    store = ds.MemStore()
+    seen = []
+
+    class SpyPru(object):
+        def __getattr__(self, name):
+            f = getattr(opru, name)
+            if name != 'proj_alg_ric_newtonadi':
+                return f
+
+            def wrapped(**k):
+                seen.append(None if k.get('mtxoldb') is None else np.array(k['mtxoldb']))
+                return f(**k)
+            return wrapped
+
+    def one_pass(cns):
+        g = dict(kw['gtdtstrargs'], data_prfx='cns%d_' % cns)
+        return ds.solve_flow_daeric(lau=olau, pru=SpyPru(), store=store, curnwtnsdict=cnd,
+                                    **dict(kw, gtdtstrargs=g))
+    fb1 = one_pass(0)
+    assert all(s is None for s in seen)                       # nothing carried in the first pass
+    for t in tmesh:
+        assert cnd[t]['w'] in store and cnd[t]['mtxtb'] in store
+    carried = {t: store[cnd[t]['mtxtb']].copy() for t in tmesh}
+    n_first = len(seen)
+    fb2 = one_pass(1)
+    second = seen[n_first:]
+    assert len(second) == len(tmesh) - 1 and all(s is not None for s in second)
+    # the drift of the first backward step of pass 2 carries sqrt(tau) * (gain stored by pass 1)
+    t_last = tmesh[-2]
+    assert np.allclose(second[0], np.sqrt(tmesh[-1] - t_last)*carried[t_last], rtol=1e-12, atol=0)
+    # the carried entries were accumulated, and both passes produced complete feedback dicts
+    assert not np.allclose(store[cnd[t_last]['mtxtb']], carried[t_last])
+    assert sorted(fb1) == sorted(fb2) == sorted(tmesh)
