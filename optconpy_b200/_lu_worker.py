@@ -19,6 +19,20 @@ def worker_init():
         os.nice(10)
     except OSError:
         pass
+    tune_malloc()
+
+
+def tune_malloc():
+    """Keep large blocks on the heap instead of mmap/munmap per allocation: SuperLU and the
+    program builder allocate and release tens of MB of work arrays per factorisation, and with
+    glibc's default thresholds every one of them is a fresh mapping that page-faults in again
+    (splu of the N=25 cavity saddle matrix: 44 -> 35 ms with this setting)."""
+    try:
+        libc = C.CDLL('libc.so.6')
+        libc.mallopt(-3, 1 << 30)      # M_MMAP_THRESHOLD
+        libc.mallopt(-1, 1 << 30)      # M_TRIM_THRESHOLD
+    except (OSError, AttributeError):
+        pass
 
 
 def order_only(args):
@@ -28,6 +42,42 @@ def order_only(args):
     data, indices, indptr, shape, opts = args[:5]
     slu = spsla.splu(sps.csc_matrix((data, indices, indptr), shape=shape), **opts)
     return np.argsort(slu.perm_c).astype(np.int32)
+
+
+_ARRANGE = dict()     # pattern -> (indices, indptr, source position of every entry) or None
+
+
+def _arranged(data, indices, indptr, shape, q, transposed):
+    """``A`` (CSC arrays), optionally transposed, then optionally permuted symmetrically by
+    ``q``, as a canonical CSC matrix.  The matrices of one run share a handful of sparsity
+    patterns, so the transposition and the fancy indexing (8 of 50 ms per matrix) are done once
+    per pattern on entry TAGS; every later matrix is one gather of its values."""
+    key = (shape, bool(transposed), hash(indices.tobytes()), hash(indptr.tobytes()),
+           None if q is None else hash(q.tobytes()))
+    if key not in _ARRANGE:
+        nnz = len(indices)
+        tags = sps.csc_matrix((np.arange(1, nnz + 1, dtype=np.float64), indices, indptr), shape=shape)
+        m = tags.T.tocsc() if transposed else tags
+        if q is not None:
+            m = m[q][:, q].tocsc()
+        m.sum_duplicates()
+        src = np.rint(m.data).astype(np.int64) - 1
+        ok = m.nnz == nnz and np.array_equal(np.sort(src), np.arange(nnz))   # no duplicate entries
+        if len(_ARRANGE) >= 16:
+            _ARRANGE.clear()
+        _ARRANGE[key] = (m.indices.copy(), m.indptr.copy(), src) if ok else None
+    ent = _ARRANGE[key]
+    if ent is None:
+        mat = sps.csc_matrix((data, indices, indptr), shape=shape)
+        if transposed:
+            mat = mat.T.tocsc()
+        if q is not None:
+            mat = mat[q][:, q].tocsc()
+        return mat
+    mat = sps.csc_matrix((data[ent[2]], ent[0], ent[1]), shape=shape)
+    mat.has_sorted_indices = True
+    mat.has_canonical_format = True      # splu's sum_duplicates() becomes a no-op
+    return mat
 
 
 def factor_arrays(args, want_order=False, transposed=False):
@@ -51,13 +101,10 @@ def factor_arrays(args, want_order=False, transposed=False):
     data, indices, indptr, shape, opts = args[:5]
     q = args[7] if len(args) > 7 else None
     n = shape[0]
-    mat = sps.csc_matrix((data, indices, indptr), shape=shape)
-    if transposed:
-        mat = mat.T.tocsc()
     o2 = dict(opts)
     if q is not None:
         o2['permc_spec'] = 'NATURAL'
-        mat = mat[q][:, q].tocsc()
+    mat = _arranged(data, indices, indptr, shape, q, transposed)
     slu = spsla.splu(mat, **o2)
     load_p, store_p = (slu.perm_c, slu.perm_r) if transposed else (slu.perm_r, slu.perm_c)
     if q is None:
@@ -68,8 +115,8 @@ def factor_arrays(args, want_order=False, transposed=False):
         perm_r[q] = load_p            # xe[perm_r[i]] = b[i]   with b' = b[q]
         perm_c[q] = store_p           # x[j] = xe[perm_c[j]]   with x[q] = y
     if transposed:
-        lo, up = slu.U, slu.L         # CSC columns of U / L = CSR rows of U^T / L^T
-        up.sort_indices()             # supernode detection needs sorted rows; the lower factor does not
+        lo, up = slu.U, slu.L         # CSC columns of U / L = CSR rows of U^T / L^T (rows of the
+        #                               upper factor unsorted: build_lu_program sorts its own copy)
     else:
         lo = sps.csr_matrix(slu.L)
         up = sps.csr_matrix(slu.U)

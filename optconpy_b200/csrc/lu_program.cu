@@ -146,40 +146,7 @@ void invert_block(const Tri& T, int32_t r0, int32_t r1, std::vector<double>* Dbu
             const int32_t c = T.ci[p];
             if (c >= r0 && c < r1) D[(size_t)(i - r0) * w + (c - r0)] = T.va[p];
         }
-    // row-oriented triangular inversion (unit-stride inner loops):
-    //   lower:  X[i,:] = (e_i - sum_{k<i} D[i,k] X[k,:]) / D[i,i]
-    //   upper:  X[i,:] = (e_i - sum_{k>i} D[i,k] X[k,:]) / D[i,i]       (D[i,i] = 1 if unit)
-    if (!T.upper) {
-        for (int i = 0; i < w; ++i) {
-            double* xi = &X[(size_t)i * w];
-            xi[i] = 1.0;
-            for (int k = 0; k < i; ++k) {
-                const double d = D[(size_t)i * w + k];
-                if (d == 0.0) continue;
-                const double* xk = &X[(size_t)k * w];
-                for (int j = 0; j <= k; ++j) xi[j] -= d * xk[j];
-            }
-            if (!T.unit) {
-                const double inv = 1.0 / D[(size_t)i * w + i];
-                for (int j = 0; j <= i; ++j) xi[j] *= inv;
-            }
-        }
-    } else {
-        for (int i = w - 1; i >= 0; --i) {
-            double* xi = &X[(size_t)i * w];
-            xi[i] = 1.0;
-            for (int k = i + 1; k < w; ++k) {
-                const double d = D[(size_t)i * w + k];
-                if (d == 0.0) continue;
-                const double* xk = &X[(size_t)k * w];
-                for (int j = k; j < w; ++j) xi[j] -= d * xk[j];
-            }
-            if (!T.unit) {
-                const double inv = 1.0 / D[(size_t)i * w + i];
-                for (int j = i; j < w; ++j) xi[j] *= inv;
-            }
-        }
-    }
+    tri_inverse(D.data(), X.data(), w, T.upper, T.unit);   // host_dense.cpp
 }
 
 static double g_inv_ms = 0.0;
@@ -328,10 +295,51 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
         set_error("factor too large for int32 program indices");
         return OCB_ERR_ARG;
     }
-    for (int64_t i = 0; i < n; ++i) {   // U rows: sorted column indices, diagonal first
+    // The supernode search compares sorted rows of U.  SuperLU hands its columns out in
+    // supernodal order, not sorted, but consistently: inside one of ITS supernodes the index
+    // list of a column is the previous column's list without the first entry, so the sorting
+    // permutation carries over (a comparison sort runs only where that chain breaks; sorting
+    // every row in the caller costs 11 ms for the N=25 cavity factor, this 1.5 ms).
+    const auto tsort0 = std::chrono::steady_clock::now();
+    std::vector<int32_t> Uci_sorted;
+    std::vector<double> Uva_sorted;
+    bool sorted = true;
+    for (int64_t i = 0; i < n && sorted; ++i)
+        for (int32_t p = Urp[i] + 1; p < Urp[i + 1]; ++p)
+            if (Uci[p - 1] >= Uci[p]) { sorted = false; break; }
+    if (!sorted) {
+        Uci_sorted.resize(Urp[n]);
+        Uva_sorted.resize(Urp[n]);
+        std::vector<int32_t> perm;    // raw positions of the current row in sorted order
+        for (int64_t i = 0; i < n; ++i) {
+            const int32_t a0 = Urp[i], len = Urp[i + 1] - a0;
+            const int32_t* raw = Uci + a0;
+            bool chain = false;
+            if (i > 0 && len > 0 && (int32_t)perm.size() == len + 1 && perm[0] == 0)
+                chain = memcmp(Uci + Urp[i - 1] + 1, raw, (size_t)len * sizeof(int32_t)) == 0;
+            if (chain) {
+                for (int32_t j = 0; j < len; ++j) perm[j] = perm[j + 1] - 1;
+                perm.resize(len);
+            } else {
+                perm.resize(len);
+                std::iota(perm.begin(), perm.end(), 0);
+                bool row_sorted = true;
+                for (int32_t j = 1; j < len && row_sorted; ++j) row_sorted = raw[j - 1] < raw[j];
+                if (!row_sorted)
+                    std::sort(perm.begin(), perm.end(), [raw](int32_t x, int32_t y) { return raw[x] < raw[y]; });
+            }
+            for (int32_t j = 0; j < len; ++j) {
+                Uci_sorted[a0 + j] = raw[perm[j]];
+                Uva_sorted[a0 + j] = Uva[a0 + perm[j]];
+            }
+        }
+        Uci = Uci_sorted.data();
+        Uva = Uva_sorted.data();
+    }
+    for (int64_t i = 0; i < n; ++i) {   // U rows: distinct column indices, diagonal first
         for (int32_t p = Urp[i] + 1; p < Urp[i + 1]; ++p)
             if (Uci[p - 1] >= Uci[p]) {
-                set_error("U rows must have sorted column indices (row %lld)", (long long)i);
+                set_error("U has a duplicate column index (row %lld)", (long long)i);
                 return OCB_ERR_ARG;
             }
         if (Urp[i + 1] <= Urp[i] || Uci[Urp[i]] > i) {
@@ -349,6 +357,7 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
         return std::chrono::duration<double, std::milli>(b - a).count();
     };
     const auto t0 = tnow();
+    if (timing) fprintf(stderr, "lu_program: sort+check %.1f ms\n", ms(tsort0, t0));
     std::vector<int32_t> starts;
     find_supernodes(n, Urp, Uci, &starts);
     P->nsuper = (int32_t)starts.size() - 1;

@@ -55,4 +55,7 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
                      const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
                      bool transposed, LuProgram* out);
 
+// X = inverse of the w x w triangular D (row-major; X zero on entry).  host_dense.cpp.
+void tri_inverse(const double* D, double* X, int w, bool upper, bool unit);
+
 }  // namespace ocb

@@ -216,6 +216,9 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
             w_mat = np.hstack([MT @ Zc, np.sqrt(cts)*tct_mat])
             oldfb = np.sqrt(cts)*cnsmtxtb if cnsmtxtb is not None else None
             xkw = dict(_factors=pre['fac']) if pre['fac'] is not None else {}
+            if hasattr(pru, 'DeviceFactor'):
+                # the uncompressed factor is only compressed below: leave it on the device
+                xkw['_lazy_zfac'] = True
             nres = pru.proj_alg_ric_newtonadi(mmat=MT, amat=ft_mat, transposed=True,
                                               mtxoldb=oldfb, jmat=jmat,
                                               bmat=np.sqrt(cts)*tb_mat,
@@ -227,8 +230,8 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
             if comprz_maxc is not None or comprz_thresh is not None:
                 Zc = pru.compress_Zsvd(Zp, thresh=comprz_thresh, k=comprz_maxc)
             else:
-                Zc = Zp
-            store.save(Zp if save_full_z else Zc, key + '__Z')
+                Zc = Zp = np.asarray(Zp)
+            store.save(np.asarray(Zp) if save_full_z else Zc, key + '__Z')
         info.update(zc_cols=Zc.shape[1])
         zc_width[0] = Zc.shape[1]
 

@@ -243,6 +243,38 @@ def newtonadi_dev(fac, Bd, Vt_b, W, z0, nwtn_adi_dict, mtxoldb=None):
     return znc, dict(nwtn_upd_fnorms=fnorms, adi_steps=adi_steps, adi_rel_norms=rels)
 
 
+class DeviceFactor(object):
+    """A low-rank factor that still lives in HBM, handed out instead of an ndarray where the
+    caller asks for it (``proj_alg_ric_newtonadi(..., _lazy_zfac=True)``).  It has ``shape``,
+    ``dtype`` and ``ndim``, turns into an ndarray on first use (``np.asarray``, ``np.save``,
+    indexing), and ``compress_Zsvd`` takes it as is.  The DRE driver (``solve_dae_ric.py:152-163``)
+    only compresses the uncompressed factor and never reads it, so the device->host copy of
+    45 MB per time step is not made unless somebody looks."""
+
+    def __init__(self, dev):
+        self._dev = dev
+        self._host = None
+
+    shape = property(lambda self: tuple(self._dev.shape))
+    dtype = property(lambda self: np.dtype(np.float64))
+    ndim = property(lambda self: self._dev.dim())
+
+    def __len__(self):
+        return self._dev.shape[0]
+
+    def __array__(self, dtype=None, copy=None):
+        if self._host is None:
+            with dv.phase('ric_d2h_factor'):
+                self._host = dv.to_host(self._dev)
+        a = self._host
+        if dtype is not None and np.dtype(dtype) != a.dtype:
+            return a.astype(dtype)
+        return a.copy() if copy else a
+
+    def __getitem__(self, idx):
+        return self.__array__()[idx]
+
+
 def proj_alg_ric_newtonadi(mmat=None, amat=None, jmat=None,
                            bmat=None, wmat=None, z0=None, mtxoldb=None,
                            transposed=False,
@@ -272,6 +304,8 @@ def proj_alg_ric_newtonadi(mmat=None, amat=None, jmat=None,
         torch.cuda.current_stream().synchronize()
     if kw.get('_return_device'):
         return dict(zfac=Z, **info)
+    if kw.get('_lazy_zfac'):
+        return dict(zfac=DeviceFactor(Z), **info)
     with dv.phase('ric_d2h_factor'):
         zh = dv.to_host(Z)
     _LAST['host'], _LAST['dev'] = zh, Z
@@ -286,6 +320,8 @@ def compress_Zsvd(Z, k=None, thresh=None, shplot=False):
     with dv.phase('compress'):
         if isinstance(Z, torch.Tensor):
             Zd = Z
+        elif isinstance(Z, DeviceFactor):
+            Zd = Z._dev
         elif Z is _LAST.get('host'):
             Zd = _LAST['dev']          # the factor this module just returned: still in HBM
         else:

@@ -292,3 +292,35 @@ def test_mtxoldb_and_nonconvergence_are_not_errors(mods, lyap_setup, cav10):
     ref, got = opru.proj_alg_ric_newtonadi(**kw), gpru.proj_alg_ric_newtonadi(**kw)
     assert got['adi_steps'] == ref['adi_steps'] == [12, 12]
     assert _zzt_relerr(got['zfac'], ref['zfac']) < TOL_FACTOR
+
+
+def test_lazy_device_factor(mods, lyap_setup, cav10):
+    """``_lazy_zfac=True`` (what the DRE driver passes): the factor stays in HBM, has the
+    ndarray's shape, converts on demand to exactly the eager result and compresses to the same
+    columns; the driver's ``save_full_z`` path stores the converted array."""
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import problems as pb, device as dv, scenarios as sc, dre_stepper as ds
+    M, F, J, _ = lyap_setup
+    cs = pb.control_setup(cav10, olau, alphau=1e-4)
+    d = dict(adi_max_steps=60, adi_newZ_reltol=1e-8, nwtn_max_steps=4, nwtn_upd_reltol=1e-8,
+             nwtn_upd_abstol=1e-12, ms=[-5.0, -3.0, -2.0, -1.5, -1.3, -1.1, -1.0])
+    kw = dict(mmat=M.T, amat=F.T, transposed=True, jmat=J, bmat=np.sqrt(0.05)*cs['tb_mat'],
+              wmat=np.sqrt(0.05)*cs['trct_mat'], z0=None, nwtn_adi_dict=d)
+    eager = gpru.proj_alg_ric_newtonadi(**kw)['zfac']
+    before = dv.STATS['d2h_bytes']
+    lazy = gpru.proj_alg_ric_newtonadi(_lazy_zfac=True, **kw)['zfac']
+    assert isinstance(lazy, gpru.DeviceFactor) and lazy.shape == eager.shape and lazy.ndim == 2
+    zc_l = gpru.compress_Zsvd(lazy, thresh=5e-5, k=50)
+    assert dv.STATS['d2h_bytes'] - before < eager.nbytes        # the big factor never crossed PCIe
+    assert np.array_equal(zc_l, gpru.compress_Zsvd(eager, thresh=5e-5, k=50))
+    assert np.array_equal(np.asarray(lazy), eager) and np.array_equal(lazy[:, :3], eager[:, :3])
+    prob, cs1, kw1 = sc.config1(glau, Nts=2)
+    s1, s2 = ds.MemStore(), ds.MemStore()
+    f1 = ds.solve_flow_daeric(lau=glau, pru=gpru, store=s1, save_full_z=True,
+                              **dict(kw1, gtdtstrargs=dict(kw1['gtdtstrargs'])))
+    f2 = ds.solve_flow_daeric(lau=glau, pru=gpru, store=s2,
+                              **dict(kw1, gtdtstrargs=dict(kw1['gtdtstrargs'])))
+    for t in f1:
+        kz = f1[t]['mtxtb'].replace('__mtxtb', '__Z')
+        assert isinstance(s1[kz], np.ndarray) and s1[kz].shape[1] >= s2[kz].shape[1]
+        assert np.array_equal(s1[f1[t]['mtxtb']], s2[f2[t]['mtxtb']])

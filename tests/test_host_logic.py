@@ -149,3 +149,26 @@ def test_outer_newton_carry(cav6):
     # the carried entries were accumulated, and both passes produced complete feedback dicts
     assert not np.allclose(store[cnd[t_last]['mtxtb']], carried[t_last])
     assert sorted(fb1) == sorted(fb2) == sorted(tmesh)
+
+
+def test_device_factor_handle_behaves_like_the_array():
+    """proj_ric_utils.DeviceFactor (the lazily downloaded ADI factor): shape/dtype/len without a
+    copy, ndarray on demand through the numpy protocol (np.asarray, np.save, slicing, hstack)."""
+    import io
+    import torch
+    from optconpy_b200 import proj_ric_utils as gpru
+    a = np.arange(12.0).reshape(4, 3)
+    f = gpru.DeviceFactor(torch.from_numpy(a.copy()))
+    assert f.shape == (4, 3) and f.ndim == 2 and len(f) == 4 and f.dtype == np.float64
+    assert f._host is None                                    # nothing fetched yet
+    assert np.array_equal(np.asarray(f), a) and f._host is not None
+    assert np.array_equal(f[:, 1:], a[:, 1:])
+    assert np.array_equal(np.hstack([f, f]), np.hstack([a, a]))
+    assert np.asarray(f, dtype=np.float32).dtype == np.float32
+    buf = io.BytesIO()
+    np.save(buf, f)
+    buf.seek(0)
+    assert np.array_equal(np.load(buf), a)
+    st = ds.MemStore()
+    st.save(f, 'z')
+    assert isinstance(st['z'], np.ndarray) and np.array_equal(st['z'], a)

@@ -233,3 +233,29 @@ def test_transposed_layout(cav10, reuse):
     arrs0 = _lu_worker.factor_arrays(a0)
     p0 = _program(arrs0, n)[0]
     assert prog[0]['nent'] <= 1.15*p0['nent'] and prog[0]['nsub_L'] + prog[0]['nsub_U'] <= 1.3*(p0['nsub_L'] + p0['nsub_U'])
+
+
+def test_unsorted_upper_rows_are_sorted_by_the_builder(cav10):
+    """SuperLU's columns come in supernodal order; build_lu_program sorts the rows of the upper
+    factor itself (counting sort): same program as from rows sorted beforehand; a duplicate
+    column index is an error."""
+    K = _saddle(cav10)
+    n = K.shape[0]
+    a = dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, 2)
+    arrs = _lu_worker.factor_arrays(a, transposed=True)
+    rp, ci = arrs[3], arrs[4]
+    assert any(np.any(np.diff(ci[rp[i]:rp[i+1]]) <= 0) for i in range(n))   # really unsorted
+    up = sps.csr_matrix((arrs[5], ci, rp), shape=(n, n))
+    up.sort_indices()
+    arrs_s = arrs[:3] + [up.indptr.astype(np.int32), up.indices.astype(np.int32), up.data] + arrs[6:]
+    p1, p2 = _program(arrs, n, flags=2), _program(arrs_s, n, flags=2)
+    assert p1[0] == p2[0]
+    for x, y in zip(p1[1:], p2[1:]):
+        assert np.array_equal(x, y)
+    lib = _cabi.load()
+    dup = ci.copy()
+    i = int(np.argmax(np.diff(rp) >= 3))
+    dup[rp[i] + 2] = dup[rp[i] + 1]
+    h = C.c_void_p()
+    rc = lib.ocb_lu_program_create(C.byref(h), n, *[x.ctypes.data for x in arrs[:4] + [dup, arrs[5]]], 2)
+    assert rc == -1 and b'duplicate' in lib.ocb_last_error()
