@@ -46,4 +46,22 @@ void tri_inverse(const double* __restrict__ D, double* __restrict__ X, int w, bo
     }
 }
 
+// P = X * T, X w x w triangular, T and P w x m row-major (P zero on entry)
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target_clones("avx512f", "avx2,fma", "default")))
+#endif
+void tri_times_dense(const double* __restrict__ X, const double* __restrict__ T, double* __restrict__ P,
+                     int w, int m, bool upper) {
+    for (int k = 0; k < w; ++k) {
+        double* __restrict__ pk = P + (size_t)k * m;
+        const int s0 = upper ? k : 0, s1 = upper ? w : k + 1;
+        for (int s = s0; s < s1; ++s) {
+            const double x = X[(size_t)k * w + s];
+            if (x == 0.0) continue;
+            const double* __restrict__ ts = T + (size_t)s * m;
+            for (int j = 0; j < m; ++j) pk[j] += x * ts[j];
+        }
+    }
+}
+
 }  // namespace ocb

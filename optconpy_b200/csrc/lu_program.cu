@@ -28,6 +28,12 @@ constexpr int YCAP = 1024;   // y-scratch rows one sub-level may use (two such r
 struct BlockPlan {
     int32_t sA = -1;   // sub-level of the A rows (-1: block needs no work)
     int32_t yoff = -1; // offset into the y region (w > 1 only)
+    bool merged = false;   // one-step block: x_t = inv(T_tt) b_t - (inv(T_tt) T[t,off]) x at sA
+};
+
+struct MergeRule {
+    int max_w = 0;         // widest block solved in one step (0: never)
+    double growth = 1.3;   // ... if its product rows hold at most growth x the entries of T[t,off]
 };
 
 struct Tri {
@@ -66,11 +72,12 @@ int find_supernodes(int64_t n, const int32_t* rp, const int32_t* ci, std::vector
 }
 
 // assign the A sub-level (and y offset) of every block of one triangular factor
-int plan_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
+int plan_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts, const MergeRule& rule,
                 std::vector<BlockPlan>* plan, int32_t* nsub, int64_t* ymax) {
     const int nb = (int)starts.size() - 1;
     plan->assign(nb, BlockPlan());
     std::vector<int32_t> done(n, -1);
+    std::vector<int32_t> seen(rule.max_w > 0 ? n : 0, -1);   // last block that touched a column
     std::vector<int32_t> yuse;
     int32_t top = -1;
     for (int bb = 0; bb < nb; ++bb) {
@@ -109,11 +116,40 @@ int plan_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
             }
         }
         BlockPlan& bp = (*plan)[t];
+        if (w > 1 && w <= rule.max_w) {
+            // entries of the product rows inv(T_tt) T[t,off]: row k holds the union of the
+            // off-block patterns of the rows it depends on (s <= k lower, s >= k upper)
+            int64_t uni = 0, mcost = 0;
+            for (int32_t kk = 0; kk < w; ++kk) {
+                const int32_t i = T.upper ? r1 - 1 - kk : r0 + kk;
+                for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) {
+                    const int32_t c = T.ci[p];
+                    if ((c < r0 || c >= r1) && seen[c] != t) { seen[c] = t; ++uni; }
+                }
+                mcost += uni;
+            }
+            bp.merged = (double)mcost <= rule.growth * (double)noff + 8.0 * w;
+        }
         if (w == 1) {
             if (T.unit && noff == 0) continue;  // unit diagonal, nothing to subtract
             bp.sA = dep + 1;
             done[r0] = bp.sA;
             top = std::max(top, bp.sA);
+        } else if (bp.merged) {
+            // results go to the y region at sA and are copied home at sA + 1; a reader at
+            // sA + 1 takes them from the y region, later ones from their home rows
+            int32_t s = dep + 1;
+            for (;;) {
+                if ((int)yuse.size() <= s) yuse.resize(s + 1, 0);
+                if (yuse[s] + w <= YCAP || yuse[s] == 0) break;
+                ++s;
+            }
+            bp.sA = s;
+            bp.yoff = yuse[s];
+            yuse[s] += w;
+            *ymax = std::max<int64_t>(*ymax, yuse[s]);
+            for (int32_t i = r0; i < r1; ++i) done[i] = s;
+            top = std::max(top, s + 1);
         } else {
             int32_t s = dep + 1;
             for (;;) {
@@ -155,19 +191,80 @@ struct RowRef {     // a row of the program before it is laid out
     int32_t block;  // supernode index
     int32_t k;      // row within the supernode
     int32_t len;    // number of entries
-    uint8_t kind;   // 0: A row, 1: B row
+    uint8_t kind;   // 0: A row, 1: B row, 2: one-step (merged) row, 3: copy of a merged result
 };
+
+struct MergedBlock {            // inverse-multiplied form of one merged block
+    std::vector<int32_t> cols;  // off-block columns in order of first appearance
+    std::vector<int32_t> ncol;  // per row k: how many of them row k uses
+    std::vector<double> X;      // w x w inverse of the diagonal block
+    std::vector<double> Pm;     // w x cols.size(): X * T[t, cols]
+};
+
+// inverse-multiplied form of the merged block t: X = inv(T_tt), Pm = X * T[t, off-block]
+void multiply_block(int64_t n, const Tri& T, int32_t r0, int32_t r1, std::vector<int32_t>* posbuf,
+                    std::vector<double>* Dbuf, std::vector<double>* Tbuf, MergedBlock* mb) {
+    const int w = r1 - r0;
+    std::vector<int32_t>& pos = *posbuf;     // column -> index in mb->cols (-1 outside this call)
+    if ((int64_t)pos.size() < n) pos.assign(n, -1);
+    invert_block(T, r0, r1, Dbuf, &mb->X);
+    mb->cols.clear();
+    mb->ncol.assign(w, 0);
+    for (int kk = 0; kk < w; ++kk) {         // rows in dependency order
+        const int k = T.upper ? w - 1 - kk : kk;
+        for (int32_t p = T.rp[r0 + k]; p < T.rp[r0 + k + 1]; ++p) {
+            const int32_t c = T.ci[p];
+            if ((c < r0 || c >= r1) && pos[c] < 0) {
+                pos[c] = (int32_t)mb->cols.size();
+                mb->cols.push_back(c);
+            }
+        }
+        mb->ncol[k] = (int32_t)mb->cols.size();
+    }
+    const int cu = (int)mb->cols.size();
+    std::vector<double>& To = *Tbuf;
+    To.assign((size_t)w * cu, 0.0);
+    for (int k = 0; k < w; ++k)
+        for (int32_t p = T.rp[r0 + k]; p < T.rp[r0 + k + 1]; ++p) {
+            const int32_t c = T.ci[p];
+            if (c < r0 || c >= r1) To[(size_t)k * cu + pos[c]] = T.va[p];
+        }
+    mb->Pm.assign((size_t)w * cu, 0.0);
+    tri_times_dense(mb->X.data(), To.data(), mb->Pm.data(), w, cu, T.upper);   // host_dense.cpp
+    for (int32_t c : mb->cols) pos[c] = -1;
+}
 
 int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                 const std::vector<BlockPlan>& plan, int32_t nsub, int64_t ymax, int max_lanes,
                 LuProgram* P) {
     const int nb = (int)starts.size() - 1;
     std::vector<std::vector<RowRef>> lev(nsub);
+    // rows of merged blocks: the sub-level that produces them and where a reader one sub-level
+    // later finds them (the y region; everybody later reads the home row)
+    std::vector<int32_t> mlev, maddr;
+    bool any_merged = false;
+    for (int t = 0; t < nb; ++t) any_merged = any_merged || plan[t].merged;
+    if (any_merged) {
+        mlev.assign(n, -1);
+        maddr.assign(n, -1);
+    }
+    auto ybase_of = [&](const BlockPlan& bp) {
+        return (int32_t)(n + (bp.sA & 1) * ymax + (bp.yoff < 0 ? 0 : bp.yoff));
+    };
     // off-block entry counts per row
     for (int t = 0; t < nb; ++t) {
         const BlockPlan& bp = plan[t];
         if (bp.sA < 0) continue;
         const int32_t r0 = starts[t], r1 = starts[t + 1], w = r1 - r0;
+        if (bp.merged) {
+            for (int k = 0; k < w; ++k) {
+                mlev[r0 + k] = bp.sA;
+                maddr[r0 + k] = ybase_of(bp) + k;
+                lev[bp.sA].push_back(RowRef{t, k, 0, 2});      // length: set when the block is formed
+                lev[bp.sA + 1].push_back(RowRef{t, k, 0, 3});
+            }
+            continue;
+        }
         for (int32_t i = r0; i < r1; ++i) {
             int32_t len = 0;
             for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) len += (T.ci[p] < r0 || T.ci[p] >= r1);
@@ -176,20 +273,34 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
         if (w > 1)
             for (int k = 0; k < w; ++k) lev[bp.sA + 1].push_back(RowRef{t, k, T.upper ? w - k : k + 1, 1});
     }
-    std::vector<double> D, X;
+    std::vector<double> D, X, Tbuf;
+    std::vector<int32_t> posbuf;
     std::vector<int32_t> inv_slot(nb, -1);
     std::vector<std::vector<double>> inv;   // inverses of the diagonal blocks of this sub-level
+    std::vector<MergedBlock> mblocks;       // merged blocks of this sub-level
     for (int32_t s = 0; s < nsub; ++s) {
         std::vector<RowRef>& rows = lev[s];
         if (rows.empty()) continue;
         inv.clear();
+        mblocks.clear();
         const auto ti0 = std::chrono::steady_clock::now();
-        for (const RowRef& rr : rows)
+        for (RowRef& rr : rows) {
             if (rr.kind == 1 && rr.k == 0) {
                 invert_block(T, starts[rr.block], starts[rr.block + 1], &D, &X);
                 inv_slot[rr.block] = (int32_t)inv.size();
                 inv.push_back(X);
+            } else if (rr.kind == 2) {
+                if (rr.k == 0) {
+                    inv_slot[rr.block] = (int32_t)mblocks.size();
+                    mblocks.emplace_back();
+                    multiply_block(n, T, starts[rr.block], starts[rr.block + 1], &posbuf, &D, &Tbuf,
+                                   &mblocks.back());
+                }
+                const MergedBlock& mb = mblocks[inv_slot[rr.block]];
+                const int w = starts[rr.block + 1] - starts[rr.block];
+                rr.len = (T.upper ? w - rr.k : rr.k + 1) + mb.ncol[rr.k];
             }
+        }
         g_inv_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ti0).count();
         std::stable_sort(rows.begin(), rows.end(), [](const RowRef& a, const RowRef& b) {
             if (a.len != b.len) return a.len > b.len;
@@ -219,6 +330,10 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
             if (!any) break;
         }
         for (size_t r = 1; r < rows.size(); ++r) gl[r] = std::min(gl[r], gl[r - 1]);  // monotone
+        // where a row of sub-level s reads the value of column c
+        auto addr = [&](int32_t c) {
+            return (any_merged && mlev[c] >= 0 && mlev[c] + 1 == s) ? maddr[c] : c;
+        };
         size_t r = 0;
         while (r < rows.size()) {
             const int g = gl[r], G = 1 << g, rmax = 32 >> g;
@@ -237,7 +352,7 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                 const RowRef& rr = rows[r + rl];
                 const BlockPlan& bp = plan[rr.block];
                 const int32_t r0 = starts[rr.block], r1 = starts[rr.block + 1], w = r1 - r0;
-                const int32_t ybase = (int32_t)(n + (bp.sA & 1) * ymax + (bp.yoff < 0 ? 0 : bp.yoff));
+                const int32_t ybase = ybase_of(bp);
                 const int32_t i = r0 + rr.k;
                 int e = 0;   // entry counter of this row
                 auto put = [&](int32_t c, double v) {
@@ -251,7 +366,7 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                     for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) {
                         const int32_t c = T.ci[p];
                         if (c < r0 || c >= r1) {
-                            put(c, T.va[p]);
+                            put(addr(c), T.va[p]);
                         } else if (c == i && !T.unit) {
                             dg = T.va[p];
                         }
@@ -264,11 +379,26 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                         P->dst.push_back(ybase + rr.k);
                         P->scale.push_back(1.0);
                     }
-                } else {
+                } else if (rr.kind == 1) {
                     const std::vector<double>& Xi = inv[inv_slot[rr.block]];
                     const int j0 = T.upper ? rr.k : 0, j1 = T.upper ? w : rr.k + 1;
                     for (int j = j0; j < j1; ++j) put(ybase + j, -Xi[(size_t)rr.k * w + j]);
                     P->init.push_back(-1);
+                    P->dst.push_back(i);
+                    P->scale.push_back(1.0);
+                } else if (rr.kind == 2) {
+                    // x_i = sum_j X[k,j] b_j - sum_c Pm[k,c] x_c: the right-hand sides b_j are
+                    // still in the home rows of this block (nobody writes them in this sub-level)
+                    const MergedBlock& mb = mblocks[inv_slot[rr.block]];
+                    const int j0 = T.upper ? rr.k : 0, j1 = T.upper ? w : rr.k + 1;
+                    for (int j = j0; j < j1; ++j) put(r0 + j, -mb.X[(size_t)rr.k * w + j]);
+                    const size_t cu = mb.cols.size();
+                    for (int32_t j = 0; j < mb.ncol[rr.k]; ++j) put(addr(mb.cols[j]), mb.Pm[(size_t)rr.k * cu + j]);
+                    P->init.push_back(-1);
+                    P->dst.push_back(ybase + rr.k);
+                    P->scale.push_back(1.0);
+                } else {
+                    P->init.push_back(ybase + rr.k);     // copy the merged result home
                     P->dst.push_back(i);
                     P->scale.push_back(1.0);
                 }
@@ -286,7 +416,7 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
 
 int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const double* Lva,
                      const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
-                     bool transposed, LuProgram* P) {
+                     bool transposed, bool merge, LuProgram* P) {
     *P = LuProgram();
     P->n = n;
     P->sub_ptr.push_back(0);
@@ -367,8 +497,15 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
     const Tri TL{Lrp, Lci, Lva, false, !transposed}, TU{Urp, Uci, Uva, true, transposed};
     std::vector<BlockPlan> planL, planU;
     int64_t ymax = 0;
-    int rc = plan_factor(n, TL, starts, &planL, &P->nsub_L, &ymax);
-    if (rc == OCB_OK) rc = plan_factor(n, TU, starts, &planU, &P->nsub_U, &ymax);
+    MergeRule rule;
+    if (merge) {
+        const char* ew = getenv("OCB_MERGE_W");
+        const char* eg = getenv("OCB_MERGE_GROWTH");
+        rule.max_w = ew ? atoi(ew) : 64;
+        rule.growth = eg ? atof(eg) : 1.3;
+    }
+    int rc = plan_factor(n, TL, starts, rule, &planL, &P->nsub_L, &ymax);
+    if (rc == OCB_OK) rc = plan_factor(n, TU, starts, rule, &planU, &P->nsub_U, &ymax);
     if (rc != OCB_OK) return rc;
     const auto t1 = tnow();
     P->ymax = ymax;
@@ -411,7 +548,7 @@ int ocb_lu_program_create(ocb_lu_program** out, int64_t n, const int32_t* h_L_ro
     OCB_ARG(out && n >= 0 && h_L_rowptr && h_U_rowptr, "lu_program_create");
     ocb_lu_program* h = new ocb_lu_program();
     const int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx,
-                                         h_U_vals, 512, (flags & 2) != 0, &h->P);
+                                         h_U_vals, 512, (flags & 2) != 0, (flags & 4) != 0, &h->P);
     if (rc != OCB_OK) {
         delete h;
         return rc;

@@ -53,8 +53,17 @@ struct LuProgram {
 // UPPER factor (rows of L^T) has the unit diagonal.
 int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const double* Lva,
                      const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
-                     bool transposed, LuProgram* out);
+                     bool transposed, bool merge, LuProgram* out);
 
+// merge = true: supernodes up to 64 rows wide (OCB_MERGE_W) are solved in ONE sub-level instead
+// of two, in inverse-multiplied form  x_t = inv(T_tt) b_t - (inv(T_tt) T[t,off]) x  (as long as
+// the product rows hold at most 1.3x the entries, OCB_MERGE_GROWTH).  The results are written to
+// the y region and copied home one sub-level later by zero-length rows, off the critical path;
+// a reader one sub-level after the block takes them from the y region.  N=25 cavity factor:
+// 140 -> 90 sub-levels for 2 % more entries and 2 ms more host time.
+//
+// P = X * T for a w x w triangular X and a dense w x m T (row-major).  host_dense.cpp.
+void tri_times_dense(const double* X, const double* T, double* P, int w, int m, bool upper);
 // X = inverse of the w x w triangular D (row-major; X zero on entry).  host_dense.cpp.
 void tri_inverse(const double* D, double* X, int w, bool upper, bool unit);
 

@@ -1100,7 +1100,7 @@ int ocb_lu_pack_host(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_co
     OCB_ARG(max_smem_optin >= 48 * 1024, "lu_pack_host: shared-memory size");
     ocb::LuProgram P;
     int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals,
-                                   ocb::trsm_threads(), (flags & 2) != 0, &P);
+                                   ocb::trsm_threads(), (flags & 2) != 0, (flags & 4) != 0, &P);
     if (rc != OCB_OK) return rc;
     return ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, (int)flags, out_image, out_bytes);
 }

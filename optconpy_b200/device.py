@@ -221,14 +221,21 @@ def _csc_args(mat, opts):
 _ORDER = dict()
 
 
+# one-step (inverse-multiplied) supernodes in the gather program, flags bit 2 of
+# ocb_lu_pack_host (lu_program.h); OCB_MERGE=0/1 overrides
+MERGE_DEFAULT = '0'
+
+
 def _pack_flags(wide, k_hint=None):
     """ocb_lu_pack_host flags: bit 0 = flat program for the wide executor, bit 1 = factorise A^T
     and take SuperLU's column-wise factors as they are (no CSC->CSR conversion on the host),
+    bit 2 = small supernodes solved in one sub-level instead of two,
     bits 4..7 = cluster size of the column-panel kernel from the expected block width
     (measured: clusters of 4 are fastest up to 33 right-hand sides - one column per cluster fits
     one wave -, clusters of 2 from 34 columns on)."""
     cl = 0 if k_hint is None else (4 if k_hint <= 33 else 2)
-    return (1 if wide else 0) | (0 if os.environ.get('OCB_NO_TRANSPOSED_LU') else 2) | (cl << 4)
+    merge = 4 if os.environ.get('OCB_MERGE', MERGE_DEFAULT) == '1' else 0
+    return (1 if wide else 0) | (0 if os.environ.get('OCB_NO_TRANSPOSED_LU') else 2) | merge | (cl << 4)
 
 
 def _pattern_key(a):

@@ -259,3 +259,65 @@ def test_unsorted_upper_rows_are_sorted_by_the_builder(cav10):
     h = C.c_void_p()
     rc = lib.ocb_lu_program_create(C.byref(h), n, *[x.ctypes.data for x in arrs[:4] + [dup, arrs[5]]], 2)
     assert rc == -1 and b'duplicate' in lib.ocb_last_error()
+
+
+@pytest.mark.parametrize('transposed', [False, True])
+def test_one_step_supernodes(cav10, transposed, monkeypatch):
+    """flags bit 2: small supernodes are solved in one sub-level (inverse-multiplied rows writing
+    to the y region, zero-length rows copying the result home one sub-level later).  Same
+    solution as the two-step program, hazard-free, clearly fewer sub-levels, bounded growth."""
+    K = _saddle(cav10)
+    n = K.shape[0]
+    base = 2 if transposed else 0
+    a = dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, base)
+    a = a + (_lu_worker.order_only(a),)
+    arrs = _lu_worker.factor_arrays(a, transposed=transposed)
+    rng = np.random.default_rng(11)
+    B = rng.standard_normal((n, 3))
+    ref = spsla.splu(K).solve(B)
+    out = {}
+    for flags in (base, base | 4):
+        prog = _program(arrs, n, flags=flags)
+        X = np.zeros((prog[0]['n_ext'], 3))
+        X[arrs[6]] = B
+        _execute(prog, X, check_hazards=True)
+        got = X[arrs[7]]
+        assert np.linalg.norm(got - ref) <= 1e-12*np.linalg.norm(ref)
+        out[flags] = prog[0]
+    two, one = out[base], out[base | 4]
+    assert one['nsub_L'] + one['nsub_U'] <= 0.7*(two['nsub_L'] + two['nsub_U'])
+    assert one['nent'] <= 1.25*two['nent'] and one['n_ext'] == n + 2*one['ymax']
+    assert one['nrows'] == two['nrows']          # A+B rows became one-step + copy rows
+    # width cap 0 -> nothing is merged: the very same program as without the flag
+    monkeypatch.setenv('OCB_MERGE_W', '1')
+    p_off, p_ref = _program(arrs, n, flags=base | 4), _program(arrs, n, flags=base)
+    assert p_off[0] == p_ref[0] and all(np.array_equal(x, y) for x, y in zip(p_off[1:], p_ref[1:]))
+    # everything merged, however much the rows grow: still exact
+    monkeypatch.setenv('OCB_MERGE_W', '512')
+    monkeypatch.setenv('OCB_MERGE_GROWTH', '1e9')
+    prog = _program(arrs, n, flags=base | 4)
+    X = np.zeros((prog[0]['n_ext'], 3))
+    X[arrs[6]] = B
+    _execute(prog, X, check_hazards=True)
+    assert np.linalg.norm(X[arrs[7]] - ref) <= 1e-12*np.linalg.norm(ref)
+    assert prog[0]['nsub_L'] + prog[0]['nsub_U'] <= one['nsub_L'] + one['nsub_U']
+
+
+def test_one_step_supernodes_dense_block():
+    """A dense matrix is one supernode: one sub-level per sweep plus the copy level."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(3)
+    Ad = rng.standard_normal((7, 7)) + 7*np.eye(7)
+    Pm, Ld, Ud = sla.lu(Ad)
+    Lc, Uc = sps.csr_matrix(Ld), sps.csr_matrix(Ud)
+    Lc.sort_indices()
+    Uc.sort_indices()
+    arrs = [Lc.indptr.astype(np.int32), Lc.indices.astype(np.int32), Lc.data,
+            Uc.indptr.astype(np.int32), Uc.indices.astype(np.int32), Uc.data]
+    prog = _program(arrs, 7, flags=4)
+    assert prog[0]['nsuper'] == 1 and prog[0]['nsub_L'] == 2 and prog[0]['nsub_U'] == 2
+    b = rng.standard_normal((7, 2))
+    X = np.zeros((prog[0]['n_ext'], 2))
+    X[:7] = Pm.T @ b
+    _execute(prog, X, check_hazards=True)
+    assert np.allclose(X[:7], np.linalg.solve(Ad, b))
