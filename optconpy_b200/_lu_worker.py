@@ -29,7 +29,8 @@ def tune_malloc():
     (splu of the N=25 cavity saddle matrix: 44 -> 35 ms with this setting)."""
     try:
         libc = C.CDLL('libc.so.6')
-        libc.mallopt(-3, 1 << 30)      # M_MMAP_THRESHOLD
+        if not libc.mallopt(-3, 1 << 30):      # M_MMAP_THRESHOLD (older glibc caps it at 32 MB)
+            libc.mallopt(-3, 32 << 20)
         libc.mallopt(-1, 1 << 30)      # M_TRIM_THRESHOLD
     except (OSError, AttributeError):
         pass

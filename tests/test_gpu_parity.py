@@ -312,8 +312,9 @@ def test_lazy_device_factor(mods, lyap_setup, cav10):
     assert isinstance(lazy, gpru.DeviceFactor) and lazy.shape == eager.shape and lazy.ndim == 2
     zc_l = gpru.compress_Zsvd(lazy, thresh=5e-5, k=50)
     assert dv.STATS['d2h_bytes'] - before < eager.nbytes        # the big factor never crossed PCIe
-    assert np.array_equal(zc_l, gpru.compress_Zsvd(eager, thresh=5e-5, k=50))
-    assert np.array_equal(np.asarray(lazy), eager) and np.array_equal(lazy[:, :3], eager[:, :3])
+    zc_e = gpru.compress_Zsvd(eager, thresh=5e-5, k=50)
+    assert zc_l.shape == zc_e.shape and _zzt_relerr(zc_l, zc_e) < 1e-12
+    assert _relerr(np.asarray(lazy), eager) < 1e-12 and _relerr(lazy[:, :3], eager[:, :3]) < 1e-12
     prob, cs1, kw1 = sc.config1(glau, Nts=2)
     s1, s2 = ds.MemStore(), ds.MemStore()
     f1 = ds.solve_flow_daeric(lau=glau, pru=gpru, store=s1, save_full_z=True,
@@ -323,4 +324,4 @@ def test_lazy_device_factor(mods, lyap_setup, cav10):
     for t in f1:
         kz = f1[t]['mtxtb'].replace('__mtxtb', '__Z')
         assert isinstance(s1[kz], np.ndarray) and s1[kz].shape[1] >= s2[kz].shape[1]
-        assert np.array_equal(s1[f1[t]['mtxtb']], s2[f2[t]['mtxtb']])
+        assert _relerr(s1[f1[t]['mtxtb']], s2[f2[t]['mtxtb']]) < 1e-10
