@@ -418,7 +418,8 @@ def main():
             def cb(tk):
                 torch.cuda.synchronize()
                 stamps.append(time.perf_counter())
-                bytes_at.append((dv.STATS['h2d_bytes'], dv.STATS['d2h_bytes']))
+                bytes_at.append((dv.STATS['h2d_bytes'], dv.STATS['d2h_bytes'],
+                                 torch.cuda.memory_stats().get('num_device_alloc', 0)))
             dv.reset_stats()
             barrier()
             if args.phases:
@@ -446,6 +447,8 @@ def main():
                        host_setup_per_step={k: (v/(S+la)) for k, v in dv.STATS.items()
                                             if k.startswith('lu_') or k == 'n_factor'},
                        lu_workers=dv._POOL['workers'], lookahead_steps=la,
+                       cuda_mallocs_in_timed_region=int(bytes_at[W+K-1][2] - bytes_at[W-1][2]),
+                       pinned_pool_segments=(len(dv._SHM['pool'].segs) if dv._SHM['pool'] is not None else 0),
                        main_thread_phase_s_per_step=dict({k: v/(S+la) for k, v in dv.PHASE.items()},
                                                          **{k: v/(S+la) for k, v in stimes.items()}),
                        note='LU setup of step k-1 runs in worker processes while the GPU works '

@@ -223,7 +223,7 @@ _ORDER = dict()
 
 # one-step (inverse-multiplied) supernodes in the gather program, flags bit 2 of
 # ocb_lu_pack_host (lu_program.h); OCB_MERGE=0/1 overrides
-MERGE_DEFAULT = '0'
+MERGE_DEFAULT = '1'
 
 
 def _pack_flags(wide, k_hint=None):
@@ -339,8 +339,13 @@ def _shm_pool(image_bytes=None):
             seg_bytes = int(image_bytes*1.3) + (1 << 20)
             try:
                 st = os.statvfs('/dev/shm')
-                if nseg*seg_bytes > 0.4*st.f_bavail*st.f_frsize:
-                    raise MemoryError('/dev/shm too small for the pinned pool')
+                fit = int(0.4*st.f_bavail*st.f_frsize)//seg_bytes
+                if fit < nseg:
+                    # fewer segments: images that find no free segment travel through a
+                    # one-off unpinned segment (slower, still correct)
+                    if fit < 4:
+                        raise MemoryError('/dev/shm too small for the pinned pool')
+                    nseg = fit
             except OSError:
                 pass
             _SHM['pool'] = _PinnedShmPool(nseg, seg_bytes)
@@ -474,6 +479,35 @@ def factorize_many(mats, lu_options=None):
     return FactorJob(mats, lu_options).result()
 
 
+_ARENA_WARM = set()
+_ARENA_CLASSES = []
+
+
+def _new_arena(nbytes):
+    """Device buffer for one factor image.  The images of one run differ by a few KB (pivoting
+    changes the fill slightly), and torch's caching allocator only reuses a freed block for a
+    request that is not larger.  Requests are therefore rounded up to STICKY size classes (the
+    first image of a new size defines one with 4 % headroom; later images up to that size use
+    it), and a new class makes the allocator cache enough blocks of it for the look-ahead
+    pipeline (per stream: the uploads run on their own).  Without this, cudaMalloc calls - each
+    one synchronises the device - kept turning up inside the timed steps whenever the size
+    sequence happened to miss the cache (host-API steps of 37 ms vs 41-89 ms)."""
+    nbytes = int(nbytes)
+    cls = next((c for c in _ARENA_CLASSES if nbytes <= c <= 1.25*nbytes + 4096), None)
+    if cls is None:
+        step = 1 << max(nbytes.bit_length() - 5, 9)
+        cls = -(-int(1.04*nbytes)//step)*step
+        _ARENA_CLASSES.append(cls)
+        _ARENA_CLASSES.sort()
+    key = (cls, torch.cuda.current_stream().cuda_stream, torch.cuda.current_device())
+    if key not in _ARENA_WARM and cls >= (4 << 20):
+        _ARENA_WARM.add(key)
+        count = min(int(os.environ.get('OCB_ARENA_PREWARM', '44')), (1 << 30)//cls)
+        warm = [torch.empty(cls, dtype=torch.uint8, device=cur_device()) for _ in range(count)]
+        del warm
+    return torch.empty(cls, dtype=torch.uint8, device=cur_device())
+
+
 class LU(object):
     """Device-resident LU factorisation ``Pr A Pc = L U`` (handle of the C ABI)."""
 
@@ -495,7 +529,7 @@ class LU(object):
         h = C.c_void_p()
         # the device image lives in a torch buffer: the caching allocator makes creating and
         # dropping a factorisation free of cudaMalloc / cudaFree (both synchronise the device)
-        self.arena = torch.empty(int(image.nbytes), dtype=torch.uint8, device=cur_device())
+        self.arena = _new_arena(int(image.nbytes))
         _cabi.check(lib.ocb_lu_create_from_image(C.byref(h), image.ctypes.data, image.nbytes,
                                                  ptr(self.arena), stream_ptr()),
                     'ocb_lu_create_from_image')

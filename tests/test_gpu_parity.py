@@ -317,8 +317,8 @@ def test_lazy_device_factor(mods, lyap_setup, cav10):
     assert _relerr(np.asarray(lazy), eager) < 1e-12 and _relerr(lazy[:, :3], eager[:, :3]) < 1e-12
     prob, cs1, kw1 = sc.config1(glau, Nts=2)
     s1, s2 = ds.MemStore(), ds.MemStore()
-    f1 = ds.solve_flow_daeric(lau=glau, pru=gpru, store=s1, save_full_z=True,
-                              **dict(kw1, gtdtstrargs=dict(kw1['gtdtstrargs'])))
+    f1 = ds.solve_flow_daeric(lau=glau, pru=gpru, store=s1,
+                              **dict(kw1, save_full_z=True, gtdtstrargs=dict(kw1['gtdtstrargs'])))
     f2 = ds.solve_flow_daeric(lau=glau, pru=gpru, store=s2,
                               **dict(kw1, gtdtstrargs=dict(kw1['gtdtstrargs'])))
     for t in f1:
