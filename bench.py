@@ -447,6 +447,7 @@ def main():
                        host_setup_per_step={k: (v/(S+la)) for k, v in dv.STATS.items()
                                             if k.startswith('lu_') or k == 'n_factor'},
                        lu_workers=dv._POOL['workers'], lookahead_steps=la,
+                       step_ms=[round(1e3*(b - a), 2) for a, b in zip(stamps[max(W-1, 0):W+K-1], stamps[max(W, 1):W+K])],
                        cuda_mallocs_in_timed_region=int(bytes_at[W+K-1][2] - bytes_at[W-1][2]),
                        pinned_pool_segments=(len(dv._SHM['pool'].segs) if dv._SHM['pool'] is not None else 0),
                        main_thread_phase_s_per_step=dict({k: v/(S+la) for k, v in dv.PHASE.items()},

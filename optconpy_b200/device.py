@@ -23,6 +23,7 @@ STATS = dict(lu_factor_s=0.0,          # SuperLU seconds summed over the workers
              lu_wait_s=0.0,            # main thread: blocked until the factors are on the device
              lu_collect_wait_s=0.0,    # collecting thread: blocked on a worker result
              lu_analyse_upload_s=0.0,  # main process: image upload + handle creation
+             lu_arena_s=0.0,           # ... of which: device buffer from the caching allocator
              n_factor=0, h2d_bytes=0, d2h_bytes=0)
 
 # wall seconds of the main thread per phase of the host API (diagnostics, bench.py e2e)
@@ -530,6 +531,7 @@ class LU(object):
         # the device image lives in a torch buffer: the caching allocator makes creating and
         # dropping a factorisation free of cudaMalloc / cudaFree (both synchronise the device)
         self.arena = _new_arena(int(image.nbytes))
+        STATS['lu_arena_s'] += time.perf_counter() - t1
         _cabi.check(lib.ocb_lu_create_from_image(C.byref(h), image.ctypes.data, image.nbytes,
                                                  ptr(self.arena), stream_ptr()),
                     'ocb_lu_create_from_image')
