@@ -484,6 +484,19 @@ _ARENA_WARM = set()
 _ARENA_CLASSES = []
 
 
+def _arena_class(nbytes, classes=_ARENA_CLASSES):
+    """Smallest known size class that holds ``nbytes`` without wasting more than a quarter, or a
+    new one: ``nbytes`` + 4 % rounded up to 1/16 .. 1/32 of its magnitude."""
+    nbytes = int(nbytes)
+    cls = next((c for c in classes if nbytes <= c <= 1.25*nbytes + 4096), None)
+    if cls is None:
+        step = 1 << max(nbytes.bit_length() - 5, 9)
+        cls = -(-int(1.04*nbytes)//step)*step
+        classes.append(cls)
+        classes.sort()
+    return cls
+
+
 def _new_arena(nbytes):
     """Device buffer for one factor image.  The images of one run differ by a few KB (pivoting
     changes the fill slightly), and torch's caching allocator only reuses a freed block for a
@@ -493,13 +506,7 @@ def _new_arena(nbytes):
     pipeline (per stream: the uploads run on their own).  Without this, cudaMalloc calls - each
     one synchronises the device - kept turning up inside the timed steps whenever the size
     sequence happened to miss the cache (host-API steps of 37 ms vs 41-89 ms)."""
-    nbytes = int(nbytes)
-    cls = next((c for c in _ARENA_CLASSES if nbytes <= c <= 1.25*nbytes + 4096), None)
-    if cls is None:
-        step = 1 << max(nbytes.bit_length() - 5, 9)
-        cls = -(-int(1.04*nbytes)//step)*step
-        _ARENA_CLASSES.append(cls)
-        _ARENA_CLASSES.sort()
+    cls = _arena_class(nbytes)
     key = (cls, torch.cuda.current_stream().cuda_stream, torch.cuda.current_device())
     if key not in _ARENA_WARM and cls >= (4 << 20):
         _ARENA_WARM.add(key)

@@ -172,3 +172,52 @@ def test_device_factor_handle_behaves_like_the_array():
     st = ds.MemStore()
     st.save(f, 'z')
     assert isinstance(st['z'], np.ndarray) and np.array_equal(st['z'], a)
+
+
+def test_arena_size_classes_are_sticky():
+    """device._arena_class: images of one run (sizes within a few per cent) share one class, so
+    the caching allocator always finds a freed block; different magnitudes get their own."""
+    from optconpy_b200 import device as dv
+    classes = []
+    first = dv._arena_class(9385216, classes)
+    assert first >= 9385216*1.04 - 1 and first <= 9385216*1.10
+    for nb in (9385216, 9300000, 9577472, 9700000):
+        assert dv._arena_class(nb, classes) == first
+    assert classes == [first]
+    small = dv._arena_class(50000, classes)
+    big = dv._arena_class(120000000, classes)
+    assert small < first < big and classes == [small, first, big]
+    assert dv._arena_class(51000, classes) == small and dv._arena_class(100, classes) >= 100
+    # a request just above a class opens the next one instead of overflowing the buffer
+    nxt = dv._arena_class(first + 1, classes)
+    assert nxt > first and dv._arena_class(first, classes) == first
+
+
+def test_worker_pattern_cache_matches_the_plain_arrangement(cav6):
+    """_lu_worker._arranged: transposition + symmetric permutation through the cached entry map
+    equals the plain scipy operations; a pattern with duplicate entries takes the plain path."""
+    from optconpy_b200 import _lu_worker as w, device as dv
+    K = dv.sadpnt_matrix(cav6['M'] + 0.1*cav6['A'], cav6['J']).tocsc()
+    n = K.shape[0]
+    rng = np.random.default_rng(4)
+    q = rng.permutation(n).astype(np.int32)
+    for transposed in (False, True):
+        for qq in (None, q):
+            w._ARRANGE.clear()
+            for rep in range(2):          # second pass: served from the cache
+                data = K.data*(1.0 + rep)
+                got = w._arranged(data, K.indices, K.indptr, K.shape, qq, transposed)
+                ref = sps.csc_matrix((data, K.indices, K.indptr), shape=K.shape)
+                ref = ref.T.tocsc() if transposed else ref
+                ref = ref[qq][:, qq].tocsc() if qq is not None else ref
+                assert got.has_canonical_format and abs(got - ref).max() == 0.0
+            assert len(w._ARRANGE) == 1 and next(iter(w._ARRANGE.values())) is not None
+    # duplicates: (0,0) stored twice
+    ind = np.array([0, 0, 1, 1], dtype=np.int32)
+    ptr = np.array([0, 3, 4], dtype=np.int32)
+    dat = np.array([1.0, 2.0, 3.0, 4.0])
+    w._ARRANGE.clear()
+    got = w._arranged(dat, ind, ptr, (2, 2), None, True)
+    assert next(iter(w._ARRANGE.values())) is None
+    assert np.array_equal(got.toarray(), np.array([[3.0, 3.0], [0.0, 4.0]]))
+    w.tune_malloc()                       # must not raise anywhere
