@@ -510,7 +510,7 @@ def _new_arena(nbytes):
     key = (cls, torch.cuda.current_stream().cuda_stream, torch.cuda.current_device())
     if key not in _ARENA_WARM and cls >= (4 << 20):
         _ARENA_WARM.add(key)
-        count = min(int(os.environ.get('OCB_ARENA_PREWARM', '44')), (1 << 30)//cls)
+        count = min(int(os.environ.get('OCB_ARENA_PREWARM', '64')), (1 << 30)//cls)
         warm = [torch.empty(cls, dtype=torch.uint8, device=cur_device()) for _ in range(count)]
         del warm
     return torch.empty(cls, dtype=torch.uint8, device=cur_device())
