@@ -114,6 +114,11 @@ int ocb_lu_program_create(ocb_lu_program** out, int64_t n,
                           const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
                           int64_t flags);
 int ocb_lu_program_destroy(ocb_lu_program* prog);
+/* The builder keeps the STRUCTURE of the last four programs by the index arrays they were built
+ * from; a factor with the same index arrays (other shift, other time step: same ordering and
+ * pivots) only has its numbers recomputed (OCB_NO_TEMPLATE=1 switches that off).  Number of
+ * builds of this process served that way: */
+int64_t ocb_lu_program_template_hits(void);
 /* info[0..11] = n, n_ext, ymax, sub-levels L, sub-levels U, #supernodes, widest supernode,
  *               #slices, #rows, #entries (padded), nnz(L) strictly lower, nnz(U) */
 int ocb_lu_program_info(const ocb_lu_program* prog, int64_t* info12);

@@ -27,6 +27,7 @@ PROTOTYPES = {
     'ocb_debug_trace': (C.c_int, [vp, i64]),
     'ocb_lu_program_create': (C.c_int, [C.POINTER(vp), i64, vp, vp, vp, vp, vp, vp, i64]),
     'ocb_lu_program_destroy': (C.c_int, [vp]),
+    'ocb_lu_program_template_hits': (i64, []),
     'ocb_lu_program_info': (C.c_int, [vp, C.POINTER(i64)]),
     'ocb_lu_program_export': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     'ocb_lu_solve_ws_bytes': (i64, [vp, i64]),

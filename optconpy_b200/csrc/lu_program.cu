@@ -8,6 +8,8 @@
 #include <string.h>
 #include <stdlib.h>
 #include <chrono>
+#include <memory>
+#include <mutex>
 #include <stdio.h>
 
 namespace ocb {
@@ -194,6 +196,17 @@ struct RowRef {     // a row of the program before it is laid out
     uint8_t kind;   // 0: A row, 1: B row, 2: one-step (merged) row, 3: copy of a merged result
 };
 
+// What a fresh build records about one triangular factor so that a later matrix with the SAME
+// index arrays only has to recompute numbers (refill_factor): the rows of every sub-level in
+// their final order and where their entries live in the sliced-ELLPACK arrays.
+struct FactorTemplate {
+    std::vector<int32_t> level_ptr;   // rows of recorded level j: [level_ptr[j], level_ptr[j+1])
+    std::vector<RowRef> rows;
+    std::vector<int32_t> q;           // program row
+    std::vector<int32_t> base;        // position of the row's entry 0
+    std::vector<uint8_t> g;           // log2(lanes per row)
+};
+
 struct MergedBlock {            // inverse-multiplied form of one merged block
     std::vector<int32_t> cols;  // off-block columns in order of first appearance
     std::vector<int32_t> ncol;  // per row k: how many of them row k uses
@@ -236,8 +249,9 @@ void multiply_block(int64_t n, const Tri& T, int32_t r0, int32_t r1, std::vector
 
 int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                 const std::vector<BlockPlan>& plan, int32_t nsub, int64_t ymax, int max_lanes,
-                LuProgram* P) {
+                LuProgram* P, FactorTemplate* rec) {
     const int nb = (int)starts.size() - 1;
+    if (rec) rec->level_ptr.assign(1, 0);
     std::vector<std::vector<RowRef>> lev(nsub);
     // rows of merged blocks: the sub-level that produces them and where a reader one sub-level
     // later finds them (the y region; everybody later reads the home row)
@@ -354,6 +368,12 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                 const int32_t r0 = starts[rr.block], r1 = starts[rr.block + 1], w = r1 - r0;
                 const int32_t ybase = ybase_of(bp);
                 const int32_t i = r0 + rr.k;
+                if (rec) {
+                    rec->rows.push_back(rr);
+                    rec->q.push_back((int32_t)P->dst.size());
+                    rec->base.push_back((int32_t)(e0 + ((size_t)rl << g)));
+                    rec->g.push_back((uint8_t)g);
+                }
                 int e = 0;   // entry counter of this row
                 auto put = [&](int32_t c, double v) {
                     const size_t pos = e0 + ((size_t)(e >> g) << 5) + ((size_t)rl << g) + (size_t)(e & (G - 1));
@@ -408,11 +428,139 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
             r = r2;
         }
         P->sub_ptr.push_back((int32_t)P->slices.size());
+        if (rec) rec->level_ptr.push_back((int32_t)rec->rows.size());
     }
     return OCB_OK;
 }
 
+// Numbers only: the rows recorded by emit_factor, for a factor with the same index arrays.
+// Mirrors the value computations of emit_factor exactly (tests compare the images byte by byte).
+int refill_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
+                  const std::vector<BlockPlan>& plan, const FactorTemplate& rec, LuProgram* P) {
+    const int nb = (int)starts.size() - 1;
+    std::vector<double> D, X, Tbuf;
+    std::vector<int32_t> posbuf;
+    std::vector<int32_t> inv_slot(nb, -1);
+    std::vector<std::vector<double>> inv;
+    std::vector<MergedBlock> mblocks;
+    for (size_t lv = 0; lv + 1 < rec.level_ptr.size(); ++lv) {
+        const int32_t a = rec.level_ptr[lv], b = rec.level_ptr[lv + 1];
+        inv.clear();
+        mblocks.clear();
+        const auto ti0 = std::chrono::steady_clock::now();
+        for (int32_t x = a; x < b; ++x) {
+            const RowRef& rr = rec.rows[x];
+            if (rr.k != 0) continue;
+            if (rr.kind == 1) {
+                invert_block(T, starts[rr.block], starts[rr.block + 1], &D, &X);
+                inv_slot[rr.block] = (int32_t)inv.size();
+                inv.push_back(X);
+            } else if (rr.kind == 2) {
+                inv_slot[rr.block] = (int32_t)mblocks.size();
+                mblocks.emplace_back();
+                multiply_block(n, T, starts[rr.block], starts[rr.block + 1], &posbuf, &D, &Tbuf, &mblocks.back());
+                const int w = starts[rr.block + 1] - starts[rr.block];
+                for (int j = 0; j < w && !T.unit; ++j)
+                    if (D[(size_t)j * w + j] == 0.0) {
+                        set_error("the %s factor has a zero pivot in row %d", T.upper ? "upper" : "lower",
+                                  starts[rr.block] + j);
+                        return OCB_ERR_SINGULAR;
+                    }
+            }
+        }
+        g_inv_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ti0).count();
+        for (int32_t x = a; x < b; ++x) {
+            const RowRef& rr = rec.rows[x];
+            const int32_t r0 = starts[rr.block], r1 = starts[rr.block + 1], w = r1 - r0;
+            const int32_t i = r0 + rr.k;
+            const int g = rec.g[x], G = 1 << g;
+            double* vbase = P->val.data() + rec.base[x];
+            int e = 0;
+            auto put = [&](double v) {
+                vbase[((size_t)(e >> g) << 5) + (size_t)(e & (G - 1))] = v;
+                ++e;
+            };
+            if (rr.kind == 0) {
+                double dg = 1.0;
+                for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) {
+                    const int32_t c = T.ci[p];
+                    if (c < r0 || c >= r1) {
+                        put(T.va[p]);
+                    } else if (c == i && !T.unit) {
+                        dg = T.va[p];
+                    }
+                }
+                if (!T.unit && dg == 0.0) {
+                    set_error("the %s factor has a zero pivot in row %d", T.upper ? "upper" : "lower", i);
+                    return OCB_ERR_SINGULAR;
+                }
+                if (w == 1) P->scale[rec.q[x]] = 1.0 / dg;
+            } else if (rr.kind == 1) {
+                const std::vector<double>& Xi = inv[inv_slot[rr.block]];
+                const int j0 = T.upper ? rr.k : 0, j1 = T.upper ? w : rr.k + 1;
+                for (int j = j0; j < j1; ++j) put(-Xi[(size_t)rr.k * w + j]);
+            } else if (rr.kind == 2) {
+                const MergedBlock& mb = mblocks[inv_slot[rr.block]];
+                const int j0 = T.upper ? rr.k : 0, j1 = T.upper ? w : rr.k + 1;
+                for (int j = j0; j < j1; ++j) put(-mb.X[(size_t)rr.k * w + j]);
+                const size_t cu = mb.cols.size();
+                for (int32_t j = 0; j < mb.ncol[rr.k]; ++j) put(mb.Pm[(size_t)rr.k * cu + j]);
+            }
+            if (e != rr.len && rr.kind != 3) {
+                set_error("program template does not match the factor (row %d)", i);
+                return OCB_ERR_ARG;
+            }
+        }
+    }
+    return OCB_OK;
+}
+
+// Structure of a program by the index arrays it was built from.  The factors of one run share
+// a handful of structures (same ordering, same pivots: every shift and every time step of the
+// cavity problem yields the SAME index arrays), so most builds only recompute numbers.
+struct ProgramTemplate {
+    int64_t n = 0;
+    int max_lanes = 0;
+    bool transposed = false, merge = false;
+    MergeRule rule;
+    std::vector<int32_t> Lrp, Lci, Urp, Uci;        // the key (raw, as handed in)
+    std::vector<int32_t> Uci_sorted, Uperm;         // sorted rows of U and where each entry came from
+    std::vector<int32_t> starts;
+    std::vector<BlockPlan> planL, planU;
+    FactorTemplate recL, recU;
+    LuProgram P;                                    // everything but the numbers (val is empty)
+    int64_t nent = 0;
+    uint64_t stamp = 0;
+    size_t bytes() const {
+        return sizeof(int32_t) * (Lrp.size() + Lci.size() + Urp.size() + Uci.size() + Uci_sorted.size() +
+                                  Uperm.size() + P.col.size() + 3 * P.dst.size() + 4 * recL.rows.size() +
+                                  4 * recU.rows.size()) + sizeof(double) * P.scale.size();
+    }
+};
+constexpr size_t TEMPLATE_BYTES_MAX = 256u << 20;   // all cached structures of one process
+
+std::mutex g_tmpl_mutex;
+std::vector<std::unique_ptr<ProgramTemplate>> g_templates;
+uint64_t g_tmpl_clock = 0;
+
+bool same_ints(const std::vector<int32_t>& a, const int32_t* b, size_t count) {
+    return a.size() == count && (count == 0 || memcmp(a.data(), b, count * sizeof(int32_t)) == 0);
+}
+
+MergeRule merge_rule(bool merge) {
+    MergeRule rule;
+    if (merge) {
+        const char* ew = getenv("OCB_MERGE_W");
+        const char* eg = getenv("OCB_MERGE_GROWTH");
+        rule.max_w = ew ? atoi(ew) : 64;
+        rule.growth = eg ? atof(eg) : 1.3;
+    }
+    return rule;
+}
+
 }  // namespace
+
+int64_t g_template_hits = 0;
 
 int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const double* Lva,
                      const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
@@ -424,6 +572,66 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
     if ((int64_t)Lrp[n] + Urp[n] + 2 * n >= (int64_t)INT32_MAX / 2) {
         set_error("factor too large for int32 program indices");
         return OCB_ERR_ARG;
+    }
+    const bool timing = getenv("OCB_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const MergeRule rule = merge_rule(merge);
+    const bool use_templates = getenv("OCB_NO_TEMPLATE") == nullptr;
+    if (use_templates) {
+        // a structure seen before?  then only the numbers are recomputed
+        const auto tt0 = tnow();
+        std::unique_lock<std::mutex> lock(g_tmpl_mutex);
+        ProgramTemplate* hit = nullptr;
+        for (auto& t : g_templates)
+            if (t->n == n && t->max_lanes == max_lanes && t->transposed == transposed && t->merge == merge &&
+                t->rule.max_w == rule.max_w && t->rule.growth == rule.growth &&
+                same_ints(t->Lrp, Lrp, (size_t)n + 1) && same_ints(t->Urp, Urp, (size_t)n + 1) &&
+                same_ints(t->Lci, Lci, (size_t)Lrp[n]) && same_ints(t->Uci, Uci, (size_t)Urp[n])) {
+                hit = t.get();
+                break;
+            }
+        if (hit) {
+            const auto tt1 = tnow();
+            hit->stamp = ++g_tmpl_clock;
+            *P = hit->P;                                  // structure; the numbers follow
+            P->val.assign((size_t)hit->nent, 0.0);
+            const auto tt2 = tnow();
+            std::vector<double> Uva_sorted;
+            const int32_t* Ucs = Uci;
+            const double* Uvs = Uva;
+            if (!hit->Uperm.empty()) {
+                Uva_sorted.resize(hit->Uperm.size());
+                for (size_t j = 0; j < hit->Uperm.size(); ++j) Uva_sorted[j] = Uva[hit->Uperm[j]];
+                Ucs = hit->Uci_sorted.data();
+                Uvs = Uva_sorted.data();
+            }
+            const Tri TL{Lrp, Lci, Lva, false, !transposed}, TU{Urp, Ucs, Uvs, true, transposed};
+            int rc = refill_factor(n, TL, hit->starts, hit->planL, hit->recL, P);
+            if (rc == OCB_OK) rc = refill_factor(n, TU, hit->starts, hit->planU, hit->recU, P);
+            ++g_template_hits;
+            if (timing) {
+                fprintf(stderr, "lu_program: structure template hit, numbers refilled in %.1f ms (lookup %.1f, copy %.1f, block inverses %.1f ms)\n",
+                        ms(tt0, tnow()), ms(tt0, tt1), ms(tt1, tt2), g_inv_ms);
+                g_inv_ms = 0.0;
+            }
+            return rc;
+        }
+    }
+    std::unique_ptr<ProgramTemplate> tmpl;
+    if (use_templates) {
+        tmpl.reset(new ProgramTemplate());
+        tmpl->n = n;
+        tmpl->max_lanes = max_lanes;
+        tmpl->transposed = transposed;
+        tmpl->merge = merge;
+        tmpl->rule = rule;
+        tmpl->Lrp.assign(Lrp, Lrp + n + 1);
+        tmpl->Urp.assign(Urp, Urp + n + 1);
+        tmpl->Lci.assign(Lci, Lci + Lrp[n]);
+        tmpl->Uci.assign(Uci, Uci + Urp[n]);
     }
     // The supernode search compares sorted rows of U.  SuperLU hands its columns out in
     // supernodal order, not sorted, but consistently: inside one of ITS supernodes the index
@@ -462,7 +670,10 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
                 Uci_sorted[a0 + j] = raw[perm[j]];
                 Uva_sorted[a0 + j] = Uva[a0 + perm[j]];
             }
+            if (tmpl)
+                for (int32_t j = 0; j < len; ++j) tmpl->Uperm.push_back(a0 + perm[j]);
         }
+        if (tmpl) tmpl->Uci_sorted = Uci_sorted;
         Uci = Uci_sorted.data();
         Uva = Uva_sorted.data();
     }
@@ -481,11 +692,6 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
             return OCB_ERR_ARG;
         }
     }
-    const bool timing = getenv("OCB_TIMING") != nullptr;
-    auto tnow = [] { return std::chrono::steady_clock::now(); };
-    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-        return std::chrono::duration<double, std::milli>(b - a).count();
-    };
     const auto t0 = tnow();
     if (timing) fprintf(stderr, "lu_program: sort+check %.1f ms\n", ms(tsort0, t0));
     std::vector<int32_t> starts;
@@ -497,13 +703,6 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
     const Tri TL{Lrp, Lci, Lva, false, !transposed}, TU{Urp, Uci, Uva, true, transposed};
     std::vector<BlockPlan> planL, planU;
     int64_t ymax = 0;
-    MergeRule rule;
-    if (merge) {
-        const char* ew = getenv("OCB_MERGE_W");
-        const char* eg = getenv("OCB_MERGE_GROWTH");
-        rule.max_w = ew ? atoi(ew) : 64;
-        rule.growth = eg ? atof(eg) : 1.3;
-    }
     int rc = plan_factor(n, TL, starts, rule, &planL, &P->nsub_L, &ymax);
     if (rc == OCB_OK) rc = plan_factor(n, TU, starts, rule, &planU, &P->nsub_U, &ymax);
     if (rc != OCB_OK) return rc;
@@ -518,15 +717,37 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
         for (int32_t p = Urp[i]; p < Urp[i + 1]; ++p) P->nnzU += (Uci[p] != i) || !transposed;
     }
     const auto t2 = tnow();
-    rc = emit_factor(n, TL, starts, planL, P->nsub_L, ymax, max_lanes, P);
+    rc = emit_factor(n, TL, starts, planL, P->nsub_L, ymax, max_lanes, P, tmpl ? &tmpl->recL : nullptr);
     const auto t3 = tnow();
     P->nsub_L = (int32_t)P->nsub();
-    if (rc == OCB_OK) rc = emit_factor(n, TU, starts, planU, P->nsub_U, ymax, max_lanes, P);
+    if (rc == OCB_OK)
+        rc = emit_factor(n, TU, starts, planU, P->nsub_U, ymax, max_lanes, P, tmpl ? &tmpl->recU : nullptr);
     P->nsub_U = (int32_t)P->nsub() - P->nsub_L;
     if (timing) {
         fprintf(stderr, "lu_program: supernodes+plan %.1f ms, reserve %.1f ms, emit L %.1f ms, emit U %.1f ms (block inverses %.1f ms)\n",
                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, tnow()), g_inv_ms);
         g_inv_ms = 0.0;
+    }
+    if (rc == OCB_OK && tmpl) {
+        tmpl->starts = starts;
+        tmpl->planL = planL;
+        tmpl->planU = planU;
+        tmpl->P = *P;
+        tmpl->nent = P->nent();
+        std::vector<double>().swap(tmpl->P.val);       // padding is zero, the rest is refilled
+        std::unique_lock<std::mutex> lock(g_tmpl_mutex);
+        tmpl->stamp = ++g_tmpl_clock;
+        size_t total = tmpl->bytes();
+        for (auto& t : g_templates) total += t->bytes();
+        // keep the four most recently used structures, and no more than 256 MB of them
+        while (!g_templates.empty() && (g_templates.size() >= 4 || total > TEMPLATE_BYTES_MAX)) {
+            size_t oldest = 0;
+            for (size_t j = 1; j < g_templates.size(); ++j)
+                if (g_templates[j]->stamp < g_templates[oldest]->stamp) oldest = j;
+            total -= g_templates[oldest]->bytes();
+            g_templates.erase(g_templates.begin() + oldest);
+        }
+        if (total <= TEMPLATE_BYTES_MAX) g_templates.push_back(std::move(tmpl));
     }
     return rc;
 }
@@ -556,6 +777,8 @@ int ocb_lu_program_create(ocb_lu_program** out, int64_t n, const int32_t* h_L_ro
     *out = h;
     return OCB_OK;
 }
+
+int64_t ocb_lu_program_template_hits(void) { return ocb::g_template_hits; }
 
 int ocb_lu_program_destroy(ocb_lu_program* prog) {
     delete prog;

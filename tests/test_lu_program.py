@@ -321,3 +321,78 @@ def test_one_step_supernodes_dense_block():
     X[:7] = Pm.T @ b
     _execute(prog, X, check_hazards=True)
     assert np.allclose(X[:7], np.linalg.solve(Ad, b))
+
+
+@pytest.mark.parametrize('flags', [2, 6, 0])
+def test_structure_template_refills_numbers_only(cav10, flags, monkeypatch):
+    """A second factor with the SAME index arrays (other shift: same ordering, same pivots) is
+    served from the cached structure: only numbers are recomputed.  The result must be the very
+    program a fresh build gives - compared array by array - and the device images must be
+    identical byte for byte; a zero pivot is still reported; other structures miss."""
+    lib = _cabi.load()
+    transposed = bool(flags & 2)
+    Ks = [_saddle(cav10, mu=mu) for mu in (-1.0, -2.5)]
+    n = Ks[0].shape[0]
+    a0 = dv._csc_args(Ks[0], dict(dv.LU_OPTIONS)) + (232448, flags)
+    q = _lu_worker.order_only(a0)
+    arrs = [_lu_worker.factor_arrays(dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, flags, q),
+                                     transposed=transposed) for K in Ks]
+    for x, y in zip(arrs[0][:2] + arrs[0][3:5], arrs[1][:2] + arrs[1][3:5]):
+        assert np.array_equal(x, y)                    # same structure, other numbers
+    monkeypatch.setenv('OCB_NO_TEMPLATE', '1')
+    fresh = [_program(a, n, flags=flags) for a in arrs]
+    fresh_img = [_lu_worker.pack_image(a, n, 232448, flags) for a in arrs]
+    monkeypatch.delenv('OCB_NO_TEMPLATE')
+    h0 = lib.ocb_lu_program_template_hits()
+    first = _program(arrs[0], n, flags=flags)          # records (or hits an earlier test's entry)
+    h1 = lib.ocb_lu_program_template_hits()
+    second = _program(arrs[1], n, flags=flags)
+    assert lib.ocb_lu_program_template_hits() == h1 + 1 and h1 - h0 in (0, 1)
+    for got, ref in ((first, fresh[0]), (second, fresh[1])):
+        assert got[0] == ref[0]
+        for x, y in zip(got[1:], ref[1:]):
+            assert np.array_equal(x, y)
+    for a, ref in zip(arrs, fresh_img):
+        assert np.array_equal(_lu_worker.pack_image(a, n, 232448, flags), ref)
+    # the refilled program solves the second system
+    rng = np.random.default_rng(2)
+    B = rng.standard_normal((n, 2))
+    X = np.zeros((second[0]['n_ext'], 2))
+    X[arrs[1][6]] = B
+    _execute(second, X, check_hazards=True)
+    assert np.linalg.norm(Ks[1] @ X[arrs[1][7]] - B) <= 1e-12*np.linalg.norm(B)
+    # zero pivot: reported by the refill as by the fresh build
+    piv = 0 if transposed else 3                       # the factor that carries the pivots
+    bad = [x.copy() for x in arrs[1]]
+    rp, ci = bad[piv], bad[piv + 1]
+    row = n//2
+    bad[piv + 2][rp[row] + int(np.argmax(ci[rp[row]:rp[row+1]] == row))] = 0.0
+    h = C.c_void_p()
+    rc = lib.ocb_lu_program_create(C.byref(h), n, *[x.ctypes.data for x in bad[:6]], flags)
+    assert rc == -3 and b'zero pivot' in lib.ocb_last_error()
+    # another structure (coarser factor of another matrix) does not hit
+    h2 = lib.ocb_lu_program_template_hits()
+    K3 = _saddle(cav10, mu=-1.0) + sps.identity(n, format='csc')*1e-3     # new pattern (pressure block)
+    a3 = _lu_worker.factor_arrays(dv._csc_args(K3, dict(dv.LU_OPTIONS)) + (232448, flags), transposed=transposed)
+    p3 = _program(a3, n, flags=flags)
+    assert lib.ocb_lu_program_template_hits() == h2
+    X = np.zeros((p3[0]['n_ext'], 2))
+    X[a3[6]] = B
+    _execute(p3, X)
+    assert np.linalg.norm(K3 @ X[a3[7]] - B) <= 1e-11*np.linalg.norm(B)
+
+
+def test_structure_templates_are_evicted_not_leaked():
+    """More than four structures in flight: the least recently used one goes; everything stays
+    correct (diagonal systems of different sizes are different structures)."""
+    lib = _cabi.load()
+    for rep in range(2):
+        for n in range(3, 10):
+            Lc = sps.identity(n, format='csr')
+            Uc = sps.diags(np.arange(1.0, n+1) + rep).tocsr()
+            arrs = [Lc.indptr.astype(np.int32), Lc.indices.astype(np.int32), Lc.data,
+                    Uc.indptr.astype(np.int32), Uc.indices.astype(np.int32), Uc.data]
+            prog = _program(arrs, n)
+            X = np.ones((prog[0]['n_ext'], 1))
+            _execute(prog, X)
+            assert np.allclose(X[:n, 0], 1.0/(np.arange(1.0, n+1) + rep))
