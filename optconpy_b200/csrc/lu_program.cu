@@ -732,10 +732,11 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
         tmpl->starts = starts;
         tmpl->planL = planL;
         tmpl->planU = planU;
+        std::unique_lock<std::mutex> lock(g_tmpl_mutex);
+        P->structure_id = ++g_tmpl_clock;
         tmpl->P = *P;
         tmpl->nent = P->nent();
         std::vector<double>().swap(tmpl->P.val);       // padding is zero, the rest is refilled
-        std::unique_lock<std::mutex> lock(g_tmpl_mutex);
         tmpl->stamp = ++g_tmpl_clock;
         size_t total = tmpl->bytes();
         for (auto& t : g_templates) total += t->bytes();

@@ -41,6 +41,7 @@ struct LuProgram {
     std::vector<double> scale;           // per row
     std::vector<int32_t> col;            // per padded entry (indices into xe)
     std::vector<double> val;
+    uint64_t structure_id = 0;           // programs built from the same index arrays share it (0: none)
     int64_t nrows() const { return (int64_t)dst.size(); }
     int64_t nent() const { return (int64_t)col.size(); }
     int64_t nsub() const { return (int64_t)sub_ptr.size() - 1; }

@@ -25,6 +25,9 @@
 // Algorithmic bytes per solve: 12*(nnzL+nnzU) + 16*(n+1) + 32*n*k.
 #include "common.cuh"
 #include "lu_program.h"
+#include <chrono>
+#include <mutex>
+#include <memory>
 #include <vector>
 #include <algorithm>
 #include <string.h>
@@ -520,7 +523,13 @@ static int64_t batch_bytes(const LuProgram& P, const std::vector<Piece>& b, int 
     return record_bytes((int64_t)b.size(), nsl, rows, ent);
 }
 
-static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl, unsigned char* rec) {
+struct SliceDest {   // where the numbers of one program slice live in the image
+    int32_t slice;
+    int64_t val_off, scale_off;
+};
+
+static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl, unsigned char* rec,
+                         int64_t rec_off = 0, std::vector<SliceDest>* dests = nullptr) {
     int64_t nsl, nrows, nent;
     batch_counts(P, b, cl, &nsl, &nrows, &nent);
     const int64_t npiece = (int64_t)b.size();
@@ -571,6 +580,7 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl
             memcpy(scale + r, P.scale.data() + sl.q0, (size_t)nr * 8);
             for (int q = 0; q < ne; ++q) col[e + q] = (uint16_t)P.col[sl.ebase + q];
             memcpy(val + e, P.val.data() + sl.ebase, (size_t)ne * 8);
+            if (dests) dests->push_back(SliceDest{s, rec_off + off_val + (int64_t)e * 8, rec_off + off_scale + (int64_t)r * 8});
             r += nr;
             e += ne;
         }
@@ -587,9 +597,60 @@ enum { M_MAGIC = 0, M_TOTAL, M_N, M_NEXT, M_NNZL, M_NNZU, M_NSUBL, M_NSUBU, M_NS
        M_F_SLICE = 48, M_F_ROWSLICE, M_F_DST, M_F_INIT, M_F_SCALE, M_F_COL, M_F_VAL, M_F_SUBROW,
        M_COUNT = 64 };
 
+// Images of programs with the same structure differ in the two permutations and in the numbers
+// only: keep the last images by structure and rewrite just those parts.
+struct ImageTemplate {
+    uint64_t structure_id = 0, stamp = 0;
+    int max_smem_optin = 0, flags = 0;
+    std::vector<unsigned char> img;
+    std::vector<SliceDest> dests;
+    int64_t o_pr = 0, o_pc = 0, o_fscale = -1, o_fval = -1;
+};
+static std::mutex g_img_mutex;
+static std::vector<std::unique_ptr<ImageTemplate>> g_img_templates;
+static uint64_t g_img_clock = 0;
+constexpr size_t IMAGE_TEMPLATE_MAX_BYTES = 64u << 20;
+
 // choose ring geometry + panel placement and pack the image
 static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t* h_perm_c,
                       int max_smem_optin, int flags, unsigned char** img_out, int64_t* bytes_out) {
+    const bool use_templates = P.structure_id != 0 && getenv("OCB_NO_TEMPLATE") == nullptr;
+    if (use_templates) {
+        std::unique_lock<std::mutex> lock(g_img_mutex);
+        for (auto& t : g_img_templates)
+            if (t->structure_id == P.structure_id && t->max_smem_optin == max_smem_optin && t->flags == flags) {
+                t->stamp = ++g_img_clock;
+                unsigned char* img = (unsigned char*)malloc(t->img.size());
+                if (!img) {
+                    set_error("lu_pack_host: out of memory");
+                    return OCB_ERR_CAPACITY;
+                }
+                memcpy(img, t->img.data(), t->img.size());
+                if (P.n > 0) {
+                    memcpy(img + t->o_pr, h_perm_r, (size_t)P.n * 4);
+                    memcpy(img + t->o_pc, h_perm_c, (size_t)P.n * 4);
+                }
+                for (const SliceDest& d : t->dests) {
+                    const Slice& sl = P.slices[d.slice];
+                    memcpy(img + d.val_off, P.val.data() + sl.ebase, (size_t)sl.trips * 32 * 8);
+                    memcpy(img + d.scale_off, P.scale.data() + sl.q0, (size_t)(sl.glog_nrows >> 8) * 8);
+                }
+                if (t->o_fscale >= 0) {
+                    memcpy(img + t->o_fscale, P.scale.data(), (size_t)P.nrows() * 8);
+                    memcpy(img + t->o_fval, P.val.data(), (size_t)P.nent() * 8);
+                }
+                *img_out = img;
+                *bytes_out = (int64_t)t->img.size();
+                return OCB_OK;
+            }
+    }
+    std::unique_ptr<ImageTemplate> tmpl;
+    if (use_templates) {
+        tmpl.reset(new ImageTemplate());
+        tmpl->structure_id = P.structure_id;
+        tmpl->max_smem_optin = max_smem_optin;
+        tmpl->flags = flags;
+    }
     const int64_t smem_cap = (int64_t)max_smem_optin - 1024 - 192;
     const int64_t xe1 = (P.n_ext + 1) * 8;   // bytes of a one-column panel (+ the token slot)
     int kp_smem = 0, nst = 2, cl = 4;   // two large stages: a bulk copy has ~0.35 us of fixed cost
@@ -686,7 +747,8 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
     for (int r = 0; r < cl; ++r) {
         memcpy(img + o_bo[r], off[r].data(), off[r].size() * 8);
         for (size_t b = 0; b < batches[r].size(); ++b)
-            write_record(P, batches[r][b], cl, img + o_st[r] + off[r][b]);
+            write_record(P, batches[r][b], cl, img + o_st[r] + off[r][b], o_st[r] + off[r][b],
+                         tmpl ? &tmpl->dests : nullptr);
     }
     meta[M_FLAT] = want_flat ? 1 : 0;
     meta[M_NSUB] = nsub;
@@ -710,6 +772,24 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
             const Slice& f = P.slices[P.sub_ptr[sb]];
             submax[sb] = P.sub_ptr[sb] < nsl ? (f.trips << (f.glog_nrows & 255)) : 0;
         }
+    }
+    if (tmpl && (size_t)total <= IMAGE_TEMPLATE_MAX_BYTES) {
+        tmpl->img.assign(img, img + total);
+        tmpl->o_pr = o_pr;
+        tmpl->o_pc = o_pc;
+        if (want_flat) {
+            tmpl->o_fscale = o_f[4];
+            tmpl->o_fval = o_f[6];
+        }
+        std::unique_lock<std::mutex> lock(g_img_mutex);
+        tmpl->stamp = ++g_img_clock;
+        if (g_img_templates.size() >= 4) {                      // keep the four most recently used
+            size_t oldest = 0;
+            for (size_t j = 1; j < g_img_templates.size(); ++j)
+                if (g_img_templates[j]->stamp < g_img_templates[oldest]->stamp) oldest = j;
+            g_img_templates.erase(g_img_templates.begin() + oldest);
+        }
+        g_img_templates.push_back(std::move(tmpl));
     }
     return OCB_OK;
 }
@@ -1102,7 +1182,12 @@ int ocb_lu_pack_host(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_co
     int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals,
                                    ocb::trsm_threads(), (flags & 2) != 0, (flags & 4) != 0, &P);
     if (rc != OCB_OK) return rc;
-    return ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, (int)flags, out_image, out_bytes);
+    const auto t0 = std::chrono::steady_clock::now();
+    rc = ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, (int)flags, out_image, out_bytes);
+    if (getenv("OCB_TIMING"))
+        fprintf(stderr, "lu_pack_host: image packed in %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    return rc;
 }
 
 void ocb_host_free(void* p) { free(p); }

@@ -323,7 +323,7 @@ def test_one_step_supernodes_dense_block():
     assert np.allclose(X[:7], np.linalg.solve(Ad, b))
 
 
-@pytest.mark.parametrize('flags', [2, 6, 0])
+@pytest.mark.parametrize('flags', [2, 6, 0, 3, 7])
 def test_structure_template_refills_numbers_only(cav10, flags, monkeypatch):
     """A second factor with the SAME index arrays (other shift: same ordering, same pivots) is
     served from the cached structure: only numbers are recomputed.  The result must be the very
