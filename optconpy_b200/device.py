@@ -24,6 +24,7 @@ STATS = dict(lu_factor_s=0.0,          # SuperLU seconds summed over the workers
              lu_collect_wait_s=0.0,    # collecting thread: blocked on a worker result
              lu_analyse_upload_s=0.0,  # main process: image upload + handle creation
              lu_arena_s=0.0,           # ... of which: device buffer from the caching allocator
+             lu_unpinned_uploads=0,    # images that did not travel through a pinned pool segment
              n_factor=0, h2d_bytes=0, d2h_bytes=0)
 
 # wall seconds of the main thread per phase of the host API (diagnostics, bench.py e2e)
@@ -461,6 +462,7 @@ class FactorJob(object):
                     continue
                 if slot is not None:
                     shp.release(slot)
+                STATS['lu_unpinned_uploads'] += 1
                 shm = shared_memory.SharedMemory(name=name)
                 try:
                     img = np.frombuffer(shm.buf, dtype=np.uint8, count=nbytes)
