@@ -104,6 +104,28 @@ def test_lu_solve_wide_executor_small_n(dv, sad):
     assert X.shape == (NV, 700) and _relerr(X, ref_lu.solve(full)[:NV]) < 1e-11
 
 
+@pytest.mark.parametrize('wide', [False, True])
+def test_lu_solve_one_step_supernodes(dv, sad, wide, monkeypatch):
+    """OCB_MERGE=1 (flags bit 2 of ocb_lu_pack_host): the program with one-step supernodes has
+    clearly fewer sub-levels and gives the same solutions through the cluster kernel (narrow and
+    two-wave blocks) and through the wide executor."""
+    rng = np.random.default_rng(31)
+    n = sad.shape[0]
+    ref_lu = spsla.splu(sad)
+    monkeypatch.setenv('OCB_MERGE', '0')
+    two = dv.LU(sad, wide=wide)
+    monkeypatch.setenv('OCB_MERGE', '1')
+    one = dv.LU(sad, wide=wide)
+    lv = lambda lu: lu.info['levelsL'] + lu.info['levelsU']
+    assert lv(one) <= 0.8*lv(two) and one.info['program_rows'] == two.info['program_rows']
+    for k in ((3, 40, 160) if not wide else (5, 700)):
+        B = rng.standard_normal((n, k))
+        ref = ref_lu.solve(B)
+        Bd = dv.to_dev(B)
+        X1, X2 = dv.to_host(one.solve(Bd)), dv.to_host(two.solve(Bd))
+        assert _relerr(X1, ref) < 1e-11 and _relerr(X1, X2) < 1e-12
+
+
 def test_lu_solve_global_panel_path(dv):
     """n large enough that the column panel does not fit shared memory: wide executor."""
     from optconpy_b200 import problems as pb
