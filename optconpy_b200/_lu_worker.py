@@ -53,7 +53,9 @@ def _arranged(data, indices, indptr, shape, q, transposed):
     ``q``, as a canonical CSC matrix.  The matrices of one run share a handful of sparsity
     patterns, so the transposition and the fancy indexing (8 of 50 ms per matrix) are done once
     per pattern on entry TAGS; every later matrix is one gather of its values."""
-    key = (shape, bool(transposed), hash(indices.tobytes()), hash(indptr.tobytes()),
+    import zlib
+    ib, pb = indices.tobytes(), indptr.tobytes()
+    key = (shape, bool(transposed), len(ib), hash(ib), zlib.crc32(ib), hash(pb),
            None if q is None else hash(q.tobytes()))
     if key not in _ARRANGE:
         nnz = len(indices)

@@ -648,6 +648,7 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
     if (!sorted) {
         Uci_sorted.resize(Urp[n]);
         Uva_sorted.resize(Urp[n]);
+        if (tmpl) tmpl->Uperm.reserve(Urp[n]);
         std::vector<int32_t> perm;    // raw positions of the current row in sorted order
         for (int64_t i = 0; i < n; ++i) {
             const int32_t a0 = Urp[i], len = Urp[i + 1] - a0;
