@@ -396,3 +396,34 @@ def test_structure_templates_are_evicted_not_leaked():
             X = np.ones((prog[0]['n_ext'], 1))
             _execute(prog, X)
             assert np.allclose(X[:n, 0], 1.0/(np.arange(1.0, n+1) + rep))
+
+
+@pytest.mark.parametrize('flags', [0, 2, 6])
+def test_program_on_unstructured_pattern(cav10, flags):
+    """The reference's own test perturbs F with a random sparse matrix of density 0.03
+    (tests/test_units_compfacres_compress.py:49-52): no mesh structure, more off-diagonal pivots,
+    much denser factors.  Builder, one-step supernodes and the numpy execution must not care."""
+    M, A, J = cav10['M'], cav10['A'], cav10['J']
+    NV = cav10['NV']
+    F = -M - 0.1*A - sps.random(NV, NV, density=0.03, format='csr', random_state=11)
+    K = dv.sadpnt_matrix(sps.csr_matrix(F.T - 2.0*M.T), J)
+    n = K.shape[0]
+    transposed = bool(flags & 2)
+    a = dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, flags)
+    a = a + (_lu_worker.order_only(a),)
+    arrs = _lu_worker.factor_arrays(a, transposed=transposed)
+    prog = _program(arrs, n, flags=flags)
+    rng = np.random.default_rng(13)
+    B = rng.standard_normal((n, 4))
+    X = np.zeros((prog[0]['n_ext'], 4))
+    X[arrs[6]] = B
+    _execute(prog, X, check_hazards=True)
+    got = X[arrs[7]]
+    ref = spsla.splu(K).solve(B)
+    assert np.linalg.norm(got - ref) <= 1e-10*np.linalg.norm(ref)
+    # cond(K) ~ 6e7 and ||x|| ~ 1e7 ||b||: the residual is measured normwise.  (Solving with the
+    # explicit inverses of wide diagonal blocks is not backward stable row by row as
+    # substitution is: relative to ||b|| this residual is 5e-7 where SuperLU reaches 3e-9.)
+    assert np.linalg.norm(K @ got - B) <= 1e-13*sps.linalg.norm(K)*np.linalg.norm(got)
+    img = _lu_worker.pack_image(arrs, n, 232448, flags | (2 << 4))
+    assert img.nbytes > 0 and prog[0]['n_ext'] == n + 2*prog[0]['ymax']
