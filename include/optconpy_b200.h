@@ -83,6 +83,14 @@ int ocb_lu_pack_host(int64_t n,
                      const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
                      const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin,
                      int64_t flags, unsigned char** out_image, int64_t* out_bytes);
+/* The same, building the image directly in the caller's buffer (e.g. a page-locked shared-memory
+ * segment): no intermediate copy.  OCB_ERR_CAPACITY if it does not fit; *out_bytes then holds
+ * the size the image needs. */
+int ocb_lu_pack_host_into(int64_t n,
+                          const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
+                          const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
+                          const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin,
+                          int64_t flags, unsigned char* dst, int64_t dst_capacity, int64_t* out_bytes);
 void ocb_host_free(void* p);
 int ocb_lu_create_from_image(ocb_lu** out, const unsigned char* h_image, int64_t bytes,
                              void* d_arena, void* stream);

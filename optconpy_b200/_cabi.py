@@ -20,6 +20,8 @@ PROTOTYPES = {
     'ocb_lu_destroy': (C.c_int, [vp]),
     'ocb_lu_pack_host': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64,
                                    C.POINTER(vp), C.POINTER(i64)]),
+    'ocb_lu_pack_host_into': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, i64,
+                                        C.POINTER(i64)]),
     'ocb_host_free': (None, [vp]),
     'ocb_lu_create_from_image': (C.c_int, [C.POINTER(vp), vp, i64, vp, vp]),
     'ocb_lu_info': (C.c_int, [vp, C.POINTER(i64)]),

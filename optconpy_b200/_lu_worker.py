@@ -181,6 +181,7 @@ def factor_image(args):
 
 
 _ATTACHED = dict()
+_ADDRESS = dict()
 
 
 def _attach(name):
@@ -205,6 +206,21 @@ def factor_image_to_shm(args, slot=None):
     flags = args[6] if len(args) > 6 else 0
     arrs, order = factor_arrays(args, want_order=True, transposed=bool(flags & 2))
     t1 = time.perf_counter()
+    if slot is not None:
+        # build the image right in the pinned segment (no intermediate buffer, no copy)
+        from optconpy_b200 import _cabi
+        lib = _cabi.load()
+        seg = _attach(slot[0])
+        if slot[0] not in _ADDRESS:        # one exported view per segment, kept for the process lifetime
+            _ADDRESS[slot[0]] = C.addressof(C.c_char.from_buffer(seg.buf))
+        dst = _ADDRESS[slot[0]]
+        nbytes = C.c_int64(0)
+        rc = lib.ocb_lu_pack_host_into(args[3][0], *[a.ctypes.data for a in arrs], int(args[5]), int(flags),
+                                       dst, int(slot[1]), C.byref(nbytes))
+        if rc == 0:
+            return None, nbytes.value, t1 - t0, time.perf_counter() - t1, order
+        if rc != -5:                      # anything but "does not fit": a real error
+            _cabi.check(rc, 'ocb_lu_pack_host_into')
     ci = _CImage(arrs, args[3][0], args[5], flags)
     try:
         nbytes = ci.view.nbytes

@@ -612,15 +612,19 @@ static uint64_t g_img_clock = 0;
 constexpr size_t IMAGE_TEMPLATE_MAX_BYTES = 64u << 20;
 
 // choose ring geometry + panel placement and pack the image
+// dst / dst_capacity (optional): build the image there if it fits (*img_out == dst then),
+// otherwise in a malloc'ed buffer
 static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t* h_perm_c,
-                      int max_smem_optin, int flags, unsigned char** img_out, int64_t* bytes_out) {
+                      int max_smem_optin, int flags, unsigned char** img_out, int64_t* bytes_out,
+                      unsigned char* dst = nullptr, int64_t dst_capacity = 0) {
     const bool use_templates = P.structure_id != 0 && getenv("OCB_NO_TEMPLATE") == nullptr;
     if (use_templates) {
         std::unique_lock<std::mutex> lock(g_img_mutex);
         for (auto& t : g_img_templates)
             if (t->structure_id == P.structure_id && t->max_smem_optin == max_smem_optin && t->flags == flags) {
                 t->stamp = ++g_img_clock;
-                unsigned char* img = (unsigned char*)malloc(t->img.size());
+                unsigned char* img = (dst && (int64_t)t->img.size() <= dst_capacity)
+                                         ? dst : (unsigned char*)malloc(t->img.size());
                 if (!img) {
                     set_error("lu_pack_host: out of memory");
                     return OCB_ERR_CAPACITY;
@@ -722,7 +726,13 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         }
     }
     const int64_t total = o;
-    unsigned char* img = (unsigned char*)calloc((size_t)total, 1);   // zero pages on demand
+    unsigned char* img;
+    if (dst && total <= dst_capacity) {
+        img = dst;
+        memset(img, 0, (size_t)total);
+    } else {
+        img = (unsigned char*)calloc((size_t)total, 1);   // zero pages on demand
+    }
     if (!img) {
         set_error("lu_pack_host: out of memory");
         return OCB_ERR_CAPACITY;
@@ -1188,6 +1198,29 @@ int ocb_lu_pack_host(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_co
         fprintf(stderr, "lu_pack_host: image packed in %.1f ms\n",
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return rc;
+}
+
+int ocb_lu_pack_host_into(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
+                          const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
+                          const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin, int64_t flags,
+                          unsigned char* dst, int64_t dst_capacity, int64_t* out_bytes) {
+    OCB_ARG(n >= 0 && dst && dst_capacity >= 0 && out_bytes, "lu_pack_host_into");
+    OCB_ARG(h_L_rowptr && h_U_rowptr && h_perm_r && h_perm_c, "lu_pack_host_into: null pointer");
+    OCB_ARG(max_smem_optin >= 48 * 1024, "lu_pack_host_into: shared-memory size");
+    ocb::LuProgram P;
+    int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals,
+                                   ocb::trsm_threads(), (flags & 2) != 0, (flags & 4) != 0, &P);
+    if (rc != OCB_OK) return rc;
+    unsigned char* img = nullptr;
+    rc = ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, (int)flags, &img, out_bytes, dst, dst_capacity);
+    if (rc != OCB_OK) return rc;
+    if (img != dst) {   // did not fit: *out_bytes tells how much room the image needs
+        free(img);
+        ocb::set_error("lu_pack_host_into: the image needs %lld bytes, the buffer has %lld",
+                       (long long)*out_bytes, (long long)dst_capacity);
+        return OCB_ERR_CAPACITY;
+    }
+    return OCB_OK;
 }
 
 void ocb_host_free(void* p) { free(p); }

@@ -427,3 +427,45 @@ def test_program_on_unstructured_pattern(cav10, flags):
     assert np.linalg.norm(K @ got - B) <= 1e-13*sps.linalg.norm(K)*np.linalg.norm(got)
     img = _lu_worker.pack_image(arrs, n, 232448, flags | (2 << 4))
     assert img.nbytes > 0 and prog[0]['n_ext'] == n + 2*prog[0]['ymax']
+
+
+def test_worker_builds_the_image_in_the_callers_segment(cav10):
+    """_lu_worker.factor_image_to_shm with a slot: ocb_lu_pack_host_into writes the image straight
+    into the (pinned) shared-memory segment - same bytes as the malloc'ed image, fresh build and
+    template hit alike; a segment that is too small falls back to a one-off segment."""
+    from multiprocessing import shared_memory
+    K = _saddle(cav10)
+    n = K.shape[0]
+    flags = 2 | (2 << 4)
+    a = dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, flags)
+    a = a + (_lu_worker.order_only(a),)
+    ref = _lu_worker.pack_image(_lu_worker.factor_arrays(a, transposed=True), n, 232448, flags)
+    seg = shared_memory.SharedMemory(create=True, size=ref.nbytes + 4096)
+    try:
+        np.frombuffer(seg.buf, dtype=np.uint8)[:] = 0xAB            # stale content must not survive
+        for rep in range(2):                                         # fresh build, then template hit
+            name, nbytes, tf, tp, order = _lu_worker.factor_image_to_shm(a, (seg.name, seg.size))
+            assert name is None and nbytes == ref.nbytes
+            assert np.array_equal(np.frombuffer(seg.buf, dtype=np.uint8, count=nbytes), ref)
+        name, nbytes, tf, tp, order = _lu_worker.factor_image_to_shm(a, (seg.name, 1000))
+        assert name is not None and nbytes == ref.nbytes
+        one = shared_memory.SharedMemory(name=name)
+        try:
+            assert np.array_equal(np.frombuffer(one.buf, dtype=np.uint8, count=nbytes), ref)
+        finally:
+            one.close()
+            one.unlink()
+        lib = _cabi.load()
+        assert b'needs' in lib.ocb_last_error()
+    finally:
+        _lu_worker._ADDRESS.pop(seg.name, None)
+        att = _lu_worker._ATTACHED.pop(seg.name, None)
+        import gc
+        gc.collect()
+        for s_ in (att, seg):
+            try:
+                if s_ is not None:
+                    s_.close()
+            except BufferError:
+                pass
+        seg.unlink()
