@@ -91,6 +91,22 @@ int ocb_lu_pack_host_into(int64_t n,
                           const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
                           const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin,
                           int64_t flags, unsigned char* dst, int64_t dst_capacity, int64_t* out_bytes);
+/* The same with a RESIDUAL GUARD (what the LU workers call): the finished gather program is
+ * executed on the host for one fixed pseudo-random right-hand side and *out_backerr receives the
+ * normwise backward error ||b - A x|| / (||A||_F ||x|| + ||b||) against the ORIGINAL matrix A
+ * (CSC arrays).  It covers both error sources the reference's spsla.factorized does not have -
+ * the relaxed pivoting of the host LU and the explicit inverses of the supernode blocks - so
+ * the caller can re-factorise with full partial pivoting and flags bit 3 (no supernode wider
+ * than 32 rows, no one-step blocks) when it is too large.  dst != NULL: build in the caller's
+ * buffer (as ocb_lu_pack_host_into); dst == NULL: *out_image is malloc'ed. */
+int ocb_lu_pack_host_checked(int64_t n,
+                             const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
+                             const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
+                             const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin,
+                             int64_t flags, unsigned char* dst, int64_t dst_capacity,
+                             unsigned char** out_image, int64_t* out_bytes,
+                             const int32_t* h_A_colptr, const int32_t* h_A_rowidx, const double* h_A_vals,
+                             double* out_backerr);
 void ocb_host_free(void* p);
 int ocb_lu_create_from_image(ocb_lu** out, const unsigned char* h_image, int64_t bytes,
                              void* d_arena, void* stream);
@@ -157,6 +173,13 @@ int64_t ocb_gram_ws_bytes(int64_t n, int64_t ka, int64_t kb);
 int ocb_gram(const double* d_Z, int64_t ldz, int64_t ka,
              const double* d_W, int64_t ldw, int64_t kb, int64_t n,
              double* d_G, int64_t ldg, void* d_ws, int64_t ws_bytes, void* stream);
+
+/* Measured FP64 peak of the device this runs on (roofline denominator of the FP64-bound
+ * kernels; MEASURED_PEAKS.json only has HBM and bf16): register-only chains of DMMA.8x8x4
+ * (kind 0, the FP64 tensor pipe the Gram / tall products use) or DFMA (kind 1), ctas_per_sm
+ * CTAs of 256 threads per SM, timed with CUDA events.  d_sink: one device double. */
+int ocb_fp64_peak(int kind, int64_t iters, int64_t ctas_per_sm, double* h_tflops, double* d_sink,
+                  void* stream);
 
 /* C (n x kc) = alpha * Z (n x k) * T (k x kc) + beta * C   (DMMA; `Z*V_k`, `Z*(Z^T tB)`) */
 int ocb_tall_gemm(const double* d_Z, int64_t ldz, int64_t n, int64_t k,

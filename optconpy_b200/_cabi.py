@@ -22,6 +22,9 @@ PROTOTYPES = {
                                    C.POINTER(vp), C.POINTER(i64)]),
     'ocb_lu_pack_host_into': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, i64,
                                         C.POINTER(i64)]),
+    'ocb_lu_pack_host_checked': (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, i64,
+                                           C.POINTER(vp), C.POINTER(i64), vp, vp, vp,
+                                           C.POINTER(C.c_double)]),
     'ocb_host_free': (None, [vp]),
     'ocb_lu_create_from_image': (C.c_int, [C.POINTER(vp), vp, i64, vp, vp]),
     'ocb_lu_info': (C.c_int, [vp, C.POINTER(i64)]),
@@ -38,6 +41,7 @@ PROTOTYPES = {
     'ocb_prof_collect': (C.c_int, [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
     'ocb_gram_ws_bytes': (i64, [i64, i64, i64]),
     'ocb_gram': (C.c_int, [f64p, i64, i64, f64p, i64, i64, i64, f64p, i64, vp, i64, vp]),
+    'ocb_fp64_peak': (C.c_int, [C.c_int, i64, i64, C.POINTER(C.c_double), vp, vp]),
     'ocb_tall_gemm': (C.c_int, [f64p, i64, i64, i64, f64p, i64, i64, f64p, i64,
                                 C.c_double, C.c_double, vp]),
     'ocb_sym_eig': (C.c_int, [f64p, i64, i64, f64p, f64p, i64, C.POINTER(C.c_int32), vp]),

@@ -139,17 +139,42 @@ def factor_arrays(args, want_order=False, transposed=False):
     return out
 
 
-class _CImage(object):
-    """Device image in a C buffer (``ocb_lu_pack_host``); ``view`` is a uint8 numpy view,
-    ``free()`` releases it."""
+# Residual guard: the host LU runs with relaxed pivoting (diag_pivot_thresh=0.01,
+# symmetric mode) and the device solve multiplies by explicit inverses of the supernode blocks;
+# the reference's ``spsla.factorized`` does neither.  Every factor image is therefore checked
+# where it is built: the finished gather program is executed on the host for one right-hand
+# side and the normwise backward error against the ORIGINAL matrix must stay below GUARD_TOL,
+# else the matrix is factorised again with full partial pivoting and narrow supernodes.
+GUARD_TOL = 2e-15
+SAFE_FLAG = 8          # ocb_lu_pack_host flags bit 3: supernodes <= 32 rows, no one-step blocks
 
-    def __init__(self, arrs, n, smem_optin, flags=0):
+
+def _guard_tol():
+    import os
+    v = os.environ.get('OCB_LU_GUARD_TOL')
+    return GUARD_TOL if v is None else float(v)      # <= 0 switches the guard off
+
+
+class _CImage(object):
+    """Device image in a C buffer (``ocb_lu_pack_host_checked``); ``view`` is a uint8 numpy
+    view, ``free()`` releases it; ``backerr`` is the guard's backward error (None: not checked)."""
+
+    def __init__(self, arrs, n, smem_optin, flags=0, amat=None):
         from optconpy_b200 import _cabi
         self._lib = _cabi.load()
         img, nbytes = C.c_void_p(), C.c_int64(0)
-        _cabi.check(self._lib.ocb_lu_pack_host(n, *[a.ctypes.data for a in arrs], int(smem_optin),
-                                               int(flags), C.byref(img), C.byref(nbytes)),
-                    'ocb_lu_pack_host')
+        self.backerr = None
+        if amat is None:
+            _cabi.check(self._lib.ocb_lu_pack_host(n, *[a.ctypes.data for a in arrs], int(smem_optin),
+                                                   int(flags), C.byref(img), C.byref(nbytes)),
+                        'ocb_lu_pack_host')
+        else:
+            be = C.c_double(0.0)
+            _cabi.check(self._lib.ocb_lu_pack_host_checked(
+                n, *[a.ctypes.data for a in arrs], int(smem_optin), int(flags), None, 0,
+                C.byref(img), C.byref(nbytes), *[a.ctypes.data for a in amat], C.byref(be)),
+                'ocb_lu_pack_host_checked')
+            self.backerr = be.value
         self._ptr = img
         self.view = np.ctypeslib.as_array(C.cast(img, C.POINTER(C.c_uint8)), shape=(nbytes.value,))
 
@@ -169,15 +194,80 @@ def pack_image(arrs, n, smem_optin, flags=0):
         ci.free()
 
 
+def _amat_arrays(args):
+    """int32/FP64 CSC arrays of the ORIGINAL matrix for the residual guard."""
+    data, indices, indptr = args[:3]
+    return (np.ascontiguousarray(indptr, dtype=np.int32), np.ascontiguousarray(indices, dtype=np.int32),
+            np.ascontiguousarray(data, dtype=np.float64))
+
+
+def _safe_args(args):
+    """The same job with full partial pivoting (what ``spsla.factorized`` does) and the safe
+    program layout; keeps the cached ordering if there is one."""
+    opts = dict(args[4])
+    opts['diag_pivot_thresh'] = 1.0
+    opts['options'] = dict(opts.get('options', {}), SymmetricMode=False)
+    flags = (args[6] if len(args) > 6 else 0) | SAFE_FLAG
+    return args[:4] + (opts, args[5], flags) + tuple(args[7:])
+
+
+def _build(args, slot=None):
+    """Factorise + analyse + pack (guarded).  Returns (name-or-None, image-or-None, nbytes,
+    seconds factor, seconds pack, ordering, guard) where guard = (backward error of the image
+    handed out, 1 if it is the safe re-factorisation else 0)."""
+    from optconpy_b200 import _cabi
+    lib = _cabi.load()
+    tol = _guard_tol()
+    amat = _amat_arrays(args) if tol > 0 else None
+    tf = tp = 0.0
+    order = None
+    safe = 0
+    while True:
+        t0 = time.perf_counter()
+        flags = args[6] if len(args) > 6 else 0
+        arrs, o2 = factor_arrays(args, want_order=True, transposed=bool(flags & 2))
+        order = o2 if order is None else order
+        t1 = time.perf_counter()
+        tf += t1 - t0
+        n = args[3][0]
+        img, backerr, nbytes = None, None, 0
+        if slot is not None:
+            # build the image right in the pinned segment (no intermediate buffer, no copy)
+            seg = _attach(slot[0])
+            if slot[0] not in _ADDRESS:    # one exported view per segment, kept for the process lifetime
+                _ADDRESS[slot[0]] = C.addressof(C.c_char.from_buffer(seg.buf))
+            nb = C.c_int64(0)
+            if amat is None:
+                rc = lib.ocb_lu_pack_host_into(n, *[a.ctypes.data for a in arrs], int(args[5]), int(flags),
+                                               _ADDRESS[slot[0]], int(slot[1]), C.byref(nb))
+            else:
+                be = C.c_double(0.0)
+                rc = lib.ocb_lu_pack_host_checked(n, *[a.ctypes.data for a in arrs], int(args[5]),
+                                                  int(flags), _ADDRESS[slot[0]], int(slot[1]), None,
+                                                  C.byref(nb), *[a.ctypes.data for a in amat], C.byref(be))
+                backerr = be.value
+            if rc == 0:
+                nbytes = nb.value
+            elif rc != -5:                    # anything but "does not fit": a real error
+                _cabi.check(rc, 'ocb_lu_pack_host_checked')
+            else:
+                slot = None                   # too small: hand the image back another way
+        if slot is None:
+            ci = _CImage(arrs, n, args[5], flags, amat=amat)
+            img, backerr, nbytes = ci.view.copy(), ci.backerr, ci.view.nbytes
+            ci.free()
+        tp += time.perf_counter() - t1
+        if backerr is None or backerr <= tol or safe:
+            return slot, img, nbytes, tf, tp, order, (backerr, safe)
+        args = _safe_args(args)
+        safe = 1
+
+
 def factor_image(args):
-    """(data, indices, indptr, shape, lu_options, smem_optin) -> (image, seconds factor,
-    seconds analyse+pack)."""
-    t0 = time.perf_counter()
-    flags = args[6] if len(args) > 6 else 0
-    arrs, order = factor_arrays(args, want_order=True, transposed=bool(flags & 2))
-    t1 = time.perf_counter()
-    img = pack_image(arrs, args[3][0], args[5], flags)
-    return img, t1 - t0, time.perf_counter() - t1, order
+    """(data, indices, indptr, shape, lu_options, smem_optin[, flags, q]) -> (image, seconds
+    factor, seconds analyse+pack, ordering, guard)."""
+    _, img, _, tf, tp, order, guard = _build(args)
+    return img, tf, tp, order, guard
 
 
 _ATTACHED = dict()
@@ -200,38 +290,13 @@ def factor_image_to_shm(args, slot=None):
     the main process's page-locked pool: if the image fits it is written there (the upload is
     then a plain DMA); otherwise a fresh segment is created.
     Returns (name or None if the slot was used, nbytes, seconds factor, seconds analyse+pack,
-    ordering for later matrices of the same pattern or None)."""
+    ordering for later matrices of the same pattern or None, guard)."""
     from multiprocessing import shared_memory
-    t0 = time.perf_counter()
-    flags = args[6] if len(args) > 6 else 0
-    arrs, order = factor_arrays(args, want_order=True, transposed=bool(flags & 2))
-    t1 = time.perf_counter()
-    if slot is not None:
-        # build the image right in the pinned segment (no intermediate buffer, no copy)
-        from optconpy_b200 import _cabi
-        lib = _cabi.load()
-        seg = _attach(slot[0])
-        if slot[0] not in _ADDRESS:        # one exported view per segment, kept for the process lifetime
-            _ADDRESS[slot[0]] = C.addressof(C.c_char.from_buffer(seg.buf))
-        dst = _ADDRESS[slot[0]]
-        nbytes = C.c_int64(0)
-        rc = lib.ocb_lu_pack_host_into(args[3][0], *[a.ctypes.data for a in arrs], int(args[5]), int(flags),
-                                       dst, int(slot[1]), C.byref(nbytes))
-        if rc == 0:
-            return None, nbytes.value, t1 - t0, time.perf_counter() - t1, order
-        if rc != -5:                      # anything but "does not fit": a real error
-            _cabi.check(rc, 'ocb_lu_pack_host_into')
-    ci = _CImage(arrs, args[3][0], args[5], flags)
-    try:
-        nbytes = ci.view.nbytes
-        if slot is not None and nbytes <= slot[1]:
-            seg = _attach(slot[0])
-            np.frombuffer(seg.buf, dtype=np.uint8, count=nbytes)[:] = ci.view
-            return None, nbytes, t1 - t0, time.perf_counter() - t1, order
-        shm = shared_memory.SharedMemory(create=True, size=max(nbytes, 64))
-        np.frombuffer(shm.buf, dtype=np.uint8, count=nbytes)[:] = ci.view
-    finally:
-        ci.free()
+    used, img, nbytes, tf, tp, order, guard = _build(args, slot)
+    if used is not None:
+        return None, nbytes, tf, tp, order, guard
+    shm = shared_memory.SharedMemory(create=True, size=max(nbytes, 64))
+    np.frombuffer(shm.buf, dtype=np.uint8, count=nbytes)[:] = img
     name = shm.name
     shm.close()
-    return name, nbytes, t1 - t0, time.perf_counter() - t1, order
+    return name, nbytes, tf, tp, order, guard

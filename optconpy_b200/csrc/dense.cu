@@ -423,9 +423,63 @@ int smw_core_inv(const double* C, int64_t ldc, int m, double* Sinv, int* flag, c
     return OCB_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// FP64 peak micro-benchmark (roofline denominator of the FP64-bound kernels): register-only
+// chains of DMMA.8x8x4 (kind 0) or DFMA (kind 1), 8 independent accumulator pairs per thread.
+// ---------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int64_t iters, double seed, double* __restrict__ sink) {
+    double c[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j][0] = seed * (threadIdx.x + j); c[j][1] = seed; }
+    double a = 1.0 + seed, b = 1.0 - seed;
+    for (int64_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (KIND == 0) {
+                dmma_8x8x4(c[j][0], c[j][1], a, b);
+            } else {
+                c[j][0] = fma(a, c[j][0], b);
+                c[j][1] = fma(b, c[j][1], a);
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+    if (s == 123.456) sink[0] = s;   // keeps the chains alive
+}
+
 }  // namespace ocb
 
 extern "C" {
+
+int ocb_fp64_peak(int kind, int64_t iters, int64_t ctas_per_sm, double* h_tflops, double* d_sink, void* stream) {
+    using namespace ocb;
+    OCB_ARG((kind == 0 || kind == 1) && iters > 0 && ctas_per_sm >= 1 && ctas_per_sm <= 8 && h_tflops && d_sink,
+            "fp64_peak");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    OCB_CUDA(cudaEventCreate(&e0));
+    OCB_CUDA(cudaEventCreate(&e1));
+    const unsigned blocks = (unsigned)(sm_count() * ctas_per_sm);
+    for (int rep = 0; rep < 2; ++rep) {   // first pass warms up
+        OCB_CUDA(cudaEventRecord(e0, st));
+        if (kind == 0) fp64_peak_kernel<0><<<blocks, 256, 0, st>>>(iters, 1e-9, d_sink);
+        else fp64_peak_kernel<1><<<blocks, 256, 0, st>>>(iters, 1e-9, d_sink);
+        OCB_LAUNCH_CHECK();
+        OCB_CUDA(cudaEventRecord(e1, st));
+        OCB_CUDA(cudaEventSynchronize(e1));
+    }
+    float ms = 0.f;
+    OCB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // per thread and iteration: kind 0: 8 DMMA = 8 * 512 flops per WARP; kind 1: 16 DFMA = 32 flops
+    const double per_block = kind == 0 ? 8.0 * 8.0 * 512.0 : 256.0 * 32.0;
+    *h_tflops = per_block * (double)iters * (double)blocks / ((double)ms * 1e-3) / 1e12;
+    return OCB_OK;
+}
 
 int64_t ocb_gram_ws_bytes(int64_t n, int64_t ka, int64_t kb) {
     int nsplit;

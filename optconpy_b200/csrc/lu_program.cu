@@ -53,14 +53,14 @@ inline int pow2ceil(int64_t v) {
 }
 
 // supernodes: maximal runs of rows i, i+1, ... of U with  struct(U_i) \ {i} == struct(U_{i+1})
-int find_supernodes(int64_t n, const int32_t* rp, const int32_t* ci, std::vector<int32_t>* starts) {
+int find_supernodes(int64_t n, const int32_t* rp, const int32_t* ci, int wcap, std::vector<int32_t>* starts) {
     starts->clear();
     starts->push_back(0);
     int w = 1;
     for (int64_t i = 0; i + 1 < n; ++i) {
         const int32_t a0 = rp[i], a1 = rp[i + 1], b0 = rp[i + 1], b1 = rp[i + 2];
         bool same = false;
-        if (a1 > a0 && ci[a0] == i && (a1 - a0 - 1) == (b1 - b0) && b1 > b0 && w < wmax())
+        if (a1 > a0 && ci[a0] == i && (a1 - a0 - 1) == (b1 - b0) && b1 > b0 && w < wcap)
             same = memcmp(ci + a0 + 1, ci + b0, (size_t)(b1 - b0) * sizeof(int32_t)) == 0;
         if (same) {
             ++w;
@@ -520,7 +520,7 @@ int refill_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
 // cavity problem yields the SAME index arrays), so most builds only recompute numbers.
 struct ProgramTemplate {
     int64_t n = 0;
-    int max_lanes = 0;
+    int max_lanes = 0, wcap = 0;
     bool transposed = false, merge = false;
     MergeRule rule;
     std::vector<int32_t> Lrp, Lci, Urp, Uci;        // the key (raw, as handed in)
@@ -564,7 +564,8 @@ int64_t g_template_hits = 0;
 
 int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const double* Lva,
                      const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
-                     bool transposed, bool merge, LuProgram* P) {
+                     bool transposed, bool merge, LuProgram* P, int wmax_cap) {
+    const int wcap = wmax_cap > 0 ? std::min(wmax_cap, wmax()) : wmax();
     *P = LuProgram();
     P->n = n;
     P->sub_ptr.push_back(0);
@@ -586,7 +587,8 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
         std::unique_lock<std::mutex> lock(g_tmpl_mutex);
         ProgramTemplate* hit = nullptr;
         for (auto& t : g_templates)
-            if (t->n == n && t->max_lanes == max_lanes && t->transposed == transposed && t->merge == merge &&
+            if (t->n == n && t->max_lanes == max_lanes && t->wcap == wcap && t->transposed == transposed &&
+                t->merge == merge &&
                 t->rule.max_w == rule.max_w && t->rule.growth == rule.growth &&
                 same_ints(t->Lrp, Lrp, (size_t)n + 1) && same_ints(t->Urp, Urp, (size_t)n + 1) &&
                 same_ints(t->Lci, Lci, (size_t)Lrp[n]) && same_ints(t->Uci, Uci, (size_t)Urp[n])) {
@@ -625,6 +627,7 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
         tmpl.reset(new ProgramTemplate());
         tmpl->n = n;
         tmpl->max_lanes = max_lanes;
+        tmpl->wcap = wcap;
         tmpl->transposed = transposed;
         tmpl->merge = merge;
         tmpl->rule = rule;
@@ -696,7 +699,7 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
     const auto t0 = tnow();
     if (timing) fprintf(stderr, "lu_program: sort+check %.1f ms\n", ms(tsort0, t0));
     std::vector<int32_t> starts;
-    find_supernodes(n, Urp, Uci, &starts);
+    find_supernodes(n, Urp, Uci, wcap, &starts);
     P->nsuper = (int32_t)starts.size() - 1;
     for (size_t t = 0; t + 1 < starts.size(); ++t) P->max_w = std::max(P->max_w, starts[t + 1] - starts[t]);
     // layout 0: unit lower L, upper U with the pivots (P A Q = L U);  transposed layout: the
@@ -754,6 +757,38 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
     return rc;
 }
 
+void execute_program_host(const LuProgram& P, const int32_t* perm_r, const int32_t* perm_c,
+                          const double* b, double* x) {
+    std::vector<double> xe((size_t)P.n_ext + 1, 0.0), out;
+    for (int64_t i = 0; i < P.n; ++i) xe[perm_r[i]] = b[i];
+    for (int64_t sb = 0; sb < P.nsub(); ++sb) {
+        // rows of one sub-level are independent, but a row may overwrite its own init slot:
+        // compute the whole sub-level, then store (the kernels do the same behind a barrier)
+        out.clear();
+        for (int32_t s = P.sub_ptr[sb]; s < P.sub_ptr[sb + 1]; ++s) {
+            const Slice& sl = P.slices[s];
+            const int g = sl.glog_nrows & 255, nr = sl.glog_nrows >> 8, G = 1 << g;
+            for (int r = 0; r < nr; ++r) {
+                const int32_t q = sl.q0 + r;
+                double acc = 0.0;
+                for (int u = 0; u < sl.trips; ++u) {
+                    const size_t base = (size_t)sl.ebase + ((size_t)u << 5) + ((size_t)r << g);
+                    for (int l = 0; l < G; ++l) acc = fma(P.val[base + l], xe[P.col[base + l]], acc);
+                }
+                const double ini = P.init[q] >= 0 ? xe[P.init[q]] : 0.0;
+                out.push_back((ini - acc) * P.scale[q]);
+            }
+        }
+        size_t o = 0;
+        for (int32_t s = P.sub_ptr[sb]; s < P.sub_ptr[sb + 1]; ++s) {
+            const Slice& sl = P.slices[s];
+            const int nr = sl.glog_nrows >> 8;
+            for (int r = 0; r < nr; ++r) xe[P.dst[sl.q0 + r]] = out[o++];
+        }
+    }
+    for (int64_t j = 0; j < P.n; ++j) x[j] = xe[perm_c[j]];
+}
+
 }  // namespace ocb
 
 // ---------------------------------------------------------------------------------
@@ -771,7 +806,8 @@ int ocb_lu_program_create(ocb_lu_program** out, int64_t n, const int32_t* h_L_ro
     OCB_ARG(out && n >= 0 && h_L_rowptr && h_U_rowptr, "lu_program_create");
     ocb_lu_program* h = new ocb_lu_program();
     const int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx,
-                                         h_U_vals, 512, (flags & 2) != 0, (flags & 4) != 0, &h->P);
+                                         h_U_vals, 512, (flags & 2) != 0, (flags & 4) != 0, &h->P,
+                                         (flags & 8) ? 32 : 0);
     if (rc != OCB_OK) {
         delete h;
         return rc;

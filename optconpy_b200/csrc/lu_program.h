@@ -54,7 +54,14 @@ struct LuProgram {
 // UPPER factor (rows of L^T) has the unit diagonal.
 int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const double* Lva,
                      const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
-                     bool transposed, bool merge, LuProgram* out);
+                     bool transposed, bool merge, LuProgram* out, int wmax_cap = 0);
+// wmax_cap > 0: no supernode wider than that (the "safe" layout of the residual guard: the
+// inverse of a narrow triangular block is far better conditioned than that of a 512-row one).
+
+// Host execution of the program for ONE right-hand side (what the CUDA kernels do, serially):
+// x = Pc U^-1 L^-1 Pr b.  Used by the residual guard of ocb_lu_pack_host_checked and by tests.
+void execute_program_host(const LuProgram& P, const int32_t* perm_r, const int32_t* perm_c,
+                          const double* b, double* x);
 
 // merge = true: supernodes up to 64 rows wide (OCB_MERGE_W) are solved in ONE sub-level instead
 // of two, in inverse-multiplied form  x_t = inv(T_tt) b_t - (inv(T_tt) T[t,off]) x  (as long as

@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <string.h>
 #include <stdlib.h>
+#include <math.h>
 
 struct ocb_lu {
     int64_t n = 0, n_ext = 0;
@@ -1181,6 +1182,60 @@ int lu_solve_impl(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_
 
 extern "C" {
 
+// Common body of the three packing entry points.  dst != null: build there (OCB_ERR_CAPACITY if
+// it does not fit); otherwise *img_out is malloc'ed.  A_* != null: residual guard - the program
+// is executed on the host for one pseudo-random right-hand side and the normwise backward
+// error ||b - A x|| / (||A||_F ||x|| + ||b||) of the ORIGINAL matrix (CSC) is returned.
+static int pack_common(int64_t n, const int32_t* Lrp, const int32_t* Lci, const double* Lva,
+                       const int32_t* Urp, const int32_t* Uci, const double* Uva, const int32_t* perm_r,
+                       const int32_t* perm_c, int64_t max_smem_optin, int64_t flags, unsigned char* dst,
+                       int64_t dst_capacity, unsigned char** img_out, int64_t* out_bytes,
+                       const int32_t* A_colptr, const int32_t* A_rowidx, const double* A_vals,
+                       double* out_backerr) {
+    ocb::LuProgram P;
+    int rc = ocb::build_lu_program(n, Lrp, Lci, Lva, Urp, Uci, Uva, ocb::trsm_threads(), (flags & 2) != 0,
+                                   (flags & 4) != 0 && !(flags & 8), &P, (flags & 8) ? 32 : 0);
+    if (rc != OCB_OK) return rc;
+    if (out_backerr) *out_backerr = 0.0;
+    if (A_colptr && A_rowidx && A_vals && out_backerr && n > 0) {
+        std::vector<double> b((size_t)n), x((size_t)n), r;
+        uint64_t sd = 0x9e3779b97f4a7c15ULL;   // fixed pseudo-random right-hand side in [-1, 1)
+        for (int64_t i = 0; i < n; ++i) {
+            sd = sd * 6364136223846793005ULL + 1442695040888963407ULL;
+            b[i] = (double)(int64_t)(sd >> 11) / 4503599627370496.0 - 1.0;
+        }
+        ocb::execute_program_host(P, perm_r, perm_c, b.data(), x.data());
+        r = b;
+        double a2 = 0.0, x2 = 0.0, b2 = 0.0, r2 = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            const double xj = x[j];
+            x2 += xj * xj;
+            for (int32_t p = A_colptr[j]; p < A_colptr[j + 1]; ++p) {
+                r[A_rowidx[p]] -= A_vals[p] * xj;
+                a2 += A_vals[p] * A_vals[p];
+            }
+        }
+        for (int64_t i = 0; i < n; ++i) { r2 += r[i] * r[i]; b2 += b[i] * b[i]; }
+        const double den = sqrt(a2) * sqrt(x2) + sqrt(b2);
+        *out_backerr = (r2 == r2 && den > 0.0 && den == den) ? sqrt(r2) / den : 1.0;   // NaN -> 1
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned char* img = nullptr;
+    rc = ocb::pack_image(P, perm_r, perm_c, (int)max_smem_optin, (int)flags, &img, out_bytes, dst, dst_capacity);
+    if (getenv("OCB_TIMING"))
+        fprintf(stderr, "lu_pack_host: image packed in %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    if (rc != OCB_OK) return rc;
+    if (dst && img != dst) {   // did not fit: *out_bytes tells how much room the image needs
+        free(img);
+        ocb::set_error("lu_pack_host_into: the image needs %lld bytes, the buffer has %lld",
+                       (long long)*out_bytes, (long long)dst_capacity);
+        return OCB_ERR_CAPACITY;
+    }
+    if (img_out) *img_out = img;
+    return OCB_OK;
+}
+
 int ocb_lu_pack_host(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
                      const int32_t* h_U_rowptr, const int32_t* h_U_colidx, const double* h_U_vals,
                      const int32_t* h_perm_r, const int32_t* h_perm_c, int64_t max_smem_optin, int64_t flags,
@@ -1188,16 +1243,9 @@ int ocb_lu_pack_host(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_co
     OCB_ARG(n >= 0 && out_image && out_bytes, "lu_pack_host");
     OCB_ARG(h_L_rowptr && h_U_rowptr && h_perm_r && h_perm_c, "lu_pack_host: null pointer");
     OCB_ARG(max_smem_optin >= 48 * 1024, "lu_pack_host: shared-memory size");
-    ocb::LuProgram P;
-    int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals,
-                                   ocb::trsm_threads(), (flags & 2) != 0, (flags & 4) != 0, &P);
-    if (rc != OCB_OK) return rc;
-    const auto t0 = std::chrono::steady_clock::now();
-    rc = ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, (int)flags, out_image, out_bytes);
-    if (getenv("OCB_TIMING"))
-        fprintf(stderr, "lu_pack_host: image packed in %.1f ms\n",
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-    return rc;
+    return pack_common(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals, h_perm_r,
+                       h_perm_c, max_smem_optin, flags, nullptr, 0, out_image, out_bytes, nullptr, nullptr,
+                       nullptr, nullptr);
 }
 
 int ocb_lu_pack_host_into(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_colidx, const double* h_L_vals,
@@ -1207,20 +1255,24 @@ int ocb_lu_pack_host_into(int64_t n, const int32_t* h_L_rowptr, const int32_t* h
     OCB_ARG(n >= 0 && dst && dst_capacity >= 0 && out_bytes, "lu_pack_host_into");
     OCB_ARG(h_L_rowptr && h_U_rowptr && h_perm_r && h_perm_c, "lu_pack_host_into: null pointer");
     OCB_ARG(max_smem_optin >= 48 * 1024, "lu_pack_host_into: shared-memory size");
-    ocb::LuProgram P;
-    int rc = ocb::build_lu_program(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals,
-                                   ocb::trsm_threads(), (flags & 2) != 0, (flags & 4) != 0, &P);
-    if (rc != OCB_OK) return rc;
-    unsigned char* img = nullptr;
-    rc = ocb::pack_image(P, h_perm_r, h_perm_c, (int)max_smem_optin, (int)flags, &img, out_bytes, dst, dst_capacity);
-    if (rc != OCB_OK) return rc;
-    if (img != dst) {   // did not fit: *out_bytes tells how much room the image needs
-        free(img);
-        ocb::set_error("lu_pack_host_into: the image needs %lld bytes, the buffer has %lld",
-                       (long long)*out_bytes, (long long)dst_capacity);
-        return OCB_ERR_CAPACITY;
-    }
-    return OCB_OK;
+    return pack_common(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals, h_perm_r,
+                       h_perm_c, max_smem_optin, flags, dst, dst_capacity, nullptr, out_bytes, nullptr, nullptr,
+                       nullptr, nullptr);
+}
+
+int ocb_lu_pack_host_checked(int64_t n, const int32_t* h_L_rowptr, const int32_t* h_L_colidx,
+                             const double* h_L_vals, const int32_t* h_U_rowptr, const int32_t* h_U_colidx,
+                             const double* h_U_vals, const int32_t* h_perm_r, const int32_t* h_perm_c,
+                             int64_t max_smem_optin, int64_t flags, unsigned char* dst, int64_t dst_capacity,
+                             unsigned char** out_image, int64_t* out_bytes, const int32_t* h_A_colptr,
+                             const int32_t* h_A_rowidx, const double* h_A_vals, double* out_backerr) {
+    OCB_ARG(n >= 0 && out_bytes && (dst || out_image), "lu_pack_host_checked");
+    OCB_ARG(h_L_rowptr && h_U_rowptr && h_perm_r && h_perm_c, "lu_pack_host_checked: null pointer");
+    OCB_ARG(max_smem_optin >= 48 * 1024, "lu_pack_host_checked: shared-memory size");
+    OCB_ARG(h_A_colptr && h_A_rowidx && h_A_vals && out_backerr, "lu_pack_host_checked: matrix");
+    return pack_common(n, h_L_rowptr, h_L_colidx, h_L_vals, h_U_rowptr, h_U_colidx, h_U_vals, h_perm_r,
+                       h_perm_c, max_smem_optin, flags, dst, dst_capacity, out_image, out_bytes, h_A_colptr,
+                       h_A_rowidx, h_A_vals, out_backerr);
 }
 
 void ocb_host_free(void* p) { free(p); }

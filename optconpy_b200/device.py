@@ -6,6 +6,7 @@ library loader raises if the extension is missing.
 """
 import ctypes as C
 import os
+import threading
 import time
 
 import numpy as np
@@ -25,6 +26,8 @@ STATS = dict(lu_factor_s=0.0,          # SuperLU seconds summed over the workers
              lu_analyse_upload_s=0.0,  # main process: image upload + handle creation
              lu_arena_s=0.0,           # ... of which: device buffer from the caching allocator
              lu_unpinned_uploads=0,    # images that did not travel through a pinned pool segment
+             lu_guard_refactors=0,     # residual guard: matrices factorised again in safe mode
+             lu_guard_max_backerr=0.0,  # ... largest backward error of an image handed out
              n_factor=0, h2d_bytes=0, d2h_bytes=0)
 
 # wall seconds of the main thread per phase of the host API (diagnostics, bench.py e2e)
@@ -190,6 +193,10 @@ class DeviceCSR(object):
 
 
 _POOL = dict(pool=None, workers=0)
+# the look-ahead thread of the DRE stepper and the main thread both create jobs: every lazily
+# created singleton below (worker pool, pinned pool, upload thread, ordering cache) is built
+# under this lock, so that two threads never spawn (and leak) a second copy
+_LOCK = threading.RLock()
 
 
 def _lu_pool():
@@ -203,13 +210,29 @@ def _lu_pool():
     want = int(want)
     if want <= 1:
         return None
-    if _POOL['pool'] is None or _POOL['workers'] != want:
-        if _POOL['pool'] is not None:
-            _POOL['pool'].terminate()
-        from . import _lu_worker
-        _POOL['pool'] = mp.get_context('spawn').Pool(want, initializer=_lu_worker.worker_init)
-        _POOL['workers'] = want
-    return _POOL['pool']
+    with _LOCK:
+        if _POOL['pool'] is None or _POOL['workers'] != want:
+            if _POOL['pool'] is not None:
+                _POOL['pool'].terminate()
+            from . import _lu_worker
+            _POOL['pool'] = mp.get_context('spawn').Pool(want, initializer=_lu_worker.worker_init)
+            _POOL['workers'] = want
+        return _POOL['pool']
+
+
+def _record_guard(guard):
+    """Book-keeping of the workers' residual guard (``_lu_worker._build``)."""
+    if guard is None or guard[0] is None:
+        return
+    backerr, safe = guard
+    from . import _lu_worker
+    STATS['lu_guard_refactors'] += int(safe)
+    STATS['lu_guard_max_backerr'] = max(STATS['lu_guard_max_backerr'], float(backerr))
+    if safe and backerr > _lu_worker._guard_tol():
+        import warnings
+        warnings.warn('optconpy_b200: backward error %.1e of a saddle-point factorisation is above '
+                      'the guard tolerance even with full partial pivoting (matrix close to '
+                      'singular?)' % backerr, RuntimeWarning)
 
 
 def _csc_args(mat, opts):
@@ -250,14 +273,15 @@ def _with_order(a, opts):
     if os.environ.get('OCB_NO_ORDER_REUSE') or opts.get('permc_spec') == 'NATURAL':
         return a, None
     key = _pattern_key(a)
-    if key not in _ORDER:
-        # first matrix of this pattern: get the ordering NOW (one synchronous SuperLU run), so
-        # that no queued job runs the slow path or produces the larger factor
-        from . import _lu_worker
-        t0 = time.perf_counter()
-        _ORDER[key] = _lu_worker.order_only(a)
-        STATS['lu_order_s'] += time.perf_counter() - t0
-    return a + (_ORDER[key],), key
+    with _LOCK:
+        if key not in _ORDER:
+            # first matrix of this pattern: get the ordering NOW (one synchronous SuperLU run), so
+            # that no queued job runs the slow path or produces the larger factor
+            from . import _lu_worker
+            t0 = time.perf_counter()
+            _ORDER[key] = _lu_worker.order_only(a)
+            STATS['lu_order_s'] += time.perf_counter() - t0
+        return a + (_ORDER[key],), key
 
 
 _SMEM_OPTIN = dict()
@@ -334,6 +358,11 @@ def _shm_pool(image_bytes=None):
     """The pinned pool (created after the first image told us the size), or None."""
     if _SHM['disabled'] or os.environ.get('OCB_NO_PINNED_POOL'):
         return None
+    with _LOCK:
+        return _shm_pool_locked(image_bytes)
+
+
+def _shm_pool_locked(image_bytes):
     if _SHM['pool'] is None and image_bytes is not None:
         try:
             world = max(int(os.environ.get('WORLD_SIZE', '1')), 1)
@@ -359,7 +388,7 @@ def _shm_pool(image_bytes=None):
     return _SHM['pool']
 
 
-_UPLOADER = dict(pool=None)
+_UPLOADER = dict()
 
 
 def _uploader_init(device_index):
@@ -367,12 +396,38 @@ def _uploader_init(device_index):
     torch.cuda.set_stream(torch.cuda.Stream())      # thread-local: uploads leave the compute stream alone
 
 
-def _uploader():
-    if _UPLOADER['pool'] is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _UPLOADER['pool'] = ThreadPoolExecutor(max_workers=1, initializer=_uploader_init,
-                                               initargs=(torch.cuda.current_device(),))
-    return _UPLOADER['pool']
+def _uploader(device_index):
+    """One upload thread PER DEVICE, bound to ``device_index`` - the device of the thread that
+    created the job, not whatever is current in the thread that happens to get here first (a
+    look-ahead thread starts on device 0 whatever the main thread selected)."""
+    with _LOCK:
+        if device_index not in _UPLOADER:
+            from concurrent.futures import ThreadPoolExecutor
+            _UPLOADER[device_index] = ThreadPoolExecutor(max_workers=1, initializer=_uploader_init,
+                                                         initargs=(device_index,))
+        return _UPLOADER[device_index]
+
+
+_MAIN_DEVICE = dict(index=None)
+
+
+def bind_thread_to_device(index=None):
+    """Make the calling thread use CUDA device ``index`` (default: the device that was current
+    in the thread that last called :func:`lookahead_thread_init`).  CUDA's current device is
+    per thread; helper threads call this first."""
+    index = _MAIN_DEVICE['index'] if index is None else index
+    if index is not None:
+        torch.cuda.set_device(index)
+
+
+def lookahead_thread_init():
+    """Called on the MAIN thread: returns the initializer for helper threads that submit
+    factorisation jobs on its behalf (``dre_stepper`` look-ahead), bound to the device that is
+    current now."""
+    require_cuda()
+    index = torch.cuda.current_device()
+    _MAIN_DEVICE['index'] = index
+    return lambda: bind_thread_to_device(index)
 
 
 class FactorJob(object):
@@ -382,6 +437,7 @@ class FactorJob(object):
     def __init__(self, mats, lu_options=None, wide=False, k_hint=None):
         from . import _lu_worker
         require_cuda()
+        self.device = torch.cuda.current_device()      # results are uploaded to THIS device
         opts = dict(LU_OPTIONS if lu_options is None else lu_options)
         t0 = time.perf_counter()
         so = smem_optin()
@@ -414,7 +470,7 @@ class FactorJob(object):
         CUDA stream (copy engine), so that the main thread does not spend its time in
         pageable host-to-device copies; ``result()`` then only joins."""
         if self._future is None and self._done is None and not os.environ.get('OCB_NO_UPLOAD_THREAD'):
-            self._future = _uploader().submit(self._collect)
+            self._future = _uploader(self.device).submit(self._collect)
         return self
 
     def result(self):
@@ -430,22 +486,35 @@ class FactorJob(object):
     def _collect(self):
         if self._done is not None:
             return self._done
+        if torch.cuda.current_device() != self.device:
+            torch.cuda.set_device(self.device)
         out = []
         if self._async is None:
-            for (img, tf, tp, order), key in zip(self._sync, self._keys):
+            for (img, tf, tp, order, guard), key in zip(self._sync, self._keys):
                 STATS['lu_factor_s'] += tf
                 STATS['lu_worker_pack_s'] += tp
+                _record_guard(guard)
                 if order is not None and key is not None:
                     _ORDER.setdefault(key, order)
                 out.append(LU(None, image=img))
         else:
             from multiprocessing import shared_memory
-            for ar, slot, key in zip(self._async, self._slots, self._keys):
+            shp0 = _shm_pool()
+            for idx, (ar, slot, key) in enumerate(zip(self._async, self._slots, self._keys)):
                 t0 = time.perf_counter()
                 try:
-                    name, nbytes, tf, tp, order = ar.get(timeout=float(os.environ.get('OCB_LU_TIMEOUT_S', '900')))
+                    name, nbytes, tf, tp, order, guard = ar.get(
+                        timeout=float(os.environ.get('OCB_LU_TIMEOUT_S', '900')))
                 except Exception as exc:        # a dead worker would otherwise block forever
+                    # give the pinned segments of this and all later jobs back to the pool (the
+                    # pool would otherwise shrink for good)
+                    if shp0 is not None:
+                        for sl in self._slots[idx:]:
+                            if sl is not None:
+                                shp0.release(sl)
+                    self._slots = [None]*len(self._slots)
                     raise RuntimeError('optconpy_b200: host LU worker failed or timed out: %r' % (exc,))
+                _record_guard(guard)
                 if order is not None and key is not None:
                     _ORDER.setdefault(key, order)
                 STATS['lu_collect_wait_s'] += time.perf_counter() - t0
@@ -529,7 +598,8 @@ class LU(object):
             from . import _lu_worker
             opts = dict(LU_OPTIONS if lu_options is None else lu_options)
             a, key = _with_order(_csc_args(mat, opts) + (smem_optin(), _pack_flags(wide)), opts)
-            image, tf, tp, order = _lu_worker.factor_image(a)
+            image, tf, tp, order, guard = _lu_worker.factor_image(a)
+            _record_guard(guard)
             if order is not None and key is not None:
                 _ORDER.setdefault(key, order)
             STATS['lu_factor_s'] += tf
@@ -801,6 +871,26 @@ def _adi_call(lib, harr, sarr, nsh, NV, NP, Mt, W, k, Ufb, m, Vt, maxsteps, step
         ptr(Vt.rowptr) if m else 0, ptr(Vt.colidx) if m else 0, ptr(Vt.vals) if m else 0,
         int(min(maxsteps, steps_cap)), float(reltol), ptr(Z), Z.stride(0), Z.shape[1],
         rel, C.byref(nst), ptr(ws), wsb, stream_ptr()))
+
+
+_FP64_PEAK = dict()
+
+
+def fp64_peak(kind='dmma'):
+    """Measured FP64 peak (TFLOP/s) of the current device: ``'dmma'`` = the FP64 tensor pipe
+    (DMMA.8x8x4 chains), ``'dfma'`` = the FP64 FMA pipe.  Best of 1/2/4 CTAs per SM; cached."""
+    lib = require_cuda()
+    key = (torch.cuda.current_device(), kind)
+    if key not in _FP64_PEAK:
+        sink = torch.zeros(1, dtype=torch.float64, device=cur_device())
+        best = 0.0
+        for cps in (1, 2, 4):
+            tf = C.c_double(0.0)
+            _cabi.check(lib.ocb_fp64_peak(0 if kind == 'dmma' else 1, 20000, cps, C.byref(tf),
+                                          ptr(sink), stream_ptr()), 'ocb_fp64_peak')
+            best = max(best, tf.value)
+        _FP64_PEAK[key] = best
+    return _FP64_PEAK[key]
 
 
 def launch_count():

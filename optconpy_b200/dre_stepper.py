@@ -85,7 +85,8 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
                       get_datastr=None, gtdtstrargs=None,
                       check_c_consist=True,
                       lau=None, pru=None, store=None, verbose=False,
-                      stepinfo=None, step_callback=None, lookahead=4, timing=None):
+                      stepinfo=None, step_callback=None, lookahead=4, timing=None,
+                      private_extensions=True):
     """Same keyword signature as the reference's ``solve_flow_daeric`` plus
     ``lau``/``pru`` (backend modules), ``store`` and ``stepinfo`` (optional list
     that receives per-step diagnostics).  Returns the ``feedbackthroughdict``
@@ -95,7 +96,11 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
     on ``t`` only, not on the Riccati solution, so when the backend offers
     ``pru.factors_async`` / ``lau.sadlu_async`` the sparse LU setup of the next
     ``lookahead`` steps is started (host worker processes) before the device work of step
-    ``k``; the numbers are the same with or without it."""
+    ``k``; the numbers are the same with or without it.
+
+    ``private_extensions=False`` (with ``lookahead=0``): call the backend through the
+    reference's signatures ONLY - no ``_factors`` / ``_lazy_zfac`` / ``sadlu`` keywords - i.e.
+    exactly what ``solve_dae_ric.py:152-163,192-194`` executes (bench.py ``e2e_plain``)."""
     if lau is None or pru is None:
         from . import lin_alg_utils as _lau, proj_ric_utils as _pru
         lau, pru = lau or _lau, pru or _pru
@@ -147,7 +152,8 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         store.save(wc, curnwtnsdict[tE]['w'])
         store.save(mtxtb, curnwtnsdict[tE]['mtxtb'])
 
-    can_prefetch = bool(lookahead) and hasattr(pru, 'factors_async') and hasattr(lau, 'sadlu_async')
+    can_prefetch = (bool(lookahead) and private_extensions and hasattr(pru, 'factors_async')
+                    and hasattr(lau, 'sadlu_async'))
 
     def prepare(tk):
         """Everything of step tk that depends on t only (incl. background factorisations)."""
@@ -174,7 +180,10 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
     if can_prefetch:
         import sys
         from concurrent.futures import ThreadPoolExecutor
-        pool = ThreadPoolExecutor(max_workers=1)
+        # CUDA's current device is per thread: the helper thread is bound to the device of THIS
+        # thread (a fresh thread starts on device 0 whatever the caller selected)
+        tinit = getattr(pru, 'lookahead_thread_init', None)
+        pool = ThreadPoolExecutor(max_workers=1, initializer=tinit() if tinit is not None else None)
         # this thread drives the GPU with many short blocking calls; each one has to win the
         # GIL back from the helper threads (assembly, pickling), which by default may keep it
         # for 5 ms at a time
@@ -216,7 +225,7 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
             w_mat = np.hstack([MT @ Zc, np.sqrt(cts)*tct_mat])
             oldfb = np.sqrt(cts)*cnsmtxtb if cnsmtxtb is not None else None
             xkw = dict(_factors=pre['fac']) if pre['fac'] is not None else {}
-            if hasattr(pru, 'DeviceFactor'):
+            if private_extensions and hasattr(pru, 'DeviceFactor'):
                 # the uncompressed factor is only compressed below: leave it on the device
                 xkw['_lazy_zfac'] = True
             nres = pru.proj_alg_ric_newtonadi(mmat=MT, amat=ft_mat, transposed=True,

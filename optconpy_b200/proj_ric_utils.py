@@ -22,7 +22,9 @@ import torch
 from . import device as dv
 
 __all__ = ['solve_proj_lyap_stein', 'proj_alg_ric_newtonadi', 'compress_Zsvd',
-           'get_mTzzTtb', 'comp_proj_lyap_res_norm', 'factors_async']
+           'get_mTzzTtb', 'comp_proj_lyap_res_norm', 'factors_async', 'lookahead_thread_init']
+
+lookahead_thread_init = dv.lookahead_thread_init
 
 DEFAULT_SHIFTS = [-30.0, -20.0, -10.0, -5.0, -3.0, -1.0]
 

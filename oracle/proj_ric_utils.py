@@ -19,6 +19,22 @@ from . import lin_alg_utils as lau
 
 DEFAULT_SHIFTS = [-30.0, -20.0, -10.0, -5.0, -3.0, -1.0]
 
+# Baseline variant "LU cached across Newton steps" (bench.py cpu_baseline):
+# None = factorise the shifted matrices in every call, as a straightforward implementation
+# does; a dict = reuse a factorisation whenever the same shifted matrix comes again (the
+# Newton steps of one Riccati solve share them).  Numbers are identical either way.
+LU_CACHE = None
+
+
+def _shifted_lu(At, Mt, jmat, mu):
+    if LU_CACHE is None:
+        return lau.SadLU(lau.sadpnt_matrix(At + mu*Mt, jmat))
+    key = (float(mu), At.shape, At.nnz, float(At.data.sum()), float(np.abs(At.data).sum()),
+           float(Mt.data.sum()), id(jmat))
+    if key not in LU_CACHE:
+        LU_CACHE[key] = lau.SadLU(lau.sadpnt_matrix(At + mu*Mt, jmat))
+    return LU_CACHE[key]
+
 
 def _dense(a):
     if sps.issparse(a):
@@ -59,7 +75,7 @@ def solve_proj_lyap_stein(amat=None, jmat=None, wmat=None, mmat=None,
     else:
         ut, vt = None, None
     for mu in ms:
-        alu = lau.SadLU(lau.sadpnt_matrix(At + mu*Mt, jmat))
+        alu = _shifted_lu(At, Mt, jmat, mu)
         lus.append(alu)
         if ut is not None:
             sinvs.append(lau.get_Sinv_smw(alu, umat=ut, vmat=vt))

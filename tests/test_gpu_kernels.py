@@ -225,3 +225,9 @@ def test_errors_are_loud(dv, sad):
     B = torch.zeros((sad.shape[0] + 1, 2), dtype=torch.float64, device='cuda')
     with pytest.raises(_cabi.OcbError):
         lu.solve(B)
+
+
+def test_fp64_peak_microbenchmark(dv):
+    """The measured FP64 denominators (DMMA tensor pipe, DFMA pipe) are sane B200 numbers."""
+    dm, df = dv.fp64_peak('dmma'), dv.fp64_peak('dfma')
+    assert 5.0 < dm < 120.0 and 5.0 < df < 120.0, (dm, df)

@@ -51,8 +51,26 @@ def _worker(rank, world, port, outdir):
     r0, r1 = par.column_slice(prob['NV'], rank, world)
     MZrows = dv.DeviceCSR(M).matmul(Zall)[r0:r1].contiguous()
     G = par.sharded_gram_dev(Zrows, MZrows)
+    # the look-ahead thread and the upload thread must work on THIS rank's device,
+    # not on device 0 (nothing here pre-creates the uploader on the main thread)
+    import optconpy_b200.lin_alg_utils as glau
+    from optconpy_b200 import scenarios as sc, dre_stepper as ds
+    os.environ['OCB_LU_WORKERS'] = '2'
+    prob1, cs1, kw1 = sc.config1(glau, Nts=2)
+    devs = []
+    orig = dv.LU.__init__
+
+    def spy(self, *a, **k):
+        orig(self, *a, **k)
+        devs.append(self.arena.device.index)
+    dv.LU.__init__ = spy
+    s2 = ds.MemStore()
+    f2 = ds.solve_flow_daeric(lau=glau, pru=gpru, store=s2, lookahead=2, **kw1)
+    dv.LU.__init__ = orig
+    t0 = sorted(f2)[0]
     np.savez(os.path.join(outdir, 'rank%d.npz' % rank), Zl=dv.to_host(Zl), rel=np.array(rel),
-             Zall=dv.to_host(Zall), G=dv.to_host(G))
+             Zall=dv.to_host(Zall), G=dv.to_host(G), lu_devices=np.array(devs),
+             gain=s2[f2[t0]['mtxtb']])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,6 +98,11 @@ def test_column_sharded_adi_two_gpus(tmp_path):
     ka = Z.shape[1]
     D = R[:, :ka] @ R[:, :ka].T - R[:, ka:] @ R[:, ka:].T
     assert np.linalg.norm(D) <= 1e-9*np.linalg.norm(Zr.T @ Zr)
+    # every factor image of rank r was uploaded to device r (look-ahead + upload threads), and
+    # both ranks computed the same DRE gains
+    for r in range(world):
+        assert outs[r]['lu_devices'].size > 0 and (outs[r]['lu_devices'] == r).all()
+    assert np.allclose(outs[0]['gain'], outs[1]['gain'], rtol=1e-12, atol=0)
     # Gram all-reduce: identical on both ranks, equals Z^T M Z
     assert np.array_equal(outs[0]['G'], outs[1]['G'])
     assert np.allclose(outs[0]['G'], Z.T @ (M @ Z), rtol=1e-11, atol=1e-13)

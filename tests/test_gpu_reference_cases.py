@@ -1,0 +1,214 @@
+"""GPU parity on the cases the reference and the benchmark are actually quoted on
+("close the parity holes on what you measure"):
+
+* the reference's ONLY test (``tests/test_units_compfacres_compress.py:15-106``: N=15 cavity,
+  ``F = -M - 0.1 A - sprand(0.03)``, ``adi_max_steps=50``, ``adi_newZ_reltol=1e-11``, the five
+  identities, ``lau.app_luinv_to_spmat``, ``compress_Zsvd(thresh=1e-6)``) run through the
+  CUDA modules - seeded, because the original draws unseeded random data,
+* BASELINE config[1] (driven cavity N=25, ``run_optcont.py`` parameters - the bench
+  workload): two backward DRE steps, CUDA modules against the oracle,
+* config 2b (``driv_cav_cont.py``) and config 3 at its stated 44 x 16 channel mesh,
+* the helpers of SURVEY rows a10/a11 that no other test calls on the CUDA side.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import scipy.sparse.linalg as spsla
+
+pytestmark = pytest.mark.gpu
+
+TOL_FACTOR = 1e-9      # north_star: Z Z^T and feedback gains
+TOL_TRAJ = 1e-8        # north_star: DRE trajectory quantities
+
+
+def _relerr(a, b):
+    return np.linalg.norm(a - b)/max(np.linalg.norm(b), 1e-300)
+
+
+def _zzt_relerr(Za, Zb):
+    ka = Za.shape[1]
+    R = np.linalg.qr(np.hstack([Za, Zb]), mode='r')
+    D = R[:, :ka] @ R[:, :ka].T - R[:, ka:] @ R[:, ka:].T
+    return np.linalg.norm(D)/np.linalg.norm(Zb.T @ Zb)
+
+
+@pytest.fixture(scope='module')
+def mods():
+    import optconpy_b200.lin_alg_utils as glau
+    import optconpy_b200.proj_ric_utils as gpru
+    from oracle import lin_alg_utils as olau, proj_ric_utils as opru
+    return glau, gpru, olau, opru
+
+
+@pytest.fixture(scope='module')
+def ref_case():
+    """Inputs of the reference's test, seeded (it uses unseeded randn / sps.rand)."""
+    from optconpy_b200 import problems as pb
+    prob = pb.drivcav_problem(15, 1.0)          # nu=1 as get_stokessysmats(..., nu=1), :31
+    M, A, J = prob['M'], prob['A'], prob['J']
+    NV, NY = prob['NV'], 5
+    assert NV == 1682 and J.shape[0] == 255     # N=15 -> NV=1682, NP=255
+    F = -M - 0.1*A - sps.random(NV, NV, density=0.03, format='csr', random_state=11)
+    W = np.random.default_rng(12).standard_normal((NV, NY))
+    d = dict(adi_max_steps=50, adi_newZ_reltol=1e-11, nwtn_max_steps=24, nwtn_upd_reltol=4e-7,
+             nwtn_upd_abstol=4e-7, full_upd_norm_check=True, verbose=False)
+    return M, F, J, W, d
+
+
+@pytest.mark.timeout(900)
+def test_reference_unit_test_on_cuda_modules(mods, ref_case):
+    """tests/test_units_compfacres_compress.py:49-106 with ``pru``/``lau`` = the CUDA modules.
+    The assertions are the reference's (``np.allclose`` defaults); on top, the CUDA results are
+    compared with the oracle's on the same inputs."""
+    lau, pru, olau, opru = mods
+    from optconpy_b200 import device as dv
+    M, F, J, W, d = ref_case
+    NV = M.shape[0]
+    dv.reset_stats()
+    res = pru.solve_proj_lyap_stein(amat=F, mmat=M, jmat=J, wmat=W, adi_dict=d)
+    Z = res['zfac']
+    # this perturbed F is the matrix on which explicit block inverses lose accuracy (DESIGN K1):
+    # the residual guard must have re-factorised its shifted matrices in safe mode
+    assert dv.STATS['lu_guard_refactors'] >= 1
+    assert dv.STATS['lu_guard_max_backerr'] < 2e-15
+
+    MtZ = M.T @ Z
+    MtXM = np.dot(MtZ, MtZ.T)
+    FtXM = F.T @ (np.dot(Z, Z.T) @ M.toarray())
+
+    Mlu = lau.SadLU(M.tocsc())                        # the CUDA stand-in of spsla.factorized
+    MinvJt = lau.app_luinv_to_spmat(Mlu, J.T)         # :71
+    MinvJt_sp = lau.app_luinv_to_spmat(spsla.factorized(M.tocsc()), J.T)   # scipy callable, as :70
+    assert _relerr(MinvJt, MinvJt_sp) < 1e-12
+    Sinv = np.linalg.inv(J @ MinvJt)
+    P = np.eye(NV) - np.dot(MinvJt, Sinv @ J.toarray())
+    PtW = np.dot(P.T, W)
+    ProjRes = np.dot(P.T, np.dot(FtXM, P)) + np.dot(np.dot(P.T, FtXM.T), P) + np.dot(PtW, PtW.T)
+    resn = np.linalg.norm(ProjRes)
+    ownresn = np.sqrt(pru.comp_proj_lyap_res_norm(Z, F, M, W, J))
+    # 1. smart fnorm comp (:85-86)
+    assert np.allclose(np.linalg.norm(MtXM), np.linalg.norm(np.dot(MtZ.T, MtZ)))
+    # 2. smart comp of ress (:89)
+    assert np.allclose(resn, ownresn)
+    # reduction of Z (:92)
+    Zred = pru.compress_Zsvd(Z, k=None, thresh=1e-6, shplot=True)
+    MtZr = M.T @ Zred
+    MtXMr = np.dot(MtZr, MtZr.T)
+    # 3. reduction is 'projected' (:97)
+    assert np.allclose(MtXMr, np.dot(P.T, np.dot(MtXMr, P)))
+    # 4. diff in apprx (:100-101)
+    assert np.allclose(np.linalg.norm(np.dot(MtZ.T, MtZ)), np.linalg.norm(np.dot(MtZr.T, MtZr)))
+    # 5. residual of the reduced factor (:104-106)
+    ownresr = np.sqrt(pru.comp_proj_lyap_res_norm(Zred, F, M, W, J))
+    assert np.allclose(ownresr, resn)
+
+    # CUDA vs oracle on the same inputs
+    ref = opru.solve_proj_lyap_stein(amat=F, mmat=M, jmat=J, wmat=W, adi_dict=d)
+    assert Z.shape == ref['zfac'].shape                               # same iteration count
+    assert np.allclose(res['adi_rel_newZ_norms'], ref['adi_rel_newZ_norms'], rtol=1e-6, atol=0)
+    assert _zzt_relerr(Z, ref['zfac']) < TOL_FACTOR
+    ores = np.sqrt(opru.comp_proj_lyap_res_norm(ref['zfac'], F, M, W, J))
+    assert abs(ownresn - ores) <= 1e-7*ores
+    zo = opru.compress_Zsvd(ref['zfac'], k=None, thresh=1e-6)
+    assert Zred.shape == zo.shape and _zzt_relerr(Zred, zo) < TOL_FACTOR
+
+
+def test_lau_helpers_a10_a11(mods, cav10):
+    """``app_luinv_to_spmat``, ``get_Sinv_smw``, ``app_smw_inv``, ``comp_sqfnrm_factrd_lyap_res``
+     on the CUDA side against the oracle."""
+    glau, gpru, olau, opru = mods
+    M, A, J = cav10['M'], cav10['A'], cav10['J']
+    NV, NP = cav10['NV'], cav10['NP']
+    rng = np.random.default_rng(21)
+    amat = M.T + 0.1*A.T
+    K = olau.sadpnt_matrix(amat, J)
+    n = NV + NP
+    galu, oalu = glau.SadLU(K), olau.SadLU(K)
+    # a10: LU-inverse applied to a sparse matrix -> dense
+    Zs = sps.random(n, 6, density=0.05, random_state=3, format='csr')
+    got, ref = glau.app_luinv_to_spmat(galu, Zs), olau.app_luinv_to_spmat(oalu, Zs)
+    assert isinstance(got, np.ndarray) and got.shape == ref.shape == (n, 6)
+    assert _relerr(got, ref) < 1e-11
+    # a11: SMW pieces.  U dense (n x m), V sparse (m x n)
+    U = np.vstack([1e-2*rng.standard_normal((NV, 8)), np.zeros((NP, 8))])
+    V = sps.hstack([sps.random(8, NV, density=0.03, random_state=5, format='csr'),
+                    sps.csr_matrix((8, NP))], format='csr')
+    sg, so = glau.get_Sinv_smw(galu, umat=U, vmat=V), olau.get_Sinv_smw(oalu, umat=U, vmat=V)
+    assert sg.shape == (8, 8) and _relerr(sg, so) < 1e-10
+    rhs = rng.standard_normal((n, 3))
+    xo = olau.app_smw_inv(oalu, umat=U, vmat=V, rhsa=rhs, Sinv=so)
+    for kw in (dict(Sinv=sg), dict()):                  # with and without a precomputed core
+        xg = glau.app_smw_inv(galu, umat=U, vmat=V, rhsa=rhs, **kw)
+        assert _relerr(xg, xo) < 1e-10
+    dense = (K - sps.csr_matrix(U) @ V).toarray()
+    assert np.linalg.norm(dense @ xg - rhs) < 1e-10*np.linalg.norm(rhs)
+    # no low-rank part: plain solve; a matrix instead of a handle is factorised on the fly
+    assert _relerr(glau.app_smw_inv(galu, rhsa=rhs), oalu(rhs)) < 1e-11
+    assert _relerr(glau.app_smw_inv(K, umat=U, vmat=V, rhsa=rhs), xo) < 1e-10
+    # a11: factored Lyapunov-residual norm
+    A1, B1, C1 = (rng.standard_normal((NV, k)) for k in (7, 7, 3))
+    fg, fo = glau.comp_sqfnrm_factrd_lyap_res(A1, B1, C1), olau.comp_sqfnrm_factrd_lyap_res(A1, B1, C1)
+    assert abs(fg - fo) <= 1e-11*fo
+    big = A1 @ B1.T + B1 @ A1.T + C1 @ C1.T
+    assert abs(fg - np.linalg.norm(big)**2) <= 1e-10*fo
+
+
+@pytest.mark.timeout(900)
+def test_config2_bench_workload_parity(mods):
+    """BASELINE config[1] = the bench workload: cavity N=25 with the run_optcont.py parameters,
+    the first two backward steps from t=tE.  Gains and w < 1e-8, Z Z^T < 1e-9, equal ADI step
+    counts and equal compressed widths."""
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import scenarios as sc, dre_stepper as ds
+    prob, cs, kw = sc.config2(olau, N=25)
+    assert prob['NV'] == 4802 and prob['NP'] == 675
+    kw['tmesh'] = kw['tmesh'][-3:]
+    so, sg, io, ig = ds.MemStore(), ds.MemStore(), [], []
+    fo = ds.solve_flow_daeric(lau=olau, pru=opru, store=so, stepinfo=io,
+                              **dict(kw, gtdtstrargs=dict(kw['gtdtstrargs'])))
+    fg = ds.solve_flow_daeric(lau=glau, pru=gpru, store=sg, stepinfo=ig,
+                              **dict(kw, gtdtstrargs=dict(kw['gtdtstrargs'])))
+    assert sorted(fo) == sorted(fg) and len(io) == len(ig) == 2
+    for a, b in zip(io, ig):
+        assert a['adi_steps'] == b['adi_steps']
+        assert a['zp_cols'] == b['zp_cols'] and a['zc_cols'] == b['zc_cols']
+    for t in fo:
+        assert _relerr(sg[fg[t]['mtxtb']], so[fo[t]['mtxtb']]) < TOL_TRAJ
+        assert _relerr(sg[fg[t]['w']], so[fo[t]['w']]) < TOL_TRAJ
+        kz = fo[t]['mtxtb'].replace('__mtxtb', '__Z')
+        assert _zzt_relerr(sg[kz], so[kz]) < TOL_FACTOR
+
+
+@pytest.mark.timeout(900)
+def test_config2b_driv_cav_cont_parity(mods):
+    """Config 2b (driv_cav_cont.py:8-30: N=25, Nts=40, nu=1e-2, alphau=1e-4, k<=60, default
+    shifts): first backward step, through the plain reference signatures (no look-ahead)."""
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import scenarios as sc, dre_stepper as ds
+    prob, cs, kw = sc.config2b(olau, N=25)
+    kw['tmesh'] = kw['tmesh'][-2:]
+    so, sg, io, ig = ds.MemStore(), ds.MemStore(), [], []
+    fo = ds.solve_flow_daeric(lau=olau, pru=opru, store=so, stepinfo=io,
+                              **dict(kw, gtdtstrargs=dict(kw['gtdtstrargs'])))
+    fg = ds.solve_flow_daeric(lau=glau, pru=gpru, store=sg, stepinfo=ig, lookahead=0,
+                              **dict(kw, gtdtstrargs=dict(kw['gtdtstrargs'])))
+    assert io[0]['adi_steps'] == ig[0]['adi_steps'] and io[0]['zc_cols'] == ig[0]['zc_cols']
+    for t in fo:
+        assert _relerr(sg[fg[t]['mtxtb']], so[fo[t]['mtxtb']]) < TOL_TRAJ
+        assert _relerr(sg[fg[t]['w']], so[fo[t]['w']]) < TOL_TRAJ
+
+
+@pytest.mark.timeout(900)
+def test_config3_stated_mesh_parity(mods):
+    """Config 3 at its stated size (cyl_wake_cont.py:8-28 parameters, 44 x 16 channel mesh,
+    nu = 0.15/60): the steady-state branch optcont_main.py:488-514."""
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import scenarios as sc
+    prob, cs, kw = sc.config3(olau)
+    kw['nwtn_adi_dict'] = dict(kw['nwtn_adi_dict'], nwtn_max_steps=6)
+    ro = sc.steady_state_feedback(prob, cs, lau=olau, pru=opru, **kw)
+    rg = sc.steady_state_feedback(prob, cs, lau=glau, pru=gpru, **kw)
+    assert rg['info']['adi_steps'] == ro['info']['adi_steps']
+    assert _zzt_relerr(rg['Z'], ro['Z']) < TOL_FACTOR
+    assert _relerr(rg['mtxtb'], ro['mtxtb']) < TOL_FACTOR
+    assert _relerr(rg['w'], ro['w']) < TOL_TRAJ

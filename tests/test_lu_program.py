@@ -444,10 +444,10 @@ def test_worker_builds_the_image_in_the_callers_segment(cav10):
     try:
         np.frombuffer(seg.buf, dtype=np.uint8)[:] = 0xAB            # stale content must not survive
         for rep in range(2):                                         # fresh build, then template hit
-            name, nbytes, tf, tp, order = _lu_worker.factor_image_to_shm(a, (seg.name, seg.size))
+            name, nbytes, tf, tp, order, guard = _lu_worker.factor_image_to_shm(a, (seg.name, seg.size))
             assert name is None and nbytes == ref.nbytes
             assert np.array_equal(np.frombuffer(seg.buf, dtype=np.uint8, count=nbytes), ref)
-        name, nbytes, tf, tp, order = _lu_worker.factor_image_to_shm(a, (seg.name, 1000))
+        name, nbytes, tf, tp, order, guard = _lu_worker.factor_image_to_shm(a, (seg.name, 1000))
         assert name is not None and nbytes == ref.nbytes
         one = shared_memory.SharedMemory(name=name)
         try:
@@ -469,3 +469,40 @@ def test_worker_builds_the_image_in_the_callers_segment(cav10):
             except BufferError:
                 pass
         seg.unlink()
+
+
+def test_residual_guard_refactorises_in_safe_mode(monkeypatch):
+    """the workers check every factor image where it is built - the finished program
+    is executed on the host for one right-hand side (``ocb_lu_pack_host_checked``) and a
+    backward error above the tolerance triggers a second factorisation with full partial
+    pivoting and supernodes of at most 32 rows.  The reference test's randomly perturbed F
+    (cond ~1e8, one 512-row block) is the case that needs it; the Oseen matrices never do."""
+    prob = pb.drivcav_problem(15, 1.0)
+    M, A, J = prob['M'], prob['A'], prob['J']
+    NV = prob['NV']
+    oseen = _saddle(prob)
+    Fp = -M - 0.1*A - sps.random(NV, NV, density=0.03, format='csr', random_state=11)
+    hard = dv.sadpnt_matrix(Fp.T - 1.0*M.T, J)
+    monkeypatch.delenv('OCB_LU_GUARD_TOL', raising=False)
+    tol = _lu_worker._guard_tol()
+    flags = 2 | 4 | (2 << 4)
+    img, tf, tp, order, guard = _lu_worker.factor_image(dv._csc_args(oseen, dict(dv.LU_OPTIONS)) + (232448, flags))
+    assert guard[1] == 0 and guard[0] < 0.1*tol                 # fast path, far below the tolerance
+    img, tf, tp, order, guard = _lu_worker.factor_image(dv._csc_args(hard, dict(dv.LU_OPTIONS)) + (232448, flags))
+    assert guard[1] == 1 and guard[0] <= tol                    # re-factorised; now at substitution level
+    # guard off: the fast image is handed out, with the larger error
+    monkeypatch.setenv('OCB_LU_GUARD_TOL', '-1')
+    img2, tf, tp, order, guard2 = _lu_worker.factor_image(dv._csc_args(hard, dict(dv.LU_OPTIONS)) + (232448, flags))
+    assert guard2 == (None, 0) and img2.nbytes != img.nbytes
+    # the safe layout itself: no supernode wider than 32 rows, still reproduces SuperLU
+    n = hard.shape[0]
+    arrs = _lu_worker.factor_arrays(_lu_worker._safe_args(dv._csc_args(hard, dict(dv.LU_OPTIONS)) + (232448, flags)),
+                                    transposed=True)
+    prog = _program(arrs, n, flags=2 | 8)
+    assert prog[0]['max_w'] <= 32
+    B = np.random.default_rng(5).standard_normal((n, 2))
+    X = np.zeros((prog[0]['n_ext'], 2))
+    X[arrs[6]] = B
+    _execute(prog, X)
+    got = X[arrs[7]]
+    assert np.linalg.norm(hard @ got - B) <= 1e-14*sps.linalg.norm(hard)*np.linalg.norm(got)
