@@ -214,8 +214,14 @@ int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K,
  * Low-rank part (optional, m columns): Ue = [d_Ufb (NV x m dense); 0],
  * Ve = [Vt (m x NV) CSR, 0]  applied by Sherman-Morrison-Woodbury.
  * Blocks V_i are written side by side into d_Z (NV x ldz), block i at column i*k.
- * Stops after step i when ||V_i||_F / ||[V_1..V_i]||_F <= reltol or i == maxsteps.
- * h_relnorms (maxsteps doubles) receives the ratios; *h_steps the number of blocks. */
+ * Stops after step i when ||V_i||_F / ||[V_1..V_i]||_F <= reltol or i == maxsteps
+ * (maxsteps <= 8192).  The test is evaluated ON THE DEVICE (last CTA of the fused update kernel,
+ * same arithmetic and order as a host loop: z += v; rel = sqrt(v / z)); the host enqueues
+ * iterations in batches and every kernel of an iteration past the converged one returns at
+ * once, so there is no host round trip per step (OCB_ADI_CHUNK=1 restores one).
+ * h_relnorms (maxsteps doubles) receives the ratios; *h_steps the number of blocks.
+ * Threading: the library keeps one pinned scratch block and one side stream per process - call
+ * its entry points from one host thread at a time per device (distinct streams are fine). */
 /* Column-sharded runs: every rank iterates on its own slice of the right-hand-side
  * columns; the stopping test needs the GLOBAL ||V_i||_F^2.  When a hook is set (per calling
  * thread; NULL clears it) ocb_adi_run passes the local value through it after every step and

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace cg = cooperative_groups;
@@ -24,9 +25,12 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const double* __restr
                                                           int64_t ka, const double* __restrict__ W,
                                                           int64_t ldw, int64_t kb, int64_t n,
                                                           int64_t rows_per_split,
-                                                          double* __restrict__ P /*[split][ka][kb]*/) {
+                                                          double* __restrict__ P /*[split][ka][kb]*/,
+                                                          int sym) {
     __shared__ double Zs[GR_RK * GR_LD];
     __shared__ double Ws[GR_RK * GR_LD];
+    // sym: W == Z, G is symmetric: only the tiles on and below the diagonal are computed
+    if (sym && blockIdx.x < blockIdx.y) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t a0 = (int64_t)blockIdx.x * GR_TM, b0 = (int64_t)blockIdx.y * GR_TN;
     const int64_t r_beg = (int64_t)blockIdx.z * rows_per_split;
@@ -83,12 +87,15 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const double* __restr
 
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ P, int64_t ka,
                                                          int64_t kb, int nsplit,
-                                                         double* __restrict__ G, int64_t ldg) {
+                                                         double* __restrict__ G, int64_t ldg, int sym) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ka * kb) return;
+    int64_t r = e / kb, c = e % kb;
+    int64_t src = e;
+    if (sym && (r / GR_TM) < (c / GR_TN)) src = c * kb + r;   // tile above the diagonal: mirror
     double s = 0.0;
-    for (int z = 0; z < nsplit; ++z) s += P[(int64_t)z * ka * kb + e];
-    G[(e / kb) * ldg + (e % kb)] = s;
+    for (int z = 0; z < nsplit; ++z) s += P[(int64_t)z * ka * kb + src];
+    G[r * ldg + c] = s;
 }
 
 static void gram_plan(int64_t n, int64_t ka, int64_t kb, int* nsplit, int64_t* rps) {
@@ -105,6 +112,7 @@ static void gram_plan(int64_t n, int64_t ka, int64_t kb, int* nsplit, int64_t* r
 int gram_impl(const double* Z, int64_t ldz, int64_t ka, const double* W, int64_t ldw, int64_t kb,
               int64_t n, double* G, int64_t ldg, void* ws, int64_t ws_bytes, cudaStream_t st) {
     if (ka == 0 || kb == 0) return OCB_OK;
+    const int sym = (Z == W && ldz == ldw && ka == kb && ka > GR_TM) ? 1 : 0;   // G = Z^T Z
     int nsplit;
     int64_t rps;
     gram_plan(n, ka, kb, &nsplit, &rps);
@@ -114,10 +122,10 @@ int gram_impl(const double* Z, int64_t ldz, int64_t ka, const double* W, int64_t
         return OCB_ERR_CAPACITY;
     }
     dim3 grid((unsigned)((ka + GR_TM - 1) / GR_TM), (unsigned)((kb + GR_TN - 1) / GR_TN), nsplit);
-    gram_partial_kernel<<<grid, 256, 0, st>>>(Z, ldz, ka, W, ldw, kb, n, rps, (double*)ws);
+    gram_partial_kernel<<<grid, 256, 0, st>>>(Z, ldz, ka, W, ldw, kb, n, rps, (double*)ws, sym);
     OCB_LAUNCH_CHECK();
     gram_reduce_kernel<<<(unsigned)((ka * kb + 255) / 256), 256, 0, st>>>((const double*)ws, ka, kb,
-                                                                         nsplit, G, ldg);
+                                                                         nsplit, G, ldg, sym);
     OCB_LAUNCH_CHECK();
     return OCB_OK;
 }
@@ -352,10 +360,178 @@ __global__ void __launch_bounds__(256) jacobi_kernel(double* __restrict__ G, int
     }
 }
 
+// Small matrices (k <= EIG_SMALL_MAX): the same cyclic Jacobi in ONE CTA with G and V in shared
+// memory - a round costs two __syncthreads instead of two grid-wide barriers (the cooperative
+// kernel above spends ~1 us per barrier: 0.9 ms at k = 58, this one ~0.1 ms).
+constexpr int EIG_SMALL_MAX = 104;   // 2 * 104 * 105 doubles = 171 KB of shared memory
+
+__global__ void __launch_bounds__(1024) jacobi_small_kernel(double* __restrict__ Gg, int64_t ldg, int k,
+                                                           double* __restrict__ lam,
+                                                           double* __restrict__ Vg, int64_t ldv,
+                                                           int max_sweeps, double tol2,
+                                                           int* __restrict__ sweeps_out) {
+    extern __shared__ double sm[];
+    const int ld = k | 1;                        // odd leading dimension: fewer bank conflicts
+    double* G = sm;
+    double* V = G + (size_t)k * ld;
+    double* cs = V + (size_t)k * ld;             // c[np], s[np]
+    int* pq = (int*)(cs + 2 * ((k + 1) / 2 + 1));   // p[np], q[np]
+    __shared__ double red[2][32];
+    __shared__ double tot[2];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int kp = (k + 1) & ~1, np = kp / 2;
+    for (int e = tid; e < k * k; e += nth) {
+        const int r = e / k, c = e % k;
+        G[r * ld + c] = Gg[(int64_t)r * ldg + c];
+        V[r * ld + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int e = tid; e < k * k; e += nth) {
+            const int r = e / k, c = e % k;
+            const double v = G[r * ld + c];
+            if (r == c) dg = fma(v, v, dg); else off = fma(v, v, off);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            off += __shfl_xor_sync(0xffffffffu, off, o);
+            dg += __shfl_xor_sync(0xffffffffu, dg, o);
+        }
+        if ((tid & 31) == 0) { red[0][tid >> 5] = off; red[1][tid >> 5] = dg; }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0, b = 0.0;
+            for (int w = 0; w < (nth >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
+            tot[0] = a; tot[1] = b;
+        }
+        __syncthreads();
+        if (tot[0] <= tol2 * tot[1]) break;
+        for (int round = 0; round < kp - 1; ++round) {
+            for (int t = tid; t < np; t += nth) {
+                int p, q;
+                if (t == 0) { p = kp - 1; q = round; }
+                else {
+                    p = (round + t) % (kp - 1);
+                    q = (round - t + (kp - 1)) % (kp - 1);
+                }
+                if (p > q) { const int tmp = p; p = q; q = tmp; }
+                double c = 1.0, s = 0.0;
+                if (q < k) {
+                    const double app = G[p * ld + p], aqq = G[q * ld + q];
+                    const double apq = 0.5 * (G[p * ld + q] + G[q * ld + p]);
+                    if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * sqrt(fabs(app * aqq))) {
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double tt = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(tt * tt + 1.0);
+                        s = tt * c;
+                    }
+                } else { q = -1; }
+                pq[t] = p; pq[np + t] = q; cs[t] = c; cs[np + t] = s;
+            }
+            __syncthreads();
+            const int nblk = np * np;
+            for (int e = tid; e < nblk + k * np; e += nth) {
+                if (e < nblk) {
+                    const int a = e / np, b = e % np;
+                    const int pa = pq[a], qa = pq[np + a], pb = pq[b], qb = pq[np + b];
+                    const double ca = cs[a], sa = cs[np + a], cb = cs[b], sb = cs[np + b];
+                    if (qa < 0 && qb < 0) {
+                    } else if (qa < 0) {
+                        double* gp = G + pa * ld;
+                        const double g0 = gp[pb], g1 = gp[qb];
+                        gp[pb] = cb * g0 - sb * g1;
+                        gp[qb] = sb * g0 + cb * g1;
+                    } else if (qb < 0) {
+                        double* g0p = G + pa * ld + pb;
+                        double* g1p = G + qa * ld + pb;
+                        const double g0 = *g0p, g1 = *g1p;
+                        *g0p = ca * g0 - sa * g1;
+                        *g1p = sa * g0 + ca * g1;
+                    } else {
+                        double* rp = G + pa * ld;
+                        double* rq = G + qa * ld;
+                        const double g00 = rp[pb], g01 = rp[qb], g10 = rq[pb], g11 = rq[qb];
+                        const double h00 = cb * g00 - sb * g01, h01 = sb * g00 + cb * g01;
+                        const double h10 = cb * g10 - sb * g11, h11 = sb * g10 + cb * g11;
+                        double n00 = ca * h00 - sa * h10, n10 = sa * h00 + ca * h10;
+                        double n01 = ca * h01 - sa * h11, n11 = sa * h01 + ca * h11;
+                        if (a == b) { n01 = 0.0; n10 = 0.0; }
+                        rp[pb] = n00; rp[qb] = n01; rq[pb] = n10; rq[qb] = n11;
+                    }
+                } else {
+                    const int f = e - nblk;
+                    const int r = f / np, b = f % np;
+                    const int pb = pq[b], qb = pq[np + b];
+                    if (qb >= 0) {
+                        double* vr = V + r * ld;
+                        const double cb = cs[b], sb = cs[np + b];
+                        const double v0 = vr[pb], v1 = vr[qb];
+                        vr[pb] = cb * v0 - sb * v1;
+                        vr[qb] = sb * v0 + cb * v1;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // eigenvalues sorted descending (ties: lower index first), columns of V permuted accordingly
+    for (int i = tid; i < k; i += nth) {
+        const double li = G[i * ld + i];
+        int rank = 0;
+        for (int j = 0; j < k; ++j) {
+            const double lj = G[j * ld + j];
+            rank += (lj > li) || (lj == li && j < i);
+        }
+        pq[i] = rank;                // np + np >= k entries available
+        lam[rank] = li;
+    }
+    __syncthreads();
+    for (int e = tid; e < k * k; e += nth) {
+        const int r = e / k, c = e % k;
+        Vg[(int64_t)r * ldv + pq[c]] = V[r * ld + c];
+    }
+    if (tid == 0) *sweeps_out = sweep;
+}
+
+// d_sweeps (optional device int): when given, the sweep count is left on the device and the call
+// does not synchronise (the caller reads it together with its own results)
+int sym_eig_async(double* G, int64_t ldg, int64_t k, double* lam, double* V, int64_t ldv,
+                  int* d_sweeps, cudaStream_t st) {
+    if (k == 0) return OCB_OK;
+    if (k > EIG_SMALL_MAX) return -100;   // caller falls back to the cooperative kernel
+    const int ld = (int)k | 1;
+    const size_t smem = (size_t)(2 * k * ld + 2 * ((k + 1) / 2 + 1)) * sizeof(double) +
+                        (size_t)(2 * ((k + 1) / 2) + 2) * sizeof(int) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        OCB_CUDA(cudaFuncSetAttribute(jacobi_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    jacobi_small_kernel<<<1, 1024, smem, st>>>(G, ldg, (int)k, lam, V, ldv, 40, 1e-30, d_sweeps);
+    OCB_LAUNCH_CHECK();
+    return OCB_OK;
+}
+
 int sym_eig_impl(double* G, int64_t ldg, int64_t k, double* lam, double* V, int64_t ldv,
                  int32_t* h_sweeps, cudaStream_t st) {
     if (k == 0) { if (h_sweeps) *h_sweeps = 0; return OCB_OK; }
     if (k > EIG_MAXK) { set_error("sym_eig: k=%lld > %d", (long long)k, EIG_MAXK); return OCB_ERR_ARG; }
+    static const bool no_small = getenv("OCB_NO_SMALL_EIG") != nullptr;
+    if (k <= EIG_SMALL_MAX && !no_small) {
+        static int* d_sw = nullptr;
+        if (!d_sw) OCB_CUDA(cudaMalloc((void**)&d_sw, sizeof(int)));
+        const int rc = sym_eig_async(G, ldg, k, lam, V, ldv, d_sw, st);
+        if (rc) return rc;
+        if (h_sweeps) {
+            int sw = 0;
+            OCB_CUDA(cudaMemcpyAsync(&sw, d_sw, sizeof(int), cudaMemcpyDeviceToHost, st));
+            OCB_CUDA(cudaStreamSynchronize(st));
+            *h_sweeps = sw;
+            if (sw >= 40) { set_error("sym_eig: no convergence in 40 sweeps"); return OCB_ERR_NOCONV; }
+        }
+        return OCB_OK;
+    }
     int per_sm = 0;
     OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_kernel, 256, 0));
     const int64_t np = (k + 1) / 2;

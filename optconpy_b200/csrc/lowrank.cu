@@ -3,6 +3,7 @@
 //   * the LR-ADI loop with Sherman-Morrison-Woodbury corrections (K6/K7 fused update + norm)
 //   * single SMW saddle-point solves, the feedback product  Mt (Z (Z^T tB)).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <math.h>
 #include <vector>
@@ -14,16 +15,19 @@ namespace ocb {
 // from the other translation units
 int spmm_launch(int64_t nrows, const int32_t* rp, const int32_t* ci, const double* va,
                 const double* X, int64_t ldx, double* Y, int64_t ldy, int64_t k, double alpha,
-                double beta, cudaStream_t st);
+                double beta, cudaStream_t st, const int* skip = nullptr);
 int lu_solve_impl(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_b, double* X,
                   int64_t ldx, int64_t nrows_x, int64_t k, void* ws, int64_t ws_bytes,
-                  cudaStream_t st);
+                  cudaStream_t st, const int* skip = nullptr);
+void lu_solve_prof_discard_last(int64_t n);
 int gram_impl(const double* Z, int64_t ldz, int64_t ka, const double* W, int64_t ldw, int64_t kb,
               int64_t n, double* G, int64_t ldg, void* ws, int64_t ws_bytes, cudaStream_t st);
 int tall_gemm_impl(const double* Z, int64_t ldz, int64_t n, int64_t k, const double* T, int64_t ldt,
                    int64_t kc, double* C, int64_t ldc, double alpha, double beta, cudaStream_t st);
 int sym_eig_impl(double* G, int64_t ldg, int64_t k, double* lam, double* V, int64_t ldv,
                  int32_t* h_sweeps, cudaStream_t st);
+int sym_eig_async(double* G, int64_t ldg, int64_t k, double* lam, double* V, int64_t ldv,
+                  int* d_sweeps, cudaStream_t st);
 int smw_core_inv(const double* C, int64_t ldc, int m, double* Sinv, int* flag, cudaStream_t st);
 
 // optional hook that turns the local ||V_i||_F^2 of an ADI step into the global one when the
@@ -201,16 +205,126 @@ __global__ void scale_cols_kernel(const double* __restrict__ U, int64_t ldu, int
     Us[(int64_t)i * lds + j] = U[(int64_t)i * ldu + j] / sqrt(lam[j]);
 }
 
+// ---------------------------------------------------------------------------------
+// Gram route (K <= GRAM_K_MAX): G = Z^T Z once on the FP64 tensor pipe (DMMA, symmetric half),
+// then the SAME pivoted Cholesky on the explicit K x K matrix in ONE cooperative kernel: one
+// grid-wide barrier per pivot, no pass over Z per pivot and no host round trip in the loop.
+//   step t:  p = argmax d (ties: lowest index);  stop if t == rmax or d_p <= eta * d_max(0)
+//            Rt[j][t] = (G[j][p] - sum_{s<t} Rt[p][s] Rt[j][s]) / sqrt(d_p);  d[j] -= Rt[j][t]^2
+// ---------------------------------------------------------------------------------
+constexpr int64_t GRAM_K_MAX = 4096;
+constexpr int CG_THREADS = 256, CG_MAXBLOCKS = 64;
+
+__global__ void __launch_bounds__(CG_THREADS) chol_gram_kernel(const double* __restrict__ G, int64_t ldg,
+                                                              int64_t K, int rmax, double eta,
+                                                              double* __restrict__ Rt, int64_t ldr,
+                                                              double* __restrict__ d,
+                                                              double* __restrict__ pval, int* __restrict__ pidx,
+                                                              CholState* __restrict__ st) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double rp[1024];
+    __shared__ double bv[CG_THREADS / 32];
+    __shared__ int bi[CG_THREADS / 32];
+    __shared__ double sp_val;
+    __shared__ int sp_idx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gsize = (int64_t)gridDim.x * blockDim.x;
+    auto better = [](double v, int i, double bvv, int bii) {
+        return v > bvv || (v == bvv && i >= 0 && (bii < 0 || i < bii));
+    };
+    // local arg-max of d over the columns of this CTA -> pval/pidx[blockIdx.x]
+    auto publish = [&](double best, int arg) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (better(ov, oi, best, arg)) { best = ov; arg = oi; }
+        }
+        if (lane == 0) { bv[warp] = best; bi[warp] = arg; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < CG_THREADS / 32; ++w)
+                if (better(bv[w], bi[w], best, arg)) { best = bv[w]; arg = bi[w]; }
+            pval[blockIdx.x] = best;
+            pidx[blockIdx.x] = arg;
+        }
+    };
+    {
+        double best = -1.0;
+        int arg = -1;
+        for (int64_t j = gtid; j < K; j += gsize) {
+            const double v = G[j * ldg + j];
+            d[j] = v;
+            if (better(v, (int)j, best, arg)) { best = v; arg = (int)j; }
+        }
+        publish(best, arg);
+    }
+    grid.sync();
+    double d0max = 0.0;
+    for (int t = 0;; ++t) {
+        // every CTA reduces the partial arg-maxima (identical result everywhere)
+        if (warp == 0) {
+            double best = -1.0;
+            int arg = -1;
+            for (int b = lane; b < (int)gridDim.x; b += 32)
+                if (better(pval[b], pidx[b], best, arg)) { best = pval[b]; arg = pidx[b]; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (better(ov, oi, best, arg)) { best = ov; arg = oi; }
+            }
+            if (lane == 0) { sp_val = best; sp_idx = arg; }
+        }
+        __syncthreads();
+        const double dp = sp_val;
+        const int p = sp_idx;
+        if (t == 0) d0max = dp;
+        if (t >= rmax || p < 0 || !(dp > eta * d0max) || !(dp > 0.0)) {
+            if (gtid == 0) { st->done = 1; st->rank = t; st->d0max = d0max; }
+            return;   // uniform over the grid
+        }
+        for (int s2 = tid; s2 < t; s2 += blockDim.x) rp[s2] = Rt[(int64_t)p * ldr + s2];
+        __syncthreads();
+        const double inv = 1.0 / sqrt(dp);
+        double best = -1.0;
+        int arg = -1;
+        for (int64_t j = gtid; j < K; j += gsize) {
+            const double* rj = Rt + j * ldr;
+            double s0 = 0.0, s1 = 0.0;
+            int s2 = 0;
+            for (; s2 + 1 < t; s2 += 2) { s0 = fma(rp[s2], rj[s2], s0); s1 = fma(rp[s2 + 1], rj[s2 + 1], s1); }
+            if (s2 < t) s0 = fma(rp[s2], rj[s2], s0);
+            const double row = (G[j * ldg + p] - (s0 + s1)) * inv;
+            Rt[j * ldr + t] = row;
+            const double dj = ((int)j == p) ? -1.0 : d[j] - row * row;
+            d[j] = dj;
+            if (better(dj, (int)j, best, arg)) { best = dj; arg = (int)j; }
+        }
+        __syncthreads();   // bv/bi/rp are reused
+        publish(best, arg);
+        grid.sync();
+    }
+}
+
 struct CompressWs {
-    double *d, *Rt, *S, *U, *lam, *Us, *T, *gws, *gpart;
+    double *d, *Rt, *S, *U, *lam, *Us, *T, *gws, *gpart, *G, *pval;
+    int *pidx, *sweeps;
     CholState* st;
     int64_t gws_bytes;
 };
+
+static bool gram_route(int64_t K) {
+    static const bool off = getenv("OCB_COMPRESS_IMPLICIT") != nullptr;
+    return !off && K <= GRAM_K_MAX;
+}
 
 static int64_t compress_carve(void* ws, int64_t bytes, int64_t n, int64_t K, int64_t rmax, CompressWs* o) {
     WsCarver c(ws, bytes);
     CompressWs w;
     w.st = c.take<CholState>(1);
+    w.sweeps = c.take<int>(4);
+    w.pval = c.take<double>(CG_MAXBLOCKS);
+    w.pidx = c.take<int>(CG_MAXBLOCKS);
     w.d = c.take<double>(K);
     w.gpart = c.take<double>(K * CH_SPLIT);
     w.Rt = c.take<double>(K * rmax);
@@ -220,6 +334,11 @@ static int64_t compress_carve(void* ws, int64_t bytes, int64_t n, int64_t K, int
     w.Us = c.take<double>(rmax * rmax);
     w.T = c.take<double>(K * rmax);
     w.gws_bytes = ocb_gram_ws_bytes(K, rmax, rmax);
+    w.G = nullptr;
+    if (gram_route(K)) {
+        w.G = c.take<double>(K * K);
+        w.gws_bytes = std::max(w.gws_bytes, ocb_gram_ws_bytes(n, K, K));
+    }
     w.gws = (double*)c.take<char>(w.gws_bytes);
     if (o) *o = w;
     return c.off + 256;
@@ -253,45 +372,75 @@ int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K, double th
     double* hp = pinned_scratch();
     OCB_ARG(hp != nullptr, "pinned scratch allocation failed");
     OCB_CUDA(cudaMemsetAsync(w.st, 0, sizeof(CholState), st));
-    const unsigned cblocks = (unsigned)((K + 31) / 32);
-    chol_colsq_kernel<<<cblocks, CH_THREADS, 0, st>>>(d_Z, ldz, n, K, w.d);
-    OCB_LAUNCH_CHECK();
     CholState* hst = (CholState*)hp;
-    int t = 0;
-    bool done = false;
-    while (!done) {
-        const int batch_end = (int)std::min<int64_t>(rmax, t + 32);
-        for (; t < batch_end; ++t) {
-            chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
-            OCB_LAUNCH_CHECK();
-            chol_col_kernel<<<dim3(cblocks, CH_SPLIT), CH_THREADS, 0, st>>>(d_Z, ldz, n, K, w.gpart, w.st);
-            OCB_LAUNCH_CHECK();
-            chol_col_finish_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(w.gpart, K, t, w.Rt, rmax,
-                                                                                w.d, w.st);
-            OCB_LAUNCH_CHECK();
-        }
-        if (t >= rmax) {  // closes the factorisation at rank rmax if the rule never fired
-            chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
-            OCB_LAUNCH_CHECK();
-        }
+    int rc;
+    if (w.G) {
+        // Gram route: one DMMA product, then the whole pivoted Cholesky in one cooperative launch
+        rc = gram_impl(d_Z, ldz, K, d_Z, ldz, K, n, w.G, K, w.gws, w.gws_bytes, st);
+        if (rc) return rc;
+        int per_sm = 0;
+        OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_gram_kernel, CG_THREADS, 0));
+        int64_t blocks = std::min<int64_t>((K + CG_THREADS - 1) / CG_THREADS * 4, CG_MAXBLOCKS);
+        blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)std::max(per_sm, 1) * sm_count()));
+        const double* Gc = w.G;
+        int64_t ldg = K, Kk = K, ldr = rmax;
+        int rmx = (int)rmax;
+        void* args[] = {(void*)&Gc, &ldg, &Kk, &rmx, &eta, &w.Rt, &ldr, &w.d, &w.pval, &w.pidx, &w.st};
+        OCB_CUDA(cudaLaunchCooperativeKernel((void*)chol_gram_kernel, dim3((unsigned)blocks), dim3(CG_THREADS),
+                                             args, 0, st));
+        count_launch();
         OCB_CUDA(cudaMemcpyAsync(hst, w.st, sizeof(CholState), cudaMemcpyDeviceToHost, st));
         OCB_CUDA(cudaStreamSynchronize(st));
-        done = hst->done != 0;
+    } else {
+        const unsigned cblocks = (unsigned)((K + 31) / 32);
+        chol_colsq_kernel<<<cblocks, CH_THREADS, 0, st>>>(d_Z, ldz, n, K, w.d);
+        OCB_LAUNCH_CHECK();
+        int t = 0;
+        bool done = false;
+        while (!done) {
+            const int batch_end = (int)std::min<int64_t>(rmax, t + 32);
+            for (; t < batch_end; ++t) {
+                chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
+                OCB_LAUNCH_CHECK();
+                chol_col_kernel<<<dim3(cblocks, CH_SPLIT), CH_THREADS, 0, st>>>(d_Z, ldz, n, K, w.gpart, w.st);
+                OCB_LAUNCH_CHECK();
+                chol_col_finish_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(w.gpart, K, t, w.Rt, rmax,
+                                                                                    w.d, w.st);
+                OCB_LAUNCH_CHECK();
+            }
+            if (t >= rmax) {  // closes the factorisation at rank rmax if the rule never fired
+                chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
+                OCB_LAUNCH_CHECK();
+            }
+            OCB_CUDA(cudaMemcpyAsync(hst, w.st, sizeof(CholState), cudaMemcpyDeviceToHost, st));
+            OCB_CUDA(cudaStreamSynchronize(st));
+            done = hst->done != 0;
+        }
     }
     const int r = hst->rank;
     h_info3[1] = r;
     if (r == 0) return OCB_OK;
     // core: S = R R^T (r x r) = Rt^T Rt, eigen-decomposition, sigma = sqrt(lam)
-    int rc = gram_impl(w.Rt, rmax, r, w.Rt, rmax, r, K, w.S, rmax, w.gws, w.gws_bytes, st);
+    rc = gram_impl(w.Rt, rmax, r, w.Rt, rmax, r, K, w.S, rmax, w.gws, w.gws_bytes, st);
     if (rc) return rc;
     int32_t sweeps = 0;
-    rc = sym_eig_impl(w.S, rmax, r, w.lam, w.U, rmax, &sweeps, st);
-    if (rc) return rc;
-    h_info3[2] = sweeps;
     double* hlam = hp + 64;
     OCB_ARG(r <= 1900, "compress: rank above pinned scratch");
+    rc = sym_eig_async(w.S, rmax, r, w.lam, w.U, rmax, w.sweeps, st);
+    const bool small_eig = rc == OCB_OK;
+    if (rc == -100) {
+        rc = sym_eig_impl(w.S, rmax, r, w.lam, w.U, rmax, &sweeps, st);
+        if (rc) return rc;
+    } else if (rc) {
+        return rc;
+    } else {
+        OCB_CUDA(cudaMemcpyAsync(hp + 32, w.sweeps, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     OCB_CUDA(cudaMemcpyAsync(hlam, w.lam, r * sizeof(double), cudaMemcpyDeviceToHost, st));
     OCB_CUDA(cudaStreamSynchronize(st));
+    if (small_eig) sweeps = *(int*)(hp + 32);
+    if (sweeps >= 40) { set_error("compress: Jacobi did not converge in 40 sweeps"); return OCB_ERR_NOCONV; }
+    h_info3[2] = sweeps;
     int keep = 0;
     for (int i = 0; i < r; ++i) {
         const double sg = hlam[i] > 0.0 ? sqrt(hlam[i]) : 0.0;
@@ -323,9 +472,25 @@ int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K, double th
 // =================================================================================
 namespace ocb {
 
+// Device-resident state of one LR-ADI run (or one SMW solve): the stopping test
+//     ||V_i||_F / ||[V_1..V_i]||_F <= reltol
+// is evaluated ON THE DEVICE by the last CTA of the update kernel, in the same arithmetic and
+// order the host loop used (z += v; rel = sqrt(v / z)), so that the iteration count is the
+// oracle's.  Once `done` is set every later kernel of the loop returns immediately: the host
+// enqueues iterations ahead without a round trip per step and reads the state only now and then.
+struct AdiState {
+    double z_nsq;           // running ||Z||_F^2
+    double v_nsq;           // ||V_i||_F^2 of the last executed step
+    int done;               // 1: converged, later launches are no-ops
+    int steps;              // executed steps
+    int singular;           // SMW core was singular (smw_core_inv_kernel)
+    unsigned int counter;   // CTA arrival counter of the update kernel (per call: re-entrant)
+};
+
 // S2 (m x k) = Sinv (m x m) * small (m x k)
 __global__ void smw_s2_kernel(const double* __restrict__ Sinv, int m, const double* __restrict__ small,
-                              int64_t k, double* __restrict__ S2) {
+                              int64_t k, double* __restrict__ S2, const int* __restrict__ skip) {
+    if (skip && *skip) return;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (int64_t)m * k) return;
     const int r = (int)(e / k);
@@ -335,9 +500,8 @@ __global__ void smw_s2_kernel(const double* __restrict__ Sinv, int m, const doub
     S2[e] = s;
 }
 
-__device__ unsigned int g_upd_counter = 0;
-
-// Vnew = a*Vold + b*(Y + AiU*S2);  *nrm2 = ||Vnew||_F^2  (per-CTA partials, last CTA sums in order)
+// Vnew = a*Vold + b*(Y + AiU*S2);  ||Vnew||_F^2 (per-CTA partials, last CTA sums in order) and,
+// with decide_step >= 0, the stopping test of ADI step decide_step
 template <int MMAX>
 __global__ void __launch_bounds__(256) adi_update_kernel(const double* __restrict__ Vold, int64_t ldv,
                                                         const double* __restrict__ Y, int64_t ldy,
@@ -346,12 +510,15 @@ __global__ void __launch_bounds__(256) adi_update_kernel(const double* __restric
                                                         double* __restrict__ Vnew, int64_t ldn,
                                                         int64_t nrows, int64_t k, double a, double b,
                                                         double* __restrict__ partials,
-                                                        double* __restrict__ nrm2,
+                                                        AdiState* __restrict__ state,
                                                         const double* __restrict__ Sinv,
-                                                        const double* __restrict__ small) {
+                                                        const double* __restrict__ small,
+                                                        int decide_step, double reltol,
+                                                        double* __restrict__ relnorms) {
     extern __shared__ double s2s[];   // fused variant: S2 = Sinv * small, recomputed per CTA
     __shared__ double red[8];
     __shared__ bool last;
+    if (state->done) return;          // uniform over the grid (set by an earlier launch)
     if (MMAX > 0 && Sinv != nullptr) {
         // same formula and summation order as smw_s2_kernel: bit-identical, one launch less
         for (int64_t e = threadIdx.x; e < (int64_t)m * k; e += blockDim.x) {
@@ -387,7 +554,7 @@ __global__ void __launch_bounds__(256) adi_update_kernel(const double* __restric
         for (int w = 0; w < 8; ++w) s += red[w];
         partials[blockIdx.x] = s;
         __threadfence();
-        const unsigned int done = atomicAdd(&g_upd_counter, 1u);
+        const unsigned int done = atomicAdd(&state->counter, 1u);
         last = (done == gridDim.x - 1);
     }
     __syncthreads();
@@ -395,8 +562,16 @@ __global__ void __launch_bounds__(256) adi_update_kernel(const double* __restric
         __threadfence();
         double s = 0.0;
         for (unsigned int bI = 0; bI < gridDim.x; ++bI) s += ((volatile double*)partials)[bI];
-        *nrm2 = s;
-        g_upd_counter = 0;
+        state->v_nsq = s;
+        state->counter = 0;
+        if (decide_step >= 0) {
+            const double z = state->z_nsq + s;
+            state->z_nsq = z;
+            const double rel = z > 0.0 ? sqrt(s / z) : 0.0;
+            relnorms[decide_step] = rel;
+            state->steps = decide_step + 1;
+            if (!(rel > reltol)) state->done = 1;
+        }
     }
 }
 
@@ -408,27 +583,19 @@ constexpr int64_t UPD_FUSE_MAX = 4096;   // m*k doubles of shared memory for the
 // m*k <= UPD_FUSE_MAX); otherwise S2 must hold it already.
 static int adi_update(const double* Vold, int64_t ldv, const double* Y, int64_t ldy, const double* AiU,
                       int64_t lda, int m, const double* S2, double* Vnew, int64_t ldn, int64_t nrows,
-                      int64_t k, double a, double b, double* partials, double* nrm2, cudaStream_t st,
-                      const double* Sinv = nullptr, const double* small = nullptr) {
+                      int64_t k, double a, double b, double* partials, AdiState* state, cudaStream_t st,
+                      const double* Sinv = nullptr, const double* small = nullptr, int decide_step = -1,
+                      double reltol = 0.0, double* relnorms = nullptr) {
     const int64_t total = nrows * k;
     const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(UPD_MAXBLOCKS, (total + 1023) / 1024));
     const size_t smem = (m > 0 && Sinv) ? (size_t)m * k * sizeof(double) : 0;
     if (m > 0)
-        adi_update_kernel<1><<<blocks, 256, smem, st>>>(Vold, ldv, Y, ldy, AiU, lda, m, S2, Vnew, ldn, nrows, k, a, b, partials, nrm2, Sinv, small);
+        adi_update_kernel<1><<<blocks, 256, smem, st>>>(Vold, ldv, Y, ldy, AiU, lda, m, S2, Vnew, ldn, nrows, k, a, b, partials, state, Sinv, small, decide_step, reltol, relnorms);
     else
-        adi_update_kernel<0><<<blocks, 256, 0, st>>>(Vold, ldv, Y, ldy, AiU, lda, 0, S2, Vnew, ldn, nrows, k, a, b, partials, nrm2, nullptr, nullptr);
+        adi_update_kernel<0><<<blocks, 256, 0, st>>>(Vold, ldv, Y, ldy, AiU, lda, 0, S2, Vnew, ldn, nrows, k, a, b, partials, state, nullptr, nullptr, decide_step, reltol, relnorms);
     OCB_LAUNCH_CHECK();
     return OCB_OK;
 }
-
-struct SmwWs {
-    double *AiU;      // [nshifts][nrows_aiu][m]
-    double *Sinv;     // [nshifts][m][m]
-    double *core;     // [m][m]
-    double *small;    // [m][k]
-    double *S2;       // [m][k]
-    int* flag;
-};
 
 // prepare the SMW pieces of one factorisation: AiU = A^-1 [U;0] (first nrows rows), Sinv
 static int smw_prepare(const ocb_lu* lu, int64_t NV, const double* Ufb, int64_t ldu, int m,
@@ -453,6 +620,8 @@ int ocb_adi_set_norm_hook(void (*hook)(double*, void*), void* ctx) {
     return OCB_OK;
 }
 
+constexpr int64_t ADI_MAXSTEPS_CAP = 8192;   // device array of relative norms
+
 int64_t ocb_adi_ws_bytes(int64_t n_sad, int64_t k, int64_t m, int64_t nshifts, ocb_lu* const* lus) {
     using namespace ocb;
     int64_t lws = 0;
@@ -462,8 +631,8 @@ int64_t ocb_adi_ws_bytes(int64_t n_sad, int64_t k, int64_t m, int64_t nshifts, o
     c.take<double>(n_sad * k);                   // T = Mt V
     c.take<double>(n_sad * k);                   // Y
     c.take<double>(UPD_MAXBLOCKS);               // partials
-    c.take<double>(8);                           // norm
-    c.take<int>(8);                              // flag
+    c.take<AdiState>(1);                         // device-resident loop state
+    c.take<double>(ADI_MAXSTEPS_CAP);            // relative norms
     c.take<double>(nshifts * n_sad * std::max<int64_t>(m, 1));
     c.take<double>(nshifts * m * m + 1);
     c.take<double>(nshifts * m * m + 1);
@@ -472,6 +641,11 @@ int64_t ocb_adi_ws_bytes(int64_t n_sad, int64_t k, int64_t m, int64_t nshifts, o
     c.take<char>(lws);
     return c.off + 256;
 }
+
+// number of steps the previous run of this thread took: the first batch of iterations that is
+// enqueued without looking at the result (consecutive Newton steps / time steps of the DRE take
+// nearly the same number of ADI steps)
+static thread_local int64_t g_adi_steps_hint = 0;
 
 int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int64_t NV, int64_t NP,
                 const int32_t* d_Mt_rowptr, const int32_t* d_Mt_colidx, const double* d_Mt_vals,
@@ -483,7 +657,7 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
     OCB_ARG(lus && h_shifts && nshifts >= 1 && NV >= 1 && NP >= 0 && k >= 1, "adi sizes");
     OCB_ARG(d_Mt_rowptr && d_W && d_Z && h_relnorms && h_steps && d_ws, "adi null");
     OCB_ARG(m == 0 || (d_Ufb && d_Vt_rowptr && m <= 32 && ldu >= m), "adi low-rank part");
-    OCB_ARG(maxsteps >= 1 && ldw >= k, "adi steps/ld");
+    OCB_ARG(maxsteps >= 1 && maxsteps <= ADI_MAXSTEPS_CAP && ldw >= k, "adi steps/ld");
     for (int64_t i = 0; i < nshifts; ++i) OCB_ARG(h_shifts[i] < 0.0, "adi shifts must be negative reals");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_sad = NV + NP;
@@ -499,8 +673,8 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
     double* T = c.take<double>(n_sad * k);
     double* Y = c.take<double>(n_sad * k);
     double* partials = c.take<double>(UPD_MAXBLOCKS);
-    double* dnorm = c.take<double>(8);
-    int* flag = c.take<int>(8);
+    AdiState* state = c.take<AdiState>(1);
+    double* drel = c.take<double>(ADI_MAXSTEPS_CAP);
     double* AiU = c.take<double>(nshifts * n_sad * std::max<int64_t>(m, 1));
     double* Sinv = c.take<double>(nshifts * m * m + 1);
     double* core = c.take<double>(nshifts * m * m + 1);
@@ -509,9 +683,11 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
     void* lws = c.take<char>(lws_bytes);
     double* hp = pinned_scratch();
     OCB_ARG(hp != nullptr, "pinned scratch allocation failed");
-    OCB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 8, st));
+    AdiState* hstate = (AdiState*)hp;
+    OCB_CUDA(cudaMemsetAsync(state, 0, sizeof(AdiState), st));
+    int* flag = &state->singular;
+    const int* skip = &state->done;
     std::vector<char> prepared(nshifts, 0);
-    (void)T;
     // The Sherman-Morrison-Woodbury pieces of the shifts (A_i^-1 U, 8 columns each) do not
     // depend on the iteration: they are all launched up front on a side stream, so that they
     // fill the SMs the narrow ADI solves leave idle; the main stream waits for shift i's
@@ -532,75 +708,106 @@ int ocb_adi_run(ocb_lu* const* lus, const double* h_shifts, int64_t nshifts, int
             }
         }
     }
+    // error paths below must not leave side-stream work running on the caller's workspace
+    auto fail = [&](int rc) {
+        if (side) cudaStreamSynchronize(side->s);
+        cudaStreamSynchronize(st);
+        return rc;
+    };
 
+    // One ADI iteration = SpMM, multi-RHS solve, (SMW: small SpMM), fused update + norm + the
+    // stopping test.  The test runs on the device; the host only enqueues.  It looks at the
+    // state after a first batch sized by the previous run and then every few steps; the
+    // iterations enqueued past the converged one are no-ops (their kernels see done = 1).
+    const bool hooked = g_norm_hook != nullptr;   // column-sharded run: the host decides, step by step
+    static const int chunk_env = getenv("OCB_ADI_CHUNK") ? atoi(getenv("OCB_ADI_CHUNK")) : 0;
+    const int64_t chunk_next = chunk_env > 0 ? chunk_env : 4;
+    int64_t chunk = hooked ? 1 : (chunk_env > 0 ? chunk_env : (g_adi_steps_hint > 1 ? g_adi_steps_hint : 8));
     double z_nsq = 0.0;
-    int64_t step = 0;
+    int64_t step = 0;          // iterations enqueued so far
+    int64_t steps_done = 0;    // iterations that really ran
+    bool done = false;
     *h_steps = 0;
-    while (step < maxsteps) {
-        if ((step + 1) * k > z_capacity_cols || (step + 1) * k > ldz) {
-            set_error("adi: Z capacity (%lld cols) exhausted at step %lld", (long long)z_capacity_cols,
-                      (long long)step);
-            return OCB_ERR_CAPACITY;
-        }
-        const int64_t i = step % nshifts, ip = (step + nshifts - 1) % nshifts;
-        const ocb_lu* lu = lus[i];
-        int rc;
-        if (m > 0 && !prepared[i]) {
-            if (side) {
-                OCB_CUDA(cudaStreamWaitEvent(st, side->ev[i], 0));
+    while (!done && step < maxsteps) {
+        const int64_t batch_end = std::min<int64_t>(maxsteps, step + chunk);
+        for (; step < batch_end; ++step) {
+            if ((step + 1) * k > z_capacity_cols || (step + 1) * k > ldz) {
+                set_error("adi: Z capacity (%lld cols) exhausted at step %lld", (long long)z_capacity_cols,
+                          (long long)step);
+                return fail(OCB_ERR_CAPACITY);
+            }
+            const int64_t i = step % nshifts, ip = (step + nshifts - 1) % nshifts;
+            const ocb_lu* lu = lus[i];
+            int rc;
+            if (m > 0 && !prepared[i]) {
+                if (side) {
+                    OCB_CUDA(cudaStreamWaitEvent(st, side->ev[i], 0));
+                } else {
+                    rc = smw_prepare(lu, NV, d_Ufb, ldu, (int)m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals,
+                                     AiU + i * NV * m, NV, core + i * m * m, Sinv + i * m * m, flag, lws,
+                                     lws_bytes, st);
+                    if (rc) return fail(rc);
+                }
+                prepared[i] = 1;
+            }
+            const double* Vprev = step > 0 ? d_Z + (step - 1) * k : nullptr;
+            double* Vnew = d_Z + step * k;
+            if (step == 0) {
+                rc = lu_solve_impl(lu, d_W, ldw, NV, Y, k, NV, k, lws, lws_bytes, st, skip);
             } else {
-                rc = smw_prepare(lu, NV, d_Ufb, ldu, (int)m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals,
-                                 AiU + i * NV * m, NV, core + i * m * m, Sinv + i * m * m, flag, lws,
-                                 lws_bytes, st);
-                if (rc) return rc;
+                rc = spmm_launch(NV, d_Mt_rowptr, d_Mt_colidx, d_Mt_vals, Vprev, ldz, T, k, k, 1.0, 0.0, st, skip);
+                if (rc) return fail(rc);
+                rc = lu_solve_impl(lu, T, k, NV, Y, k, NV, k, lws, lws_bytes, st, skip);
             }
-            prepared[i] = 1;
-        }
-        const double* Vprev = step > 0 ? d_Z + (step - 1) * k : nullptr;
-        double* Vnew = d_Z + step * k;
-        if (step == 0) {
-            rc = lu_solve_impl(lu, d_W, ldw, NV, Y, k, NV, k, lws, lws_bytes, st);
-        } else {
-            rc = spmm_launch(NV, d_Mt_rowptr, d_Mt_colidx, d_Mt_vals, Vprev, ldz, T, k, k, 1.0, 0.0, st);
-            if (rc) return rc;
-            rc = lu_solve_impl(lu, T, k, NV, Y, k, NV, k, lws, lws_bytes, st);
-        }
-        if (rc) return rc;
-        const bool fuse_s2 = m > 0 && m * k <= UPD_FUSE_MAX;
-        if (m > 0) {
-            rc = spmm_launch(m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals, Y, k, small, k, k, 1.0, 0.0, st);
-            if (rc) return rc;
-            if (!fuse_s2) {
-                smw_s2_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, st>>>(Sinv + i * m * m, (int)m, small, k, S2);
-                OCB_LAUNCH_CHECK();
+            if (rc) return fail(rc);
+            const bool fuse_s2 = m > 0 && m * k <= UPD_FUSE_MAX;
+            if (m > 0) {
+                rc = spmm_launch(m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals, Y, k, small, k, k, 1.0, 0.0, st, skip);
+                if (rc) return fail(rc);
+                if (!fuse_s2) {
+                    smw_s2_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, st>>>(Sinv + i * m * m, (int)m, small, k, S2, skip);
+                    OCB_LAUNCH_CHECK();
+                }
             }
+            double a, b;
+            if (step == 0) { a = 0.0; b = sqrt(-2.0 * h_shifts[0]); }
+            else {
+                const double cs = sqrt(h_shifts[i] / h_shifts[ip]);
+                a = cs;
+                b = -cs * (h_shifts[i] + h_shifts[ip]);
+            }
+            rc = adi_update(Vprev, ldz, Y, k, AiU + i * NV * m, m, (int)m, S2, Vnew, ldz, NV, k, a, b,
+                            partials, state, st, fuse_s2 ? Sinv + i * m * m : nullptr, fuse_s2 ? small : nullptr,
+                            hooked ? -1 : (int)step, reltol, drel);
+            if (rc) return fail(rc);
         }
-        double a, b;
-        if (step == 0) { a = 0.0; b = sqrt(-2.0 * h_shifts[0]); }
-        else {
-            const double cs = sqrt(h_shifts[i] / h_shifts[ip]);
-            a = cs;
-            b = -cs * (h_shifts[i] + h_shifts[ip]);
-        }
-        rc = adi_update(Vprev, ldz, Y, k, AiU + i * NV * m, m, (int)m, S2, Vnew, ldz, NV, k, a, b,
-                        partials, dnorm, st, fuse_s2 ? Sinv + i * m * m : nullptr, fuse_s2 ? small : nullptr);
-        if (rc) return rc;
-        OCB_CUDA(cudaMemcpyAsync(hp, dnorm, sizeof(double), cudaMemcpyDeviceToHost, st));
-        OCB_CUDA(cudaMemcpyAsync(hp + 1, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OCB_CUDA(cudaMemcpyAsync(hstate, state, sizeof(AdiState), cudaMemcpyDeviceToHost, st));
         OCB_CUDA(cudaStreamSynchronize(st));
-        if (*(int*)(hp + 1) != 0) {
-            set_error("adi: singular Sherman-Morrison-Woodbury core at shift %lld", (long long)i);
-            return OCB_ERR_SINGULAR;
+        if (hstate->singular != 0) {
+            set_error("adi: singular Sherman-Morrison-Woodbury core");
+            return fail(OCB_ERR_SINGULAR);
         }
-        double v_nsq = hp[0];
-        if (g_norm_hook) g_norm_hook(&v_nsq, g_norm_hook_ctx);   // column-sharded run: global norm
-        z_nsq += v_nsq;
-        const double rel = z_nsq > 0.0 ? sqrt(v_nsq / z_nsq) : 0.0;
-        h_relnorms[step] = rel;
-        ++step;
-        *h_steps = step;
-        if (!(rel > reltol)) break;
+        if (hooked) {
+            double v_nsq = hstate->v_nsq;
+            g_norm_hook(&v_nsq, g_norm_hook_ctx);   // global ||V_i||_F^2 (the caller all-reduces)
+            z_nsq += v_nsq;
+            const double rel = z_nsq > 0.0 ? sqrt(v_nsq / z_nsq) : 0.0;
+            h_relnorms[step - 1] = rel;
+            steps_done = step;
+            done = !(rel > reltol);
+        } else {
+            steps_done = hstate->steps;
+            done = hstate->done != 0;
+        }
+        chunk = hooked ? 1 : chunk_next;
     }
+    if (!hooked) {
+        OCB_CUDA(cudaMemcpyAsync(h_relnorms, drel, (size_t)steps_done * sizeof(double), cudaMemcpyDeviceToHost, st));
+        OCB_CUDA(cudaStreamSynchronize(st));
+        lu_solve_prof_discard_last(step - steps_done);   // no-op launches leave the roofline statistics
+        g_adi_steps_hint = steps_done;
+    }
+    *h_steps = steps_done;
     if (side)   // the workspace may be reused by the caller: order the main stream after all side work
         OCB_CUDA(cudaStreamWaitEvent(st, side->ev[nshifts - 1], 0));
     return OCB_OK;
@@ -618,8 +825,7 @@ int64_t ocb_smw_solve_ws_bytes(const ocb_lu* lu, int64_t k, int64_t m) {
     c.take<double>(m * k + 1);
     c.take<double>(m * k + 1);
     c.take<double>(UPD_MAXBLOCKS);
-    c.take<double>(8);
-    c.take<int>(8);
+    c.take<AdiState>(1);
     c.take<char>(ocb_lu_solve_ws_bytes(lu, std::max(k, m)));
     return c.off + 256;
 }
@@ -650,13 +856,13 @@ int ocb_smw_solve(const ocb_lu* lu, int64_t NV, const double* d_B, int64_t ldb, 
     double* small = c.take<double>(m * k + 1);
     double* S2 = c.take<double>(m * k + 1);
     double* partials = c.take<double>(UPD_MAXBLOCKS);
-    double* dnorm = c.take<double>(8);
-    int* flag = c.take<int>(8);
+    AdiState* state = c.take<AdiState>(1);
     void* lws = c.take<char>(lws_bytes);
     if (m == 0) return lu_solve_impl(lu, d_B, ldb, nrows_b, d_X, ldx, nrows_x, k, lws, lws_bytes, st);
     double* hp = pinned_scratch();
     OCB_ARG(hp != nullptr, "pinned scratch allocation failed");
-    OCB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 8, st));
+    OCB_CUDA(cudaMemsetAsync(state, 0, sizeof(AdiState), st));
+    int* flag = &state->singular;
     int rc = smw_prepare(lu, NV, d_Ufb, ldu, (int)m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals, AiU, n, core,
                          Sinv, flag, lws, lws_bytes, st);
     if (rc) return rc;
@@ -664,13 +870,13 @@ int ocb_smw_solve(const ocb_lu* lu, int64_t NV, const double* d_B, int64_t ldb, 
     if (rc) return rc;
     rc = spmm_launch(m, d_Vt_rowptr, d_Vt_colidx, d_Vt_vals, Y, k, small, k, k, 1.0, 0.0, st);
     if (rc) return rc;
-    smw_s2_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, st>>>(Sinv, (int)m, small, k, S2);
+    smw_s2_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, st>>>(Sinv, (int)m, small, k, S2, nullptr);
     OCB_LAUNCH_CHECK();
-    rc = adi_update(nullptr, 0, Y, k, AiU, m, (int)m, S2, d_X, ldx, nrows_x, k, 0.0, 1.0, partials, dnorm, st);
+    rc = adi_update(nullptr, 0, Y, k, AiU, m, (int)m, S2, d_X, ldx, nrows_x, k, 0.0, 1.0, partials, state, st);
     if (rc) return rc;
-    OCB_CUDA(cudaMemcpyAsync(hp + 1, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OCB_CUDA(cudaMemcpyAsync(hp, state, sizeof(AdiState), cudaMemcpyDeviceToHost, st));
     OCB_CUDA(cudaStreamSynchronize(st));
-    if (*(int*)(hp + 1) != 0) {
+    if (((AdiState*)hp)->singular != 0) {
         set_error("smw_solve: singular Sherman-Morrison-Woodbury core");
         return OCB_ERR_SINGULAR;
     }

@@ -14,7 +14,9 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int32_t*
                                                    const double* __restrict__ vals,
                                                    const double* __restrict__ X, int64_t ldx,
                                                    double* __restrict__ Y, int64_t ldy, int64_t k,
-                                                   double alpha, double beta) {
+                                                   double alpha, double beta,
+                                                   const int* __restrict__ skip) {
+    if (skip && *skip) return;   // device-side stop flag of the ADI loop (lowrank.cu)
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= nrows) return;
@@ -54,19 +56,19 @@ __global__ void __launch_bounds__(256) spmm_kernel(int64_t nrows, const int32_t*
 
 int spmm_launch(int64_t nrows, const int32_t* rp, const int32_t* ci, const double* va,
                 const double* X, int64_t ldx, double* Y, int64_t ldy, int64_t k, double alpha,
-                double beta, cudaStream_t st) {
+                double beta, cudaStream_t st, const int* skip) {
     if (nrows == 0 || k == 0) return OCB_OK;
     const int wpb = 8;
     dim3 block(32 * wpb);
     if (k <= 32) {
         dim3 grid((unsigned)((nrows + wpb - 1) / wpb), 1);
-        spmm_kernel<1><<<grid, block, 0, st>>>(nrows, rp, ci, va, X, ldx, Y, ldy, k, alpha, beta);
+        spmm_kernel<1><<<grid, block, 0, st>>>(nrows, rp, ci, va, X, ldx, Y, ldy, k, alpha, beta, skip);
     } else if (k <= 64) {
         dim3 grid((unsigned)((nrows + wpb - 1) / wpb), 1);
-        spmm_kernel<2><<<grid, block, 0, st>>>(nrows, rp, ci, va, X, ldx, Y, ldy, k, alpha, beta);
+        spmm_kernel<2><<<grid, block, 0, st>>>(nrows, rp, ci, va, X, ldx, Y, ldy, k, alpha, beta, skip);
     } else {
         dim3 grid((unsigned)((nrows + wpb - 1) / wpb), (unsigned)((k + 127) / 128));
-        spmm_kernel<4><<<grid, block, 0, st>>>(nrows, rp, ci, va, X, ldx, Y, ldy, k, alpha, beta);
+        spmm_kernel<4><<<grid, block, 0, st>>>(nrows, rp, ci, va, X, ldx, Y, ldy, k, alpha, beta, skip);
     }
     OCB_LAUNCH_CHECK();
     return OCB_OK;
@@ -82,5 +84,5 @@ extern "C" int ocb_spmm(int64_t nrows, int64_t ncols, const int32_t* d_rowptr,
     OCB_ARG(nrows == 0 || k == 0 || (d_rowptr && d_X && d_Y), "null pointer");
     OCB_ARG(d_X != d_Y, "X and Y must not alias");
     return ocb::spmm_launch(nrows, d_rowptr, d_colidx, d_vals, d_X, ldx, d_Y, ldy, k, alpha, beta,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, nullptr);
 }

@@ -86,6 +86,7 @@ struct SolveArgs {
     int nbatch[8];
     int stage_bytes, nstages;
     int tma_chunk, debug_skip;
+    const int* skip;    // device flag: non-zero = this launch is a no-op (ADI loop already converged)
     long long* trace;   // debug: clock64() of CTA 0 after every sub-level barrier (null: off)
 };
 
@@ -205,6 +206,7 @@ __device__ __forceinline__ void issue_batch(unsigned char* dst, const unsigned c
 template <int KP, int CL>
 __global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(const SolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.skip && *a.skip) return;   // uniform over the grid: written by an earlier kernel of the stream
     // layout: [ring: nstages * stage_bytes][mbarriers full/empty/level: 192 bytes][xe panel: n_ext*KP doubles]
     unsigned char* ring = smem_raw;
     uint64_t* full = (uint64_t*)(smem_raw + (size_t)a.nstages * a.stage_bytes);
@@ -885,10 +887,13 @@ static int launch_stream(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) 
 // clusters of CL CTAs (one CTA per SM at this shared-memory size) that can be resident at once
 template <int KP, int CL>
 static int max_clusters(const ocb_lu* lu) {
+    // per (KP, CL) instantiation and shared-memory size (factors of different problems differ)
+    static size_t cache_smem[9] = {0};
     static int cache[9] = {0};
-    const int slot = KP;   // per (KP, CL) instantiation; shared memory is the same for one problem size
-    if (cache[slot] > 0) return cache[slot];
+    const int slot = KP;
     const size_t smem = (size_t)lu->nstages * lu->stage_bytes + 192 + (size_t)(lu->n_ext + 1) * KP * sizeof(double);
+    if (cache[slot] > 0 && cache_smem[slot] == smem) return cache[slot];
+    cache_smem[slot] = smem;
     cudaFuncSetAttribute(sptrsm_stream_kernel<KP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
     cudaLaunchConfig_t cfg;
@@ -945,6 +950,7 @@ struct WideArgs {
     double* xe;
     int64_t ldx;
     int ntile;   // column tiles of 32*T per row
+    const int* skip;
 };
 
 static int wide_min_k() {
@@ -966,6 +972,7 @@ static int64_t wide_ldx(int64_t k) {
 }
 
 __global__ void __launch_bounds__(256) wide_load_kernel(const SolveArgs a, double* xe, int64_t ldx) {
+    if (a.skip && *a.skip) return;
     // xe[perm_r[i], :] = [b[i, :], 0...]; rows >= nrows_b are zero
     const int64_t total = a.n * ldx;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -977,6 +984,7 @@ __global__ void __launch_bounds__(256) wide_load_kernel(const SolveArgs a, doubl
 }
 
 __global__ void __launch_bounds__(256) wide_store_kernel(const SolveArgs a, const double* xe, int64_t ldx) {
+    if (a.skip && *a.skip) return;
     const int64_t total = a.nrows_x * a.k;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = e / a.k, c = e - j * a.k;
@@ -990,6 +998,7 @@ __global__ void __launch_bounds__(256) wide_store_kernel(const SolveArgs a, cons
 template <int T>
 __global__ void __launch_bounds__(256) wide_level_kernel(const WideArgs a, int q0, int q1, int wlog) {
     __shared__ double red[8][T][32];
+    if (a.skip && *a.skip) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpr = 1 << wlog, rows_per_cta = 8 >> wlog;
     const int rowgroup = blockIdx.x / a.ntile, tile = blockIdx.x - rowgroup * a.ntile;
@@ -1064,6 +1073,7 @@ static int wide_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     w.slices = lu->f_slices; w.rowslice = lu->f_rowslice; w.dst = lu->f_dst; w.init = lu->f_init;
     w.col = lu->f_col; w.scale = lu->f_scale; w.val = lu->f_val;
     w.xe = xe; w.ldx = ldx;
+    w.skip = a.skip;
     w.ntile = (int)(ldx / (32 * T));
     const int nsub = (int)lu->sub_row.size() - 1;
     for (int sb = 0; sb < nsub; ++sb) {
@@ -1090,6 +1100,7 @@ static int wide_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
 struct SolveProf {
     bool on = false;
     std::vector<cudaEvent_t> ev;
+    std::vector<double> bytes;   // algorithmic bytes of every timed launch
     size_t used = 0;
     double alg_bytes = 0.0;
     long long launches = 0;
@@ -1099,8 +1110,9 @@ static long long* g_trace_buf = nullptr;
 
 static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_b, double* X,
                              int64_t ldx, int64_t nrows_x, int64_t k, void* ws, int64_t ws_bytes,
-                             cudaStream_t st) {
+                             cudaStream_t st, const int* skip) {
     SolveArgs a;
+    a.skip = skip;
     a.perm_r = lu->perm_r;
     a.perm_c = lu->perm_c;
     a.n = lu->n;
@@ -1160,22 +1172,36 @@ static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int
 
 int lu_solve_impl(const ocb_lu* lu, const double* B, int64_t ldb, int64_t nrows_b, double* X,
                   int64_t ldx, int64_t nrows_x, int64_t k, void* ws, int64_t ws_bytes,
-                  cudaStream_t st) {
+                  cudaStream_t st, const int* skip) {
     if (k == 0 || lu->n == 0) return OCB_OK;
-    if (!g_prof.on) return lu_solve_dispatch(lu, B, ldb, nrows_b, X, ldx, nrows_x, k, ws, ws_bytes, st);
+    if (!g_prof.on) return lu_solve_dispatch(lu, B, ldb, nrows_b, X, ldx, nrows_x, k, ws, ws_bytes, st, skip);
     if (g_prof.used + 2 > g_prof.ev.size()) {
         const size_t old = g_prof.ev.size();
         g_prof.ev.resize(old + 1024);
         for (size_t i = old; i < g_prof.ev.size(); ++i) OCB_CUDA(cudaEventCreate(&g_prof.ev[i]));
     }
     OCB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used], st));
-    const int rc = lu_solve_dispatch(lu, B, ldb, nrows_b, X, ldx, nrows_x, k, ws, ws_bytes, st);
+    const int rc = lu_solve_dispatch(lu, B, ldb, nrows_b, X, ldx, nrows_x, k, ws, ws_bytes, st, skip);
     OCB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used + 1], st));
     g_prof.used += 2;
     g_prof.launches += 1;
-    g_prof.alg_bytes += 12.0 * (double)(lu->nnzL + lu->nnzU) + 16.0 * (double)(lu->n + 1) +
-                        32.0 * (double)lu->n * (double)k;
+    const double ab = 12.0 * (double)(lu->nnzL + lu->nnzU) + 16.0 * (double)(lu->n + 1) +
+                      32.0 * (double)lu->n * (double)k;
+    g_prof.alg_bytes += ab;
+    g_prof.bytes.push_back(ab);
     return rc;
+}
+
+// the last n timed launches were no-ops (their skip flag was set: the ADI loop had converged
+// before they ran): they did no work, so they leave the statistics again
+void lu_solve_prof_discard_last(int64_t n) {
+    if (!g_prof.on) return;
+    for (; n > 0 && g_prof.launches > 0 && !g_prof.bytes.empty(); --n) {
+        g_prof.alg_bytes -= g_prof.bytes.back();
+        g_prof.bytes.pop_back();
+        g_prof.used -= 2;
+        g_prof.launches -= 1;
+    }
 }
 
 }  // namespace ocb
@@ -1328,6 +1354,7 @@ int ocb_prof_enable(int on) {
     ocb::g_prof.used = 0;
     ocb::g_prof.alg_bytes = 0.0;
     ocb::g_prof.launches = 0;
+    ocb::g_prof.bytes.clear();
     return OCB_OK;
 }
 
@@ -1396,6 +1423,6 @@ int ocb_lu_solve(const ocb_lu* lu, const double* d_B, int64_t ldb, int64_t nrows
     OCB_ARG(ldb >= k && ldx >= k, "lu_solve: leading dimension < k");
     OCB_ARG(k == 0 || (d_B && d_X), "lu_solve: null pointer");
     return ocb::lu_solve_impl(lu, d_B, ldb, nrows_b, d_X, ldx, nrows_x, k, d_ws, ws_bytes,
-                              (cudaStream_t)stream);
+                              (cudaStream_t)stream, nullptr);
 }
 }

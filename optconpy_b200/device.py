@@ -775,8 +775,15 @@ def sym_eig(G):
     return lam, V, sw.value
 
 
-def compress(Z, thresh=None, k=None, eta=1e-14, rmax=None):
-    """Device version of ``compress_Zsvd``: returns (Zc device tensor, info dict)."""
+# Singular values below COMPRESS_DELTA * sigma_max are not resolved reliably by a Gram matrix in
+# FP64 (lambda = sigma^2 carries an absolute error of ~eps * sigma_max^2); a threshold below
+# that is honoured by DEFLATION: the resolved part is projected out of Z and the remainder -
+# whose own sigma_max is now small - goes through the same kernels again.
+COMPRESS_DELTA = 1e-5
+COMPRESS_NOISE = 1e-13
+
+
+def _compress_once(Z, thresh, k, eta, rmax):
     lib = require_cuda()
     n, K = Z.shape
     assert Z.stride(1) == 1
@@ -794,8 +801,45 @@ def compress(Z, thresh=None, k=None, eta=1e-14, rmax=None):
                                  ptr(Zc), Zc.stride(0), cap, ptr(sig), info,
                                  ptr(ws), wsb, stream_ptr()), 'ocb_compress')
     keep = int(info[0])
+    if int(info[1]) >= rmax and rmax < min(K, n) and (k is None or keep < int(k)):
+        import warnings
+        warnings.warn('optconpy_b200: compress_Zsvd reached its rank limit of %d before the stopping '
+                      'rule fired; directions beyond it were dropped' % rmax, RuntimeWarning)
     return Zc[:, :keep], dict(kept=keep, chol_rank=int(info[1]), sweeps=int(info[2]),
                               sigma=sig[:int(info[1])])
+
+
+def compress(Z, thresh=None, k=None, eta=1e-14, rmax=None, _smax0=None, _level=0):
+    """Device version of ``compress_Zsvd``: returns (Zc device tensor, info dict).
+    ``Zc = Z V`` with V the right singular vectors of the singular values ``> thresh`` (at most
+    ``k``), computed from Gram matrices on the FP64 tensor pipe; thresholds below the resolution
+    of one Gram matrix (``COMPRESS_DELTA * sigma_max``) are reached by deflation levels."""
+    Zc, info = _compress_once(Z, thresh, k, eta, rmax)
+    info['levels'] = _level + 1
+    if thresh is None or info['chol_rank'] == 0:
+        return Zc, info
+    sig = info['sigma'].cpu().numpy()
+    smax = float(sig[0])
+    smax0 = smax if _smax0 is None else _smax0
+    if (thresh >= COMPRESS_DELTA*smax or (k is not None and info['kept'] >= int(k))
+            or smax <= COMPRESS_NOISE*smax0 or _level >= 3):
+        return Zc, info
+    # the part this level resolves: sigma > DELTA * sigma_max (a prefix: sigma is sorted)
+    k1 = int((sig > COMPRESS_DELTA*smax).sum())
+    if k1 == 0 or k1 > info['kept']:
+        return Zc, info
+    Zc1 = Zc[:, :k1].contiguous()
+    sg1 = torch.from_numpy(sig[:k1].copy()).to(Z.device)
+    Q1 = (Zc1/sg1).contiguous()                       # ~ left singular vectors U_1
+    lam, Wq, _ = sym_eig(gram(Q1, Q1))                # re-orthonormalise: Q1 <- Q1 W lam^-1/2
+    Q1 = tall_gemm(Q1, (Wq/torch.sqrt(lam)).contiguous())
+    Z2 = Z - tall_gemm(Q1, gram(Q1, Z))               # (I - Q1 Q1^T) Z
+    t2 = max(float(thresh), COMPRESS_NOISE*smax0)
+    Zc2, info2 = compress(Z2.contiguous(), thresh=t2, k=None if k is None else int(k) - k1, eta=eta,
+                          rmax=rmax, _smax0=smax0, _level=_level + 1)
+    out = torch.cat([Zc1, Zc2], dim=1).contiguous()
+    return out, dict(kept=out.shape[1], chol_rank=info['chol_rank'], sweeps=info['sweeps'],
+                     sigma=torch.cat([info['sigma'][:k1], info2['sigma']]), levels=info2['levels'])
 
 
 def feedback(Mt, Z, tB, alpha=1.0):
@@ -858,6 +902,12 @@ def adi_run(lus, shifts, NV, NP, Mt, W, maxsteps, reltol, Ufb=None, Vt=None, nor
             lib.ocb_adi_set_norm_hook(None, None)
     _cabi.check(rc, 'ocb_adi_run')
     steps = int(nst.value)
+    if steps_cap < int(maxsteps) and steps == steps_cap and rel[steps-1] > reltol:
+        import warnings
+        warnings.warn('optconpy_b200: LR-ADI stopped after %d of %d allowed steps because the factor '
+                      'buffer (%d columns per step) would not fit the free device memory; the factor '
+                      'is not the one adi_max_steps=%d would give' % (steps, maxsteps, k, maxsteps),
+                      RuntimeWarning)
     # clone, not contiguous(): when the iteration used the whole buffer the slice IS contiguous
     # and contiguous() would hand out a view of the workspace that the next call overwrites
     return Z[:, :steps*k].clone(memory_format=torch.contiguous_format), [rel[i] for i in range(steps)]
