@@ -74,8 +74,8 @@ int ocb_lu_destroy(ocb_lu* lu);
  * rows wide are solved in ONE sub-level, x_t = inv(T_tt) b_t - (inv(T_tt) T[t,off]) x, instead of
  * two (about a third fewer sub-level barriers for ~2 % more entries).  flags bits 4..7: cluster size of the column-panel kernel, 1 / 2 / 4 / 8 (0 = default 4;
  * 4 is fastest up to 33 right-hand sides, 2 from 34 to ~150).  flags bit 0: also include the flat program of the wide, all-columns-at-once
- * executor that ocb_lu_solve uses for k >= 640 right-hand sides; it is always included when
- * the column panel does not fit shared memory); ocb_lu_create_from_image uploads it with one copy into d_arena (bytes long,
+ * executor (its PANEL form, see ocb_lu_program_solve_host) that ocb_lu_solve uses for k >= 640
+ * right-hand sides; it is always included when the column panel does not fit shared memory); ocb_lu_create_from_image uploads it with one copy into d_arena (bytes long,
  * 256-byte aligned, owned by the caller and kept alive until ocb_lu_destroy; NULL: the library
  * allocates and frees its own). */
 int ocb_lu_pack_host(int64_t n,
@@ -150,6 +150,14 @@ int ocb_lu_program_info(const ocb_lu_program* prog, int64_t* info12);
 int ocb_lu_program_export(const ocb_lu_program* prog, int32_t* h_sub_ptr, int32_t* h_slice4,
                           int32_t* h_dst, int32_t* h_init, double* h_scale,
                           int32_t* h_col, double* h_val);
+/* Host execution of the program for ONE right-hand side, x = A^-1 b (what the kernels do, serially;
+ * the residual guard and the CPU tests use it).  mode 0: the row program; mode 1: its PANEL form
+ * (up to 8 rows of a supernode share one zero-padded column list, values interleaved - the layout of
+ * the register-blocked all-columns-at-once executor; max_pad bounds the padding, <= 1 = default 1.6);
+ * h_stats4 (optional, mode 1) = panels, stored values, actual entries, sub-levels. */
+int ocb_lu_program_solve_host(const ocb_lu_program* prog, const int32_t* h_perm_r, const int32_t* h_perm_c,
+                              const double* h_b, double* h_x, int64_t mode, double max_pad,
+                              int64_t* h_stats4);
 /* bytes of device workspace ocb_lu_solve needs for k right-hand sides (0 when the column-panel
  * kernel is used; n_ext x roundup(k) doubles for the wide executor) */
 int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k);

@@ -757,6 +757,142 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
     return rc;
 }
 
+void build_panels(const LuProgram& P, double max_pad, PanelProgram* out) {
+    PanelProgram& Q = *out;
+    Q = PanelProgram();
+    Q.n = P.n;
+    Q.n_ext = P.n_ext;
+    Q.sub_ptr.push_back(0);
+    struct Row { int32_t q, dst, init; std::vector<std::pair<int32_t, double>> e; };
+    std::vector<Row> rows;
+    std::vector<int32_t> order, ucols;
+    std::vector<Panel> lvl;
+    std::vector<double> lscale;
+    std::vector<std::vector<int32_t>> lcols;
+    std::vector<std::vector<double>> lvals;
+    for (int64_t sb = 0; sb < P.nsub(); ++sb) {
+        rows.clear();
+        for (int32_t s = P.sub_ptr[sb]; s < P.sub_ptr[sb + 1]; ++s) {
+            const Slice& sl = P.slices[s];
+            const int g = sl.glog_nrows & 255, nr = sl.glog_nrows >> 8, G = 1 << g;
+            for (int r = 0; r < nr; ++r) {
+                Row rw;
+                rw.q = sl.q0 + r;
+                rw.dst = P.dst[rw.q];
+                rw.init = P.init[rw.q];
+                for (int u = 0; u < sl.trips; ++u) {
+                    const size_t base = (size_t)sl.ebase + ((size_t)u << 5) + ((size_t)r << g);
+                    for (int l = 0; l < G; ++l)
+                        if (P.val[base + l] != 0.0) rw.e.emplace_back(P.col[base + l], P.val[base + l]);
+                }
+                std::sort(rw.e.begin(), rw.e.end());
+                Q.entries_actual += (int64_t)rw.e.size();
+                rows.push_back(std::move(rw));
+            }
+        }
+        order.resize(rows.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return rows[a].dst < rows[b].dst; });
+        lvl.clear(); lscale.clear(); lcols.clear(); lvals.clear();
+        size_t i = 0;
+        while (i < order.size()) {
+            // grow a panel from row i: consecutive destinations and initial rows, bounded padding
+            size_t j = i + 1;
+            ucols.clear();
+            for (auto& e : rows[order[i]].e) ucols.push_back(e.first);
+            int64_t sum = (int64_t)rows[order[i]].e.size();
+            while (j < order.size() && (int)(j - i) < PANEL_ROWS) {
+                const Row& a = rows[order[j - 1]];
+                const Row& b = rows[order[j]];
+                if (b.dst != a.dst + 1) break;
+                if (!((a.init < 0 && b.init < 0) || (a.init >= 0 && b.init == a.init + 1))) break;
+                std::vector<int32_t> merged;
+                merged.reserve(ucols.size() + b.e.size());
+                size_t x = 0, y = 0;
+                while (x < ucols.size() || y < b.e.size()) {
+                    if (y >= b.e.size() || (x < ucols.size() && ucols[x] < b.e[y].first)) merged.push_back(ucols[x++]);
+                    else if (x >= ucols.size() || b.e[y].first < ucols[x]) merged.push_back(b.e[y++].first);
+                    else { merged.push_back(ucols[x]); ++x; ++y; }
+                }
+                const int64_t cnt = (int64_t)(j - i) + 1;
+                const int64_t s2 = sum + (int64_t)b.e.size();
+                if ((double)merged.size() * (double)cnt > max_pad * (double)s2 + 8.0) break;
+                ucols.swap(merged);
+                sum = s2;
+                ++j;
+            }
+            Panel pn;
+            pn.cbase = 0;
+            pn.ncol = (int32_t)ucols.size();
+            pn.dst0 = rows[order[i]].dst;
+            pn.init0 = rows[order[i]].init;
+            pn.nrows = (int32_t)(j - i);
+            pn.pad[0] = pn.pad[1] = pn.pad[2] = 0;
+            std::vector<double> pv((size_t)ucols.size() * PANEL_ROWS, 0.0);
+            for (size_t r = i; r < j; ++r) {
+                const Row& rw = rows[order[r]];
+                size_t x = 0;
+                for (auto& e : rw.e) {
+                    while (ucols[x] < e.first) ++x;
+                    pv[x * PANEL_ROWS + (r - i)] = e.second;
+                }
+                lscale.push_back(P.scale[rw.q]);
+            }
+            for (size_t r = j - i; r < (size_t)PANEL_ROWS; ++r) lscale.push_back(0.0);
+            lvl.push_back(pn);
+            lcols.push_back(ucols);
+            lvals.push_back(std::move(pv));
+            i = j;
+        }
+        // longest panels first (load balance: the executor deals panels to CTAs in order)
+        std::vector<int32_t> po(lvl.size());
+        std::iota(po.begin(), po.end(), 0);
+        std::stable_sort(po.begin(), po.end(), [&](int32_t a, int32_t b) { return lvl[a].ncol > lvl[b].ncol; });
+        for (int32_t pi : po) {
+            Panel pn = lvl[pi];
+            pn.cbase = (int32_t)Q.pcol.size();
+            Q.pcol.insert(Q.pcol.end(), lcols[pi].begin(), lcols[pi].end());
+            Q.pval.insert(Q.pval.end(), lvals[pi].begin(), lvals[pi].end());
+            while (pn.ncol & 3) {   // the executor reads 4 entries per step: pad with 0 * xe[0]
+                Q.pcol.push_back(0);
+                Q.pval.insert(Q.pval.end(), PANEL_ROWS, 0.0);
+                ++pn.ncol;
+            }
+            Q.scale.insert(Q.scale.end(), lscale.begin() + (size_t)pi * PANEL_ROWS,
+                           lscale.begin() + (size_t)(pi + 1) * PANEL_ROWS);
+            Q.panels.push_back(pn);
+        }
+        Q.sub_ptr.push_back((int32_t)Q.panels.size());
+    }
+}
+
+void execute_panels_host(const PanelProgram& Q, const int32_t* perm_r, const int32_t* perm_c,
+                         const double* b, double* x) {
+    std::vector<double> xe((size_t)Q.n_ext + 1, 0.0), out;
+    for (int64_t i = 0; i < Q.n; ++i) xe[perm_r[i]] = b[i];
+    for (int64_t sb = 0; sb < Q.nsub(); ++sb) {
+        out.clear();
+        for (int32_t pi = Q.sub_ptr[sb]; pi < Q.sub_ptr[sb + 1]; ++pi) {
+            const Panel& pn = Q.panels[pi];
+            double acc[PANEL_ROWS] = {0};
+            for (int32_t p = 0; p < pn.ncol; ++p) {
+                const double xv = xe[Q.pcol[pn.cbase + p]];
+                for (int r = 0; r < PANEL_ROWS; ++r) acc[r] = fma(Q.pval[((size_t)pn.cbase + p) * PANEL_ROWS + r], xv, acc[r]);
+            }
+            for (int r = 0; r < pn.nrows; ++r) {
+                const double ini = pn.init0 >= 0 ? xe[pn.init0 + r] : 0.0;
+                out.push_back((ini - acc[r]) * Q.scale[(size_t)pi * PANEL_ROWS + r]);
+            }
+        }
+        size_t o = 0;
+        for (int32_t pi = Q.sub_ptr[sb]; pi < Q.sub_ptr[sb + 1]; ++pi) {
+            const Panel& pn = Q.panels[pi];
+            for (int r = 0; r < pn.nrows; ++r) xe[pn.dst0 + r] = out[o++];
+        }
+    }
+    for (int64_t j = 0; j < Q.n; ++j) x[j] = xe[perm_c[j]];
+}
+
 void execute_program_host(const LuProgram& P, const int32_t* perm_r, const int32_t* perm_c,
                           const double* b, double* x) {
     std::vector<double> xe((size_t)P.n_ext + 1, 0.0), out;
@@ -817,6 +953,26 @@ int ocb_lu_program_create(ocb_lu_program** out, int64_t n, const int32_t* h_L_ro
 }
 
 int64_t ocb_lu_program_template_hits(void) { return ocb::g_template_hits; }
+
+int ocb_lu_program_solve_host(const ocb_lu_program* prog, const int32_t* h_perm_r, const int32_t* h_perm_c,
+                              const double* h_b, double* h_x, int64_t mode, double max_pad,
+                              int64_t* h_stats4) {
+    OCB_ARG(prog && h_perm_r && h_perm_c && h_b && h_x && (mode == 0 || mode == 1), "lu_program_solve_host");
+    if (mode == 0) {
+        ocb::execute_program_host(prog->P, h_perm_r, h_perm_c, h_b, h_x);
+        return OCB_OK;
+    }
+    ocb::PanelProgram Q;
+    ocb::build_panels(prog->P, max_pad > 1.0 ? max_pad : 1.6, &Q);
+    ocb::execute_panels_host(Q, h_perm_r, h_perm_c, h_b, h_x);
+    if (h_stats4) {
+        h_stats4[0] = (int64_t)Q.panels.size();
+        h_stats4[1] = (int64_t)Q.pcol.size() * ocb::PANEL_ROWS;   // stored values (zero padding included)
+        h_stats4[2] = Q.entries_actual;
+        h_stats4[3] = Q.nsub();
+    }
+    return OCB_OK;
+}
 
 int ocb_lu_program_destroy(ocb_lu_program* prog) {
     delete prog;

@@ -58,6 +58,38 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
 // wmax_cap > 0: no supernode wider than that (the "safe" layout of the residual guard: the
 // inverse of a narrow triangular block is far better conditioned than that of a 512-row one).
 
+// ---------------------------------------------------------------------------------
+// PANEL form of the same program, for the all-columns-at-once executor (large n / wide blocks).
+// Up to 8 rows of one sub-level with consecutive destinations (rows of one supernode) form a
+// PANEL that shares ONE column list: the union of the rows' lists, values zero padded and stored
+// interleaved (val[p][8]).  The executor then loads every x row once per panel and uses it for
+// 8 rows (register blocking): 1 byte of x per FMA instead of 8.  Rows of the upper factor
+// inside a supernode have identical lists (no padding); the lower factor pads ~1.4x.
+// ---------------------------------------------------------------------------------
+constexpr int PANEL_ROWS = 8;
+struct Panel {
+    int32_t cbase;    // first entry of the column list (pcol); values at pval[(cbase + p) * 8 + r]
+    int32_t ncol;
+    int32_t dst0;     // row r writes xe[dst0 + r]
+    int32_t init0;    // row r starts from xe[init0 + r] (-1: from zero)
+    int32_t nrows;    // 1..8
+    int32_t pad[3];
+};
+struct PanelProgram {
+    int64_t n = 0, n_ext = 0;
+    std::vector<int32_t> sub_ptr;     // panels of sub-level s: [sub_ptr[s], sub_ptr[s+1]), longest first
+    std::vector<Panel> panels;
+    std::vector<double> scale;        // 8 per panel
+    std::vector<int32_t> pcol;
+    std::vector<double> pval;         // 8 per column entry
+    int64_t entries_actual = 0;       // non-padding entries (= flops / 2 per right-hand side)
+    int64_t nsub() const { return (int64_t)sub_ptr.size() - 1; }
+};
+// max_pad: a row joins a panel only while (union size * rows) <= max_pad * (sum of row lengths)
+void build_panels(const LuProgram& P, double max_pad, PanelProgram* out);
+void execute_panels_host(const PanelProgram& Q, const int32_t* perm_r, const int32_t* perm_c,
+                         const double* b, double* x);
+
 // Host execution of the program for ONE right-hand side (what the CUDA kernels do, serially):
 // x = Pc U^-1 L^-1 Pr b.  Used by the residual guard of ocb_lu_pack_host_checked and by tests.
 void execute_program_host(const LuProgram& P, const int32_t* perm_r, const int32_t* perm_c,

@@ -58,6 +58,14 @@ struct ocb_lu {
     const double *f_scale = nullptr, *f_val = nullptr;
     std::vector<int32_t> sub_row;     // host: first program row of every sub-level (nsub + 1)
     std::vector<int32_t> sub_maxlen;  // host: longest (padded) row of every sub-level
+    // panel program (lu_program.h): register-blocked form for the all-columns-at-once executor
+    bool has_panels = false;
+    const ocb::Panel* p_panels = nullptr;
+    const double *p_scale = nullptr, *p_val = nullptr;
+    const int32_t* p_col = nullptr;
+    int64_t npanels = 0, panel_entries = 0, panel_entries_actual = 0;
+    std::vector<int32_t> sub_pan;      // host: first panel of every sub-level (nsub + 1)
+    std::vector<int32_t> sub_maxcol;   // host: longest column list of every sub-level
 };
 
 namespace ocb {
@@ -593,11 +601,12 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl
 // Self-describing host image of a factorisation: [meta int64[32]] perm_r | perm_c | batch
 // offsets | batch stream.  Built without any CUDA call (worker processes build it next to the
 // host LU); ocb_lu_create_from_image uploads it with one allocation and one copy.
-constexpr int64_t IMG_MAGIC = 0x4f43424c55303033LL;   // "OCBLU003"
+constexpr int64_t IMG_MAGIC = 0x4f43424c55303034LL;   // "OCBLU004"
 enum { M_MAGIC = 0, M_TOTAL, M_N, M_NEXT, M_NNZL, M_NNZU, M_NSUBL, M_NSUBU, M_NSUPER, M_MAXW, M_NSLICE,
        M_NROWS, M_NENT, M_OPR, M_OPC, M_CL, M_STAGEB, M_NSTAGES, M_KPSMEM, M_FLAT, M_NSUB,
        M_OBO = 24, M_OST = 32, M_NBATCH = 40,                  // one slot per cluster rank
        M_F_SLICE = 48, M_F_ROWSLICE, M_F_DST, M_F_INIT, M_F_SCALE, M_F_COL, M_F_VAL, M_F_SUBROW,
+       M_P_PANEL = 56, M_P_SCALE, M_P_COL, M_P_VAL, M_P_SUB, M_NPANEL, M_PENT, M_PENT_ACTUAL,
        M_COUNT = 64 };
 
 // Images of programs with the same structure differ in the two permutations and in the numbers
@@ -695,7 +704,16 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         cl = 0;
         for (int r = 0; r < 8; ++r) batches[r].clear();
     }
-    const bool want_flat = (flags & 1) || kp_smem == 0;
+    const bool want_wide = (flags & 1) || kp_smem == 0;
+    static const bool legacy_flat = getenv("OCB_WIDE_LEGACY") != nullptr;
+    const bool want_flat = want_wide && legacy_flat;
+    const bool want_panels = want_wide && !legacy_flat;
+    PanelProgram Q;
+    if (want_panels) {
+        const char* e_pad = getenv("OCB_PANEL_MAXPAD");
+        build_panels(P, e_pad ? atof(e_pad) : 1.6, &Q);
+        tmpl.reset();   // the template refill below does not cover the panel values
+    }
     std::vector<int64_t> off[8];
     int64_t maxb = 16;
     for (int r = 0; r < cl; ++r) {
@@ -725,6 +743,16 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         const int64_t sz[8] = {nsl * 16, nr * 4, nr * 4, nr * 4, nr * 8, ne * 4, ne * 8, 2 * (nsub + 1) * 4};
         for (int i = 0; i < 8; ++i) {
             o_f[i] = o;
+            o = align_up(o + std::max<int64_t>(sz[i], 16), 256);
+        }
+    }
+    int64_t o_p[5] = {0};
+    if (want_panels) {
+        const int64_t npn = (int64_t)Q.panels.size(), npc = (int64_t)Q.pcol.size(), nsb = Q.nsub();
+        const int64_t sz[5] = {npn * (int64_t)sizeof(Panel), npn * PANEL_ROWS * 8, npc * 4,
+                               npc * PANEL_ROWS * 8, 2 * (nsb + 1) * 4};
+        for (int i = 0; i < 5; ++i) {
+            o_p[i] = o;
             o = align_up(o + std::max<int64_t>(sz[i], 16), 256);
         }
     }
@@ -785,6 +813,24 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
             const Slice& f = P.slices[P.sub_ptr[sb]];
             submax[sb] = P.sub_ptr[sb] < nsl ? (f.trips << (f.glog_nrows & 255)) : 0;
         }
+    }
+    meta[M_NPANEL] = 0;
+    if (want_panels) {
+        const int64_t npn = (int64_t)Q.panels.size(), npc = (int64_t)Q.pcol.size(), nsb = Q.nsub();
+        for (int i = 0; i < 5; ++i) meta[M_P_PANEL + i] = o_p[i];
+        meta[M_NPANEL] = npn;
+        meta[M_PENT] = npc;
+        meta[M_PENT_ACTUAL] = Q.entries_actual;
+        meta[M_NSUB] = nsb;
+        if (npn) memcpy(img + o_p[0], Q.panels.data(), (size_t)npn * sizeof(Panel));
+        if (npn) memcpy(img + o_p[1], Q.scale.data(), (size_t)npn * PANEL_ROWS * 8);
+        if (npc) memcpy(img + o_p[2], Q.pcol.data(), (size_t)npc * 4);
+        if (npc) memcpy(img + o_p[3], Q.pval.data(), (size_t)npc * PANEL_ROWS * 8);
+        int32_t* sp = (int32_t*)(img + o_p[4]);
+        memcpy(sp, Q.sub_ptr.data(), (size_t)(nsb + 1) * 4);
+        int32_t* smax = sp + nsb + 1;   // panels of a sub-level are sorted: the first is the longest
+        for (int64_t sb = 0; sb < nsb; ++sb)
+            smax[sb] = Q.sub_ptr[sb] < Q.sub_ptr[sb + 1] ? Q.panels[Q.sub_ptr[sb]].ncol : 0;
     }
     if (tmpl && (size_t)total <= IMAGE_TEMPLATE_MAX_BYTES) {
         tmpl->img.assign(img, img + total);
@@ -854,6 +900,19 @@ static int upload_image(ocb_lu* lu, const unsigned char* img, int64_t bytes, voi
         const int32_t* sr = (const int32_t*)(img + meta[M_F_SUBROW]);
         lu->sub_row.assign(sr, sr + meta[M_NSUB] + 1);
         lu->sub_maxlen.assign(sr + meta[M_NSUB] + 1, sr + 2 * meta[M_NSUB] + 1);
+    }
+    lu->has_panels = meta[M_NPANEL] > 0;
+    if (lu->has_panels) {
+        lu->p_panels = (const ocb::Panel*)(lu->arena + meta[M_P_PANEL]);
+        lu->p_scale = (const double*)(lu->arena + meta[M_P_SCALE]);
+        lu->p_col = (const int32_t*)(lu->arena + meta[M_P_COL]);
+        lu->p_val = (const double*)(lu->arena + meta[M_P_VAL]);
+        lu->npanels = meta[M_NPANEL];
+        lu->panel_entries = meta[M_PENT];
+        lu->panel_entries_actual = meta[M_PENT_ACTUAL];
+        const int32_t* sp = (const int32_t*)(img + meta[M_P_SUB]);
+        lu->sub_pan.assign(sp, sp + meta[M_NSUB] + 1);
+        lu->sub_maxcol.assign(sp + meta[M_NSUB] + 1, sp + 2 * meta[M_NSUB] + 1);
     }
     return OCB_OK;
 }
@@ -963,7 +1022,7 @@ static int wide_min_k() {
     return v;
 }
 static bool use_wide(const ocb_lu* lu, int64_t k) {
-    return lu->has_flat && (lu->kp_smem_max == 0 || k >= wide_min_k());
+    return (lu->has_flat || lu->has_panels) && (lu->kp_smem_max == 0 || k >= wide_min_k());
 }
 static int wide_tiles(int64_t k) { return k <= 32 ? 1 : (k <= 64 ? 2 : 4); }
 static int64_t wide_ldx(int64_t k) {
@@ -1095,6 +1154,161 @@ static int wide_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     return OCB_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// panel executor: the wide executor with REGISTER BLOCKING over the rows of a supernode
+// ---------------------------------------------------------------------------------
+// A panel = up to 8 rows of one sub-level that share one column list (lu_program.h).  A warp
+// owns one panel and 32*T consecutive columns (lane = column): per list entry it loads ONE x row
+// segment (coalesced 256 bytes per 32 columns) and the 8 row values (one uniform 64-byte load)
+// and issues 8*T FMAs - 1 byte of x per FMA instead of the 8 of the row-by-row executor, which
+// turns the kernel from L2-bandwidth bound into FP64 bound.  Long lists are split over 2^wlog
+// warps of the CTA and combined through shared memory (fixed order: deterministic).
+struct PanelArgs {
+    const Panel* panels;
+    const double *scale, *val;
+    const int32_t* col;
+    double* xe;
+    int64_t ldx;
+    int ntile;
+    const int* skip;
+};
+
+template <int T>
+__global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int p0, int p1, int wlog) {
+    extern __shared__ double pred[];   // [warp][8][T][32] partial sums when a list is split
+    if (a.skip && *a.skip) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpr = 1 << wlog, ppc = 8 >> wlog;
+    const int grp = blockIdx.x / a.ntile, tile = blockIdx.x - grp * a.ntile;
+    const int pi = p0 + grp * ppc + (warp >> wlog);
+    const int wr = warp & (wpr - 1);
+    const bool valid = pi < p1;
+    double* xc = a.xe + (int64_t)tile * (32 * T) + lane;
+    double acc[PANEL_ROWS][T];
+#pragma unroll
+    for (int r = 0; r < PANEL_ROWS; ++r)
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[r][t] = 0.0;
+    int4 pn0 = make_int4(0, 0, 0, -1);
+    int nrows = 0;
+    if (valid) {
+        pn0 = __ldg((const int4*)(a.panels + pi));          // cbase, ncol, dst0, init0
+        nrows = __ldg(&a.panels[pi].nrows);
+        const int ncol = pn0.y;
+        int per = ((ncol >> 2) + wpr - 1) / wpr * 4;          // chunk of this warp, multiple of 4
+        const int e0 = wr * per, e1 = min(ncol, e0 + per);
+        const int32_t* cp = a.col + pn0.x;
+        const double2* vp = (const double2*)(a.val + (int64_t)pn0.x * PANEL_ROWS);
+        for (int e = e0; e < e1; e += 4) {
+            const int4 j4 = __ldg((const int4*)(cp + e));    // cbase and e are multiples of 4
+            const int jj[4] = {j4.x, j4.y, j4.z, j4.w};
+            double xv[4][T];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int t = 0; t < T; ++t) xv[u][t] = xc[(int64_t)jj[u] * a.ldx + 32 * t];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double2* v2 = vp + (int64_t)(e + u) * (PANEL_ROWS / 2);
+#pragma unroll
+                for (int h = 0; h < PANEL_ROWS / 2; ++h) {
+                    const double2 vv = __ldg(v2 + h);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        acc[2 * h][t] = fma(vv.x, xv[u][t], acc[2 * h][t]);
+                        acc[2 * h + 1][t] = fma(vv.y, xv[u][t], acc[2 * h + 1][t]);
+                    }
+                }
+            }
+        }
+    }
+    if (wlog > 0) {
+        double* mine = pred + (size_t)warp * (PANEL_ROWS * T * 32);
+#pragma unroll
+        for (int r = 0; r < PANEL_ROWS; ++r)
+#pragma unroll
+            for (int t = 0; t < T; ++t) mine[(r * T + t) * 32 + lane] = acc[r][t];
+        __syncthreads();
+        if (wr == 0) {
+            for (int w2 = 1; w2 < wpr; ++w2) {
+                const double* other = pred + (size_t)(warp + w2) * (PANEL_ROWS * T * 32);
+#pragma unroll
+                for (int r = 0; r < PANEL_ROWS; ++r)
+#pragma unroll
+                    for (int t = 0; t < T; ++t) acc[r][t] += other[(r * T + t) * 32 + lane];
+            }
+        }
+    }
+    if (valid && wr == 0) {
+        const double* sc = a.scale + (int64_t)pi * PANEL_ROWS;
+#pragma unroll
+        for (int r = 0; r < PANEL_ROWS; ++r) {
+            if (r < nrows) {
+                const double s = __ldg(sc + r);
+                double* xd = xc + (int64_t)(pn0.z + r) * a.ldx;
+                if (pn0.w >= 0) {
+                    const double* xi = xc + (int64_t)(pn0.w + r) * a.ldx;
+#pragma unroll
+                    for (int t = 0; t < T; ++t) xd[32 * t] = (xi[32 * t] - acc[r][t]) * s;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < T; ++t) xd[32 * t] = -acc[r][t] * s;
+                }
+            }
+        }
+    }
+}
+
+template <int T>
+static int panel_launch(const PanelArgs& w, int p0, int p1, int wlog, cudaStream_t st) {
+    const int ppc = 8 >> wlog;
+    const unsigned blocks = (unsigned)(((p1 - p0) + ppc - 1) / ppc) * (unsigned)w.ntile;
+    const size_t smem = wlog > 0 ? (size_t)8 * PANEL_ROWS * T * 32 * sizeof(double) : 0;
+    static bool attr = false;
+    if (!attr) {
+        OCB_CUDA(cudaFuncSetAttribute(panel_level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      8 * PANEL_ROWS * T * 32 * (int)sizeof(double)));
+        attr = true;
+    }
+    panel_level_kernel<T><<<blocks, 256, smem, st>>>(w, p0, p1, wlog);
+    OCB_LAUNCH_CHECK();
+    return OCB_OK;
+}
+
+static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
+    const int T = wide_tiles(a.k);
+    const int64_t ldx = wide_ldx(a.k);
+    double* xe = a.ws;
+    const unsigned lblocks = (unsigned)std::min<int64_t>((a.n * ldx + 255) / 256, 148 * 16);
+    wide_load_kernel<<<lblocks, 256, 0, st>>>(a, xe, ldx);
+    OCB_LAUNCH_CHECK();
+    PanelArgs w;
+    w.panels = lu->p_panels; w.scale = lu->p_scale; w.val = lu->p_val; w.col = lu->p_col;
+    w.xe = xe; w.ldx = ldx; w.skip = a.skip;
+    w.ntile = (int)(ldx / (32 * T));
+    const int nsub = (int)lu->sub_pan.size() - 1;
+    const int64_t want_warps = (int64_t)sm_count() * 8;
+    for (int sb = 0; sb < nsub; ++sb) {
+        const int p0 = lu->sub_pan[sb], p1 = lu->sub_pan[sb + 1];
+        if (p1 <= p0) continue;
+        // split long lists over the warps of a CTA while the sub-level has too few tasks to
+        // fill the machine (the top separators: a few dozen panels with thousands of columns)
+        const int64_t tasks = (int64_t)(p1 - p0) * w.ntile;
+        const int maxcol = lu->sub_maxcol[sb];
+        int wlog = 0;
+        while (wlog < 3 && (tasks << wlog) < want_warps && (maxcol >> (wlog + 1)) >= 32) ++wlog;
+        int rc;
+        if (T == 1) rc = panel_launch<1>(w, p0, p1, wlog, st);
+        else if (T == 2) rc = panel_launch<2>(w, p0, p1, wlog, st);
+        else rc = panel_launch<4>(w, p0, p1, wlog, st);
+        if (rc) return rc;
+    }
+    const unsigned sblocks = (unsigned)std::min<int64_t>((a.nrows_x * a.k + 255) / 256, 148 * 16);
+    wide_store_kernel<<<std::max(1u, sblocks), 256, 0, st>>>(a, xe, ldx);
+    OCB_LAUNCH_CHECK();
+    return OCB_OK;
+}
+
 // optional per-launch timing of the solve kernel (bench.py roofline): CUDA events on the
 // launching stream around every solve launch, summed on collect
 struct SolveProf {
@@ -1160,7 +1374,7 @@ static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int
             set_error("lu_solve: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
             return OCB_ERR_CAPACITY;
         }
-        return wide_solve(lu, a, st);
+        return lu->has_panels ? panel_solve(lu, a, st) : wide_solve(lu, a, st);
     }
     switch (lu->cl) {
         case 8: return launch_cluster<8>(lu, a, st);

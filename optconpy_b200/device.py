@@ -248,7 +248,7 @@ _ORDER = dict()
 
 # one-step (inverse-multiplied) supernodes in the gather program, flags bit 2 of
 # ocb_lu_pack_host (lu_program.h); OCB_MERGE=0/1 overrides
-MERGE_DEFAULT = '0'
+MERGE_DEFAULT = '1'
 
 
 def _pack_flags(wide, k_hint=None):

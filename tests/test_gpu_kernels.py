@@ -134,12 +134,26 @@ def test_lu_solve_global_panel_path(dv):
     n = S.shape[0]
     assert n*2*8 > 227*1024
     rng = np.random.default_rng(5)
-    B = rng.standard_normal((n, 11))
     lu = dv.LU(S)
-    X = dv.to_host(lu.solve(dv.to_dev(B)))
-    assert np.linalg.norm(S @ X - B)/np.linalg.norm(B) < 1e-11
-    ref = spsla.splu(S).solve(B)
-    assert _relerr(X, ref) < 1e-10
+    slu = spsla.splu(S)
+    for k in (11, 48, 130):          # one, two and four column tiles per warp (panel executor)
+        B = rng.standard_normal((n, k))
+        X = dv.to_host(lu.solve(dv.to_dev(B)))
+        assert np.linalg.norm(S @ X - B)/np.linalg.norm(B) < 1e-11
+        assert _relerr(X, slu.solve(B)) < 1e-10
+        X2 = dv.to_host(lu.solve(dv.to_dev(B)))
+        assert np.array_equal(X, X2)                  # deterministic
+
+
+def test_gram_symmetric_half(dv):
+    """G = Z^T Z with the same block on both sides: only the tiles on and below the diagonal are
+    computed on the tensor pipe, the rest is mirrored."""
+    rng = np.random.default_rng(77)
+    Z = rng.standard_normal((3000, 200))
+    Zd = dv.to_dev(Z)
+    G = dv.to_host(dv.gram(Zd, Zd))
+    assert _relerr(G, Z.T @ Z) < 1e-13
+    assert np.array_equal(G, G.T)
 
 
 @pytest.mark.parametrize('shape', [(722, 5, 5), (1000, 66, 66), (4802, 130, 8), (333, 7, 129)])

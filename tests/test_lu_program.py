@@ -506,3 +506,31 @@ def test_residual_guard_refactorises_in_safe_mode(monkeypatch):
     _execute(prog, X)
     got = X[arrs[7]]
     assert np.linalg.norm(hard @ got - B) <= 1e-14*sps.linalg.norm(hard)*np.linalg.norm(got)
+
+
+@pytest.mark.parametrize('flags', [2, 2 | 4])
+def test_panel_form_reproduces_the_program(cav10, flags):
+    """The PANEL form of the program (register-blocked layout of the all-columns-at-once
+    executor: up to 8 rows of a supernode share one zero-padded column list) solves the same
+    system: host execution of both forms against SuperLU, and the padding stays bounded."""
+    K = _saddle(cav10)
+    n = K.shape[0]
+    lib = _cabi.load()
+    arrs = _lu_worker.factor_arrays(dv._csc_args(K, dict(dv.LU_OPTIONS)), transposed=True)
+    h = C.c_void_p()
+    _cabi.check(lib.ocb_lu_program_create(C.byref(h), n, *[a.ctypes.data for a in arrs[:6]], flags), 'create')
+    b = np.random.default_rng(3).standard_normal(n)
+    ref = spsla.splu(K).solve(b)
+    xs = []
+    stats = (C.c_int64*4)()
+    for mode in (0, 1):
+        x = np.zeros(n)
+        _cabi.check(lib.ocb_lu_program_solve_host(h, arrs[6].ctypes.data, arrs[7].ctypes.data,
+                                                  b.ctypes.data, x.ctypes.data, mode, 0.0, stats), 'solve_host')
+        assert np.linalg.norm(x - ref) <= 1e-12*np.linalg.norm(ref)
+        xs.append(x)
+    lib.ocb_lu_program_destroy(h)
+    assert np.linalg.norm(xs[0] - xs[1]) <= 1e-13*np.linalg.norm(ref)
+    npanels, stored, actual, nsub = [int(v) for v in stats]
+    assert npanels > 0 and actual > 0
+    assert stored <= 2.2*actual            # zero padding (union lists + rows up to 8) stays bounded
