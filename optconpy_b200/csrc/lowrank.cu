@@ -352,76 +352,35 @@ int64_t ocb_compress_ws_bytes(int64_t n, int64_t K, int64_t rmax) {
     return ocb::compress_carve(nullptr, 0, n, K, rmax, nullptr);
 }
 
-int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K, double thresh, int64_t kmax,
-                 double eta, int64_t rmax, double* d_Zc, int64_t ldzc, int64_t zc_capacity_cols,
-                 double* d_sigma, int64_t* h_info3, void* d_ws, int64_t ws_bytes, void* stream) {
-    using namespace ocb;
-    OCB_ARG(n >= 0 && K >= 0 && ldz >= K && rmax >= 1 && rmax <= 1024, "compress sizes");
-    OCB_ARG(d_Z && d_Zc && h_info3 && d_ws, "compress null");
-    OCB_ARG(eta > 0.0 && eta < 1e-6, "compress eta");
-    cudaStream_t st = (cudaStream_t)stream;
-    h_info3[0] = h_info3[1] = h_info3[2] = 0;
-    if (K == 0 || n == 0) return OCB_OK;
-    rmax = std::min<int64_t>(rmax, std::min(K, n));
-    CompressWs w;
-    const int64_t need = compress_carve(d_ws, ws_bytes, n, K, rmax, &w);
-    if (need > ws_bytes) {
-        set_error("compress: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
-        return OCB_ERR_CAPACITY;
-    }
-    double* hp = pinned_scratch();
-    OCB_ARG(hp != nullptr, "pinned scratch allocation failed");
-    OCB_CUDA(cudaMemsetAsync(w.st, 0, sizeof(CholState), st));
-    CholState* hst = (CholState*)hp;
-    int rc;
-    if (w.G) {
-        // Gram route: one DMMA product, then the whole pivoted Cholesky in one cooperative launch
-        rc = gram_impl(d_Z, ldz, K, d_Z, ldz, K, n, w.G, K, w.gws, w.gws_bytes, st);
-        if (rc) return rc;
-        int per_sm = 0;
-        OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_gram_kernel, CG_THREADS, 0));
-        int64_t blocks = std::min<int64_t>((K + CG_THREADS - 1) / CG_THREADS * 4, CG_MAXBLOCKS);
-        blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)std::max(per_sm, 1) * sm_count()));
-        const double* Gc = w.G;
-        int64_t ldg = K, Kk = K, ldr = rmax;
-        int rmx = (int)rmax;
-        void* args[] = {(void*)&Gc, &ldg, &Kk, &rmx, &eta, &w.Rt, &ldr, &w.d, &w.pval, &w.pidx, &w.st};
-        OCB_CUDA(cudaLaunchCooperativeKernel((void*)chol_gram_kernel, dim3((unsigned)blocks), dim3(CG_THREADS),
-                                             args, 0, st));
-        count_launch();
-        OCB_CUDA(cudaMemcpyAsync(hst, w.st, sizeof(CholState), cudaMemcpyDeviceToHost, st));
-        OCB_CUDA(cudaStreamSynchronize(st));
-    } else {
-        const unsigned cblocks = (unsigned)((K + 31) / 32);
-        chol_colsq_kernel<<<cblocks, CH_THREADS, 0, st>>>(d_Z, ldz, n, K, w.d);
-        OCB_LAUNCH_CHECK();
-        int t = 0;
-        bool done = false;
-        while (!done) {
-            const int batch_end = (int)std::min<int64_t>(rmax, t + 32);
-            for (; t < batch_end; ++t) {
-                chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
-                OCB_LAUNCH_CHECK();
-                chol_col_kernel<<<dim3(cblocks, CH_SPLIT), CH_THREADS, 0, st>>>(d_Z, ldz, n, K, w.gpart, w.st);
-                OCB_LAUNCH_CHECK();
-                chol_col_finish_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(w.gpart, K, t, w.Rt, rmax,
-                                                                                    w.d, w.st);
-                OCB_LAUNCH_CHECK();
-            }
-            if (t >= rmax) {  // closes the factorisation at rank rmax if the rule never fired
-                chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
-                OCB_LAUNCH_CHECK();
-            }
-            OCB_CUDA(cudaMemcpyAsync(hst, w.st, sizeof(CholState), cudaMemcpyDeviceToHost, st));
-            OCB_CUDA(cudaStreamSynchronize(st));
-            done = hst->done != 0;
-        }
-    }
-    const int r = hst->rank;
-    h_info3[1] = r;
-    if (r == 0) return OCB_OK;
-    // core: S = R R^T (r x r) = Rt^T Rt, eigen-decomposition, sigma = sqrt(lam)
-    rc = gram_impl(w.Rt, rmax, r, w.Rt, rmax, r, K, w.S, rmax, w.gws, w.gws_bytes, st);
+}  // extern "C"
+
+namespace ocb {
+
+// pivoted Cholesky of the explicit Gram matrix in one cooperative launch -> Rt, *rank (host)
+static int chol_from_gram(const double* G, int64_t ldg, int64_t K, int64_t rmax, double eta, const CompressWs& w,
+                          CholState* hst, cudaStream_t st) {
+    int per_sm = 0;
+    OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_gram_kernel, CG_THREADS, 0));
+    int64_t blocks = std::min<int64_t>((K + CG_THREADS - 1) / CG_THREADS * 4, CG_MAXBLOCKS);
+    blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)std::max(per_sm, 1) * sm_count()));
+    int64_t Kk = K, ldr = rmax, ldg2 = ldg;
+    int rmx = (int)rmax;
+    double* Rt = w.Rt; double* d = w.d; double* pval = w.pval; int* pidx = w.pidx; CholState* dst = w.st;
+    void* args[] = {(void*)&G, &ldg2, &Kk, &rmx, &eta, &Rt, &ldr, &d, &pval, &pidx, &dst};
+    OCB_CUDA(cudaLaunchCooperativeKernel((void*)chol_gram_kernel, dim3((unsigned)blocks), dim3(CG_THREADS),
+                                         args, 0, st));
+    count_launch();
+    OCB_CUDA(cudaMemcpyAsync(hst, w.st, sizeof(CholState), cudaMemcpyDeviceToHost, st));
+    OCB_CUDA(cudaStreamSynchronize(st));
+    return OCB_OK;
+}
+
+// From the Cholesky factor Rt (K x r): core S = Rt^T Rt, its eigen-decomposition, the kept count
+// and T (K x keep) = Rt U_keep Sigma_keep^-1  (the right singular vectors: Zc = Z T).
+static int finish_from_rt(int64_t K, int r, int64_t rmax, double thresh, int64_t kmax, const CompressWs& w,
+                          double* d_T, int64_t ldt, int64_t t_capacity_cols, double* d_sigma, int64_t* h_info3,
+                          double* hp, cudaStream_t st) {
+    int rc = gram_impl(w.Rt, rmax, r, w.Rt, rmax, r, K, w.S, rmax, w.gws, w.gws_bytes, st);
     if (rc) return rc;
     int32_t sweeps = 0;
     double* hlam = hp + 64;
@@ -454,15 +413,118 @@ int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K, double th
         OCB_CUDA(cudaStreamSynchronize(st));
     }
     if (keep == 0) return OCB_OK;
-    if (keep > zc_capacity_cols || ldzc < keep) {
-        set_error("compress: %d columns kept but capacity is %lld", keep, (long long)zc_capacity_cols);
+    if (keep > t_capacity_cols || ldt < keep) {
+        set_error("compress: %d columns kept but capacity is %lld", keep, (long long)t_capacity_cols);
         return OCB_ERR_CAPACITY;
     }
     scale_cols_kernel<<<(r * keep + 255) / 256, 256, 0, st>>>(w.U, rmax, r, keep, w.lam, w.Us, rmax);
     OCB_LAUNCH_CHECK();
-    // T (K x keep) = Rt (K x r) Us (r x keep);  Zc = Z T
-    rc = tall_gemm_impl(w.Rt, rmax, K, r, w.Us, rmax, keep, w.T, rmax, 1.0, 0.0, st);
+    return tall_gemm_impl(w.Rt, rmax, K, r, w.Us, rmax, keep, d_T, ldt, 1.0, 0.0, st);
+}
+
+}  // namespace ocb
+
+extern "C" {
+
+int64_t ocb_compress_gram_ws_bytes(int64_t K, int64_t rmax) {
+    // the Gram matrix itself is the caller's: only the small pieces
+    return ocb::compress_carve(nullptr, 0, 0, K + ocb::GRAM_K_MAX + 1, rmax, nullptr);
+}
+
+int ocb_compress_from_gram(const double* d_G, int64_t ldg, int64_t K, double thresh, int64_t kmax, double eta,
+                           int64_t rmax, double* d_T, int64_t ldt, int64_t t_capacity_cols, double* d_sigma,
+                           int64_t* h_info3, void* d_ws, int64_t ws_bytes, void* stream) {
+    using namespace ocb;
+    OCB_ARG(d_G && K >= 1 && ldg >= K && rmax >= 1 && rmax <= 1024 && d_T && h_info3 && d_ws, "compress_from_gram");
+    OCB_ARG(eta > 0.0 && eta < 1e-6, "compress eta");
+    cudaStream_t st = (cudaStream_t)stream;
+    h_info3[0] = h_info3[1] = h_info3[2] = 0;
+    rmax = std::min<int64_t>(rmax, K);
+    CompressWs w;
+    const int64_t need = compress_carve(d_ws, ws_bytes, 0, K + GRAM_K_MAX + 1, rmax, &w);   // no G inside
+    if (need > ws_bytes) {
+        set_error("compress_from_gram: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+        return OCB_ERR_CAPACITY;
+    }
+    double* hp = pinned_scratch();
+    OCB_ARG(hp != nullptr, "pinned scratch allocation failed");
+    OCB_CUDA(cudaMemsetAsync(w.st, 0, sizeof(CholState), st));
+    CholState* hst = (CholState*)hp;
+    int rc = chol_from_gram(d_G, ldg, K, rmax, eta, w, hst, st);
     if (rc) return rc;
+    const int r = hst->rank;
+    h_info3[1] = r;
+    if (r == 0) return OCB_OK;
+    return finish_from_rt(K, r, rmax, thresh, kmax, w, d_T, ldt, t_capacity_cols, d_sigma, h_info3, hp, st);
+}
+
+int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K, double thresh, int64_t kmax,
+                 double eta, int64_t rmax, double* d_Zc, int64_t ldzc, int64_t zc_capacity_cols,
+                 double* d_sigma, int64_t* h_info3, void* d_ws, int64_t ws_bytes, void* stream) {
+    using namespace ocb;
+    OCB_ARG(n >= 0 && K >= 0 && ldz >= K && rmax >= 1 && rmax <= 1024, "compress sizes");
+    OCB_ARG(d_Z && d_Zc && h_info3 && d_ws, "compress null");
+    OCB_ARG(eta > 0.0 && eta < 1e-6, "compress eta");
+    cudaStream_t st = (cudaStream_t)stream;
+    h_info3[0] = h_info3[1] = h_info3[2] = 0;
+    if (K == 0 || n == 0) return OCB_OK;
+    rmax = std::min<int64_t>(rmax, std::min(K, n));
+    CompressWs w;
+    const int64_t need = compress_carve(d_ws, ws_bytes, n, K, rmax, &w);
+    if (need > ws_bytes) {
+        set_error("compress: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+        return OCB_ERR_CAPACITY;
+    }
+    double* hp = pinned_scratch();
+    OCB_ARG(hp != nullptr, "pinned scratch allocation failed");
+    OCB_CUDA(cudaMemsetAsync(w.st, 0, sizeof(CholState), st));
+    CholState* hst = (CholState*)hp;
+    int rc;
+    if (w.G) {
+        // Gram route: one DMMA product, then the whole pivoted Cholesky in one cooperative launch
+        rc = gram_impl(d_Z, ldz, K, d_Z, ldz, K, n, w.G, K, w.gws, w.gws_bytes, st);
+        if (rc) return rc;
+        rc = chol_from_gram(w.G, K, K, rmax, eta, w, hst, st);
+        if (rc) return rc;
+    } else {
+        const unsigned cblocks = (unsigned)((K + 31) / 32);
+        chol_colsq_kernel<<<cblocks, CH_THREADS, 0, st>>>(d_Z, ldz, n, K, w.d);
+        OCB_LAUNCH_CHECK();
+        int t = 0;
+        bool done = false;
+        while (!done) {
+            const int batch_end = (int)std::min<int64_t>(rmax, t + 32);
+            for (; t < batch_end; ++t) {
+                chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
+                OCB_LAUNCH_CHECK();
+                chol_col_kernel<<<dim3(cblocks, CH_SPLIT), CH_THREADS, 0, st>>>(d_Z, ldz, n, K, w.gpart, w.st);
+                OCB_LAUNCH_CHECK();
+                chol_col_finish_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(w.gpart, K, t, w.Rt, rmax,
+                                                                                    w.d, w.st);
+                OCB_LAUNCH_CHECK();
+            }
+            if (t >= rmax) {  // closes the factorisation at rank rmax if the rule never fired
+                chol_pick_kernel<<<1, 1024, 0, st>>>(w.d, K, t, (int)rmax, eta, w.st);
+                OCB_LAUNCH_CHECK();
+            }
+            OCB_CUDA(cudaMemcpyAsync(hst, w.st, sizeof(CholState), cudaMemcpyDeviceToHost, st));
+            OCB_CUDA(cudaStreamSynchronize(st));
+            done = hst->done != 0;
+        }
+    }
+    const int r = hst->rank;
+    h_info3[1] = r;
+    if (r == 0) return OCB_OK;
+    // T (K x keep) = right singular vectors;  Zc = Z T
+    rc = finish_from_rt(K, r, rmax, thresh, kmax, w, w.T, rmax, std::min<int64_t>(zc_capacity_cols, rmax),
+                        d_sigma, h_info3, hp, st);
+    if (rc) return rc;
+    const int keep = (int)h_info3[0];
+    if (keep == 0) return OCB_OK;
+    if (ldzc < keep) {
+        set_error("compress: %d columns kept but ldzc is %lld", keep, (long long)ldzc);
+        return OCB_ERR_CAPACITY;
+    }
     return tall_gemm_impl(d_Z, ldz, n, K, w.T, rmax, keep, d_Zc, ldzc, 1.0, 0.0, st);
 }
 }

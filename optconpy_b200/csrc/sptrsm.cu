@@ -1173,7 +1173,10 @@ struct PanelArgs {
     const int* skip;
 };
 
-template <int T>
+// U = list entries per loop iteration.  The loads of an iteration are issued before its FMAs and
+// the column indices of the NEXT iteration are fetched one iteration ahead, so that the chain
+// "index -> x row" (two dependent global loads) is off the critical path.
+template <int T, int U>
 __global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int p0, int p1, int wlog) {
     extern __shared__ double pred[];   // [warp][8][T][32] partial sums when a list is split
     if (a.skip && *a.skip) return;
@@ -1194,29 +1197,43 @@ __global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int
     if (valid) {
         pn0 = __ldg((const int4*)(a.panels + pi));          // cbase, ncol, dst0, init0
         nrows = __ldg(&a.panels[pi].nrows);
-        const int ncol = pn0.y;
-        int per = ((ncol >> 2) + wpr - 1) / wpr * 4;          // chunk of this warp, multiple of 4
+        const int ncol = pn0.y;                               // multiple of 4
+        const int per = ((ncol >> 2) + wpr - 1) / wpr * 4;    // chunk of this warp, multiple of 4
         const int e0 = wr * per, e1 = min(ncol, e0 + per);
         const int32_t* cp = a.col + pn0.x;
         const double2* vp = (const double2*)(a.val + (int64_t)pn0.x * PANEL_ROWS);
-        for (int e = e0; e < e1; e += 4) {
-            const int4 j4 = __ldg((const int4*)(cp + e));    // cbase and e are multiples of 4
-            const int jj[4] = {j4.x, j4.y, j4.z, j4.w};
-            double xv[4][T];
+        int jn[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; u += 4) {
+            const int4 j4 = (e0 + u < e1) ? __ldg((const int4*)(cp + e0 + u)) : make_int4(0, 0, 0, 0);
+            jn[u] = j4.x; jn[u + 1] = j4.y; jn[u + 2] = j4.z; jn[u + 3] = j4.w;
+        }
+        for (int e = e0; e < e1; e += U) {
+            int jj[U];
 #pragma unroll
-                for (int t = 0; t < T; ++t) xv[u][t] = xc[(int64_t)jj[u] * a.ldx + 32 * t];
+            for (int u = 0; u < U; ++u) jj[u] = jn[u];
+            double xv[U][T];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double2* v2 = vp + (int64_t)(e + u) * (PANEL_ROWS / 2);
+            for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int h = 0; h < PANEL_ROWS / 2; ++h) {
-                    const double2 vv = __ldg(v2 + h);
+                for (int t = 0; t < T; ++t) xv[u][t] = (e + u < e1) ? xc[(int64_t)jj[u] * a.ldx + 32 * t] : 0.0;
 #pragma unroll
-                    for (int t = 0; t < T; ++t) {
-                        acc[2 * h][t] = fma(vv.x, xv[u][t], acc[2 * h][t]);
-                        acc[2 * h + 1][t] = fma(vv.y, xv[u][t], acc[2 * h + 1][t]);
+            for (int u = 0; u < U; u += 4) {   // indices of the next iteration
+                const int4 j4 = (e + U + u < e1) ? __ldg((const int4*)(cp + e + U + u)) : make_int4(0, 0, 0, 0);
+                jn[u] = j4.x; jn[u + 1] = j4.y; jn[u + 2] = j4.z; jn[u + 3] = j4.w;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (e + u < e1) {   // warp-uniform
+                    const double2* v2 = vp + (int64_t)(e + u) * (PANEL_ROWS / 2);
+#pragma unroll
+                    for (int h = 0; h < PANEL_ROWS / 2; ++h) {
+                        const double2 vv = __ldg(v2 + h);
+#pragma unroll
+                        for (int t = 0; t < T; ++t) {
+                            acc[2 * h][t] = fma(vv.x, xv[u][t], acc[2 * h][t]);
+                            acc[2 * h + 1][t] = fma(vv.y, xv[u][t], acc[2 * h + 1][t]);
+                        }
                     }
                 }
             }
@@ -1259,25 +1276,47 @@ __global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int
     }
 }
 
-template <int T>
+template <int T, int U>
 static int panel_launch(const PanelArgs& w, int p0, int p1, int wlog, cudaStream_t st) {
     const int ppc = 8 >> wlog;
     const unsigned blocks = (unsigned)(((p1 - p0) + ppc - 1) / ppc) * (unsigned)w.ntile;
     const size_t smem = wlog > 0 ? (size_t)8 * PANEL_ROWS * T * 32 * sizeof(double) : 0;
     static bool attr = false;
     if (!attr) {
-        OCB_CUDA(cudaFuncSetAttribute(panel_level_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        OCB_CUDA(cudaFuncSetAttribute(panel_level_kernel<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       8 * PANEL_ROWS * T * 32 * (int)sizeof(double)));
         attr = true;
     }
-    panel_level_kernel<T><<<blocks, 256, smem, st>>>(w, p0, p1, wlog);
+    panel_level_kernel<T, U><<<blocks, 256, smem, st>>>(w, p0, p1, wlog);
     OCB_LAUNCH_CHECK();
     return OCB_OK;
 }
 
+// column tiles of 32 * T per warp: narrow tiles (T = 1) give the most warps in flight per SM (the
+// gathers are latency bound); OCB_PANEL_T / OCB_PANEL_U override for experiments
+static int panel_tiles(int64_t k) {
+    static int force = -1;
+    if (force < 0) {
+        const char* e = getenv("OCB_PANEL_T");
+        force = e ? atoi(e) : 0;
+    }
+    if (force == 1 || force == 2 || force == 4) return (k <= 32) ? 1 : ((k <= 64 && force > 2) ? 2 : force);
+    return k <= 32 ? 1 : 2;
+}
+static int64_t panel_ldx(int64_t k) {
+    const int64_t w = 32 * panel_tiles(k);
+    return (k + w - 1) / w * w;
+}
+
 static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
-    const int T = wide_tiles(a.k);
-    const int64_t ldx = wide_ldx(a.k);
+    const int T = panel_tiles(a.k);
+    const int64_t ldx = panel_ldx(a.k);
+    static int U = 0;
+    if (U == 0) {
+        const char* e = getenv("OCB_PANEL_U");
+        U = e ? atoi(e) : 8;
+        if (U != 4 && U != 8) U = 8;
+    }
     double* xe = a.ws;
     const unsigned lblocks = (unsigned)std::min<int64_t>((a.n * ldx + 255) / 256, 148 * 16);
     wide_load_kernel<<<lblocks, 256, 0, st>>>(a, xe, ldx);
@@ -1287,7 +1326,7 @@ static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     w.xe = xe; w.ldx = ldx; w.skip = a.skip;
     w.ntile = (int)(ldx / (32 * T));
     const int nsub = (int)lu->sub_pan.size() - 1;
-    const int64_t want_warps = (int64_t)sm_count() * 8;
+    const int64_t want_warps = (int64_t)sm_count() * 16;
     for (int sb = 0; sb < nsub; ++sb) {
         const int p0 = lu->sub_pan[sb], p1 = lu->sub_pan[sb + 1];
         if (p1 <= p0) continue;
@@ -1298,9 +1337,9 @@ static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
         int wlog = 0;
         while (wlog < 3 && (tasks << wlog) < want_warps && (maxcol >> (wlog + 1)) >= 32) ++wlog;
         int rc;
-        if (T == 1) rc = panel_launch<1>(w, p0, p1, wlog, st);
-        else if (T == 2) rc = panel_launch<2>(w, p0, p1, wlog, st);
-        else rc = panel_launch<4>(w, p0, p1, wlog, st);
+        if (T == 1) rc = U == 4 ? panel_launch<1, 4>(w, p0, p1, wlog, st) : panel_launch<1, 8>(w, p0, p1, wlog, st);
+        else if (T == 2) rc = U == 4 ? panel_launch<2, 4>(w, p0, p1, wlog, st) : panel_launch<2, 8>(w, p0, p1, wlog, st);
+        else rc = U == 4 ? panel_launch<4, 4>(w, p0, p1, wlog, st) : panel_launch<4, 8>(w, p0, p1, wlog, st);
         if (rc) return rc;
     }
     const unsigned sblocks = (unsigned)std::min<int64_t>((a.nrows_x * a.k + 255) / 256, 148 * 16);
@@ -1625,7 +1664,8 @@ int ocb_lu_stats(const ocb_lu* lu, int64_t* info8) {
 
 int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k) {
     if (!lu || !ocb::use_wide(lu, k)) return 0;
-    return lu->n_ext * ocb::wide_ldx(k) * (int64_t)sizeof(double);
+    const int64_t ldx = std::max(ocb::wide_ldx(k), ocb::panel_ldx(k));
+    return lu->n_ext * ldx * (int64_t)sizeof(double);
 }
 
 int ocb_lu_solve(const ocb_lu* lu, const double* d_B, int64_t ldb, int64_t nrows_b, double* d_X,
