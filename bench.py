@@ -390,6 +390,91 @@ def run_sweep(meshes, ks, reps, rank, world, peak_gbs):
     return out
 
 
+def run_sharded(rank, world, k_total, steps, nx, ny, peak_gbs):
+    """north_star (d) on BASELINE config[3] ("cylinder wake fine mesh, ~1e5 velocity dofs"): ONE
+    LR-ADI Lyapunov solve on the 200 x 62 channel Oseen operator with ``k_total`` right-hand-side
+    columns SHARDED over the ranks (strong scaling: the block is the same at every N), followed by
+    the column compression of the factor - row re-shard, partial Gram products on the FP64 tensor
+    pipe, K x K all-reduce (peer memory when the box offers symmetric memory, NCCL otherwise).
+    The six shifted factorisations of the setup are dealt to the ranks (shift sharding) and shared
+    through host shared memory.  Times are CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from optconpy_b200 import problems as pb, device as dv, parallel as par, proj_ric_utils as gpru
+    cm = par.ShardComm() if world > 1 else None
+    prob = pb.channel_problem(nx, ny, 2.5e-3)
+    M, A, J = prob['M'], prob['A'], prob['J']
+    ly = prob['mesh'].ly
+    convc = pb.convection_matrix(prob, lambda xy: np.stack([4.0*xy[:, 1]*(ly-xy[:, 1])/ly**2,
+                                                            np.zeros(len(xy))], 1))
+    NV, NP = prob['NV'], prob['NP']
+    At, Mt = (-A - convc).T.tocsr(), M.T.tocsr()
+    W = np.random.default_rng(0).standard_normal((NV, k_total))
+    dv.reset_stats()
+    t0 = time.perf_counter()
+    fac = gpru.ShiftedFactors(At, Mt, J, gpru.DEFAULT_SHIFTS, wide=True, shared=cm)
+    lus = fac.lus
+    fac.Mt_dev
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    setup_s = time.perf_counter() - t0
+    Wd = dv.to_dev(W)
+    d = dict(adi_max_steps=int(steps), adi_newZ_reltol=1e-300)
+
+    def one():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        if cm is None:
+            Zl, rel = gpru._stein_dev(fac, Wd, d)
+            widths = [Zl.shape[1]]
+        else:
+            Zl, widths, rel = par.sharded_stein(cm, fac, Wd, d)
+        ev[1].record()
+        if cm is None:
+            Zc, cinfo = dv.compress(Zl, thresh=1e-8*float(np.sqrt(k_total)), k=None)
+        else:
+            Zc, cinfo = par.sharded_compress(cm, Zl, widths, thresh=1e-8*float(np.sqrt(k_total)), k=None)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], dtype=torch.float64,
+                         device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()], rel, Zc, cinfo, widths
+    one()                                   # warm-up (allocations, symmetric buffers, module loads)
+    (ms_adi, ms_cmp), rel, Zc, cinfo, widths = one()
+    i = lus[0].info
+    nnz = int(i['nnzL'] + i['nnzU'])
+    n = int(i['n'])
+    kl = max(1, k_total//world)
+    fl = 2.0*nnz*k_total*steps
+    ab = steps*(12.0*nnz + 16.0*(n + 1) + 32.0*n*k_total)
+    K = int(sum(widths))
+    return dict(workload='channel %d x %d (cyl_wake_cont.py params, Re=60): NV %d, NP %d, n %d; LR-ADI '
+                         'Lyapunov solve, %d right-hand-side columns (seed 0), %d ADI steps over the '
+                         '6 built-in shifts, then compress_Zsvd of the %d-column factor'
+                         % (nx, ny, NV, NP, n, k_total, steps, K),
+                n_gpus=world, scaling='strong', columns_total=k_total, columns_per_rank=kl,
+                adi_steps=int(steps), ms_adi=ms_adi, ms_compress=ms_cmp,
+                rhs_columns_per_s=1e3*k_total*steps/ms_adi,
+                saddle_solves_per_s=1e3*steps/ms_adi,
+                solve_fp64_TFs=fl/ms_adi/1e9, solve_alg_GBs=ab/ms_adi/1e6,
+                solve_frac_hbm=ab/ms_adi/1e6/peak_gbs/max(world, 1),
+                nnz_LU=nnz, sublevels=int(i['levelsL'] + i['levelsU']),
+                compressed_cols=int(Zc.shape[1]), factor_cols=K,
+                rel_norms=[float(r) for r in rel],
+                transport=('single GPU' if cm is None else cm.transport),
+                symm_mem_error=(None if cm is None else cm.symm_error),
+                bytes_peer_memory_per_rank=(0 if cm is None else int(cm.bytes_p2p)//2),
+                bytes_nccl_per_rank=(0 if cm is None else int(cm.bytes_nccl)//2),
+                collectives='per ADI step: 1 all-reduced scalar (stopping test); compression: column->row '
+                            're-shard + K x K Gram all-reduce + row all-gather of the compressed factor',
+                setup_s=setup_s, setup_note='6 shifted saddle-point LUs (host SuperLU + analysis + panel '
+                'packing), dealt to the ranks and shared through POSIX shared memory; one-off '
+                'minimum-degree ordering included')
+
+
 def _quiet_stdout():
     """Library chatter (NCCL's version banner, ...) must not share stdout with the ONE JSON
     line: route fd 1 to stderr for the run and return a file on the real stdout."""
@@ -417,6 +502,10 @@ def main():
     ap.add_argument('--ref-lu-cache', type=int, default=1,
                     help='reference arm: reuse the shifted LUs across the Newton steps of a time '
                          'step (1, the best-effort scipy baseline) or factorise per Newton step (0)')
+    ap.add_argument('--sharded-k', type=int, default=512,
+                    help='columns of the column-sharded config-4 LR-ADI section (0 = skip)')
+    ap.add_argument('--sharded-steps', type=int, default=6)
+    ap.add_argument('--sharded-mesh', default='200,62')
     ap.add_argument('--phases', action='store_true', help='extra untimed pass with per-phase CUDA events + cProfile of the e2e loop (diagnostics on stderr)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -663,6 +752,11 @@ def main():
         sweep = run_sweep([int(v) for v in args.sweep_meshes.split(',')],
                           [int(v) for v in args.sweep_k.split(',')], 5, rank, world, peak)
 
+    sharded = None
+    if args.sharded_k > 0:
+        nx_, ny_ = [int(v) for v in args.sharded_mesh.split(',')]
+        sharded = run_sharded(rank, world, args.sharded_k, args.sharded_steps, nx_, ny_, peak)
+
     if rank == 0:
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W,
                    ms_per_step=ms_max/K, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -677,7 +771,7 @@ def main():
                                    'value, included in e2e; lu_factor_s / lu_worker_pack_s are '
                                    'summed over the workers'),
                    saddle_solves_per_s=solves/(ms_max*1e-3),
-                   saddle_sweep=sweep,
+                   saddle_sweep=sweep, sharded_config4=sharded,
                    rhs_columns_per_s=sum(sum(a)*0 for a in []) or None,
                    step_ms=step_ms, step_phase_ms=step_phases,
                    steps_info=[dict(tau=float(i['tau']), adi_steps=i['adi_steps'],

@@ -118,6 +118,9 @@ int ocb_lu_info(const ocb_lu* lu, int64_t* info8);
 /* info[0..7] = rows of the extended vector (n + y scratch), #supernodes, widest supernode,
  *              #slices, #program rows, #program entries (padded), ring stage bytes, ring stages */
 int ocb_lu_stats(const ocb_lu* lu, int64_t* info8);
+/* profiling aid: number of sub-levels of the panel program (0: none); h_out3 (optional, 3 per
+ * sub-level) = panels, longest column list, 0 */
+int64_t ocb_lu_panel_levels(const ocb_lu* lu, int64_t* h_out3, int64_t capacity_levels);
 /* debugging aid (OCB_TRSM_TRACE=1): SM clock of CTA 0 after the panel load and after every
  * sub-level barrier of the most recent solve */
 int ocb_debug_trace(int64_t* h_out, int64_t count);
@@ -212,6 +215,29 @@ int ocb_compress(const double* d_Z, int64_t ldz, int64_t n, int64_t K,
                  double* d_Zc, int64_t ldzc, int64_t zc_capacity_cols,
                  double* d_sigma, int64_t* h_info3,
                  void* d_ws, int64_t ws_bytes, void* stream);
+
+/* The replicated half of the same compression, from a K x K Gram matrix G = Z^T Z the caller
+ * already holds (column-sharded runs: G is the all-reduced sum of the ranks' partial products,
+ * SURVEY 8e): pivoted Cholesky + core eigen-decomposition -> T (K x keep, row-major) with
+ * Zc = Z T, so every rank can apply T to its own rows of Z.  h_info3 as ocb_compress. */
+int64_t ocb_compress_gram_ws_bytes(int64_t K, int64_t rmax);
+int ocb_compress_from_gram(const double* d_G, int64_t ldg, int64_t K, double thresh, int64_t kmax,
+                           double eta, int64_t rmax, double* d_T, int64_t ldt, int64_t t_capacity_cols,
+                           double* d_sigma, int64_t* h_info3, void* d_ws, int64_t ws_bytes, void* stream);
+
+/* ---- peer-memory movement for column-sharded runs -------------------------
+ * d_dst_peer / h_peer_ptrs are DEVICE pointers into buffers of other GPUs mapped into this
+ * process (symmetric memory over NVLink / NVSwitch); ordering between the ranks is the caller's
+ * (a symmetric-memory barrier between the phases).
+ *   ocb_p2p_put2d:     dst[r*ldd + c] = src[r*lds + c] (P2P stores): the column -> row re-shard of
+ *                      the factor before the Gram product, the all-gather of the compressed rows
+ *   ocb_p2p_sum_peers: out[e] = sum_g peer_g[e], ranks in fixed order (P2P loads): the K x K Gram
+ *                      all-reduce as the epilogue of the local partial products; bitwise the same
+ *                      result on every rank. */
+int ocb_p2p_put2d(const double* d_src, int64_t lds, int64_t nrows, int64_t ncols, double* d_dst_peer,
+                  int64_t ldd, void* stream);
+int ocb_p2p_sum_peers(const double* const* h_peer_ptrs, int64_t world, int64_t count, double* d_out,
+                      void* stream);
 
 /* ---- K6/K7 + the LR-ADI loop: pru.solve_proj_lyap_stein -------------------------
  * (tests/test_units_compfacres_compress.py:62-64; called by

@@ -29,6 +29,7 @@ PROTOTYPES = {
     'ocb_lu_create_from_image': (C.c_int, [C.POINTER(vp), vp, i64, vp, vp]),
     'ocb_lu_info': (C.c_int, [vp, C.POINTER(i64)]),
     'ocb_lu_stats': (C.c_int, [vp, C.POINTER(i64)]),
+    'ocb_lu_panel_levels': (i64, [vp, vp, i64]),
     'ocb_debug_trace': (C.c_int, [vp, i64]),
     'ocb_lu_program_create': (C.c_int, [C.POINTER(vp), i64, vp, vp, vp, vp, vp, vp, i64]),
     'ocb_lu_program_destroy': (C.c_int, [vp]),
@@ -49,6 +50,11 @@ PROTOTYPES = {
     'ocb_compress_ws_bytes': (i64, [i64, i64, i64]),
     'ocb_compress': (C.c_int, [f64p, i64, i64, i64, C.c_double, i64, C.c_double, i64,
                                f64p, i64, i64, f64p, C.POINTER(i64), vp, i64, vp]),
+    'ocb_compress_gram_ws_bytes': (i64, [i64, i64]),
+    'ocb_compress_from_gram': (C.c_int, [f64p, i64, i64, C.c_double, i64, C.c_double, i64,
+                                         f64p, i64, i64, f64p, C.POINTER(i64), vp, i64, vp]),
+    'ocb_p2p_put2d': (C.c_int, [f64p, i64, i64, i64, f64p, i64, vp]),
+    'ocb_p2p_sum_peers': (C.c_int, [C.POINTER(vp), i64, i64, f64p, vp]),
     'ocb_adi_set_norm_hook': (C.c_int, [vp, vp]),
     'ocb_adi_ws_bytes': (i64, [i64, i64, i64, i64, C.POINTER(vp)]),
     'ocb_adi_run': (C.c_int, [C.POINTER(vp), C.POINTER(C.c_double), i64, i64, i64,

@@ -64,6 +64,7 @@ struct ocb_lu {
     const double *p_scale = nullptr, *p_val = nullptr;
     const int32_t* p_col = nullptr;
     int64_t npanels = 0, panel_entries = 0, panel_entries_actual = 0;
+    const int32_t* p_sub_dev = nullptr;   // device copy: sub_pan (nsub + 1) followed by sub_maxcol (nsub)
     std::vector<int32_t> sub_pan;      // host: first panel of every sub-level (nsub + 1)
     std::vector<int32_t> sub_maxcol;   // host: longest column list of every sub-level
 };
@@ -911,6 +912,7 @@ static int upload_image(ocb_lu* lu, const unsigned char* img, int64_t bytes, voi
         lu->panel_entries = meta[M_PENT];
         lu->panel_entries_actual = meta[M_PENT_ACTUAL];
         const int32_t* sp = (const int32_t*)(img + meta[M_P_SUB]);
+        lu->p_sub_dev = (const int32_t*)(lu->arena + meta[M_P_SUB]);
         lu->sub_pan.assign(sp, sp + meta[M_NSUB] + 1);
         lu->sub_maxcol.assign(sp + meta[M_NSUB] + 1, sp + 2 * meta[M_NSUB] + 1);
     }
@@ -1308,6 +1310,292 @@ static int64_t panel_ldx(int64_t k) {
     return (k + w - 1) / w * w;
 }
 
+// ---------------------------------------------------------------------------------
+// persistent, column-chunked panel executor (the default for the wide path)
+// ---------------------------------------------------------------------------------
+// The level-by-level executor above streams the whole n_ext x k block through every
+// sub-level: for n ~ 1e5 and k = 1024 the block (0.7 GB) is far larger than the L2, every x row
+// is re-read from HBM dozens of times over the ~190 sub-levels and the solve runs at the speed
+// of 256-byte random HBM reads (measured: 2.5 TFLOP/s).  Here the block is cut into CHUNKS of
+// 32*T columns that stay resident in the 126 MB L2 for a whole pass over the program:
+//   * the SMs are split into G GROUPS; a group takes one chunk through load -> all sub-levels
+//     -> store, then the next chunk (chunk = group, group + G, ...); G chunks are in flight, sized
+//     so that together they fit the L2;
+//   * ONE launch per solve: the sub-level barrier is a counter/generation barrier among the
+//     co-resident CTAs of a group (cooperative launch), not a kernel boundary;
+//   * inside a sub-level the panels are dealt to the CTAs of the group; a warp owns a panel
+//     (8 rows, register blocked) x the chunk's columns (lane = column).
+struct GroupBar {
+    unsigned int count, gen;
+    unsigned int pad[30];
+};
+
+struct PersistArgs {
+    SolveArgs a;
+    PanelArgs p;
+    const int32_t* sub_pan;      // device: first panel of every sub-level (nsub + 1), then longest list (nsub)
+    int nsub, ngroups, cpg, nchunks;
+    GroupBar* bars;
+    int* err;
+};
+
+__device__ __forceinline__ bool group_barrier(GroupBar* bar, unsigned int ncta, unsigned int& gen, int* err) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // publish this CTA's x rows
+        const unsigned int want = gen + 1;
+        if (atomicAdd(&bar->count, 1u) == ncta - 1) {
+            bar->count = 0;
+            __threadfence();
+            atomicExch(&bar->gen, want);
+        } else {
+            unsigned long long spins = 0;
+            while (*((volatile unsigned int*)&bar->gen) != want) {
+                if (++spins > (1ull << 31)) { atomicExch(err, 1); break; }   // watchdog: never hang the GPU
+                __nanosleep(20);
+            }
+        }
+        __threadfence();                                   // acquire: invalidates this SM's L1
+    }
+    ++gen;
+    __syncthreads();
+    return true;
+}
+
+template <int T, int U>
+__global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q) {
+    extern __shared__ double pred[];   // [warp][8][T][32] partial sums when a list is split
+    if (q.p.skip && *q.p.skip) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int group = blockIdx.x / q.cpg, gcta = blockIdx.x - group * q.cpg;
+    if (group >= q.ngroups) return;
+    GroupBar* bar = q.bars + group;
+    unsigned int gen = 0;
+    const SolveArgs& a = q.a;
+    const int64_t ldx = q.p.ldx;
+    constexpr int CW = 32 * T;
+    for (int chunk = group; chunk < q.nchunks; chunk += q.ngroups) {
+        const int64_t c0 = (int64_t)chunk * CW;
+        // ---- load: xe[perm_r[i], c0 + c] = B[i, c0 + c] (0 beyond nrows_b / k)
+        for (int64_t e = (int64_t)gcta * 256 + tid; e < a.n * CW; e += (int64_t)q.cpg * 256) {
+            const int64_t i = e / CW, c = c0 + (e - i * CW);
+            double v = 0.0;
+            if (i < a.nrows_b && c < a.k) v = a.B[i * a.ldb + c];
+            q.p.xe[(int64_t)__ldg(a.perm_r + i) * ldx + c] = v;
+        }
+        group_barrier(bar, q.cpg, gen, q.err);
+        double* xc = q.p.xe + c0 + lane;
+        for (int sb = 0; sb < q.nsub; ++sb) {
+            const int p0 = __ldg(q.sub_pan + sb), p1 = __ldg(q.sub_pan + sb + 1);
+            const int np = p1 - p0;
+            if (np > 0) {
+                const int maxcol = __ldg(q.sub_pan + q.nsub + 1 + sb);
+                int wlog = 0;   // split long lists while the sub-level has fewer panels than the group has warps
+                while (wlog < 3 && (np << wlog) < q.cpg * 8 && (maxcol >> (wlog + 1)) >= 32) ++wlog;
+                const int wpr = 1 << wlog, ppc = 8 >> wlog;
+                const int units = (np + ppc - 1) / ppc;
+                const int wr = warp & (wpr - 1);
+                for (int unit = gcta; unit < units; unit += q.cpg) {
+                    const int pi = p0 + unit * ppc + (warp >> wlog);
+                    const bool valid = pi < p1;
+                    double acc[PANEL_ROWS][T];
+#pragma unroll
+                    for (int r = 0; r < PANEL_ROWS; ++r)
+#pragma unroll
+                        for (int t = 0; t < T; ++t) acc[r][t] = 0.0;
+                    int4 pn0 = make_int4(0, 0, 0, -1);
+                    int nrows = 0;
+                    if (valid) {
+                        pn0 = __ldg((const int4*)(q.p.panels + pi));
+                        nrows = __ldg(&q.p.panels[pi].nrows);
+                        const int ncol = pn0.y;
+                        const int per = ((ncol >> 2) + wpr - 1) / wpr * 4;
+                        const int e0 = wr * per, e1 = min(ncol, e0 + per);
+                        const int32_t* cp = q.p.col + pn0.x;
+                        const double2* vp = (const double2*)(q.p.val + (int64_t)pn0.x * PANEL_ROWS);
+                        int jn[U];
+#pragma unroll
+                        for (int u = 0; u < U; u += 4) {
+                            const int4 j4 = (e0 + u < e1) ? __ldg((const int4*)(cp + e0 + u)) : make_int4(0, 0, 0, 0);
+                            jn[u] = j4.x; jn[u + 1] = j4.y; jn[u + 2] = j4.z; jn[u + 3] = j4.w;
+                        }
+                        for (int e = e0; e < e1; e += U) {
+                            double xv[U][T];
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+#pragma unroll
+                                for (int t = 0; t < T; ++t)
+                                    xv[u][t] = (e + u < e1) ? xc[(int64_t)jn[u] * ldx + 32 * t] : 0.0;
+#pragma unroll
+                            for (int u = 0; u < U; u += 4) {
+                                const int4 j4 = (e + U + u < e1) ? __ldg((const int4*)(cp + e + U + u))
+                                                                 : make_int4(0, 0, 0, 0);
+                                jn[u] = j4.x; jn[u + 1] = j4.y; jn[u + 2] = j4.z; jn[u + 3] = j4.w;
+                            }
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                if (e + u < e1) {
+                                    const double2* v2 = vp + (int64_t)(e + u) * (PANEL_ROWS / 2);
+#pragma unroll
+                                    for (int h = 0; h < PANEL_ROWS / 2; ++h) {
+                                        const double2 vv = __ldg(v2 + h);
+#pragma unroll
+                                        for (int t = 0; t < T; ++t) {
+                                            acc[2 * h][t] = fma(vv.x, xv[u][t], acc[2 * h][t]);
+                                            acc[2 * h + 1][t] = fma(vv.y, xv[u][t], acc[2 * h + 1][t]);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (wlog > 0) {
+                        double* mine = pred + (size_t)warp * (PANEL_ROWS * T * 32);
+#pragma unroll
+                        for (int r = 0; r < PANEL_ROWS; ++r)
+#pragma unroll
+                            for (int t = 0; t < T; ++t) mine[(r * T + t) * 32 + lane] = acc[r][t];
+                        __syncthreads();
+                        if (wr == 0) {
+                            for (int w2 = 1; w2 < wpr; ++w2) {
+                                const double* other = pred + (size_t)(warp + w2) * (PANEL_ROWS * T * 32);
+#pragma unroll
+                                for (int r = 0; r < PANEL_ROWS; ++r)
+#pragma unroll
+                                    for (int t = 0; t < T; ++t) acc[r][t] += other[(r * T + t) * 32 + lane];
+                            }
+                        }
+                        __syncthreads();   // pred is reused by the next unit
+                    }
+                    if (valid && wr == 0) {
+                        const double* sc = q.p.scale + (int64_t)pi * PANEL_ROWS;
+#pragma unroll
+                        for (int r = 0; r < PANEL_ROWS; ++r) {
+                            if (r < nrows) {
+                                const double sv = __ldg(sc + r);
+                                double* xd = xc + (int64_t)(pn0.z + r) * ldx;
+                                if (pn0.w >= 0) {
+                                    const double* xi = xc + (int64_t)(pn0.w + r) * ldx;
+#pragma unroll
+                                    for (int t = 0; t < T; ++t) xd[32 * t] = (xi[32 * t] - acc[r][t]) * sv;
+                                } else {
+#pragma unroll
+                                    for (int t = 0; t < T; ++t) xd[32 * t] = -acc[r][t] * sv;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            group_barrier(bar, q.cpg, gen, q.err);
+        }
+        // ---- store: X[j, c0 + c] = xe[perm_c[j], c0 + c]  (NaN if the watchdog fired)
+        const bool bad = *((volatile int*)q.err) != 0;
+        for (int64_t e = (int64_t)gcta * 256 + tid; e < a.nrows_x * CW; e += (int64_t)q.cpg * 256) {
+            const int64_t j = e / CW, c = c0 + (e - j * CW);
+            if (c < a.k) {
+                const double v = q.p.xe[(int64_t)__ldg(a.perm_c + j) * ldx + c];
+                a.X[j * a.ldx + c] = bad ? __longlong_as_double(0x7ff8000000000000LL) : v;
+            }
+        }
+    }
+}
+
+constexpr int64_t PERSIST_TAIL_BYTES = 8192;   // group barriers + error flag behind the xe block
+
+template <int T, int U>
+static int persist_launch(PersistArgs q, int ctas_per_sm_want, cudaStream_t st) {
+    const size_t smem = (size_t)8 * PANEL_ROWS * T * 32 * sizeof(double);
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        OCB_CUDA(cudaFuncSetAttribute(panel_persist_kernel<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_persist_kernel<T, U>, 256, smem));
+    }
+    if (per_sm < 1) {
+        set_error("persistent solve: the kernel does not fit an SM");
+        return OCB_ERR_CUDA;
+    }
+    // all CTAs must be co-resident (they wait for one another): as many per SM as fit, at most the wish
+    q.cpg = std::max(1, std::min(ctas_per_sm_want, per_sm) * sm_count() / q.ngroups);
+    void* args[] = {(void*)&q};
+    OCB_CUDA(cudaLaunchCooperativeKernel((void*)panel_persist_kernel<T, U>, dim3((unsigned)(q.ngroups * q.cpg)),
+                                         dim3(256), args, smem, st));
+    count_launch();
+    return OCB_OK;
+}
+
+static int persist_ctas_per_sm() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("OCB_PERSIST_CTAS_PER_SM");
+        v = e ? atoi(e) : 2;
+        if (v < 1 || v > 4) v = 2;
+    }
+    return v;
+}
+
+// plan of a persistent solve: column tiles per warp (T), groups, chunks
+struct PersistPlan { int T, ngroups, nchunks; int64_t ldx; };
+static PersistPlan persist_plan(const ocb_lu* lu, int64_t k) {
+    static int64_t l2_budget = 0;
+    static int force_t = -1, force_g = -1;
+    if (l2_budget == 0) {
+        const char* e = getenv("OCB_PERSIST_L2_MB");
+        l2_budget = (int64_t)(e ? atoi(e) : 80) << 20;
+        const char* e2 = getenv("OCB_PANEL_T");
+        force_t = e2 ? atoi(e2) : 0;
+        const char* e3 = getenv("OCB_PERSIST_GROUPS");
+        force_g = e3 ? atoi(e3) : 0;
+    }
+    PersistPlan pl;
+    const int64_t bytes32 = lu->n_ext * 32 * 8;
+    int T = 1;
+    if (k > 32) {
+        T = 2;
+        if (k > 64 && 4 * bytes32 * 2 <= l2_budget) T = 4;
+        while (T > 1 && T * bytes32 * 2 > l2_budget) T >>= 1;   // at least two chunks in the L2
+    }
+    if (force_t == 1 || force_t == 2 || force_t == 4) T = (k <= 32) ? 1 : force_t;
+    pl.T = T;
+    const int64_t cw = 32 * T;
+    pl.nchunks = (int)((k + cw - 1) / cw);
+    pl.ldx = (int64_t)pl.nchunks * cw;
+    int64_t g = std::max<int64_t>(1, l2_budget / (T * bytes32));
+    g = std::min<int64_t>(g, 8);
+    g = std::min<int64_t>(g, pl.nchunks);
+    if (force_g >= 1 && force_g <= 16) g = std::min<int64_t>(force_g, pl.nchunks);
+    pl.ngroups = (int)g;
+    return pl;
+}
+
+static int persist_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
+    const PersistPlan pl = persist_plan(lu, a.k);
+    static int U = 0;
+    if (U == 0) {
+        const char* e = getenv("OCB_PANEL_U");
+        U = e ? atoi(e) : 8;
+        if (U != 4 && U != 8) U = 8;
+    }
+    PersistArgs q;
+    q.a = a;
+    q.p.panels = lu->p_panels; q.p.scale = lu->p_scale; q.p.val = lu->p_val; q.p.col = lu->p_col;
+    q.p.xe = a.ws; q.p.ldx = pl.ldx; q.p.skip = a.skip; q.p.ntile = 1;
+    q.sub_pan = lu->p_sub_dev;
+    q.nsub = (int)lu->sub_pan.size() - 1;
+    q.ngroups = pl.ngroups;
+    q.nchunks = pl.nchunks;
+    q.cpg = 0;   // set by persist_launch from the occupancy of the instantiation
+    unsigned char* tail = (unsigned char*)a.ws + lu->n_ext * pl.ldx * sizeof(double);
+    tail = (unsigned char*)(((uintptr_t)tail + 255) & ~(uintptr_t)255);
+    q.bars = (GroupBar*)tail;
+    q.err = (int*)(tail + 16 * sizeof(GroupBar));
+    OCB_CUDA(cudaMemsetAsync(tail, 0, 16 * sizeof(GroupBar) + 64, st));
+    const int want = persist_ctas_per_sm();
+    if (pl.T == 1) return U == 4 ? persist_launch<1, 4>(q, want, st) : persist_launch<1, 8>(q, want, st);
+    if (pl.T == 2) return U == 4 ? persist_launch<2, 4>(q, want, st) : persist_launch<2, 8>(q, want, st);
+    return U == 4 ? persist_launch<4, 4>(q, want, st) : persist_launch<4, 8>(q, want, st);
+}
+
 static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     const int T = panel_tiles(a.k);
     const int64_t ldx = panel_ldx(a.k);
@@ -1413,7 +1701,9 @@ static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int
             set_error("lu_solve: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
             return OCB_ERR_CAPACITY;
         }
-        return lu->has_panels ? panel_solve(lu, a, st) : wide_solve(lu, a, st);
+        static const bool by_level = getenv("OCB_WIDE_BY_LEVEL") != nullptr;
+        if (lu->has_panels) return by_level ? panel_solve(lu, a, st) : persist_solve(lu, a, st);
+        return wide_solve(lu, a, st);
     }
     switch (lu->cl) {
         case 8: return launch_cluster<8>(lu, a, st);
@@ -1649,6 +1939,19 @@ int ocb_debug_trace(int64_t* h_out, int64_t count) {
     return OCB_OK;
 }
 
+int64_t ocb_lu_panel_levels(const ocb_lu* lu, int64_t* h_out3, int64_t capacity_levels) {
+    // debugging / profiling aid: per sub-level {panels, longest column list, -} of the panel program
+    if (!lu || !lu->has_panels) return 0;
+    const int64_t nsub = (int64_t)lu->sub_pan.size() - 1;
+    if (h_out3)
+        for (int64_t sb = 0; sb < nsub && sb < capacity_levels; ++sb) {
+            h_out3[3 * sb] = lu->sub_pan[sb + 1] - lu->sub_pan[sb];
+            h_out3[3 * sb + 1] = lu->sub_maxcol[sb];
+            h_out3[3 * sb + 2] = 0;
+        }
+    return nsub;
+}
+
 int ocb_lu_stats(const ocb_lu* lu, int64_t* info8) {
     OCB_ARG(lu && info8, "lu_stats");
     info8[0] = lu->n_ext;
@@ -1664,8 +1967,9 @@ int ocb_lu_stats(const ocb_lu* lu, int64_t* info8) {
 
 int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k) {
     if (!lu || !ocb::use_wide(lu, k)) return 0;
-    const int64_t ldx = std::max(ocb::wide_ldx(k), ocb::panel_ldx(k));
-    return lu->n_ext * ldx * (int64_t)sizeof(double);
+    int64_t ldx = std::max(ocb::wide_ldx(k), ocb::panel_ldx(k));
+    if (lu->has_panels) ldx = std::max(ldx, ocb::persist_plan(lu, k).ldx);
+    return lu->n_ext * ldx * (int64_t)sizeof(double) + ocb::PERSIST_TAIL_BYTES;
 }
 
 int ocb_lu_solve(const ocb_lu* lu, const double* d_B, int64_t ldb, int64_t nrows_b, double* d_X,

@@ -734,13 +734,16 @@ def sadpnt_matrix(amat, jmat, jmatT=None):
                      [sps.csr_matrix(jmat), sps.csr_matrix((nnpp, nnpp))]], format='csc')
 
 
-def gram(Z, W):
+def gram(Z, W, out=None):
     """``Z^T W`` on the FP64 tensor pipe (device tensors, row-major)."""
     lib = require_cuda()
     n, ka = Z.shape
     kb = W.shape[1]
     assert W.shape[0] == n and Z.stride(1) == 1 and W.stride(1) == 1
-    G = torch.empty((ka, kb), dtype=torch.float64, device=Z.device)
+    G = torch.empty((ka, kb), dtype=torch.float64, device=Z.device) if out is None else out
+    assert G.shape == (ka, kb) and G.stride(1) == 1
+    if ka == 0 or kb == 0 or n == 0:
+        return G.zero_()
     wsb = lib.ocb_gram_ws_bytes(n, ka, kb)
     ws = workspace('gram', wsb)
     _cabi.check(lib.ocb_gram(ptr(Z), Z.stride(0), ka, ptr(W), W.stride(0), kb, n,
@@ -842,12 +845,49 @@ def compress(Z, thresh=None, k=None, eta=1e-14, rmax=None, _smax0=None, _level=0
                      sigma=torch.cat([info['sigma'][:k1], info2['sigma']]), levels=info2['levels'])
 
 
+def compress_from_gram(G, thresh=None, k=None, eta=1e-14, rmax=None):
+    """Replicated half of the compression from a K x K Gram matrix (column-sharded runs):
+    returns (T device tensor K x keep with ``Zc = Z T``, info)."""
+    lib = require_cuda()
+    K = G.shape[0]
+    rmax = int(min(K, 1024)) if rmax is None else int(min(rmax, K, 1024))
+    cap = rmax if k is None else int(min(rmax, k))
+    T = torch.empty((K, max(cap, 1)), dtype=torch.float64, device=G.device)
+    sig = torch.zeros((rmax,), dtype=torch.float64, device=G.device)
+    info = (C.c_int64*3)()
+    wsb = lib.ocb_compress_gram_ws_bytes(K, rmax)
+    ws = workspace('compress_gram', wsb)
+    _cabi.check(lib.ocb_compress_from_gram(ptr(G), G.stride(0), K, -1.0 if thresh is None else float(thresh),
+                                           0 if k is None else int(k), float(eta), rmax, ptr(T), T.stride(0),
+                                           cap, ptr(sig), info, ptr(ws), wsb, stream_ptr()),
+                'ocb_compress_from_gram')
+    keep = int(info[0])
+    return T[:, :keep], dict(kept=keep, chol_rank=int(info[1]), sweeps=int(info[2]), sigma=sig[:int(info[1])])
+
+
+def p2p_put2d(src, dst_ptr, ldd):
+    """2-D block copy of a device block into a (peer-mapped) buffer at ``dst_ptr``."""
+    lib = require_cuda()
+    assert src.dtype == torch.float64 and src.dim() == 2 and src.stride(1) == 1
+    _cabi.check(lib.ocb_p2p_put2d(ptr(src), src.stride(0), src.shape[0], src.shape[1], int(dst_ptr), int(ldd),
+                                  stream_ptr()), 'ocb_p2p_put2d')
+
+
+def p2p_sum_peers(ptrs, count, out):
+    lib = require_cuda()
+    arr = (C.c_void_p*len(ptrs))(*[int(p) for p in ptrs])
+    _cabi.check(lib.ocb_p2p_sum_peers(arr, len(ptrs), int(count), ptr(out), stream_ptr()), 'ocb_p2p_sum_peers')
+    return out
+
+
 def feedback(Mt, Z, tB, alpha=1.0):
     """``alpha * Mt (Z (Z^T tB))`` with Mt a DeviceCSR, Z and tB device blocks."""
     lib = require_cuda()
     NV, kz = Z.shape
     m = tB.shape[1]
     out = torch.empty((NV, m), dtype=torch.float64, device=Z.device)
+    if kz == 0:
+        return out.zero_()
     wsb = lib.ocb_feedback_ws_bytes(NV, kz, m)
     ws = workspace('feedback', wsb)
     _cabi.check(lib.ocb_feedback(ptr(Mt.rowptr), ptr(Mt.colidx), ptr(Mt.vals), NV,

@@ -20,6 +20,7 @@ import scipy.sparse as sps
 import torch
 
 from . import device as dv
+from . import parallel as par
 
 __all__ = ['solve_proj_lyap_stein', 'proj_alg_ric_newtonadi', 'compress_Zsvd',
            'get_mTzzTtb', 'comp_proj_lyap_res_norm', 'factors_async', 'lookahead_thread_init']
@@ -51,18 +52,25 @@ class ShiftedFactors(object):
     setup of the next time step with the device work of the current one
     (``factors_async`` / ``dre_stepper`` look-ahead)."""
 
-    def __init__(self, At, Mt, jmat, ms, Mt_dev=None, k_hint=None):
+    def __init__(self, At, Mt, jmat, ms, Mt_dev=None, k_hint=None, wide=False, shared=None):
         self.ms = [float(m) for m in ms]
         self.NV, self.NP = At.shape[0], jmat.shape[0]
         # k_hint: expected number of right-hand-side columns of the ADI blocks (picks the
-        # cluster size the factor images are packed for)
-        self._job = dv.FactorJob(_shifted_saddle_matrices(At, Mt, jmat, self.ms),
-                                 k_hint=k_hint).start_upload()
+        # cluster size the factor images are packed for); wide: also pack the panel program of
+        # the all-columns-at-once executor; shared: a parallel.ShardComm - the shifts are dealt
+        # to its ranks for the host factorisation (shift-sharded setup)
+        mats = _shifted_saddle_matrices(At, Mt, jmat, self.ms)
+        self._lus = None
+        if shared is not None:
+            self._job = None
+            self._lus = par.shared_factors(shared, mats, wide=wide, k_hint=k_hint)
+        else:
+            self._job = dv.FactorJob(mats, k_hint=k_hint, wide=wide).start_upload()
         self._Mt, self._Mt_dev = Mt, Mt_dev
 
     @property
     def lus(self):
-        return self._job.result()
+        return self._lus if self._lus is not None else self._job.result()
 
     @property
     def Mt_dev(self):
@@ -159,6 +167,12 @@ def solve_proj_lyap_stein(amat=None, jmat=None, wmat=None, mmat=None,
         # (F - U V)^T = F^T - V^T U^T: dense SMW factor V^T (NV x m), sparse factor U^T
         Ufb = dv.to_dev(_dense(vmat).T)
         Vt = dv.DeviceCSR(sps.csr_matrix(umat).T)
+    cm = par.comm()
+    if cm is not None:
+        # column-sharded over the ranks (parallel.enable): same result on every rank
+        Zl, widths, rel = par.sharded_stein(cm, fac, W, adi_dict, Ufb=Ufb, Vt=Vt)
+        zf = par.ShardedFactor(cm, Zl, widths)
+        return dict(zfac=zf if kw.get('_lazy_zfac') else np.asarray(zf), adi_rel_newZ_norms=rel)
     Z, rel = _stein_dev(fac, W, adi_dict, Ufb=Ufb, Vt=Vt)
     return dict(zfac=dv.to_host(Z), adi_rel_newZ_norms=rel)
 
@@ -301,6 +315,19 @@ def proj_alg_ric_newtonadi(mmat=None, amat=None, jmat=None,
     with dv.phase('ric_factor_wait_upload'):
         fac.lus
         fac.Mt_dev
+    cm = par.comm()
+    if cm is not None:
+        # column-sharded Newton-ADI (parallel.enable): the factor stays distributed
+        probe = None if nwtn_adi_dict.get('full_upd_norm_check', False) else \
+            dv.to_dev(_probe_vec(W.shape[0], nwtn_adi_dict))
+        with dv.phase('ric_newton_adi_device'):
+            Zl, widths, info = par.sharded_newtonadi(cm, fac, Bd, Vt_b, W, z0d, nwtn_adi_dict, mtxoldb=old,
+                                                     probe=probe)
+            torch.cuda.current_stream().synchronize()
+        zf = par.ShardedFactor(cm, Zl, widths)
+        if kw.get('_lazy_zfac') or kw.get('_return_device'):
+            return dict(zfac=zf, **info)
+        return dict(zfac=np.asarray(zf), **info)
     with dv.phase('ric_newton_adi_device'):
         Z, info = newtonadi_dev(fac, Bd, Vt_b, W, z0d, nwtn_adi_dict, mtxoldb=old)
         torch.cuda.current_stream().synchronize()
@@ -319,6 +346,10 @@ def compress_Zsvd(Z, k=None, thresh=None, shplot=False):
     rank-revealing Cholesky of the Gram matrix, Jacobi eigen-solver and the two
     tall products, all on the device."""
     dv.require_cuda()
+    if isinstance(Z, par.ShardedFactor):
+        with dv.phase('compress'):
+            Zc, info = par.sharded_compress(Z.comm, Z.local, Z.widths, thresh=thresh, k=k)
+            return dv.to_host(Zc)
     with dv.phase('compress'):
         if isinstance(Z, torch.Tensor):
             Zd = Z

@@ -10,6 +10,7 @@ the FEniCS parts replaced by :mod:`optconpy_b200.problems`:
   alphau=1e-7, gamma=1e-1, 7 shifts, y* = -/+0.1 sin(5*3.14 t)).
 * ``config2b``: ``driv_cav_cont.py:8-30`` (N=25, Nts=40, nu=1e-2, alphau=1e-4, k<=60).
 * ``config3``: ``cyl_wake_cont.py:8-28`` steady-state branch on the synthetic channel.
+* ``config4``: the same on the fine 200 x 62 channel mesh (NV ~ 1e5), columns sharded over GPUs.
 """
 import numpy as np
 
@@ -104,6 +105,13 @@ def config3(lau, nx=44, ny=16, nu=2.5e-3):
     convc = pb.convection_matrix(prob, base_flow)
     return prob, cs, dict(convc_mat=convc, nwtn_adi_dict=nwtn_adi_dict,
                           ystarvec=_ystar_zero(cs['NY'], rows=1))
+
+
+def config4(lau, nx=200, ny=62, nu=2.5e-3):
+    """BASELINE config[3]: "cylinder wake fine mesh (~1e5 velocity dofs)" - the parameters of
+    ``cyl_wake_cont.py:8-28`` (config 3) on the 200 x 62 channel mesh: NV = 97 146, NP = 12 542,
+    n = 109 688.  Steady-state branch ``optcont_main.py:451-514``."""
+    return config3(lau, nx=nx, ny=ny, nu=nu)
 
 
 def steady_state_feedback(prob, cs, convc_mat, nwtn_adi_dict, ystarvec, lau, pru,

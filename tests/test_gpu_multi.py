@@ -106,3 +106,92 @@ def test_column_sharded_adi_two_gpus(tmp_path):
     # Gram all-reduce: identical on both ranks, equals Z^T M Z
     assert np.array_equal(outs[0]['G'], outs[1]['G'])
     assert np.allclose(outs[0]['G'], Z.T @ (M @ Z), rtol=1e-11, atol=1e-13)
+
+
+def _ric_case():
+    from optconpy_b200 import problems as pb
+    from oracle import lin_alg_utils as olau
+    prob = pb.drivcav_problem(10, 1e-2)
+    M, A, J = prob['M'], prob['A'], prob['J']
+    Nc = pb.convection_matrix(prob, pb.analytic_vortex)
+    tau = 0.05
+    Ft = -(0.5*M.T + tau*(A.T + Nc.T))
+    cs = pb.control_setup(prob, olau, alphau=1e-4)
+    d = dict(adi_max_steps=120, adi_newZ_reltol=1e-9, nwtn_max_steps=8, nwtn_upd_reltol=1e-9,
+             nwtn_upd_abstol=1e-12, full_upd_norm_check=False, ms=[-5.0, -3.0, -2.0, -1.5, -1.3, -1.1, -1.0])
+    kw = dict(mmat=M.T, amat=Ft, transposed=True, jmat=J, bmat=np.sqrt(tau)*cs['tb_mat'],
+              wmat=np.sqrt(tau)*cs['trct_mat'], z0=None, nwtn_adi_dict=d)
+    return prob, cs, kw
+
+
+def _worker_public_api(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    os.environ['OCB_LU_WORKERS'] = '0'
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    import optconpy_b200.proj_ric_utils as gpru
+    from optconpy_b200 import parallel as par
+    prob, cs, kw = _ric_case()
+    out = {}
+    for name, use_symm in (('auto', None), ('nccl', False)):
+        cm = par.enable(use_symm=use_symm)
+        res = gpru.proj_alg_ric_newtonadi(_lazy_zfac=True, **kw)          # factor stays sharded
+        zc = gpru.compress_Zsvd(res['zfac'], thresh=5e-5, k=50)
+        full = np.asarray(res['zfac'])
+        gain = -gpru.get_mTzzTtb(prob['M'].T, zc, cs['tb_mat'])
+        # Newton restarted from the compressed factor (z0 replicated -> column slices), full check
+        d2 = dict(kw['nwtn_adi_dict'], nwtn_max_steps=2, full_upd_norm_check=True)
+        res2 = gpru.proj_alg_ric_newtonadi(**dict(kw, z0=zc, nwtn_adi_dict=d2))
+        out[name] = dict(transport=cm.transport, symm_error=str(cm.symm_error), zc=zc, full=full, gain=gain,
+                         adi_steps=np.array(res['adi_steps']), z2=res2['zfac'],
+                         adi_steps2=np.array(res2['adi_steps']), upd2=np.array(res2['nwtn_upd_fnorms']),
+                         bytes_p2p=cm.bytes_p2p, bytes_nccl=cm.bytes_nccl)
+    par.disable()
+    np.savez(os.path.join(outdir, 'api_rank%d.npz' % rank),
+             **{'%s_%s' % (n_, k_): v for n_, o in out.items() for k_, v in o.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_newton_and_compress_behind_the_reference_signatures(tmp_path):
+    """north_star (d) / SURVEY 8e through the PUBLIC functions: with ``parallel.enable()`` on two
+    ranks, ``proj_alg_ric_newtonadi`` and ``compress_Zsvd`` run column-sharded (peer-to-peer
+    re-shard + Gram all-reduce over symmetric memory when the box offers it, NCCL otherwise) and
+    give the oracle's iteration counts, factor products and gains on every rank."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    from oracle import proj_ric_utils as opru
+    world = 2
+    mp.start_processes(_worker_public_api, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True,
+                       start_method='spawn')
+    prob, cs, kw = _ric_case()
+    ref = opru.proj_alg_ric_newtonadi(**kw)
+    zo = opru.compress_Zsvd(ref['zfac'], thresh=5e-5, k=50)
+    gain_o = -opru.get_mTzzTtb(prob['M'].T, zo, cs['tb_mat'])
+    d2 = dict(kw['nwtn_adi_dict'], nwtn_max_steps=2, full_upd_norm_check=True)
+    ref2 = opru.proj_alg_ric_newtonadi(**dict(kw, z0=zo, nwtn_adi_dict=d2))
+
+    def zzt(Za, Zb):
+        R = np.linalg.qr(np.hstack([Za, Zb]), mode='r')
+        ka = Za.shape[1]
+        D = R[:, :ka] @ R[:, :ka].T - R[:, ka:] @ R[:, ka:].T
+        return np.linalg.norm(D)/np.linalg.norm(Zb.T @ Zb)
+    outs = [np.load(os.path.join(str(tmp_path), 'api_rank%d.npz' % r)) for r in range(world)]
+    print('transports:', [str(o['auto_transport']) for o in outs], str(outs[0]['auto_symm_error']))
+    for name in ('auto', 'nccl'):
+        for o in outs:
+            assert list(o[name + '_adi_steps']) == ref['adi_steps']
+            assert o[name + '_full'].shape == ref['zfac'].shape and zzt(o[name + '_full'], ref['zfac']) < 1e-9
+            assert o[name + '_zc'].shape == zo.shape and zzt(o[name + '_zc'], zo) < 1e-9
+            assert np.linalg.norm(o[name + '_gain'] - gain_o) < 1e-9*np.linalg.norm(gain_o)
+            assert list(o[name + '_adi_steps2']) == ref2['adi_steps']
+            assert zzt(o[name + '_z2'], ref2['zfac']) < 1e-9
+        assert np.array_equal(outs[0][name + '_zc'], outs[1][name + '_zc'])      # replicated results
+    assert str(outs[0]['nccl_transport']) == 'nccl'

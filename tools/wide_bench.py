@@ -24,6 +24,15 @@ if __name__ == '__main__':
     n = K.shape[0]
     i = lu.info
     peak = dv.fp64_peak('dfma')
+    if os.environ.get('OCB_DUMP_LEVELS'):
+        import ctypes as C
+        import numpy as np
+        from optconpy_b200 import _cabi
+        lib = _cabi.load()
+        ns = lib.ocb_lu_panel_levels(lu.handle, None, 0)
+        arr = np.zeros((max(ns, 1), 3), dtype=np.int64)
+        lib.ocb_lu_panel_levels(lu.handle, arr.ctypes.data, ns)
+        np.save(os.environ['OCB_DUMP_LEVELS'], arr)
     for k in ks:
         B = torch.randn((n, k), dtype=torch.float64, device='cuda')
         X = lu.solve(B)
