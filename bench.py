@@ -686,6 +686,7 @@ def main():
                 torch.cuda.synchronize()
                 stamps.append(time.perf_counter())
             barrier()
+            dv.reset_stats()
             ds.solve_flow_daeric(lau=glau, pru=gpru, store=ds.NpyStore(), step_callback=cbp,
                                  lookahead=0, private_extensions=False, **kw4)
             barrier()
@@ -695,6 +696,9 @@ def main():
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             e2e_plain = dict(value=world*Kp/float(tm.item()), unit=UNIT, steps=Kp, warmup=Wp,
                              ms_per_step=1e3*float(tm.item())/Kp,
+                             main_thread_phase_s_per_step={k: v/(Wp+Kp) for k, v in dv.PHASE.items()},
+                             host_setup_per_step={k: (v/(Wp+Kp)) for k, v in dv.STATS.items()
+                                                  if k.startswith('lu_') or k == 'n_factor'},
                              api='solve_flow_daeric(lookahead=0, private_extensions=False): the '
                                  'backend is called exactly as solve_dae_ric.py:152-163,192-194 '
                                  'does - no _factors / _lazy_zfac / sadlu keywords, every call '

@@ -1175,20 +1175,112 @@ struct PanelArgs {
     const int* skip;
 };
 
-// U = list entries per loop iteration.  The loads of an iteration are issued before its FMAs and
-// the column indices of the NEXT iteration are fetched one iteration ahead, so that the chain
-// "index -> x row" (two dependent global loads) is off the critical path.
-template <int T, int U>
+// Inner loop of both panel executors: one warp accumulates acc[8][T] += val[e][8] * xe[col[e], tile]
+// over the list entries [e0, e1) of one panel.  The gathers are latency bound (an x row segment
+// comes out of the L2, ~600+ cycles), so every warp runs its OWN cp.async pipeline: the x row
+// segments (32*T columns) and the 8 row values of the next NST-1 stages of 8 entries are in
+// flight into the warp's private shared-memory ring while it computes the current stage from
+// shared memory (conflict-free column reads, broadcast value reads).  No CTA-wide barrier.
+constexpr int PSTAGE_E = 8;   // list entries per stage
+
+template <int T>
+__host__ __device__ constexpr int panel_stage_doubles() { return PSTAGE_E * 32 * T + PSTAGE_E * PANEL_ROWS; }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool l1) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (l1) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// L1: x gathers may allocate in L1 (by-level executor: L1 is flushed at every launch) or must
+// bypass it (persistent executor: other SMs rewrite x rows between sub-levels of ONE launch)
+template <int T, int NST, bool L1>
+__device__ __forceinline__ void panel_accumulate(double (&acc)[PANEL_ROWS][T], double* __restrict__ ring,
+                                                 const int32_t* __restrict__ cp, const double* __restrict__ vp,
+                                                 const double* __restrict__ xtile, int64_t ldx, int e0, int e1,
+                                                 int lane) {
+    constexpr int SD = panel_stage_doubles<T>();
+    const int nstage = (e1 - e0 + PSTAGE_E - 1) / PSTAGE_E;
+    if (nstage <= 0) return;
+    // column indices one stage ahead of the copies that need them (uniform registers)
+    int4 ja = __ldg((const int4*)(cp + e0));
+    int4 jb = (e0 + 4 < e1) ? __ldg((const int4*)(cp + e0 + 4)) : make_int4(0, 0, 0, 0);
+    auto issue = [&](int s) {
+        const int e = e0 + s * PSTAGE_E;
+        double* xs = ring + (size_t)(s % NST) * SD;
+        double* vs = xs + PSTAGE_E * 32 * T;
+        const int jj[PSTAGE_E] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
+        const int nv = min(PSTAGE_E, e1 - e);   // 4 or 8 (lists are padded to multiples of 4)
+#pragma unroll
+        for (int u = 0; u < PSTAGE_E; ++u) {
+            if (u < nv) {
+                const double* src = xtile + (int64_t)jj[u] * ldx;
+#pragma unroll
+                for (int h = 0; h < (T + 1) / 2; ++h) {
+                    const int c = 2 * lane + 64 * h;
+                    if (c < 32 * T) cp_async16(xs + u * 32 * T + c, src + c, L1);
+                }
+            }
+        }
+        if (2 * lane < nv * PANEL_ROWS) cp_async16(vs + 2 * lane, vp + (int64_t)e * PANEL_ROWS + 2 * lane, true);
+        // indices of the stage after this one
+        const int en = e + PSTAGE_E;
+        ja = (en < e1) ? __ldg((const int4*)(cp + en)) : make_int4(0, 0, 0, 0);
+        jb = (en + 4 < e1) ? __ldg((const int4*)(cp + en + 4)) : make_int4(0, 0, 0, 0);
+    };
+#pragma unroll
+    for (int s = 0; s < NST - 1; ++s) {
+        if (s < nstage) issue(s);
+        cp_async_commit();
+    }
+    for (int s = 0; s < nstage; ++s) {
+        if (s + NST - 1 < nstage) issue(s + NST - 1);
+        cp_async_commit();
+        cp_async_wait<NST - 1>();
+        __syncwarp();
+        const double* xs = ring + (size_t)(s % NST) * SD;
+        const double* vs = xs + PSTAGE_E * 32 * T;
+        const int nv = min(PSTAGE_E, e1 - (e0 + s * PSTAGE_E));
+#pragma unroll
+        for (int u = 0; u < PSTAGE_E; ++u) {
+            if (u < nv) {
+                double xv[T];
+#pragma unroll
+                for (int t = 0; t < T; ++t) xv[t] = xs[u * 32 * T + lane + 32 * t];
+                const double2* v2 = (const double2*)(vs + u * PANEL_ROWS);
+#pragma unroll
+                for (int h = 0; h < PANEL_ROWS / 2; ++h) {
+                    const double2 vv = v2[h];
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        acc[2 * h][t] = fma(vv.x, xv[t], acc[2 * h][t]);
+                        acc[2 * h + 1][t] = fma(vv.y, xv[t], acc[2 * h + 1][t]);
+                    }
+                }
+            }
+        }
+        __syncwarp();   // the ring slot is overwritten by the copies issued next
+    }
+    cp_async_wait<0>();
+}
+
+template <int T, int NST>
 __global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int p0, int p1, int wlog) {
-    extern __shared__ double pred[];   // [warp][8][T][32] partial sums when a list is split
+    extern __shared__ __align__(16) double psm[];   // per warp: NST stages (also the split-list reduce buffer)
     if (a.skip && *a.skip) return;
+    constexpr int WD = NST * panel_stage_doubles<T>();
+    static_assert(WD >= PANEL_ROWS * T * 32, "reduce buffer must fit the ring");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpr = 1 << wlog, ppc = 8 >> wlog;
     const int grp = blockIdx.x / a.ntile, tile = blockIdx.x - grp * a.ntile;
     const int pi = p0 + grp * ppc + (warp >> wlog);
     const int wr = warp & (wpr - 1);
     const bool valid = pi < p1;
-    double* xc = a.xe + (int64_t)tile * (32 * T) + lane;
+    double* xt = a.xe + (int64_t)tile * (32 * T);
+    double* ring = psm + (size_t)warp * WD;
     double acc[PANEL_ROWS][T];
 #pragma unroll
     for (int r = 0; r < PANEL_ROWS; ++r)
@@ -1200,49 +1292,14 @@ __global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int
         pn0 = __ldg((const int4*)(a.panels + pi));          // cbase, ncol, dst0, init0
         nrows = __ldg(&a.panels[pi].nrows);
         const int ncol = pn0.y;                               // multiple of 4
-        const int per = ((ncol >> 2) + wpr - 1) / wpr * 4;    // chunk of this warp, multiple of 4
+        const int per = (((ncol + 7) >> 3) + wpr - 1) / wpr * 8;    // chunk of this warp: whole stages
         const int e0 = wr * per, e1 = min(ncol, e0 + per);
-        const int32_t* cp = a.col + pn0.x;
-        const double2* vp = (const double2*)(a.val + (int64_t)pn0.x * PANEL_ROWS);
-        int jn[U];
-#pragma unroll
-        for (int u = 0; u < U; u += 4) {
-            const int4 j4 = (e0 + u < e1) ? __ldg((const int4*)(cp + e0 + u)) : make_int4(0, 0, 0, 0);
-            jn[u] = j4.x; jn[u + 1] = j4.y; jn[u + 2] = j4.z; jn[u + 3] = j4.w;
-        }
-        for (int e = e0; e < e1; e += U) {
-            int jj[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) jj[u] = jn[u];
-            double xv[U][T];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int t = 0; t < T; ++t) xv[u][t] = (e + u < e1) ? xc[(int64_t)jj[u] * a.ldx + 32 * t] : 0.0;
-#pragma unroll
-            for (int u = 0; u < U; u += 4) {   // indices of the next iteration
-                const int4 j4 = (e + U + u < e1) ? __ldg((const int4*)(cp + e + U + u)) : make_int4(0, 0, 0, 0);
-                jn[u] = j4.x; jn[u + 1] = j4.y; jn[u + 2] = j4.z; jn[u + 3] = j4.w;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (e + u < e1) {   // warp-uniform
-                    const double2* v2 = vp + (int64_t)(e + u) * (PANEL_ROWS / 2);
-#pragma unroll
-                    for (int h = 0; h < PANEL_ROWS / 2; ++h) {
-                        const double2 vv = __ldg(v2 + h);
-#pragma unroll
-                        for (int t = 0; t < T; ++t) {
-                            acc[2 * h][t] = fma(vv.x, xv[u][t], acc[2 * h][t]);
-                            acc[2 * h + 1][t] = fma(vv.y, xv[u][t], acc[2 * h + 1][t]);
-                        }
-                    }
-                }
-            }
-        }
+        panel_accumulate<T, NST, true>(acc, ring, a.col + pn0.x, a.val + (int64_t)pn0.x * PANEL_ROWS, xt, a.ldx,
+                                       e0, e1, lane);
     }
     if (wlog > 0) {
-        double* mine = pred + (size_t)warp * (PANEL_ROWS * T * 32);
+        __syncthreads();
+        double* mine = ring;
 #pragma unroll
         for (int r = 0; r < PANEL_ROWS; ++r)
 #pragma unroll
@@ -1250,7 +1307,7 @@ __global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int
         __syncthreads();
         if (wr == 0) {
             for (int w2 = 1; w2 < wpr; ++w2) {
-                const double* other = pred + (size_t)(warp + w2) * (PANEL_ROWS * T * 32);
+                const double* other = psm + (size_t)(warp + w2) * WD;
 #pragma unroll
                 for (int r = 0; r < PANEL_ROWS; ++r)
 #pragma unroll
@@ -1260,6 +1317,7 @@ __global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int
     }
     if (valid && wr == 0) {
         const double* sc = a.scale + (int64_t)pi * PANEL_ROWS;
+        double* xc = xt + lane;
 #pragma unroll
         for (int r = 0; r < PANEL_ROWS; ++r) {
             if (r < nrows) {
@@ -1278,18 +1336,17 @@ __global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int
     }
 }
 
-template <int T, int U>
+template <int T, int NST>
 static int panel_launch(const PanelArgs& w, int p0, int p1, int wlog, cudaStream_t st) {
     const int ppc = 8 >> wlog;
     const unsigned blocks = (unsigned)(((p1 - p0) + ppc - 1) / ppc) * (unsigned)w.ntile;
-    const size_t smem = wlog > 0 ? (size_t)8 * PANEL_ROWS * T * 32 * sizeof(double) : 0;
+    const size_t smem = (size_t)8 * NST * panel_stage_doubles<T>() * sizeof(double);
     static bool attr = false;
     if (!attr) {
-        OCB_CUDA(cudaFuncSetAttribute(panel_level_kernel<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      8 * PANEL_ROWS * T * 32 * (int)sizeof(double)));
+        OCB_CUDA(cudaFuncSetAttribute(panel_level_kernel<T, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    panel_level_kernel<T, U><<<blocks, 256, smem, st>>>(w, p0, p1, wlog);
+    panel_level_kernel<T, NST><<<blocks, 256, smem, st>>>(w, p0, p1, wlog);
     OCB_LAUNCH_CHECK();
     return OCB_OK;
 }
@@ -1362,10 +1419,11 @@ __device__ __forceinline__ bool group_barrier(GroupBar* bar, unsigned int ncta, 
     return true;
 }
 
-template <int T, int U>
+template <int T, int NST>
 __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q) {
-    extern __shared__ double pred[];   // [warp][8][T][32] partial sums when a list is split
+    extern __shared__ __align__(16) double psm[];   // per warp: NST stages (also the split-list reduce buffer)
     if (q.p.skip && *q.p.skip) return;
+    constexpr int WD = NST * panel_stage_doubles<T>();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int group = blockIdx.x / q.cpg, gcta = blockIdx.x - group * q.cpg;
     if (group >= q.ngroups) return;
@@ -1374,6 +1432,7 @@ __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q)
     const SolveArgs& a = q.a;
     const int64_t ldx = q.p.ldx;
     constexpr int CW = 32 * T;
+    double* ring = psm + (size_t)warp * WD;
     for (int chunk = group; chunk < q.nchunks; chunk += q.ngroups) {
         const int64_t c0 = (int64_t)chunk * CW;
         // ---- load: xe[perm_r[i], c0 + c] = B[i, c0 + c] (0 beyond nrows_b / k)
@@ -1384,7 +1443,8 @@ __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q)
             q.p.xe[(int64_t)__ldg(a.perm_r + i) * ldx + c] = v;
         }
         group_barrier(bar, q.cpg, gen, q.err);
-        double* xc = q.p.xe + c0 + lane;
+        double* xt = q.p.xe + c0;
+        double* xc = xt + lane;
         for (int sb = 0; sb < q.nsub; ++sb) {
             const int p0 = __ldg(q.sub_pan + sb), p1 = __ldg(q.sub_pan + sb + 1);
             const int np = p1 - p0;
@@ -1409,48 +1469,14 @@ __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q)
                         pn0 = __ldg((const int4*)(q.p.panels + pi));
                         nrows = __ldg(&q.p.panels[pi].nrows);
                         const int ncol = pn0.y;
-                        const int per = ((ncol >> 2) + wpr - 1) / wpr * 4;
+                        const int per = (((ncol + 7) >> 3) + wpr - 1) / wpr * 8;
                         const int e0 = wr * per, e1 = min(ncol, e0 + per);
-                        const int32_t* cp = q.p.col + pn0.x;
-                        const double2* vp = (const double2*)(q.p.val + (int64_t)pn0.x * PANEL_ROWS);
-                        int jn[U];
-#pragma unroll
-                        for (int u = 0; u < U; u += 4) {
-                            const int4 j4 = (e0 + u < e1) ? __ldg((const int4*)(cp + e0 + u)) : make_int4(0, 0, 0, 0);
-                            jn[u] = j4.x; jn[u + 1] = j4.y; jn[u + 2] = j4.z; jn[u + 3] = j4.w;
-                        }
-                        for (int e = e0; e < e1; e += U) {
-                            double xv[U][T];
-#pragma unroll
-                            for (int u = 0; u < U; ++u)
-#pragma unroll
-                                for (int t = 0; t < T; ++t)
-                                    xv[u][t] = (e + u < e1) ? xc[(int64_t)jn[u] * ldx + 32 * t] : 0.0;
-#pragma unroll
-                            for (int u = 0; u < U; u += 4) {
-                                const int4 j4 = (e + U + u < e1) ? __ldg((const int4*)(cp + e + U + u))
-                                                                 : make_int4(0, 0, 0, 0);
-                                jn[u] = j4.x; jn[u + 1] = j4.y; jn[u + 2] = j4.z; jn[u + 3] = j4.w;
-                            }
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                if (e + u < e1) {
-                                    const double2* v2 = vp + (int64_t)(e + u) * (PANEL_ROWS / 2);
-#pragma unroll
-                                    for (int h = 0; h < PANEL_ROWS / 2; ++h) {
-                                        const double2 vv = __ldg(v2 + h);
-#pragma unroll
-                                        for (int t = 0; t < T; ++t) {
-                                            acc[2 * h][t] = fma(vv.x, xv[u][t], acc[2 * h][t]);
-                                            acc[2 * h + 1][t] = fma(vv.y, xv[u][t], acc[2 * h + 1][t]);
-                                        }
-                                    }
-                                }
-                            }
-                        }
+                        panel_accumulate<T, NST, false>(acc, ring, q.p.col + pn0.x,
+                                                        q.p.val + (int64_t)pn0.x * PANEL_ROWS, xt, ldx, e0, e1, lane);
                     }
                     if (wlog > 0) {
-                        double* mine = pred + (size_t)warp * (PANEL_ROWS * T * 32);
+                        __syncthreads();
+                        double* mine = ring;
 #pragma unroll
                         for (int r = 0; r < PANEL_ROWS; ++r)
 #pragma unroll
@@ -1458,14 +1484,14 @@ __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q)
                         __syncthreads();
                         if (wr == 0) {
                             for (int w2 = 1; w2 < wpr; ++w2) {
-                                const double* other = pred + (size_t)(warp + w2) * (PANEL_ROWS * T * 32);
+                                const double* other = psm + (size_t)(warp + w2) * WD;
 #pragma unroll
                                 for (int r = 0; r < PANEL_ROWS; ++r)
 #pragma unroll
                                     for (int t = 0; t < T; ++t) acc[r][t] += other[(r * T + t) * 32 + lane];
                             }
                         }
-                        __syncthreads();   // pred is reused by the next unit
+                        __syncthreads();   // the ring is reused by the next unit
                     }
                     if (valid && wr == 0) {
                         const double* sc = q.p.scale + (int64_t)pi * PANEL_ROWS;
@@ -1477,7 +1503,7 @@ __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q)
                                 if (pn0.w >= 0) {
                                     const double* xi = xc + (int64_t)(pn0.w + r) * ldx;
 #pragma unroll
-                                    for (int t = 0; t < T; ++t) xd[32 * t] = (xi[32 * t] - acc[r][t]) * sv;
+                                    for (int t = 0; t < T; ++t) xd[32 * t] = (__ldcg(xi + 32 * t) - acc[r][t]) * sv;
                                 } else {
 #pragma unroll
                                     for (int t = 0; t < T; ++t) xd[32 * t] = -acc[r][t] * sv;
@@ -1494,7 +1520,7 @@ __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q)
         for (int64_t e = (int64_t)gcta * 256 + tid; e < a.nrows_x * CW; e += (int64_t)q.cpg * 256) {
             const int64_t j = e / CW, c = c0 + (e - j * CW);
             if (c < a.k) {
-                const double v = q.p.xe[(int64_t)__ldg(a.perm_c + j) * ldx + c];
+                const double v = __ldcg(q.p.xe + (int64_t)__ldg(a.perm_c + j) * ldx + c);
                 a.X[j * a.ldx + c] = bad ? __longlong_as_double(0x7ff8000000000000LL) : v;
             }
         }
@@ -1503,13 +1529,13 @@ __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q)
 
 constexpr int64_t PERSIST_TAIL_BYTES = 8192;   // group barriers + error flag behind the xe block
 
-template <int T, int U>
+template <int T, int NST>
 static int persist_launch(PersistArgs q, int ctas_per_sm_want, cudaStream_t st) {
-    const size_t smem = (size_t)8 * PANEL_ROWS * T * 32 * sizeof(double);
+    const size_t smem = (size_t)8 * NST * panel_stage_doubles<T>() * sizeof(double);
     static int per_sm = -1;
     if (per_sm < 0) {
-        OCB_CUDA(cudaFuncSetAttribute(panel_persist_kernel<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_persist_kernel<T, U>, 256, smem));
+        OCB_CUDA(cudaFuncSetAttribute(panel_persist_kernel<T, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_persist_kernel<T, NST>, 256, smem));
     }
     if (per_sm < 1) {
         set_error("persistent solve: the kernel does not fit an SM");
@@ -1518,7 +1544,7 @@ static int persist_launch(PersistArgs q, int ctas_per_sm_want, cudaStream_t st) 
     // all CTAs must be co-resident (they wait for one another): as many per SM as fit, at most the wish
     q.cpg = std::max(1, std::min(ctas_per_sm_want, per_sm) * sm_count() / q.ngroups);
     void* args[] = {(void*)&q};
-    OCB_CUDA(cudaLaunchCooperativeKernel((void*)panel_persist_kernel<T, U>, dim3((unsigned)(q.ngroups * q.cpg)),
+    OCB_CUDA(cudaLaunchCooperativeKernel((void*)panel_persist_kernel<T, NST>, dim3((unsigned)(q.ngroups * q.cpg)),
                                          dim3(256), args, smem, st));
     count_launch();
     return OCB_OK;
@@ -1570,12 +1596,6 @@ static PersistPlan persist_plan(const ocb_lu* lu, int64_t k) {
 
 static int persist_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     const PersistPlan pl = persist_plan(lu, a.k);
-    static int U = 0;
-    if (U == 0) {
-        const char* e = getenv("OCB_PANEL_U");
-        U = e ? atoi(e) : 8;
-        if (U != 4 && U != 8) U = 8;
-    }
     PersistArgs q;
     q.a = a;
     q.p.panels = lu->p_panels; q.p.scale = lu->p_scale; q.p.val = lu->p_val; q.p.col = lu->p_col;
@@ -1591,19 +1611,19 @@ static int persist_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) 
     q.err = (int*)(tail + 16 * sizeof(GroupBar));
     OCB_CUDA(cudaMemsetAsync(tail, 0, 16 * sizeof(GroupBar) + 64, st));
     const int want = persist_ctas_per_sm();
-    if (pl.T == 1) return U == 4 ? persist_launch<1, 4>(q, want, st) : persist_launch<1, 8>(q, want, st);
-    if (pl.T == 2) return U == 4 ? persist_launch<2, 4>(q, want, st) : persist_launch<2, 8>(q, want, st);
-    return U == 4 ? persist_launch<4, 4>(q, want, st) : persist_launch<4, 8>(q, want, st);
+    if (pl.T == 1) return persist_launch<1, 4>(q, want, st);
+    if (pl.T == 2) return persist_launch<2, 3>(q, want, st);
+    return persist_launch<4, 3>(q, want, st);
 }
 
 static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     const int T = panel_tiles(a.k);
     const int64_t ldx = panel_ldx(a.k);
-    static int U = 0;
-    if (U == 0) {
-        const char* e = getenv("OCB_PANEL_U");
-        U = e ? atoi(e) : 8;
-        if (U != 4 && U != 8) U = 8;
+    static int NST = 0;
+    if (NST == 0) {
+        const char* e = getenv("OCB_PANEL_STAGES");
+        NST = e ? atoi(e) : 3;
+        if (NST != 3 && NST != 4) NST = 3;
     }
     double* xe = a.ws;
     const unsigned lblocks = (unsigned)std::min<int64_t>((a.n * ldx + 255) / 256, 148 * 16);
@@ -1625,9 +1645,9 @@ static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
         int wlog = 0;
         while (wlog < 3 && (tasks << wlog) < want_warps && (maxcol >> (wlog + 1)) >= 32) ++wlog;
         int rc;
-        if (T == 1) rc = U == 4 ? panel_launch<1, 4>(w, p0, p1, wlog, st) : panel_launch<1, 8>(w, p0, p1, wlog, st);
-        else if (T == 2) rc = U == 4 ? panel_launch<2, 4>(w, p0, p1, wlog, st) : panel_launch<2, 8>(w, p0, p1, wlog, st);
-        else rc = U == 4 ? panel_launch<4, 4>(w, p0, p1, wlog, st) : panel_launch<4, 8>(w, p0, p1, wlog, st);
+        if (T == 1) rc = panel_launch<1, 4>(w, p0, p1, wlog, st);
+        else if (T == 2) rc = NST == 4 ? panel_launch<2, 4>(w, p0, p1, wlog, st) : panel_launch<2, 3>(w, p0, p1, wlog, st);
+        else rc = panel_launch<4, 3>(w, p0, p1, wlog, st);
         if (rc) return rc;
     }
     const unsigned sblocks = (unsigned)std::min<int64_t>((a.nrows_x * a.k + 255) / 256, 148 * 16);
