@@ -1247,6 +1247,15 @@ __device__ __forceinline__ void panel_accumulate(double (&acc)[R][T], double* __
             ja = __ldg((const int4*)(cp + en));
             jb = __ldg((const int4*)(cp + en + 4));
         }
+        // the values and indices are a sequential stream that nobody has touched before (HBM):
+        // pull the lines of the stage PF_AHEAD stages ahead into the L2 now
+        constexpr int PF_AHEAD = 12;
+        const int ep = e + PF_AHEAD * PSTAGE_E;
+        if (ep < e1) {
+            const char* pv = (const char*)(vp + (int64_t)ep * R) + lane * 128;
+            if (lane * 128 < PSTAGE_E * R * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(pv));
+            if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + ep));
+        }
     };
 #pragma unroll
     for (int s = 0; s < NST - 1; ++s) {
@@ -1475,6 +1484,16 @@ static int64_t panel_ldx(int64_t k) {
     return (k + w - 1) / w * w;
 }
 
+static int panel_stages() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("OCB_PANEL_STAGES");
+        v = e ? atoi(e) : 3;
+        if (v < 2 || v > 4) v = 3;
+    }
+    return v;
+}
+
 template <int T, int NST>
 static int panel_smem_bytes() { return 8 * panel_ring_doubles<T, NST>() * (int)sizeof(double); }
 
@@ -1514,8 +1533,9 @@ static int persist_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) 
     q.bar = (GridBar*)tail;
     q.err = (int*)(tail + sizeof(GridBar));
     OCB_CUDA(cudaMemsetAsync(tail, 0, sizeof(GridBar) + 64, st));
-    if (T == 1) return persist_launch<1, 4>(q, st);
-    return persist_launch<2, 4>(q, st);
+    const int nst = panel_stages();
+    if (T == 1) return nst == 2 ? persist_launch<1, 2>(q, st) : (nst == 3 ? persist_launch<1, 3>(q, st) : persist_launch<1, 4>(q, st));
+    return nst == 2 ? persist_launch<2, 2>(q, st) : (nst == 3 ? persist_launch<2, 3>(q, st) : persist_launch<2, 4>(q, st));
 }
 
 template <int T, int NST>
@@ -1548,11 +1568,14 @@ static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     w.xe = xe; w.ldx = ldx; w.skip = a.skip;
     w.ntile = (int)(ldx / (32 * T));
     const int nsub = (int)lu->sub_pan.size() - 1;
+    const int nst = panel_stages();
     for (int sb = 0; sb < nsub; ++sb) {
         const int p0 = lu->sub_pan[sb], p1 = lu->sub_pan[sb + 1];
         if (p1 <= p0) continue;
-        const int rc = T == 1 ? panel_launch<1, 4>(w, p0, lu->sub_mid[sb], p1, lu->sub_maxcol[sb], st)
-                              : panel_launch<2, 4>(w, p0, lu->sub_mid[sb], p1, lu->sub_maxcol[sb], st);
+        const int pm = lu->sub_mid[sb], mc = lu->sub_maxcol[sb];
+        int rc;
+        if (T == 1) rc = nst == 2 ? panel_launch<1, 2>(w, p0, pm, p1, mc, st) : (nst == 3 ? panel_launch<1, 3>(w, p0, pm, p1, mc, st) : panel_launch<1, 4>(w, p0, pm, p1, mc, st));
+        else rc = nst == 2 ? panel_launch<2, 2>(w, p0, pm, p1, mc, st) : (nst == 3 ? panel_launch<2, 3>(w, p0, pm, p1, mc, st) : panel_launch<2, 4>(w, p0, pm, p1, mc, st));
         if (rc) return rc;
     }
     const unsigned sblocks = (unsigned)std::min<int64_t>((a.nrows_x * a.k + 255) / 256, 148 * 16);
