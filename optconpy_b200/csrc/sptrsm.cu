@@ -1193,9 +1193,13 @@ struct PanelArgs {
     int64_t ldx;
     int ntile;
     const int* skip;
+    double* part;        // partial sums of lists that are split over several CTAs (PART_SLOTS slots)
+    unsigned int* tick;  // arrival counters, one per (panel, column tile) of a split sub-level
 };
 
 constexpr int PSTAGE_E = 8;   // list entries per pipeline stage
+constexpr int PART_SLOTS = 1024;                                  // (panel, tile, segment) slots
+constexpr int PART_SLOT_DOUBLES = PANEL_ROWS_WIDE * 2 * 32;       // R x T x 32 at most (T <= 2)
 
 template <int R, int T>
 __host__ __device__ constexpr int panel_stage_doubles() { return PSTAGE_E * 32 * T + PSTAGE_E * R; }
@@ -1291,14 +1295,20 @@ __device__ __forceinline__ void panel_accumulate(double (&acc)[R][T], double* __
 }
 
 // One work unit of a CTA: (8 >> wlog) panels of [pbeg, pend) x one column tile; 2^wlog warps per panel.
+// cs > 1 (only with wlog = 3, one panel per CTA): the list is cut into cs SEGMENTS handled by cs
+// different CTAs; each writes its partial sums to a scratch slot and takes a ticket, and the CTA that
+// arrives last adds the cs partials IN SEGMENT ORDER (deterministic) and finishes the rows.
 // All 8 warps of the CTA call this together (it contains __syncthreads when wlog > 0).
 template <int R, int T, int NST>
 __device__ __forceinline__ void panel_unit(const PanelArgs& a, double* __restrict__ psm, int pbeg, int pend, int unit,
-                                           int tile, int wlog, int warp, int lane) {
+                                           int tile, int wlog, int cs, int warp, int lane) {
     constexpr int WD = panel_ring_doubles<T, NST>();
     static_assert(WD >= R * T * 32, "reduce buffer must fit the ring");
+    static_assert(R * T * 32 <= PART_SLOT_DOUBLES, "scratch slot too small");
     const int wpr = 1 << wlog, ppc = 8 >> wlog;
-    const int pi = pbeg + unit * ppc + (warp >> wlog);
+    const int seg = cs > 1 ? unit % cs : 0;
+    const int pu = cs > 1 ? unit / cs : unit;
+    const int pi = pbeg + pu * ppc + (warp >> wlog);
     const int wr = warp & (wpr - 1);
     const bool valid = pi < pend;
     double* xt = a.xe + (int64_t)tile * (32 * T);
@@ -1313,8 +1323,10 @@ __device__ __forceinline__ void panel_unit(const PanelArgs& a, double* __restric
         pn0 = __ldg((const int4*)(a.panels + pi));          // cbase, ncol, dst0, init0
         pn1 = __ldg((const int4*)(a.panels + pi) + 1);      // nrows, cap, vbase lo / hi
         const int ncol = pn0.y;                               // multiple of 8
-        const int per = ((ncol >> 3) + wpr - 1) / wpr * 8;    // chunk of this warp: whole stages
-        const int e0 = wr * per, e1 = min(ncol, e0 + per);
+        const int pseg = ((ncol >> 3) + cs - 1) / cs * 8;     // entries of one segment (whole stages)
+        const int s0 = min(ncol, seg * pseg), s1 = min(ncol, s0 + pseg);
+        const int per = (((s1 - s0) >> 3) + wpr - 1) / wpr * 8;   // chunk of this warp: whole stages
+        const int e0 = min(s1, s0 + wr * per), e1 = min(s1, e0 + per);
         const int64_t vb = ((int64_t)pn1.w << 32) | (uint32_t)pn1.z;
         panel_accumulate<R, T, NST>(acc, ring, a.col + pn0.x, a.val + vb, xt, a.ldx, e0, e1, lane);
     }
@@ -1337,6 +1349,34 @@ __device__ __forceinline__ void panel_unit(const PanelArgs& a, double* __restric
         __syncthreads();   // the ring is reused by the next unit
     }
     if (valid && wr == 0) {
+        if (cs > 1) {
+            const int cell = (pi - pbeg) * a.ntile + tile;            // < PART_SLOTS / cs by the level plan
+            double* slot = a.part + (size_t)(cell * cs + seg) * PART_SLOT_DOUBLES;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int t = 0; t < T; ++t) __stcg(slot + (r * T + t) * 32 + lane, acc[r][t]);
+            __threadfence();
+            __syncwarp();
+            unsigned int ticket = 0;
+            if (lane == 0) ticket = atomicAdd(a.tick + cell, 1u);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            if (ticket != (unsigned)(cs - 1)) return;                 // not the last: done
+            __threadfence();
+            if (lane == 0) a.tick[cell] = 0;                          // ready for the next sub-level
+            const double* base = a.part + (size_t)cell * cs * PART_SLOT_DOUBLES;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int t = 0; t < T; ++t) acc[r][t] = 0.0;
+            for (int sgm = 0; sgm < cs; ++sgm) {
+                const double* sl = base + (size_t)sgm * PART_SLOT_DOUBLES;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int t = 0; t < T; ++t) acc[r][t] += __ldcg(sl + (r * T + t) * 32 + lane);
+            }
+        }
         const double* sc = a.scale + (int64_t)pi * PANEL_ROWS_WIDE;
         double* xc = xt + lane;
         const int nrows = pn1.x;
@@ -1358,26 +1398,44 @@ __device__ __forceinline__ void panel_unit(const PanelArgs& a, double* __restric
     }
 }
 
+// narrow panels of a sub-level: same, with the scratch cells numbered after those of the wide panels
+template <int T, int NST>
+__device__ __forceinline__ void panel_unit_narrow(const PanelArgs& a, double* __restrict__ psm, int p0, int pm, int p1,
+                                                  int unit, int tile, int wlog, int cs, int warp, int lane) {
+    PanelArgs b = a;
+    if (cs > 1) {
+        b.part = a.part + (size_t)(pm - p0) * a.ntile * cs * PART_SLOT_DOUBLES;
+        b.tick = a.tick + (size_t)(pm - p0) * a.ntile;
+    }
+    panel_unit<PANEL_ROWS, T, NST>(b, psm, pm, p1, unit, tile, wlog, cs, warp, lane);
+}
+
 // work items of one sub-level: first the wide panels [p0, pm), then the narrow ones [pm, p1);
 // item w = unit * ntile + tile (the tiles of a panel group run side by side: its values stay hot)
 struct LevelPlan {
-    int wlog, nuw, nun;   // split, units of wide / narrow panels
+    int wlog, cs, nuw, nun;   // warps per list, CTAs per list, units of wide / narrow panels
 };
 __host__ __device__ inline LevelPlan level_plan(int p0, int pm, int p1, int maxcol, int ntile, int64_t warps) {
     LevelPlan lp;
     int wlog = 0;   // split long lists while the sub-level has fewer tasks than the machine has warps
     const int64_t tasks = (int64_t)(p1 - p0) * ntile;
     while (wlog < 3 && (tasks << wlog) < warps && (maxcol >> (wlog + 1)) >= 64) ++wlog;
+    int cs = 1;     // ... and over several CTAs when 8 warps per list are still too few
+    if (wlog == 3)
+        while (cs < 16 && ((tasks * cs) << 3) < warps && (maxcol >> 3) / (2 * cs) >= 64 &&
+               tasks * cs * 2 <= PART_SLOTS)
+            cs *= 2;
     const int ppc = 8 >> wlog;
     lp.wlog = wlog;
-    lp.nuw = (pm - p0 + ppc - 1) / ppc;
-    lp.nun = (p1 - pm + ppc - 1) / ppc;
+    lp.cs = cs;
+    lp.nuw = (pm - p0 + ppc - 1) / ppc * cs;
+    lp.nun = (p1 - pm + ppc - 1) / ppc * cs;
     return lp;
 }
 
 // ---- one launch per sub-level (OCB_WIDE_BY_LEVEL=1; kept for comparison and as a fallback) ----
 template <int T, int NST>
-__global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int p0, int pm, int p1, int wlog,
+__global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int p0, int pm, int p1, int wlog, int cs,
                                                           int nuw, int nun) {
     extern __shared__ __align__(16) double psm[];
     if (a.skip && *a.skip) return;
@@ -1385,8 +1443,8 @@ __global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int
     const int total = (nuw + nun) * a.ntile;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int unit = w / a.ntile, tile = w - unit * a.ntile;
-        if (unit < nuw) panel_unit<PANEL_ROWS_WIDE, T, NST>(a, psm, p0, pm, unit, tile, wlog, warp, lane);
-        else panel_unit<PANEL_ROWS, T, NST>(a, psm, pm, p1, unit - nuw, tile, wlog, warp, lane);
+        if (unit < nuw) panel_unit<PANEL_ROWS_WIDE, T, NST>(a, psm, p0, pm, unit, tile, wlog, cs, warp, lane);
+        else panel_unit_narrow<T, NST>(a, psm, p0, pm, p1, unit - nuw, tile, wlog, cs, warp, lane);
     }
 }
 
@@ -1451,8 +1509,27 @@ __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q)
             const int total = (lp.nuw + lp.nun) * q.p.ntile;
             for (int w = blockIdx.x; w < total; w += gridDim.x) {
                 const int unit = w / q.p.ntile, tile = w - unit * q.p.ntile;
-                if (unit < lp.nuw) panel_unit<PANEL_ROWS_WIDE, T, NST>(q.p, psm, p0, pm, unit, tile, lp.wlog, warp, lane);
-                else panel_unit<PANEL_ROWS, T, NST>(q.p, psm, pm, p1, unit - lp.nuw, tile, lp.wlog, warp, lane);
+                if (unit < lp.nuw) panel_unit<PANEL_ROWS_WIDE, T, NST>(q.p, psm, p0, pm, unit, tile, lp.wlog, lp.cs, warp, lane);
+                else panel_unit_narrow<T, NST>(q.p, psm, p0, pm, p1, unit - lp.nuw, tile, lp.wlog, lp.cs, warp, lane);
+            }
+        }
+        // while the others finish: pull the value / index streams of the NEXT sub-level into the L2
+        // (they are read once, from HBM; its first stages would otherwise pay the full DRAM latency)
+        if (sb + 1 < q.nsub) {
+            const int n0 = __ldg(q.sub + sb + 1), n1 = __ldg(q.sub + sb + 2);
+            if (n1 > n0) {
+                const int4 fa = __ldg((const int4*)(q.p.panels + n0) + 1), fc = __ldg((const int4*)(q.p.panels + n0));
+                const int4 la = __ldg((const int4*)(q.p.panels + n1 - 1) + 1), lc = __ldg((const int4*)(q.p.panels + n1 - 1));
+                const int64_t v0 = ((int64_t)fa.w << 32) | (uint32_t)fa.z;
+                const int64_t v1 = (((int64_t)la.w << 32) | (uint32_t)la.z) + (int64_t)lc.y * la.y;
+                const char* pv = (const char*)(q.p.val + v0);
+                const int64_t vbytes = min((v1 - v0) * 8, (int64_t)(48 << 20));
+                for (int64_t o = ((int64_t)blockIdx.x * 256 + tid) * 128; o < vbytes; o += (int64_t)gridDim.x * 256 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + o));
+                const char* pc = (const char*)(q.p.col + fc.x);
+                const int64_t cbytes = ((int64_t)(lc.x + lc.y) - fc.x) * 4;
+                for (int64_t o = ((int64_t)blockIdx.x * 256 + tid) * 128; o < cbytes; o += (int64_t)gridDim.x * 256 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
             }
         }
         grid_barrier(q.bar, gridDim.x, gen, q.err);
@@ -1466,7 +1543,9 @@ __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q)
     }
 }
 
-constexpr int64_t PERSIST_TAIL_BYTES = 4096;   // grid barrier + error flag behind the xe block
+// behind the xe block: grid barrier + error flag (256 B) | tickets | partial-sum slots
+constexpr int64_t PART_TICK_BYTES = PART_SLOTS * 4;
+constexpr int64_t PERSIST_TAIL_BYTES = 1024 + PART_TICK_BYTES + (int64_t)PART_SLOTS * PART_SLOT_DOUBLES * 8;
 
 // column tiles of 32 * T per warp (OCB_PANEL_T overrides for experiments)
 static int panel_tiles(int64_t k) {
@@ -1532,7 +1611,9 @@ static int persist_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) 
     tail = (unsigned char*)(((uintptr_t)tail + 255) & ~(uintptr_t)255);
     q.bar = (GridBar*)tail;
     q.err = (int*)(tail + sizeof(GridBar));
-    OCB_CUDA(cudaMemsetAsync(tail, 0, sizeof(GridBar) + 64, st));
+    q.p.tick = (unsigned int*)(tail + 512);
+    q.p.part = (double*)(tail + 512 + PART_TICK_BYTES);
+    OCB_CUDA(cudaMemsetAsync(tail, 0, 512 + PART_TICK_BYTES, st));
     const int nst = panel_stages();
     if (T == 1) return nst == 2 ? persist_launch<1, 2>(q, st) : (nst == 3 ? persist_launch<1, 3>(q, st) : persist_launch<1, 4>(q, st));
     return nst == 2 ? persist_launch<2, 2>(q, st) : (nst == 3 ? persist_launch<2, 3>(q, st) : persist_launch<2, 4>(q, st));
@@ -1551,7 +1632,7 @@ static int panel_launch(const PanelArgs& w, int p0, int pm, int p1, int maxcol, 
     const LevelPlan lp = level_plan(p0, pm, p1, maxcol, w.ntile, (int64_t)slots * 8);
     const int total = (lp.nuw + lp.nun) * w.ntile;
     if (total <= 0) return OCB_OK;
-    panel_level_kernel<T, NST><<<(unsigned)std::min(total, slots), 256, smem, st>>>(w, p0, pm, p1, lp.wlog, lp.nuw, lp.nun);
+    panel_level_kernel<T, NST><<<(unsigned)std::min(total, slots), 256, smem, st>>>(w, p0, pm, p1, lp.wlog, lp.cs, lp.nuw, lp.nun);
     OCB_LAUNCH_CHECK();
     return OCB_OK;
 }
@@ -1567,6 +1648,13 @@ static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     w.panels = lu->p_panels; w.scale = lu->p_scale; w.val = lu->p_val; w.col = lu->p_col;
     w.xe = xe; w.ldx = ldx; w.skip = a.skip;
     w.ntile = (int)(ldx / (32 * T));
+    {
+        unsigned char* tail = (unsigned char*)a.ws + lu->n_ext * ldx * sizeof(double);
+        tail = (unsigned char*)(((uintptr_t)tail + 255) & ~(uintptr_t)255);
+        w.tick = (unsigned int*)(tail + 512);
+        w.part = (double*)(tail + 512 + PART_TICK_BYTES);
+        OCB_CUDA(cudaMemsetAsync(tail, 0, 512 + PART_TICK_BYTES, st));
+    }
     const int nsub = (int)lu->sub_pan.size() - 1;
     const int nst = panel_stages();
     for (int sb = 0; sb < nsub; ++sb) {
