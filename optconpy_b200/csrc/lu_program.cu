@@ -801,7 +801,7 @@ void build_panels(const LuProgram& P, double max_pad, PanelProgram* out) {
             ucols.clear();
             for (auto& e : rows[order[i]].e) ucols.push_back(e.first);
             int64_t sum = (int64_t)rows[order[i]].e.size();
-            while (j < order.size() && (int)(j - i) < PANEL_ROWS_WIDE) {
+            while (j < order.size() && (int)(j - i) < PANEL_ROWS) {
                 const Row& a = rows[order[j - 1]];
                 const Row& b = rows[order[j]];
                 if (b.dst != a.dst + 1) break;
@@ -821,66 +821,47 @@ void build_panels(const LuProgram& P, double max_pad, PanelProgram* out) {
                 sum = s2;
                 ++j;
             }
-            // 9..11 rows would waste most of a 16-row block: keep 8 and let the rest start a new panel
-            if (j - i > (size_t)PANEL_ROWS && j - i < (size_t)PANEL_ROWS + 4) {
-                j = i + PANEL_ROWS;
-                ucols.clear();
-                for (size_t r = i; r < j; ++r)
-                    for (auto& e : rows[order[r]].e) ucols.push_back(e.first);
-                std::sort(ucols.begin(), ucols.end());
-                ucols.erase(std::unique(ucols.begin(), ucols.end()), ucols.end());
-            }
             Panel pn;
             pn.cbase = 0;
             pn.ncol = (int32_t)ucols.size();
             pn.dst0 = rows[order[i]].dst;
             pn.init0 = rows[order[i]].init;
             pn.nrows = (int32_t)(j - i);
-            pn.cap = pn.nrows > PANEL_ROWS ? PANEL_ROWS_WIDE : PANEL_ROWS;
-            pn.vbase_lo = pn.vbase_hi = 0;
-            std::vector<double> pv((size_t)ucols.size() * pn.cap, 0.0);
+            pn.pad[0] = pn.pad[1] = pn.pad[2] = 0;
+            std::vector<double> pv((size_t)ucols.size() * PANEL_ROWS, 0.0);
             for (size_t r = i; r < j; ++r) {
                 const Row& rw = rows[order[r]];
                 size_t x = 0;
                 for (auto& e : rw.e) {
                     while (ucols[x] < e.first) ++x;
-                    pv[x * pn.cap + (r - i)] = e.second;
+                    pv[x * PANEL_ROWS + (r - i)] = e.second;
                 }
                 lscale.push_back(P.scale[rw.q]);
             }
-            for (size_t r = j - i; r < (size_t)PANEL_ROWS_WIDE; ++r) lscale.push_back(0.0);
+            for (size_t r = j - i; r < (size_t)PANEL_ROWS; ++r) lscale.push_back(0.0);
             lvl.push_back(pn);
             lcols.push_back(ucols);
             lvals.push_back(std::move(pv));
             i = j;
         }
-        // wide panels first, each kind longest first (the executor deals them to CTAs in order)
+        // longest panels first (load balance: the executor deals panels to CTAs in order)
         std::vector<int32_t> po(lvl.size());
         std::iota(po.begin(), po.end(), 0);
-        std::stable_sort(po.begin(), po.end(), [&](int32_t a, int32_t b) {
-            if (lvl[a].cap != lvl[b].cap) return lvl[a].cap > lvl[b].cap;
-            return lvl[a].ncol > lvl[b].ncol;
-        });
-        int32_t mid = (int32_t)Q.panels.size();
+        std::stable_sort(po.begin(), po.end(), [&](int32_t a, int32_t b) { return lvl[a].ncol > lvl[b].ncol; });
         for (int32_t pi : po) {
             Panel pn = lvl[pi];
             pn.cbase = (int32_t)Q.pcol.size();
-            const int64_t vb = (int64_t)Q.pval.size();
-            pn.vbase_lo = (int32_t)(uint32_t)(vb & 0xffffffffLL);
-            pn.vbase_hi = (int32_t)(vb >> 32);
             Q.pcol.insert(Q.pcol.end(), lcols[pi].begin(), lcols[pi].end());
             Q.pval.insert(Q.pval.end(), lvals[pi].begin(), lvals[pi].end());
-            while (pn.ncol & 7) {   // the executor moves 8 entries per pipeline stage: pad with 0 * xe[0]
+            while (pn.ncol & 3) {   // the executor reads 4 entries per step: pad with 0 * xe[0]
                 Q.pcol.push_back(0);
-                Q.pval.insert(Q.pval.end(), pn.cap, 0.0);
+                Q.pval.insert(Q.pval.end(), PANEL_ROWS, 0.0);
                 ++pn.ncol;
             }
-            Q.scale.insert(Q.scale.end(), lscale.begin() + (size_t)pi * PANEL_ROWS_WIDE,
-                           lscale.begin() + (size_t)(pi + 1) * PANEL_ROWS_WIDE);
+            Q.scale.insert(Q.scale.end(), lscale.begin() + (size_t)pi * PANEL_ROWS,
+                           lscale.begin() + (size_t)(pi + 1) * PANEL_ROWS);
             Q.panels.push_back(pn);
-            if (pn.cap == PANEL_ROWS_WIDE) mid = (int32_t)Q.panels.size();
         }
-        Q.sub_mid.push_back(mid);
         Q.sub_ptr.push_back((int32_t)Q.panels.size());
     }
 }
@@ -893,15 +874,14 @@ void execute_panels_host(const PanelProgram& Q, const int32_t* perm_r, const int
         out.clear();
         for (int32_t pi = Q.sub_ptr[sb]; pi < Q.sub_ptr[sb + 1]; ++pi) {
             const Panel& pn = Q.panels[pi];
-            const int64_t vb = panel_vbase(pn);
-            double acc[PANEL_ROWS_WIDE] = {0};
+            double acc[PANEL_ROWS] = {0};
             for (int32_t p = 0; p < pn.ncol; ++p) {
                 const double xv = xe[Q.pcol[pn.cbase + p]];
-                for (int r = 0; r < pn.cap; ++r) acc[r] = fma(Q.pval[vb + (int64_t)p * pn.cap + r], xv, acc[r]);
+                for (int r = 0; r < PANEL_ROWS; ++r) acc[r] = fma(Q.pval[((size_t)pn.cbase + p) * PANEL_ROWS + r], xv, acc[r]);
             }
             for (int r = 0; r < pn.nrows; ++r) {
                 const double ini = pn.init0 >= 0 ? xe[pn.init0 + r] : 0.0;
-                out.push_back((ini - acc[r]) * Q.scale[(size_t)pi * PANEL_ROWS_WIDE + r]);
+                out.push_back((ini - acc[r]) * Q.scale[(size_t)pi * PANEL_ROWS + r]);
             }
         }
         size_t o = 0;
@@ -987,7 +967,7 @@ int ocb_lu_program_solve_host(const ocb_lu_program* prog, const int32_t* h_perm_
     ocb::execute_panels_host(Q, h_perm_r, h_perm_c, h_b, h_x);
     if (h_stats4) {
         h_stats4[0] = (int64_t)Q.panels.size();
-        h_stats4[1] = (int64_t)Q.pval.size();   // stored values (zero padding included)
+        h_stats4[1] = (int64_t)Q.pcol.size() * ocb::PANEL_ROWS;   // stored values (zero padding included)
         h_stats4[2] = Q.entries_actual;
         h_stats4[3] = Q.nsub();
     }

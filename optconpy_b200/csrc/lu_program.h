@@ -60,36 +60,31 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
 
 // ---------------------------------------------------------------------------------
 // PANEL form of the same program, for the all-columns-at-once executor (large n / wide blocks).
-// Up to 16 rows of one sub-level with consecutive destinations (rows of one supernode) form a
+// Up to 8 rows of one sub-level with consecutive destinations (rows of one supernode) form a
 // PANEL that shares ONE column list: the union of the rows' lists, values zero padded and stored
-// interleaved (val[p][cap], cap = 8 or 16).  The executor then loads every x row once per panel
-// and uses it for 8 / 16 rows (register blocking): 1 / 0.5 bytes of x per FMA instead of 8.  Rows
-// of the upper factor inside a supernode have identical lists (no padding); the lower factor pads.
+// interleaved (val[p][8]).  The executor then loads every x row once per panel and uses it for
+// 8 rows (register blocking): 1 byte of x per FMA instead of 8.  Rows of the upper factor
+// inside a supernode have identical lists (no padding); the lower factor pads ~1.4x.
 // ---------------------------------------------------------------------------------
-constexpr int PANEL_ROWS = 8;        // narrow panel: 8 rows per x load
-constexpr int PANEL_ROWS_WIDE = 16;  // wide panel: 16 rows per x load (runs of rows with matching lists)
+constexpr int PANEL_ROWS = 8;
 struct Panel {
-    int32_t cbase;    // first entry of the column list (pcol); a multiple of 8, ncol too (zero padded)
+    int32_t cbase;    // first entry of the column list (pcol); values at pval[(cbase + p) * 8 + r]
     int32_t ncol;
     int32_t dst0;     // row r writes xe[dst0 + r]
     int32_t init0;    // row r starts from xe[init0 + r] (-1: from zero)
-    int32_t nrows;    // 1..cap
-    int32_t cap;      // 8 or 16: rows the value block is laid out for
-    int32_t vbase_lo, vbase_hi;   // values at pval[vbase + p * cap + r]  (64-bit offset)
+    int32_t nrows;    // 1..8
+    int32_t pad[3];
 };
 struct PanelProgram {
     int64_t n = 0, n_ext = 0;
-    std::vector<int32_t> sub_ptr;     // panels of sub-level s: [sub_ptr[s], sub_ptr[s+1]): first the wide ones
-    std::vector<int32_t> sub_mid;     // ... [sub_ptr[s], sub_mid[s]) are wide (cap 16), the rest narrow;
-                                      //     each range sorted by list length, longest first
+    std::vector<int32_t> sub_ptr;     // panels of sub-level s: [sub_ptr[s], sub_ptr[s+1]), longest first
     std::vector<Panel> panels;
-    std::vector<double> scale;        // 16 per panel
+    std::vector<double> scale;        // 8 per panel
     std::vector<int32_t> pcol;
-    std::vector<double> pval;         // cap per column entry
+    std::vector<double> pval;         // 8 per column entry
     int64_t entries_actual = 0;       // non-padding entries (= flops / 2 per right-hand side)
     int64_t nsub() const { return (int64_t)sub_ptr.size() - 1; }
 };
-inline int64_t panel_vbase(const Panel& p) { return ((int64_t)p.vbase_hi << 32) | (uint32_t)p.vbase_lo; }
 // max_pad: a row joins a panel only while (union size * rows) <= max_pad * (sum of row lengths)
 void build_panels(const LuProgram& P, double max_pad, PanelProgram* out);
 void execute_panels_host(const PanelProgram& Q, const int32_t* perm_r, const int32_t* perm_c,

@@ -67,7 +67,6 @@ struct ocb_lu {
     const int32_t* p_sub_dev = nullptr;   // device copy: sub_pan (nsub + 1) followed by sub_maxcol (nsub)
     std::vector<int32_t> sub_pan;      // host: first panel of every sub-level (nsub + 1)
     std::vector<int32_t> sub_maxcol;   // host: longest column list of every sub-level
-    std::vector<int32_t> sub_mid;      // host: end of the wide (16-row) panels of every sub-level
 };
 
 namespace ocb {
@@ -603,7 +602,7 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl
 // Self-describing host image of a factorisation: [meta int64[32]] perm_r | perm_c | batch
 // offsets | batch stream.  Built without any CUDA call (worker processes build it next to the
 // host LU); ocb_lu_create_from_image uploads it with one allocation and one copy.
-constexpr int64_t IMG_MAGIC = 0x4f43424c55303035LL;   // "OCBLU005"
+constexpr int64_t IMG_MAGIC = 0x4f43424c55303034LL;   // "OCBLU004"
 enum { M_MAGIC = 0, M_TOTAL, M_N, M_NEXT, M_NNZL, M_NNZU, M_NSUBL, M_NSUBU, M_NSUPER, M_MAXW, M_NSLICE,
        M_NROWS, M_NENT, M_OPR, M_OPC, M_CL, M_STAGEB, M_NSTAGES, M_KPSMEM, M_FLAT, M_NSUB,
        M_OBO = 24, M_OST = 32, M_NBATCH = 40,                  // one slot per cluster rank
@@ -707,9 +706,11 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         for (int r = 0; r < 8; ++r) batches[r].clear();
     }
     const bool want_wide = (flags & 1) || kp_smem == 0;
-    static const bool legacy_flat = getenv("OCB_WIDE_LEGACY") != nullptr;
-    const bool want_flat = want_wide && legacy_flat;
-    const bool want_panels = want_wide && !legacy_flat;
+    // both forms travel: the row program serves narrow blocks / small factors (most warps in
+    // flight, lowest latency per sub-level), the panel program wide blocks on large factors
+    static const bool no_panels = getenv("OCB_WIDE_LEGACY") != nullptr;
+    const bool want_flat = want_wide;
+    const bool want_panels = want_wide && !no_panels;
     PanelProgram Q;
     if (want_panels) {
         const char* e_pad = getenv("OCB_PANEL_MAXPAD");
@@ -751,8 +752,8 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
     int64_t o_p[5] = {0};
     if (want_panels) {
         const int64_t npn = (int64_t)Q.panels.size(), npc = (int64_t)Q.pcol.size(), nsb = Q.nsub();
-        const int64_t sz[5] = {npn * (int64_t)sizeof(Panel), npn * PANEL_ROWS_WIDE * 8, npc * 4,
-                               (int64_t)Q.pval.size() * 8, 3 * (nsb + 1) * 4};
+        const int64_t sz[5] = {npn * (int64_t)sizeof(Panel), npn * PANEL_ROWS * 8, npc * 4,
+                               npc * PANEL_ROWS * 8, 2 * (nsb + 1) * 4};
         for (int i = 0; i < 5; ++i) {
             o_p[i] = o;
             o = align_up(o + std::max<int64_t>(sz[i], 16), 256);
@@ -825,20 +826,14 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         meta[M_PENT_ACTUAL] = Q.entries_actual;
         meta[M_NSUB] = nsb;
         if (npn) memcpy(img + o_p[0], Q.panels.data(), (size_t)npn * sizeof(Panel));
-        if (npn) memcpy(img + o_p[1], Q.scale.data(), (size_t)npn * PANEL_ROWS_WIDE * 8);
+        if (npn) memcpy(img + o_p[1], Q.scale.data(), (size_t)npn * PANEL_ROWS * 8);
         if (npc) memcpy(img + o_p[2], Q.pcol.data(), (size_t)npc * 4);
-        if (!Q.pval.empty()) memcpy(img + o_p[3], Q.pval.data(), Q.pval.size() * 8);
-        meta[M_PENT] = (int64_t)Q.pval.size();
+        if (npc) memcpy(img + o_p[3], Q.pval.data(), (size_t)npc * PANEL_ROWS * 8);
         int32_t* sp = (int32_t*)(img + o_p[4]);
         memcpy(sp, Q.sub_ptr.data(), (size_t)(nsb + 1) * 4);
-        int32_t* smax = sp + nsb + 1;   // longest list of every sub-level, then the end of its wide panels
-        int32_t* smid = smax + nsb;
-        for (int64_t sb = 0; sb < nsb; ++sb) {
-            int32_t mx = 0;
-            for (int32_t pi = Q.sub_ptr[sb]; pi < Q.sub_ptr[sb + 1]; ++pi) mx = std::max(mx, Q.panels[pi].ncol);
-            smax[sb] = mx;
-            smid[sb] = Q.sub_mid[sb];
-        }
+        int32_t* smax = sp + nsb + 1;   // panels of a sub-level are sorted: the first is the longest
+        for (int64_t sb = 0; sb < nsb; ++sb)
+            smax[sb] = Q.sub_ptr[sb] < Q.sub_ptr[sb + 1] ? Q.panels[Q.sub_ptr[sb]].ncol : 0;
     }
     if (tmpl && (size_t)total <= IMAGE_TEMPLATE_MAX_BYTES) {
         tmpl->img.assign(img, img + total);
@@ -922,7 +917,6 @@ static int upload_image(ocb_lu* lu, const unsigned char* img, int64_t bytes, voi
         lu->p_sub_dev = (const int32_t*)(lu->arena + meta[M_P_SUB]);
         lu->sub_pan.assign(sp, sp + meta[M_NSUB] + 1);
         lu->sub_maxcol.assign(sp + meta[M_NSUB] + 1, sp + 2 * meta[M_NSUB] + 1);
-        lu->sub_mid.assign(sp + 2 * meta[M_NSUB] + 1, sp + 3 * meta[M_NSUB] + 1);
     }
     return OCB_OK;
 }
@@ -1167,24 +1161,12 @@ static int wide_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------
 // panel executor: the wide executor with REGISTER BLOCKING over the rows of a supernode
 // ---------------------------------------------------------------------------------
-// A panel = up to 16 rows of one sub-level that share one column list (lu_program.h).  A warp
-// owns one panel and 32*T consecutive columns (lane = column): per list entry it needs ONE x row
-// segment and the panel's 8 / 16 row values and issues 8*T / 16*T FMAs - 1 / 0.5 bytes of x per
-// FMA instead of the 8 of the row-by-row executor.
-//
-// What bounds the solve at n ~ 1e5 (measured, profiles/r02_wide_executor.md): not HBM (DRAM
-// throughput ~1 %) but LATENCY - the x row segments come out of the L2 and a warp that loads and
-// then computes is idle for most of the round trip - and the fixed cost of one launch per
-// sub-level (~185 launches).  Hence
-//   * every warp runs its OWN cp.async pipeline: the x row segments and the values of the next
-//     NST-1 stages of 8 entries are in flight into the warp's private shared-memory ring while
-//     it computes the current stage from shared memory (conflict-free column reads, broadcast
-//     value reads); no CTA-wide barrier in the loop;
-//   * ONE persistent cooperative launch per solve: the sub-level barrier is a counter /
-//     generation barrier among the co-resident CTAs, and inside a sub-level the work items
-//     (panel group x column tile, longest lists first) are dealt round-robin to the CTAs, so
-//     that there is no wave quantisation; long lists are split over up to 8 warps of a CTA and
-//     combined through shared memory in fixed order (deterministic).
+// A panel = up to 8 rows of one sub-level that share one column list (lu_program.h).  A warp
+// owns one panel and 32*T consecutive columns (lane = column): per list entry it loads ONE x row
+// segment (coalesced 256 bytes per 32 columns) and the 8 row values (one uniform 64-byte load)
+// and issues 8*T FMAs - 1 byte of x per FMA instead of the 8 of the row-by-row executor, which
+// turns the kernel from L2-bandwidth bound into FP64 bound.  Long lists are split over 2^wlog
+// warps of the CTA and combined through shared memory (fixed order: deterministic).
 struct PanelArgs {
     const Panel* panels;
     const double *scale, *val;
@@ -1193,73 +1175,63 @@ struct PanelArgs {
     int64_t ldx;
     int ntile;
     const int* skip;
-    double* part;        // partial sums of lists that are split over several CTAs (PART_SLOTS slots)
-    unsigned int* tick;  // arrival counters, one per (panel, column tile) of a split sub-level
 };
 
-constexpr int PSTAGE_E = 8;   // list entries per pipeline stage
-constexpr int PART_SLOTS = 1024;                                  // (panel, tile, segment) slots
-constexpr int PART_SLOT_DOUBLES = PANEL_ROWS_WIDE * 2 * 32;       // R x T x 32 at most (T <= 2)
+// Inner loop of both panel executors: one warp accumulates acc[8][T] += val[e][8] * xe[col[e], tile]
+// over the list entries [e0, e1) of one panel.  The gathers are latency bound (an x row segment
+// comes out of the L2, ~600+ cycles), so every warp runs its OWN cp.async pipeline: the x row
+// segments (32*T columns) and the 8 row values of the next NST-1 stages of 8 entries are in
+// flight into the warp's private shared-memory ring while it computes the current stage from
+// shared memory (conflict-free column reads, broadcast value reads).  No CTA-wide barrier.
+constexpr int PSTAGE_E = 8;   // list entries per stage
 
-template <int R, int T>
-__host__ __device__ constexpr int panel_stage_doubles() { return PSTAGE_E * 32 * T + PSTAGE_E * R; }
-// ring of a warp: sized for the wide panels (R = 16), used by both kinds
-template <int T, int NST>
-__host__ __device__ constexpr int panel_ring_doubles() { return NST * panel_stage_doubles<PANEL_ROWS_WIDE, T>(); }
+template <int T>
+__host__ __device__ constexpr int panel_stage_doubles() { return PSTAGE_E * 32 * T + PSTAGE_E * PANEL_ROWS; }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool l1) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    if (l1) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// acc[R][T] += val[e][R] * xe[col[e], tile] over the list entries [e0, e1) (multiples of 8) of one panel
-template <int R, int T, int NST>
-__device__ __forceinline__ void panel_accumulate(double (&acc)[R][T], double* __restrict__ ring,
+// L1: x gathers may allocate in L1 (by-level executor: L1 is flushed at every launch) or must
+// bypass it (persistent executor: other SMs rewrite x rows between sub-levels of ONE launch)
+template <int T, int NST, bool L1>
+__device__ __forceinline__ void panel_accumulate(double (&acc)[PANEL_ROWS][T], double* __restrict__ ring,
                                                  const int32_t* __restrict__ cp, const double* __restrict__ vp,
                                                  const double* __restrict__ xtile, int64_t ldx, int e0, int e1,
                                                  int lane) {
-    constexpr int SD = panel_stage_doubles<R, T>();
-    const int nstage = (e1 - e0) / PSTAGE_E;
+    constexpr int SD = panel_stage_doubles<T>();
+    const int nstage = (e1 - e0 + PSTAGE_E - 1) / PSTAGE_E;
     if (nstage <= 0) return;
     // column indices one stage ahead of the copies that need them (uniform registers)
     int4 ja = __ldg((const int4*)(cp + e0));
-    int4 jb = __ldg((const int4*)(cp + e0 + 4));
+    int4 jb = (e0 + 4 < e1) ? __ldg((const int4*)(cp + e0 + 4)) : make_int4(0, 0, 0, 0);
     auto issue = [&](int s) {
         const int e = e0 + s * PSTAGE_E;
         double* xs = ring + (size_t)(s % NST) * SD;
         double* vs = xs + PSTAGE_E * 32 * T;
         const int jj[PSTAGE_E] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
+        const int nv = min(PSTAGE_E, e1 - e);   // 4 or 8 (lists are padded to multiples of 4)
 #pragma unroll
         for (int u = 0; u < PSTAGE_E; ++u) {
-            const double* src = xtile + (int64_t)jj[u] * ldx;
+            if (u < nv) {
+                const double* src = xtile + (int64_t)jj[u] * ldx;
 #pragma unroll
-            for (int h = 0; h < (T + 1) / 2; ++h) {
-                const int c = 2 * lane + 64 * h;
-                if (c < 32 * T) cp_async16(xs + u * 32 * T + c, src + c);
+                for (int h = 0; h < (T + 1) / 2; ++h) {
+                    const int c = 2 * lane + 64 * h;
+                    if (c < 32 * T) cp_async16(xs + u * 32 * T + c, src + c, L1);
+                }
             }
         }
-#pragma unroll
-        for (int h = 0; h < (PSTAGE_E * R + 63) / 64; ++h) {
-            const int c = 2 * lane + 64 * h;
-            if (c < PSTAGE_E * R) cp_async16(vs + c, vp + (int64_t)e * R + c);
-        }
-        const int en = e + PSTAGE_E;   // indices of the stage after this one
-        if (en < e1) {
-            ja = __ldg((const int4*)(cp + en));
-            jb = __ldg((const int4*)(cp + en + 4));
-        }
-        // the values and indices are a sequential stream that nobody has touched before (HBM):
-        // pull the lines of the stage PF_AHEAD stages ahead into the L2 now
-        constexpr int PF_AHEAD = 12;
-        const int ep = e + PF_AHEAD * PSTAGE_E;
-        if (ep < e1) {
-            const char* pv = (const char*)(vp + (int64_t)ep * R) + lane * 128;
-            if (lane * 128 < PSTAGE_E * R * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(pv));
-            if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + ep));
-        }
+        if (2 * lane < nv * PANEL_ROWS) cp_async16(vs + 2 * lane, vp + (int64_t)e * PANEL_ROWS + 2 * lane, true);
+        // indices of the stage after this one
+        const int en = e + PSTAGE_E;
+        ja = (en < e1) ? __ldg((const int4*)(cp + en)) : make_int4(0, 0, 0, 0);
+        jb = (en + 4 < e1) ? __ldg((const int4*)(cp + en + 4)) : make_int4(0, 0, 0, 0);
     };
 #pragma unroll
     for (int s = 0; s < NST - 1; ++s) {
@@ -1273,19 +1245,22 @@ __device__ __forceinline__ void panel_accumulate(double (&acc)[R][T], double* __
         __syncwarp();
         const double* xs = ring + (size_t)(s % NST) * SD;
         const double* vs = xs + PSTAGE_E * 32 * T;
+        const int nv = min(PSTAGE_E, e1 - (e0 + s * PSTAGE_E));
 #pragma unroll
         for (int u = 0; u < PSTAGE_E; ++u) {
-            double xv[T];
+            if (u < nv) {
+                double xv[T];
 #pragma unroll
-            for (int t = 0; t < T; ++t) xv[t] = xs[u * 32 * T + lane + 32 * t];
-            const double2* v2 = (const double2*)(vs + u * R);
+                for (int t = 0; t < T; ++t) xv[t] = xs[u * 32 * T + lane + 32 * t];
+                const double2* v2 = (const double2*)(vs + u * PANEL_ROWS);
 #pragma unroll
-            for (int h = 0; h < R / 2; ++h) {
-                const double2 vv = v2[h];
+                for (int h = 0; h < PANEL_ROWS / 2; ++h) {
+                    const double2 vv = v2[h];
 #pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    acc[2 * h][t] = fma(vv.x, xv[t], acc[2 * h][t]);
-                    acc[2 * h + 1][t] = fma(vv.y, xv[t], acc[2 * h + 1][t]);
+                    for (int t = 0; t < T; ++t) {
+                        acc[2 * h][t] = fma(vv.x, xv[t], acc[2 * h][t]);
+                        acc[2 * h + 1][t] = fma(vv.y, xv[t], acc[2 * h + 1][t]);
+                    }
                 }
             }
         }
@@ -1294,94 +1269,59 @@ __device__ __forceinline__ void panel_accumulate(double (&acc)[R][T], double* __
     cp_async_wait<0>();
 }
 
-// One work unit of a CTA: (8 >> wlog) panels of [pbeg, pend) x one column tile; 2^wlog warps per panel.
-// cs > 1 (only with wlog = 3, one panel per CTA): the list is cut into cs SEGMENTS handled by cs
-// different CTAs; each writes its partial sums to a scratch slot and takes a ticket, and the CTA that
-// arrives last adds the cs partials IN SEGMENT ORDER (deterministic) and finishes the rows.
-// All 8 warps of the CTA call this together (it contains __syncthreads when wlog > 0).
-template <int R, int T, int NST>
-__device__ __forceinline__ void panel_unit(const PanelArgs& a, double* __restrict__ psm, int pbeg, int pend, int unit,
-                                           int tile, int wlog, int cs, int warp, int lane) {
-    constexpr int WD = panel_ring_doubles<T, NST>();
-    static_assert(WD >= R * T * 32, "reduce buffer must fit the ring");
-    static_assert(R * T * 32 <= PART_SLOT_DOUBLES, "scratch slot too small");
+template <int T, int NST>
+__global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int p0, int p1, int wlog) {
+    extern __shared__ __align__(16) double psm[];   // per warp: NST stages (also the split-list reduce buffer)
+    if (a.skip && *a.skip) return;
+    constexpr int WD = NST * panel_stage_doubles<T>();
+    static_assert(WD >= PANEL_ROWS * T * 32, "reduce buffer must fit the ring");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpr = 1 << wlog, ppc = 8 >> wlog;
-    const int seg = cs > 1 ? unit % cs : 0;
-    const int pu = cs > 1 ? unit / cs : unit;
-    const int pi = pbeg + pu * ppc + (warp >> wlog);
+    const int grp = blockIdx.x / a.ntile, tile = blockIdx.x - grp * a.ntile;
+    const int pi = p0 + grp * ppc + (warp >> wlog);
     const int wr = warp & (wpr - 1);
-    const bool valid = pi < pend;
+    const bool valid = pi < p1;
     double* xt = a.xe + (int64_t)tile * (32 * T);
     double* ring = psm + (size_t)warp * WD;
-    double acc[R][T];
+    double acc[PANEL_ROWS][T];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int r = 0; r < PANEL_ROWS; ++r)
 #pragma unroll
         for (int t = 0; t < T; ++t) acc[r][t] = 0.0;
-    int4 pn0 = make_int4(0, 0, 0, -1), pn1 = make_int4(0, 0, 0, 0);
+    int4 pn0 = make_int4(0, 0, 0, -1);
+    int nrows = 0;
     if (valid) {
         pn0 = __ldg((const int4*)(a.panels + pi));          // cbase, ncol, dst0, init0
-        pn1 = __ldg((const int4*)(a.panels + pi) + 1);      // nrows, cap, vbase lo / hi
-        const int ncol = pn0.y;                               // multiple of 8
-        const int pseg = ((ncol >> 3) + cs - 1) / cs * 8;     // entries of one segment (whole stages)
-        const int s0 = min(ncol, seg * pseg), s1 = min(ncol, s0 + pseg);
-        const int per = (((s1 - s0) >> 3) + wpr - 1) / wpr * 8;   // chunk of this warp: whole stages
-        const int e0 = min(s1, s0 + wr * per), e1 = min(s1, e0 + per);
-        const int64_t vb = ((int64_t)pn1.w << 32) | (uint32_t)pn1.z;
-        panel_accumulate<R, T, NST>(acc, ring, a.col + pn0.x, a.val + vb, xt, a.ldx, e0, e1, lane);
+        nrows = __ldg(&a.panels[pi].nrows);
+        const int ncol = pn0.y;                               // multiple of 4
+        const int per = (((ncol + 7) >> 3) + wpr - 1) / wpr * 8;    // chunk of this warp: whole stages
+        const int e0 = wr * per, e1 = min(ncol, e0 + per);
+        panel_accumulate<T, NST, true>(acc, ring, a.col + pn0.x, a.val + (int64_t)pn0.x * PANEL_ROWS, xt, a.ldx,
+                                       e0, e1, lane);
     }
     if (wlog > 0) {
         __syncthreads();
+        double* mine = ring;
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < PANEL_ROWS; ++r)
 #pragma unroll
-            for (int t = 0; t < T; ++t) ring[(r * T + t) * 32 + lane] = acc[r][t];
+            for (int t = 0; t < T; ++t) mine[(r * T + t) * 32 + lane] = acc[r][t];
         __syncthreads();
         if (wr == 0) {
             for (int w2 = 1; w2 < wpr; ++w2) {
                 const double* other = psm + (size_t)(warp + w2) * WD;
 #pragma unroll
-                for (int r = 0; r < R; ++r)
+                for (int r = 0; r < PANEL_ROWS; ++r)
 #pragma unroll
                     for (int t = 0; t < T; ++t) acc[r][t] += other[(r * T + t) * 32 + lane];
             }
         }
-        __syncthreads();   // the ring is reused by the next unit
     }
     if (valid && wr == 0) {
-        if (cs > 1) {
-            const int cell = (pi - pbeg) * a.ntile + tile;            // < PART_SLOTS / cs by the level plan
-            double* slot = a.part + (size_t)(cell * cs + seg) * PART_SLOT_DOUBLES;
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int t = 0; t < T; ++t) __stcg(slot + (r * T + t) * 32 + lane, acc[r][t]);
-            __threadfence();
-            __syncwarp();
-            unsigned int ticket = 0;
-            if (lane == 0) ticket = atomicAdd(a.tick + cell, 1u);
-            ticket = __shfl_sync(0xffffffffu, ticket, 0);
-            if (ticket != (unsigned)(cs - 1)) return;                 // not the last: done
-            __threadfence();
-            if (lane == 0) a.tick[cell] = 0;                          // ready for the next sub-level
-            const double* base = a.part + (size_t)cell * cs * PART_SLOT_DOUBLES;
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int t = 0; t < T; ++t) acc[r][t] = 0.0;
-            for (int sgm = 0; sgm < cs; ++sgm) {
-                const double* sl = base + (size_t)sgm * PART_SLOT_DOUBLES;
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int t = 0; t < T; ++t) acc[r][t] += __ldcg(sl + (r * T + t) * 32 + lane);
-            }
-        }
-        const double* sc = a.scale + (int64_t)pi * PANEL_ROWS_WIDE;
+        const double* sc = a.scale + (int64_t)pi * PANEL_ROWS;
         double* xc = xt + lane;
-        const int nrows = pn1.x;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < PANEL_ROWS; ++r) {
             if (r < nrows) {
                 const double s = __ldg(sc + r);
                 double* xd = xc + (int64_t)(pn0.z + r) * a.ldx;
@@ -1398,58 +1338,53 @@ __device__ __forceinline__ void panel_unit(const PanelArgs& a, double* __restric
     }
 }
 
-// narrow panels of a sub-level: same, with the scratch cells numbered after those of the wide panels
 template <int T, int NST>
-__device__ __forceinline__ void panel_unit_narrow(const PanelArgs& a, double* __restrict__ psm, int p0, int pm, int p1,
-                                                  int unit, int tile, int wlog, int cs, int warp, int lane) {
-    PanelArgs b = a;
-    if (cs > 1) {
-        b.part = a.part + (size_t)(pm - p0) * a.ntile * cs * PART_SLOT_DOUBLES;
-        b.tick = a.tick + (size_t)(pm - p0) * a.ntile;
-    }
-    panel_unit<PANEL_ROWS, T, NST>(b, psm, pm, p1, unit, tile, wlog, cs, warp, lane);
-}
-
-// work items of one sub-level: first the wide panels [p0, pm), then the narrow ones [pm, p1);
-// item w = unit * ntile + tile (the tiles of a panel group run side by side: its values stay hot)
-struct LevelPlan {
-    int wlog, cs, nuw, nun;   // warps per list, CTAs per list, units of wide / narrow panels
-};
-__host__ __device__ inline LevelPlan level_plan(int p0, int pm, int p1, int maxcol, int ntile, int64_t warps) {
-    LevelPlan lp;
-    int wlog = 0;   // split long lists while the sub-level has fewer tasks than the machine has warps
-    const int64_t tasks = (int64_t)(p1 - p0) * ntile;
-    while (wlog < 3 && (tasks << wlog) < warps && (maxcol >> (wlog + 1)) >= 64) ++wlog;
-    int cs = 1;     // ... and over several CTAs when 8 warps per list are still too few
-    if (wlog == 3)
-        while (cs < 16 && ((tasks * cs) << 3) < warps && (maxcol >> 3) / (2 * cs) >= 64 &&
-               tasks * cs * 2 <= PART_SLOTS)
-            cs *= 2;
+static int panel_launch(const PanelArgs& w, int p0, int p1, int wlog, cudaStream_t st) {
     const int ppc = 8 >> wlog;
-    lp.wlog = wlog;
-    lp.cs = cs;
-    lp.nuw = (pm - p0 + ppc - 1) / ppc * cs;
-    lp.nun = (p1 - pm + ppc - 1) / ppc * cs;
-    return lp;
-}
-
-// ---- one launch per sub-level (OCB_WIDE_BY_LEVEL=1; kept for comparison and as a fallback) ----
-template <int T, int NST>
-__global__ void __launch_bounds__(256) panel_level_kernel(const PanelArgs a, int p0, int pm, int p1, int wlog, int cs,
-                                                          int nuw, int nun) {
-    extern __shared__ __align__(16) double psm[];
-    if (a.skip && *a.skip) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total = (nuw + nun) * a.ntile;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int unit = w / a.ntile, tile = w - unit * a.ntile;
-        if (unit < nuw) panel_unit<PANEL_ROWS_WIDE, T, NST>(a, psm, p0, pm, unit, tile, wlog, cs, warp, lane);
-        else panel_unit_narrow<T, NST>(a, psm, p0, pm, p1, unit - nuw, tile, wlog, cs, warp, lane);
+    const unsigned blocks = (unsigned)(((p1 - p0) + ppc - 1) / ppc) * (unsigned)w.ntile;
+    const size_t smem = (size_t)8 * NST * panel_stage_doubles<T>() * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        OCB_CUDA(cudaFuncSetAttribute(panel_level_kernel<T, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
     }
+    panel_level_kernel<T, NST><<<blocks, 256, smem, st>>>(w, p0, p1, wlog);
+    OCB_LAUNCH_CHECK();
+    return OCB_OK;
 }
 
-// ---- persistent: all sub-levels in one cooperative launch ----
-struct GridBar {
+// column tiles of 32 * T per warp: narrow tiles (T = 1) give the most warps in flight per SM (the
+// gathers are latency bound); OCB_PANEL_T / OCB_PANEL_U override for experiments
+static int panel_tiles(int64_t k) {
+    static int force = -1;
+    if (force < 0) {
+        const char* e = getenv("OCB_PANEL_T");
+        force = e ? atoi(e) : 0;
+    }
+    if (force == 1 || force == 2 || force == 4) return (k <= 32) ? 1 : ((k <= 64 && force > 2) ? 2 : force);
+    return k <= 32 ? 1 : 2;
+}
+static int64_t panel_ldx(int64_t k) {
+    const int64_t w = 32 * panel_tiles(k);
+    return (k + w - 1) / w * w;
+}
+
+// ---------------------------------------------------------------------------------
+// persistent, column-chunked panel executor (the default for the wide path)
+// ---------------------------------------------------------------------------------
+// The level-by-level executor above streams the whole n_ext x k block through every
+// sub-level: for n ~ 1e5 and k = 1024 the block (0.7 GB) is far larger than the L2, every x row
+// is re-read from HBM dozens of times over the ~190 sub-levels and the solve runs at the speed
+// of 256-byte random HBM reads (measured: 2.5 TFLOP/s).  Here the block is cut into CHUNKS of
+// 32*T columns that stay resident in the 126 MB L2 for a whole pass over the program:
+//   * the SMs are split into G GROUPS; a group takes one chunk through load -> all sub-levels
+//     -> store, then the next chunk (chunk = group, group + G, ...); G chunks are in flight, sized
+//     so that together they fit the L2;
+//   * ONE launch per solve: the sub-level barrier is a counter/generation barrier among the
+//     co-resident CTAs of a group (cooperative launch), not a kernel boundary;
+//   * inside a sub-level the panels are dealt to the CTAs of the group; a warp owns a panel
+//     (8 rows, register blocked) x the chunk's columns (lane = column).
+struct GroupBar {
     unsigned int count, gen;
     unsigned int pad[30];
 };
@@ -1457,13 +1392,13 @@ struct GridBar {
 struct PersistArgs {
     SolveArgs a;
     PanelArgs p;
-    const int32_t* sub;      // device: sub_ptr (nsub + 1) | longest list (nsub) | end of the wide panels (nsub)
-    int nsub;
-    GridBar* bar;
+    const int32_t* sub_pan;      // device: first panel of every sub-level (nsub + 1), then longest list (nsub)
+    int nsub, ngroups, cpg, nchunks;
+    GroupBar* bars;
     int* err;
 };
 
-__device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int ncta, unsigned int& gen, int* err) {
+__device__ __forceinline__ bool group_barrier(GroupBar* bar, unsigned int ncta, unsigned int& gen, int* err) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();                                   // publish this CTA's x rows
@@ -1475,171 +1410,223 @@ __device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int ncta, un
         } else {
             unsigned long long spins = 0;
             while (*((volatile unsigned int*)&bar->gen) != want) {
-                if (++spins > (1ull << 28)) { atomicExch(err, 1); break; }   // watchdog: never hang the GPU
+                if (++spins > (1ull << 31)) { atomicExch(err, 1); break; }   // watchdog: never hang the GPU
+                __nanosleep(20);
             }
         }
         __threadfence();                                   // acquire: invalidates this SM's L1
     }
     ++gen;
     __syncthreads();
+    return true;
 }
 
 template <int T, int NST>
 __global__ void __launch_bounds__(256) panel_persist_kernel(const PersistArgs q) {
-    extern __shared__ __align__(16) double psm[];
+    extern __shared__ __align__(16) double psm[];   // per warp: NST stages (also the split-list reduce buffer)
     if (q.p.skip && *q.p.skip) return;
+    constexpr int WD = NST * panel_stage_doubles<T>();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int group = blockIdx.x / q.cpg, gcta = blockIdx.x - group * q.cpg;
+    if (group >= q.ngroups) return;
+    GroupBar* bar = q.bars + group;
+    unsigned int gen = 0;
     const SolveArgs& a = q.a;
     const int64_t ldx = q.p.ldx;
-    unsigned int gen = 0;
-    // ---- load: xe[perm_r[i], c] = B[i, c] (0 beyond nrows_b / k)
-    for (int64_t e = (int64_t)blockIdx.x * 256 + tid; e < a.n * ldx; e += (int64_t)gridDim.x * 256) {
-        const int64_t i = e / ldx, c = e - i * ldx;
-        double v = 0.0;
-        if (i < a.nrows_b && c < a.k) v = a.B[i * a.ldb + c];
-        q.p.xe[(int64_t)__ldg(a.perm_r + i) * ldx + c] = v;
-    }
-    grid_barrier(q.bar, gridDim.x, gen, q.err);
-    const int64_t warps = (int64_t)gridDim.x * 8;
-    for (int sb = 0; sb < q.nsub; ++sb) {
-        const int p0 = __ldg(q.sub + sb), p1 = __ldg(q.sub + sb + 1);
-        if (p1 > p0) {
-            const int maxcol = __ldg(q.sub + q.nsub + 1 + sb), pm = __ldg(q.sub + 2 * q.nsub + 1 + sb);
-            const LevelPlan lp = level_plan(p0, pm, p1, maxcol, q.p.ntile, warps);
-            const int total = (lp.nuw + lp.nun) * q.p.ntile;
-            for (int w = blockIdx.x; w < total; w += gridDim.x) {
-                const int unit = w / q.p.ntile, tile = w - unit * q.p.ntile;
-                if (unit < lp.nuw) panel_unit<PANEL_ROWS_WIDE, T, NST>(q.p, psm, p0, pm, unit, tile, lp.wlog, lp.cs, warp, lane);
-                else panel_unit_narrow<T, NST>(q.p, psm, p0, pm, p1, unit - lp.nuw, tile, lp.wlog, lp.cs, warp, lane);
+    constexpr int CW = 32 * T;
+    double* ring = psm + (size_t)warp * WD;
+    for (int chunk = group; chunk < q.nchunks; chunk += q.ngroups) {
+        const int64_t c0 = (int64_t)chunk * CW;
+        // ---- load: xe[perm_r[i], c0 + c] = B[i, c0 + c] (0 beyond nrows_b / k)
+        for (int64_t e = (int64_t)gcta * 256 + tid; e < a.n * CW; e += (int64_t)q.cpg * 256) {
+            const int64_t i = e / CW, c = c0 + (e - i * CW);
+            double v = 0.0;
+            if (i < a.nrows_b && c < a.k) v = a.B[i * a.ldb + c];
+            q.p.xe[(int64_t)__ldg(a.perm_r + i) * ldx + c] = v;
+        }
+        group_barrier(bar, q.cpg, gen, q.err);
+        double* xt = q.p.xe + c0;
+        double* xc = xt + lane;
+        for (int sb = 0; sb < q.nsub; ++sb) {
+            const int p0 = __ldg(q.sub_pan + sb), p1 = __ldg(q.sub_pan + sb + 1);
+            const int np = p1 - p0;
+            if (np > 0) {
+                const int maxcol = __ldg(q.sub_pan + q.nsub + 1 + sb);
+                int wlog = 0;   // split long lists while the sub-level has fewer panels than the group has warps
+                while (wlog < 3 && (np << wlog) < q.cpg * 8 && (maxcol >> (wlog + 1)) >= 32) ++wlog;
+                const int wpr = 1 << wlog, ppc = 8 >> wlog;
+                const int units = (np + ppc - 1) / ppc;
+                const int wr = warp & (wpr - 1);
+                for (int unit = gcta; unit < units; unit += q.cpg) {
+                    const int pi = p0 + unit * ppc + (warp >> wlog);
+                    const bool valid = pi < p1;
+                    double acc[PANEL_ROWS][T];
+#pragma unroll
+                    for (int r = 0; r < PANEL_ROWS; ++r)
+#pragma unroll
+                        for (int t = 0; t < T; ++t) acc[r][t] = 0.0;
+                    int4 pn0 = make_int4(0, 0, 0, -1);
+                    int nrows = 0;
+                    if (valid) {
+                        pn0 = __ldg((const int4*)(q.p.panels + pi));
+                        nrows = __ldg(&q.p.panels[pi].nrows);
+                        const int ncol = pn0.y;
+                        const int per = (((ncol + 7) >> 3) + wpr - 1) / wpr * 8;
+                        const int e0 = wr * per, e1 = min(ncol, e0 + per);
+                        panel_accumulate<T, NST, false>(acc, ring, q.p.col + pn0.x,
+                                                        q.p.val + (int64_t)pn0.x * PANEL_ROWS, xt, ldx, e0, e1, lane);
+                    }
+                    if (wlog > 0) {
+                        __syncthreads();
+                        double* mine = ring;
+#pragma unroll
+                        for (int r = 0; r < PANEL_ROWS; ++r)
+#pragma unroll
+                            for (int t = 0; t < T; ++t) mine[(r * T + t) * 32 + lane] = acc[r][t];
+                        __syncthreads();
+                        if (wr == 0) {
+                            for (int w2 = 1; w2 < wpr; ++w2) {
+                                const double* other = psm + (size_t)(warp + w2) * WD;
+#pragma unroll
+                                for (int r = 0; r < PANEL_ROWS; ++r)
+#pragma unroll
+                                    for (int t = 0; t < T; ++t) acc[r][t] += other[(r * T + t) * 32 + lane];
+                            }
+                        }
+                        __syncthreads();   // the ring is reused by the next unit
+                    }
+                    if (valid && wr == 0) {
+                        const double* sc = q.p.scale + (int64_t)pi * PANEL_ROWS;
+#pragma unroll
+                        for (int r = 0; r < PANEL_ROWS; ++r) {
+                            if (r < nrows) {
+                                const double sv = __ldg(sc + r);
+                                double* xd = xc + (int64_t)(pn0.z + r) * ldx;
+                                if (pn0.w >= 0) {
+                                    const double* xi = xc + (int64_t)(pn0.w + r) * ldx;
+#pragma unroll
+                                    for (int t = 0; t < T; ++t) xd[32 * t] = (__ldcg(xi + 32 * t) - acc[r][t]) * sv;
+                                } else {
+#pragma unroll
+                                    for (int t = 0; t < T; ++t) xd[32 * t] = -acc[r][t] * sv;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            group_barrier(bar, q.cpg, gen, q.err);
+        }
+        // ---- store: X[j, c0 + c] = xe[perm_c[j], c0 + c]  (NaN if the watchdog fired)
+        const bool bad = *((volatile int*)q.err) != 0;
+        for (int64_t e = (int64_t)gcta * 256 + tid; e < a.nrows_x * CW; e += (int64_t)q.cpg * 256) {
+            const int64_t j = e / CW, c = c0 + (e - j * CW);
+            if (c < a.k) {
+                const double v = __ldcg(q.p.xe + (int64_t)__ldg(a.perm_c + j) * ldx + c);
+                a.X[j * a.ldx + c] = bad ? __longlong_as_double(0x7ff8000000000000LL) : v;
             }
         }
-        // while the others finish: pull the value / index streams of the NEXT sub-level into the L2
-        // (they are read once, from HBM; its first stages would otherwise pay the full DRAM latency)
-        if (sb + 1 < q.nsub) {
-            const int n0 = __ldg(q.sub + sb + 1), n1 = __ldg(q.sub + sb + 2);
-            if (n1 > n0) {
-                const int4 fa = __ldg((const int4*)(q.p.panels + n0) + 1), fc = __ldg((const int4*)(q.p.panels + n0));
-                const int4 la = __ldg((const int4*)(q.p.panels + n1 - 1) + 1), lc = __ldg((const int4*)(q.p.panels + n1 - 1));
-                const int64_t v0 = ((int64_t)fa.w << 32) | (uint32_t)fa.z;
-                const int64_t v1 = (((int64_t)la.w << 32) | (uint32_t)la.z) + (int64_t)lc.y * la.y;
-                const char* pv = (const char*)(q.p.val + v0);
-                const int64_t vbytes = min((v1 - v0) * 8, (int64_t)(48 << 20));
-                for (int64_t o = ((int64_t)blockIdx.x * 256 + tid) * 128; o < vbytes; o += (int64_t)gridDim.x * 256 * 128)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + o));
-                const char* pc = (const char*)(q.p.col + fc.x);
-                const int64_t cbytes = ((int64_t)(lc.x + lc.y) - fc.x) * 4;
-                for (int64_t o = ((int64_t)blockIdx.x * 256 + tid) * 128; o < cbytes; o += (int64_t)gridDim.x * 256 * 128)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
-            }
-        }
-        grid_barrier(q.bar, gridDim.x, gen, q.err);
-    }
-    // ---- store: X[j, c] = xe[perm_c[j], c]  (NaN if the watchdog fired)
-    const bool bad = *((volatile int*)q.err) != 0;
-    for (int64_t e = (int64_t)blockIdx.x * 256 + tid; e < a.nrows_x * a.k; e += (int64_t)gridDim.x * 256) {
-        const int64_t j = e / a.k, c = e - j * a.k;
-        const double v = q.p.xe[(int64_t)__ldg(a.perm_c + j) * ldx + c];
-        a.X[j * a.ldx + c] = bad ? __longlong_as_double(0x7ff8000000000000LL) : v;
     }
 }
 
-// behind the xe block: grid barrier + error flag (256 B) | tickets | partial-sum slots
-constexpr int64_t PART_TICK_BYTES = PART_SLOTS * 4;
-constexpr int64_t PERSIST_TAIL_BYTES = 1024 + PART_TICK_BYTES + (int64_t)PART_SLOTS * PART_SLOT_DOUBLES * 8;
-
-// column tiles of 32 * T per warp (OCB_PANEL_T overrides for experiments)
-static int panel_tiles(int64_t k) {
-    static int force = -1;
-    if (force < 0) {
-        const char* e = getenv("OCB_PANEL_T");
-        force = e ? atoi(e) : 0;
-    }
-    if (k <= 32) return 1;
-    if (force == 1 || force == 2) return force;
-    return 2;
-}
-static int64_t panel_ldx(int64_t k) {
-    const int64_t w = 32 * panel_tiles(k);
-    return (k + w - 1) / w * w;
-}
-
-static int panel_stages() {
-    static int v = 0;
-    if (v == 0) {
-        const char* e = getenv("OCB_PANEL_STAGES");
-        v = e ? atoi(e) : 3;
-        if (v < 2 || v > 4) v = 3;
-    }
-    return v;
-}
+constexpr int64_t PERSIST_TAIL_BYTES = 8192;   // group barriers + error flag behind the xe block
 
 template <int T, int NST>
-static int panel_smem_bytes() { return 8 * panel_ring_doubles<T, NST>() * (int)sizeof(double); }
-
-template <int T, int NST>
-static int persist_launch(PersistArgs q, cudaStream_t st) {
-    const int smem = panel_smem_bytes<T, NST>();
+static int persist_launch(PersistArgs q, int ctas_per_sm_want, cudaStream_t st) {
+    const size_t smem = (size_t)8 * NST * panel_stage_doubles<T>() * sizeof(double);
     static int per_sm = -1;
     if (per_sm < 0) {
-        OCB_CUDA(cudaFuncSetAttribute(panel_persist_kernel<T, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        OCB_CUDA(cudaFuncSetAttribute(panel_persist_kernel<T, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_persist_kernel<T, NST>, 256, smem));
     }
     if (per_sm < 1) {
         set_error("persistent solve: the kernel does not fit an SM");
         return OCB_ERR_CUDA;
     }
-    // all CTAs must be co-resident (they wait for one another): cooperative launch of a full machine
-    const unsigned grid = (unsigned)(per_sm * sm_count());
+    // all CTAs must be co-resident (they wait for one another): as many per SM as fit, at most the wish
+    q.cpg = std::max(1, std::min(ctas_per_sm_want, per_sm) * sm_count() / q.ngroups);
     void* args[] = {(void*)&q};
-    OCB_CUDA(cudaLaunchCooperativeKernel((void*)panel_persist_kernel<T, NST>, dim3(grid), dim3(256), args,
-                                         (size_t)smem, st));
+    OCB_CUDA(cudaLaunchCooperativeKernel((void*)panel_persist_kernel<T, NST>, dim3((unsigned)(q.ngroups * q.cpg)),
+                                         dim3(256), args, smem, st));
     count_launch();
     return OCB_OK;
 }
 
+static int persist_ctas_per_sm() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("OCB_PERSIST_CTAS_PER_SM");
+        v = e ? atoi(e) : 2;
+        if (v < 1 || v > 4) v = 2;
+    }
+    return v;
+}
+
+// plan of a persistent solve: column tiles per warp (T), groups, chunks
+struct PersistPlan { int T, ngroups, nchunks; int64_t ldx; };
+static PersistPlan persist_plan(const ocb_lu* lu, int64_t k) {
+    static int64_t l2_budget = 0;
+    static int force_t = -1, force_g = -1;
+    if (l2_budget == 0) {
+        const char* e = getenv("OCB_PERSIST_L2_MB");
+        l2_budget = (int64_t)(e ? atoi(e) : 80) << 20;
+        const char* e2 = getenv("OCB_PANEL_T");
+        force_t = e2 ? atoi(e2) : 0;
+        const char* e3 = getenv("OCB_PERSIST_GROUPS");
+        force_g = e3 ? atoi(e3) : 0;
+    }
+    PersistPlan pl;
+    const int64_t bytes32 = lu->n_ext * 32 * 8;
+    int T = 1;
+    if (k > 32) {
+        T = 2;
+        if (k > 64 && 4 * bytes32 * 2 <= l2_budget) T = 4;
+        while (T > 1 && T * bytes32 * 2 > l2_budget) T >>= 1;   // at least two chunks in the L2
+    }
+    if (force_t == 1 || force_t == 2 || force_t == 4) T = (k <= 32) ? 1 : force_t;
+    pl.T = T;
+    const int64_t cw = 32 * T;
+    pl.nchunks = (int)((k + cw - 1) / cw);
+    pl.ldx = (int64_t)pl.nchunks * cw;
+    int64_t g = std::max<int64_t>(1, l2_budget / (T * bytes32));
+    g = std::min<int64_t>(g, 8);
+    g = std::min<int64_t>(g, pl.nchunks);
+    if (force_g >= 1 && force_g <= 16) g = std::min<int64_t>(force_g, pl.nchunks);
+    pl.ngroups = (int)g;
+    return pl;
+}
+
 static int persist_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
-    const int T = panel_tiles(a.k);
-    const int64_t ldx = panel_ldx(a.k);
+    const PersistPlan pl = persist_plan(lu, a.k);
     PersistArgs q;
     q.a = a;
     q.p.panels = lu->p_panels; q.p.scale = lu->p_scale; q.p.val = lu->p_val; q.p.col = lu->p_col;
-    q.p.xe = a.ws; q.p.ldx = ldx; q.p.skip = a.skip;
-    q.p.ntile = (int)(ldx / (32 * T));
-    q.sub = lu->p_sub_dev;
+    q.p.xe = a.ws; q.p.ldx = pl.ldx; q.p.skip = a.skip; q.p.ntile = 1;
+    q.sub_pan = lu->p_sub_dev;
     q.nsub = (int)lu->sub_pan.size() - 1;
-    unsigned char* tail = (unsigned char*)a.ws + lu->n_ext * ldx * sizeof(double);
+    q.ngroups = pl.ngroups;
+    q.nchunks = pl.nchunks;
+    q.cpg = 0;   // set by persist_launch from the occupancy of the instantiation
+    unsigned char* tail = (unsigned char*)a.ws + lu->n_ext * pl.ldx * sizeof(double);
     tail = (unsigned char*)(((uintptr_t)tail + 255) & ~(uintptr_t)255);
-    q.bar = (GridBar*)tail;
-    q.err = (int*)(tail + sizeof(GridBar));
-    q.p.tick = (unsigned int*)(tail + 512);
-    q.p.part = (double*)(tail + 512 + PART_TICK_BYTES);
-    OCB_CUDA(cudaMemsetAsync(tail, 0, 512 + PART_TICK_BYTES, st));
-    const int nst = panel_stages();
-    if (T == 1) return nst == 2 ? persist_launch<1, 2>(q, st) : (nst == 3 ? persist_launch<1, 3>(q, st) : persist_launch<1, 4>(q, st));
-    return nst == 2 ? persist_launch<2, 2>(q, st) : (nst == 3 ? persist_launch<2, 3>(q, st) : persist_launch<2, 4>(q, st));
-}
-
-template <int T, int NST>
-static int panel_launch(const PanelArgs& w, int p0, int pm, int p1, int maxcol, cudaStream_t st) {
-    const int smem = panel_smem_bytes<T, NST>();
-    static int per_sm = -1;
-    if (per_sm < 0) {
-        OCB_CUDA(cudaFuncSetAttribute(panel_level_kernel<T, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, panel_level_kernel<T, NST>, 256, smem));
-        if (per_sm < 1) per_sm = 1;
-    }
-    const int slots = per_sm * sm_count();
-    const LevelPlan lp = level_plan(p0, pm, p1, maxcol, w.ntile, (int64_t)slots * 8);
-    const int total = (lp.nuw + lp.nun) * w.ntile;
-    if (total <= 0) return OCB_OK;
-    panel_level_kernel<T, NST><<<(unsigned)std::min(total, slots), 256, smem, st>>>(w, p0, pm, p1, lp.wlog, lp.cs, lp.nuw, lp.nun);
-    OCB_LAUNCH_CHECK();
-    return OCB_OK;
+    q.bars = (GroupBar*)tail;
+    q.err = (int*)(tail + 16 * sizeof(GroupBar));
+    OCB_CUDA(cudaMemsetAsync(tail, 0, 16 * sizeof(GroupBar) + 64, st));
+    const int want = persist_ctas_per_sm();
+    if (pl.T == 1) return persist_launch<1, 4>(q, want, st);
+    if (pl.T == 2) return persist_launch<2, 3>(q, want, st);
+    return persist_launch<4, 3>(q, want, st);
 }
 
 static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     const int T = panel_tiles(a.k);
     const int64_t ldx = panel_ldx(a.k);
+    static int NST = 0;
+    if (NST == 0) {
+        const char* e = getenv("OCB_PANEL_STAGES");
+        NST = e ? atoi(e) : 3;
+        if (NST != 3 && NST != 4) NST = 3;
+    }
     double* xe = a.ws;
     const unsigned lblocks = (unsigned)std::min<int64_t>((a.n * ldx + 255) / 256, 148 * 16);
     wide_load_kernel<<<lblocks, 256, 0, st>>>(a, xe, ldx);
@@ -1648,22 +1635,21 @@ static int panel_solve(const ocb_lu* lu, const SolveArgs& a, cudaStream_t st) {
     w.panels = lu->p_panels; w.scale = lu->p_scale; w.val = lu->p_val; w.col = lu->p_col;
     w.xe = xe; w.ldx = ldx; w.skip = a.skip;
     w.ntile = (int)(ldx / (32 * T));
-    {
-        unsigned char* tail = (unsigned char*)a.ws + lu->n_ext * ldx * sizeof(double);
-        tail = (unsigned char*)(((uintptr_t)tail + 255) & ~(uintptr_t)255);
-        w.tick = (unsigned int*)(tail + 512);
-        w.part = (double*)(tail + 512 + PART_TICK_BYTES);
-        OCB_CUDA(cudaMemsetAsync(tail, 0, 512 + PART_TICK_BYTES, st));
-    }
     const int nsub = (int)lu->sub_pan.size() - 1;
-    const int nst = panel_stages();
+    const int64_t want_warps = (int64_t)sm_count() * 16;
     for (int sb = 0; sb < nsub; ++sb) {
         const int p0 = lu->sub_pan[sb], p1 = lu->sub_pan[sb + 1];
         if (p1 <= p0) continue;
-        const int pm = lu->sub_mid[sb], mc = lu->sub_maxcol[sb];
+        // split long lists over the warps of a CTA while the sub-level has too few tasks to
+        // fill the machine (the top separators: a few dozen panels with thousands of columns)
+        const int64_t tasks = (int64_t)(p1 - p0) * w.ntile;
+        const int maxcol = lu->sub_maxcol[sb];
+        int wlog = 0;
+        while (wlog < 3 && (tasks << wlog) < want_warps && (maxcol >> (wlog + 1)) >= 32) ++wlog;
         int rc;
-        if (T == 1) rc = nst == 2 ? panel_launch<1, 2>(w, p0, pm, p1, mc, st) : (nst == 3 ? panel_launch<1, 3>(w, p0, pm, p1, mc, st) : panel_launch<1, 4>(w, p0, pm, p1, mc, st));
-        else rc = nst == 2 ? panel_launch<2, 2>(w, p0, pm, p1, mc, st) : (nst == 3 ? panel_launch<2, 3>(w, p0, pm, p1, mc, st) : panel_launch<2, 4>(w, p0, pm, p1, mc, st));
+        if (T == 1) rc = panel_launch<1, 4>(w, p0, p1, wlog, st);
+        else if (T == 2) rc = NST == 4 ? panel_launch<2, 4>(w, p0, p1, wlog, st) : panel_launch<2, 3>(w, p0, p1, wlog, st);
+        else rc = panel_launch<4, 3>(w, p0, p1, wlog, st);
         if (rc) return rc;
     }
     const unsigned sblocks = (unsigned)std::min<int64_t>((a.nrows_x * a.k + 255) / 256, 148 * 16);
@@ -1737,8 +1723,22 @@ static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int
             set_error("lu_solve: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
             return OCB_ERR_CAPACITY;
         }
-        static const bool by_level = getenv("OCB_WIDE_BY_LEVEL") != nullptr;
-        if (lu->has_panels) return by_level ? panel_solve(lu, a, st) : persist_solve(lu, a, st);
+        // which all-columns executor: measured on the cavity factors (profiles/r02_wide_executor.md) the
+        // register-blocked panel kernel wins for wide blocks on large factors, the row kernel elsewhere
+        static int force = -1;   // OCB_WIDE_EXECUTOR = rows | panels | persist
+        static int64_t min_k = 192, min_n = 60000;
+        if (force < 0) {
+            const char* e = getenv("OCB_WIDE_EXECUTOR");
+            force = !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'p' && e[1] == 'a' ? 2 : (e[0] == 'p' ? 3 : 0)));
+            if (getenv("OCB_WIDE_BY_LEVEL")) force = 2;
+            const char* ek = getenv("OCB_PANEL_MIN_K");
+            const char* en = getenv("OCB_PANEL_MIN_N");
+            if (ek) min_k = atoi(ek);
+            if (en) min_n = atoi(en);
+        }
+        if (lu->has_panels && force == 3) return persist_solve(lu, a, st);
+        if (lu->has_panels && (force == 2 || (force == 0 && k >= min_k && lu->n_ext >= min_n) || !lu->has_flat))
+            return panel_solve(lu, a, st);
         return wide_solve(lu, a, st);
     }
     switch (lu->cl) {
@@ -2003,7 +2003,8 @@ int ocb_lu_stats(const ocb_lu* lu, int64_t* info8) {
 
 int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k) {
     if (!lu || !ocb::use_wide(lu, k)) return 0;
-    const int64_t ldx = std::max(ocb::wide_ldx(k), ocb::panel_ldx(k));
+    int64_t ldx = std::max(ocb::wide_ldx(k), ocb::panel_ldx(k));
+    if (lu->has_panels) ldx = std::max(ldx, ocb::persist_plan(lu, k).ldx);
     return lu->n_ext * ldx * (int64_t)sizeof(double) + ocb::PERSIST_TAIL_BYTES;
 }
 
