@@ -1726,7 +1726,7 @@ static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int
         // which all-columns executor: measured on the cavity factors (profiles/r02_wide_executor.md) the
         // register-blocked panel kernel wins for wide blocks on large factors, the row kernel elsewhere
         static int force = -1;   // OCB_WIDE_EXECUTOR = rows | panels | persist
-        static int64_t min_k = 192, min_n = 60000;
+        static int64_t min_k = 96, min_n = 0;
         if (force < 0) {
             const char* e = getenv("OCB_WIDE_EXECUTOR");
             force = !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'p' && e[1] == 'a' ? 2 : (e[0] == 'p' ? 3 : 0)));
