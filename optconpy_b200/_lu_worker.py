@@ -36,13 +36,79 @@ def tune_malloc():
         pass
 
 
+def _delay_zero_diagonals(indptr, indices, diag_is_zero, q):
+    """Constrained ordering for saddle-point patterns.  ``q[i]`` = node eliminated i-th.  A node
+    with a ZERO diagonal (a pressure dof: the (2,2) block of ``[[A, J^T], [J, 0]]``) is delayed
+    until right after the first of its neighbours with a nonzero diagonal has been eliminated -
+    from then on its pivot is the Schur-complement entry ``-J a^-1 J^T != 0``, so the
+    factorisation never meets an exact zero pivot, diagonal pivoting goes through and the fill is
+    the SYMBOLIC fill of the ordering.  Without this, minimum degree eliminates pressure nodes
+    first, SuperLU has to interchange rows, and with non-symmetric values (convection) the
+    interchanges wreck the structure: 8.6x the entries and 3.3x the sub-levels on the channel
+    Oseen matrix, 6.5x / 5.8x on the cavity one."""
+    n = len(q)
+    touched = np.zeros(n, dtype=bool)
+    pending = np.zeros(n, dtype=bool)
+    out = np.empty(n, dtype=np.int32)
+    m = 0
+    for v in q:
+        if diag_is_zero[v]:
+            if touched[v]:
+                out[m] = v
+                m += 1
+            else:
+                pending[v] = True
+            continue
+        out[m] = v
+        m += 1
+        nb = indices[indptr[v]:indptr[v+1]]
+        z = nb[diag_is_zero[nb]]
+        if z.size:
+            rel = z[pending[z]]
+            touched[z] = True
+            if rel.size:
+                rel = np.unique(rel)
+                out[m:m+rel.size] = rel
+                m += rel.size
+                pending[rel] = False
+    rest = np.flatnonzero(pending)          # zero-diagonal nodes without such a neighbour: last
+    if rest.size:
+        pos = np.empty(n, dtype=np.int64)
+        pos[q] = np.arange(n)
+        rest = rest[np.argsort(pos[rest])]
+        out[m:m+rest.size] = rest
+        m += rest.size
+    assert m == n
+    return out
+
+
 def order_only(args):
-    """The fill-reducing ordering of a sparsity pattern (one full SuperLU run with its
-    minimum-degree ordering; done ONCE per pattern, before any job of that pattern is queued, so
-    that every queued factorisation already takes the fast reuse path)."""
+    """The fill-reducing ordering of a sparsity pattern, computed ONCE per pattern, before any
+    job of that pattern is queued, so that every queued factorisation takes the fast reuse path
+    (symmetric permutation + NATURAL column order, ``factor_arrays``).
+
+    Minimum degree on the PATTERN only - one SuperLU run on a diagonally dominant surrogate with
+    the symmetrised pattern, so the ordering does not depend on the values of whichever matrix
+    happens to come first - followed by the zero-diagonal constraint of
+    ``_delay_zero_diagonals`` for the saddle-point block."""
     data, indices, indptr, shape, opts = args[:5]
-    slu = spsla.splu(sps.csc_matrix((data, indices, indptr), shape=shape), **opts)
-    return np.argsort(slu.perm_c).astype(np.int32)
+    n = shape[0]
+    K = sps.csc_matrix((data, indices, indptr), shape=shape)
+    if opts.get('permc_spec', 'COLAMD') != 'MMD_AT_PLUS_A':
+        slu = spsla.splu(K, **opts)
+        return np.argsort(slu.perm_c).astype(np.int32)
+    P = sps.csc_matrix((np.ones(K.nnz), K.indices, K.indptr), shape=shape)
+    P = (P + P.T).tocsc()
+    P.data[:] = 1.0
+    S = (P + sps.identity(n, format='csc')*float(2*P.getnnz(axis=0).max() + 1)).tocsc()
+    slu = spsla.splu(S, permc_spec='MMD_AT_PLUS_A', diag_pivot_thresh=0.0,
+                     options=dict(SymmetricMode=True))
+    q = np.argsort(slu.perm_c).astype(np.int32)
+    diag_is_zero = (K.diagonal() == 0.0)
+    if not diag_is_zero.any():
+        return q
+    Pr = P.tocsr()
+    return _delay_zero_diagonals(Pr.indptr, Pr.indices, diag_is_zero, q)
 
 
 _ARRANGE = dict()     # pattern -> (indices, indptr, source position of every entry) or None
