@@ -36,6 +36,9 @@ def tune_malloc():
         pass
 
 
+ORDER_TRIAL_MAX_N = 12000
+
+
 def _delay_zero_diagonals(indptr, indices, diag_is_zero, q):
     """Constrained ordering for saddle-point patterns.  ``q[i]`` = node eliminated i-th.  A node
     with a ZERO diagonal (a pressure dof: the (2,2) block of ``[[A, J^T], [J, 0]]``) is delayed
@@ -108,7 +111,20 @@ def order_only(args):
     if not diag_is_zero.any():
         return q
     Pr = P.tocsr()
-    return _delay_zero_diagonals(Pr.indptr, Pr.indices, diag_is_zero, q)
+    qc = _delay_zero_diagonals(Pr.indptr, Pr.indices, diag_is_zero, q)
+    # Small systems whose values let plain minimum degree + threshold pivoting through (the
+    # mass-dominated DRE matrices): keep that ordering - its factors have the SAME index arrays
+    # for every shift and time step, which the structure templates of the program builder live
+    # on, while the constrained ordering's factors differ in a handful of accidental zeros.
+    # One trial factorisation of the actual matrix decides; it is only affordable when small.
+    if n <= ORDER_TRIAL_MAX_N:
+        fill_sym = slu.L.nnz + slu.U.nnz
+        qo = np.argsort(spsla.splu(K, **opts).perm_c).astype(np.int32)
+        o2 = dict(opts, permc_spec='NATURAL')          # the reuse path of factor_arrays
+        trial = spsla.splu(K[qo][:, qo].tocsc(), **o2)
+        if trial.L.nnz + trial.U.nnz <= 1.15*fill_sym:
+            return qo
+    return qc
 
 
 _ARRANGE = dict()     # pattern -> (indices, indptr, source position of every entry) or None
