@@ -447,6 +447,26 @@ def run_sharded(rank, world, k_total, steps, nx, ny, peak_gbs):
         return [float(v) for v in t.tolist()], rel, Zc, cinfo, widths
     one()                                   # warm-up (allocations, symmetric buffers, module loads)
     (ms_adi, ms_cmp), rel, Zc, cinfo, widths = one()
+    # WEAK scaling of the same solve: k_total columns PER RANK (the block grows with N; no
+    # compression - its K x K Gram matrix would grow with N^2), global stopping test as before
+    weak = None
+    if world > 1:
+        Ww = rng.standard_normal((NV, 32)) @ rng.standard_normal((32, k_total*world))/np.sqrt(32.0)
+        Wwd = dv.to_dev(Ww)
+        for rep in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            Zw, ww, relw = par.sharded_stein(cm, fac, Wwd, d)
+            e1.record()
+            torch.cuda.synchronize()
+            tw = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            del Zw
+        weak = dict(columns_total=k_total*world, columns_per_rank=k_total, ms_adi=float(tw.item()),
+                    rhs_columns_per_s=1e3*k_total*world*steps/float(tw.item()))
+    else:
+        weak = dict(columns_total=k_total, columns_per_rank=k_total, ms_adi=ms_adi,
+                    rhs_columns_per_s=1e3*k_total*steps/ms_adi)
     i = lus[0].info
     nnz = int(i['nnzL'] + i['nnzU'])
     n = int(i['n'])
@@ -466,7 +486,7 @@ def run_sharded(rank, world, k_total, steps, nx, ny, peak_gbs):
                 solve_frac_hbm=ab/ms_adi/1e6/peak_gbs/max(world, 1),
                 nnz_LU=nnz, sublevels=int(i['levelsL'] + i['levelsU']),
                 compressed_cols=int(Zc.shape[1]), factor_cols=K,
-                rel_norms=[float(r) for r in rel],
+                rel_norms=[float(r) for r in rel], weak_scaling=weak,
                 transport=('single GPU' if cm is None else cm.transport),
                 symm_mem_error=(None if cm is None else cm.symm_error),
                 bytes_peer_memory_per_rank=(0 if cm is None else int(cm.bytes_p2p)//2),
