@@ -451,12 +451,13 @@ def run_sharded(rank, world, k_total, steps, nx, ny, peak_gbs):
     # compression - its K x K Gram matrix would grow with N^2), global stopping test as before
     weak = None
     if world > 1:
-        Ww = rng.standard_normal((NV, 32)) @ rng.standard_normal((32, k_total*world))/np.sqrt(32.0)
-        Wwd = dv.to_dev(Ww)
+        Cw = rng.standard_normal((32, k_total*world))/np.sqrt(32.0)       # same on every rank (seeded)
+        base = np.random.default_rng(1).standard_normal((NV, 32))
+        Wwd = dv.to_dev(base @ Cw[:, rank*k_total:(rank+1)*k_total])      # this rank's columns only
         for rep in range(2):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            Zw, ww, relw = par.sharded_stein(cm, fac, Wwd, d)
+            Zw, relw = par.sharded_stein_local(fac, Wwd, d)
             e1.record()
             torch.cuda.synchronize()
             tw = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')

@@ -63,6 +63,26 @@ def _world(group=None):
     return 0, 1
 
 
+def sharded_stein_local(fac, Wl, adi_dict, Ufb=None, Vt=None, group=None):
+    """As ``sharded_stein_dev`` for a caller that already holds only ITS column slice ``Wl`` (blocks
+    too wide to replicate): same global stopping test, one all-reduced scalar per ADI step."""
+    import torch
+    import torch.distributed as dist
+    from . import device as dv
+    rank, world = _world(group)
+    buf = torch.zeros(1, dtype=torch.float64, device=Wl.device)
+
+    def reduce_norm(v):
+        if world == 1:
+            return v
+        buf[0] = v
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        return float(buf.item())
+    return dv.adi_run(fac.lus, fac.ms, fac.NV, fac.NP, fac.Mt_dev, Wl.contiguous(),
+                      int(adi_dict['adi_max_steps']), float(adi_dict['adi_newZ_reltol']),
+                      Ufb=Ufb, Vt=Vt, norm_reduce=reduce_norm)
+
+
 def sharded_stein_dev(fac, W, adi_dict, Ufb=None, Vt=None, group=None):
     """Column-sharded LR-ADI on the GPUs.  ``fac`` (``proj_ric_utils.ShiftedFactors``) and the
     low-rank factors ``Ufb`` / ``Vt`` are replicated on every rank, ``W`` (device, NV x k) is
