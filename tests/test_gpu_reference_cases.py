@@ -212,3 +212,31 @@ def test_config3_stated_mesh_parity(mods):
     assert _zzt_relerr(rg['Z'], ro['Z']) < TOL_FACTOR
     assert _relerr(rg['mtxtb'], ro['mtxtb']) < TOL_FACTOR
     assert _relerr(rg['w'], ro['w']) < TOL_TRAJ
+
+
+@pytest.mark.timeout(1500)
+def test_config4_fine_channel_first_newton_step(mods):
+    """BASELINE config[3] at its FULL size (channel 200 x 62: NV 97 146, NP 12 542, n 109 688;
+    cyl_wake_cont.py parameters): the first Newton step of the steady-state branch
+    (optcont_main.py:488-492: z0 = None, so the ADI block is trct_mat) with the built-in six
+    shifts, cut to 12 ADI steps so that the oracle's column-by-column SuperLU solves finish in a
+    minute.  The factors go through the all-columns executors (the column panel of n = 109 688 does
+    not fit shared memory) and the constrained minimum-degree ordering."""
+    glau, gpru, olau, opru = mods
+    from optconpy_b200 import scenarios as sc, device as dv
+    prob, cs, kw = sc.config4(olau)
+    assert prob['NV'] == 97146 and prob['NP'] == 12542
+    d = dict(kw['nwtn_adi_dict'], adi_max_steps=12, nwtn_max_steps=1)
+    M, A, J = prob['M'], prob['A'], prob['J']
+    args = dict(mmat=M, amat=-A-kw['convc_mat'], jmat=J, bmat=cs['tb_mat'], wmat=cs['trct_mat'], z0=None,
+                nwtn_adi_dict=d)
+    dv.reset_stats()
+    got = gpru.proj_alg_ric_newtonadi(**args)
+    assert dv.STATS['lu_guard_refactors'] == 0 and dv.STATS['lu_guard_max_backerr'] < 2e-15
+    ref = opru.proj_alg_ric_newtonadi(**args)
+    assert got['adi_steps'] == ref['adi_steps'] == [12]
+    assert got['zfac'].shape == ref['zfac'].shape
+    assert _zzt_relerr(got['zfac'], ref['zfac']) < TOL_FACTOR
+    ga = gpru.get_mTzzTtb(M.T, got['zfac'], cs['tb_mat'])
+    gb = opru.get_mTzzTtb(M.T, ref['zfac'], cs['tb_mat'])
+    assert _relerr(ga, gb) < TOL_FACTOR
