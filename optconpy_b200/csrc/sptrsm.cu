@@ -676,12 +676,12 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
     const bool force_global = env && env[0] == '1';
     {   // cluster size: flags bits 4..7 (the caller's hint from the expected block width), else 4
         const int hint = (flags >> 4) & 15;
-        if (hint == 1 || hint == 2 || hint == 4 || hint == 8) cl = hint;
+        if (hint == 1 || hint == 2 || hint == 3 || hint == 4 || hint == 8) cl = hint;
     }
     const char* e_cl = getenv("OCB_TRSM_CLUSTER");
     if (e_cl) {
         const int v = atoi(e_cl);
-        if (v == 1 || v == 2 || v == 4 || v == 8) cl = v;
+        if (v == 1 || v == 2 || v == 3 || v == 4 || v == 8) cl = v;
     }
     std::vector<std::vector<Piece>> batches[8];
     auto plan_all = [&](int64_t c, int ncl) {
@@ -1743,6 +1743,7 @@ static int lu_solve_dispatch(const ocb_lu* lu, const double* B, int64_t ldb, int
     }
     switch (lu->cl) {
         case 8: return launch_cluster<8>(lu, a, st);
+        case 3: return launch_cluster<3>(lu, a, st);
         case 4: return launch_cluster<4>(lu, a, st);
         case 2: return launch_cluster<2>(lu, a, st);
         default: return launch_cluster<1>(lu, a, st);
