@@ -72,8 +72,8 @@ int ocb_lu_destroy(ocb_lu* lu);
  * L^T, and h_perm_r / h_perm_c are that factorisation's perm_c / perm_r; SuperLU's compressed-
  * column output is used as is, no transposition on the host.  flags bit 2: supernodes up to 64
  * rows wide are solved in ONE sub-level, x_t = inv(T_tt) b_t - (inv(T_tt) T[t,off]) x, instead of
- * two (about a third fewer sub-level barriers for ~2 % more entries).  flags bits 4..7: cluster size of the column-panel kernel, 1 / 2 / 4 / 8 (0 = default 4;
- * 4 is fastest up to 33 right-hand sides, 2 from 34 to ~150).  flags bit 0: also include the flat program of the wide, all-columns-at-once
+ * two (about a third fewer sub-level barriers for ~2 % more entries).  flags bits 4..7: cluster size of the column-panel kernel, 1 / 2 / 3 / 4 / 8 (0 = default 4;
+ * 4 is fastest up to 33 right-hand sides, 3 up to 44, 2 from 45 to ~150).  flags bit 0: also include the flat program of the wide, all-columns-at-once
  * executor (its PANEL form, see ocb_lu_program_solve_host) that ocb_lu_solve uses for k >= 640
  * right-hand sides; it is always included when the column panel does not fit shared memory); ocb_lu_create_from_image uploads it with one copy into d_arena (bytes long,
  * 256-byte aligned, owned by the caller and kept alive until ocb_lu_destroy; NULL: the library

@@ -262,9 +262,9 @@ def _pack_flags(wide, k_hint=None):
     and take SuperLU's column-wise factors as they are (no CSC->CSR conversion on the host),
     bit 2 = small supernodes solved in one sub-level instead of two,
     bits 4..7 = cluster size of the column-panel kernel from the expected block width
-    (measured: clusters of 4 are fastest up to 33 right-hand sides - one column per cluster fits
-    one wave -, clusters of 2 from 34 columns on)."""
-    cl = 0 if k_hint is None else (4 if k_hint <= 33 else 2)
+    (measured, N=25 factor: one column per cluster while one wave of clusters covers the block -
+    clusters of 4 up to 33 right-hand sides: 135 us, of 3 up to 44: 146 us, of 2 beyond: 175 us)."""
+    cl = 0 if k_hint is None else (4 if k_hint <= 33 else (3 if k_hint <= 44 else 2))
     merge = 4 if os.environ.get('OCB_MERGE', MERGE_DEFAULT) == '1' else 0
     return (1 if wide else 0) | (0 if os.environ.get('OCB_NO_TRANSPOSED_LU') else 2) | merge | (cl << 4)
 
