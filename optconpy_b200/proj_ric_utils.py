@@ -363,7 +363,10 @@ def compress_Zsvd(Z, k=None, thresh=None, shplot=False):
         Zc, info = dv.compress(Zd, thresh=thresh, k=k)
         if isinstance(Z, torch.Tensor):
             return Zc
-        return dv.to_host(Zc)
+        Zc = Zc.contiguous()
+        zh = dv.to_host(Zc)
+        dv.remember_device_copy(zh, Zc)      # the driver hands this array straight back in
+        return zh
 
 
 def comp_proj_lyap_res_norm(Z, amat=None, mmat=None, wmat=None, jmat=None,

@@ -245,3 +245,23 @@ def test_fp64_peak_microbenchmark(dv):
     """The measured FP64 denominators (DMMA tensor pipe, DFMA pipe) are sane B200 numbers."""
     dm, df = dv.fp64_peak('dmma'), dv.fp64_peak('dfma')
     assert 5.0 < dm < 120.0 and 5.0 < df < 120.0, (dm, df)
+
+
+def test_device_copy_cache_of_returned_factors(dv):
+    """compress_Zsvd registers the device copy of the array it returns; handing that very array
+    back (as the reference driver does) skips the upload, a modified array is uploaded afresh."""
+    import optconpy_b200.proj_ric_utils as gpru
+    rng = np.random.default_rng(3)
+    Z = rng.standard_normal((900, 40)) @ rng.standard_normal((40, 120))
+    zc = gpru.compress_Zsvd(Z, thresh=1e-8)
+    before = dv.STATS['h2d_bytes']
+    t1 = dv.to_dev(zc)
+    assert dv.STATS['h2d_bytes'] == before                       # served from the cache
+    assert _relerr(dv.to_host(t1), zc) == 0.0
+    zc[3, 2] += 1.0                                              # caller modified it in place
+    t2 = dv.to_dev(zc)
+    assert dv.STATS['h2d_bytes'] > before and _relerr(dv.to_host(t2), zc) == 0.0
+    other = zc.copy()                                            # another object: never served from the cache
+    b2 = dv.STATS['h2d_bytes']
+    dv.to_dev(other)
+    assert dv.STATS['h2d_bytes'] > b2
