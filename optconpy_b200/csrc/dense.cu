@@ -87,15 +87,128 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const double* __restr
 
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ P, int64_t ka,
                                                          int64_t kb, int nsplit,
-                                                         double* __restrict__ G, int64_t ldg, int sym) {
+                                                         double* __restrict__ G, int64_t ldg, int sym,
+                                                         int tile) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ka * kb) return;
     int64_t r = e / kb, c = e % kb;
     int64_t src = e;
-    if (sym && (r / GR_TM) < (c / GR_TN)) src = c * kb + r;   // tile above the diagonal: mirror
+    if (sym && (r / tile) < (c / tile)) src = c * kb + r;   // tile above the diagonal: mirror
     double s = 0.0;
     for (int z = 0; z < nsplit; ++z) s += P[(int64_t)z * ka * kb + src];
     G[r * ldg + c] = s;
+}
+
+// ---------------------------------------------------------------------------------
+// Large Gram products (ka, kb >= 128: the K x K matrix of the compression): CTA tile 128 x 128,
+// 8 warps of 32 x 64 (4 x 8 DMMA tiles, 64 accumulator registers), row slabs of 16 staged by
+// cp.async through a 3-stage shared-memory ring - the global loads of the next two slabs are in
+// flight while the tensor pipe works on the current one.  Leading dimension 132 (= 4 mod 16): the
+// 4 rows x 4 columns a half-warp reads for one fragment fall into 32 distinct banks.
+// ---------------------------------------------------------------------------------
+constexpr int G2_T = 128, G2_RK = 16, G2_LD = 132, G2_ST = 3;
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) gram_partial_kernel2(const double* __restrict__ Z, int64_t ldz,
+                                                           int64_t ka, const double* __restrict__ W,
+                                                           int64_t ldw, int64_t kb, int64_t n,
+                                                           int64_t rows_per_split,
+                                                           double* __restrict__ P /*[split][ka][kb]*/,
+                                                           int sym) {
+    extern __shared__ __align__(16) double g2sm[];   // [stage][Z | W][G2_RK][G2_LD]
+    if (sym && blockIdx.x < blockIdx.y) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t a0 = (int64_t)blockIdx.x * G2_T, b0 = (int64_t)blockIdx.y * G2_T;
+    const int64_t r_beg = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t r_end = min(n, r_beg + rows_per_split);
+    const int m0 = (warp & 3) * 32, n0 = (warp >> 2) * 64;
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int nslab = (int)((r_end - r_beg + G2_RK - 1) / G2_RK);
+    auto issue = [&](int sl) {
+        double* zs = g2sm + (size_t)(sl % G2_ST) * (2 * G2_RK * G2_LD);
+        double* ws = zs + G2_RK * G2_LD;
+        const int64_t r0 = r_beg + (int64_t)sl * G2_RK;
+        // 16 rows x 128 columns per operand = 1024 chunks of 16 bytes: 4 per thread and operand
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ch = tid + q * 256;
+            const int rr = ch >> 6, cc = (ch & 63) * 2;
+            const int64_t r = r0 + rr;
+            const bool rok = r < r_end;
+            const int za = rok ? (int)max((int64_t)0, min((int64_t)16, (ka - (a0 + cc)) * 8)) : 0;
+            const int wa = rok ? (int)max((int64_t)0, min((int64_t)16, (kb - (b0 + cc)) * 8)) : 0;
+            // clamp the source address into the block (it is not read when the size is 0)
+            const double* zsrc = Z + (rok ? r : r_beg) * ldz + (za > 0 ? a0 + cc : 0);
+            const double* wsrc = W + (rok ? r : r_beg) * ldw + (wa > 0 ? b0 + cc : 0);
+            cp_async16_zfill(zs + rr * G2_LD + cc, zsrc, za);
+            cp_async16_zfill(ws + rr * G2_LD + cc, wsrc, wa);
+        }
+    };
+#pragma unroll
+    for (int sl = 0; sl < G2_ST - 1; ++sl) {
+        if (sl < nslab) issue(sl);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int sl = 0; sl < nslab; ++sl) {
+        if (sl + G2_ST - 1 < nslab) issue(sl + G2_ST - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(G2_ST - 1) : "memory");
+        __syncthreads();
+        const double* zs = g2sm + (size_t)(sl % G2_ST) * (2 * G2_RK * G2_LD);
+        const double* ws = zs + G2_RK * G2_LD;
+#pragma unroll
+        for (int kk = 0; kk < G2_RK / 4; ++kk) {
+            const int kr = kk * 4 + (lane & 3);
+            double af[4], bf[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = zs[kr * G2_LD + m0 + i * 8 + (lane >> 2)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bf[j] = ws[kr * G2_LD + n0 + j * 8 + (lane >> 2)];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();   // the slot is refilled by the copies issued next
+    }
+    double* Pz = P + (int64_t)blockIdx.z * ka * kb;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t gr = a0 + m0 + i * 8 + (lane >> 2);
+            const int64_t gc = b0 + n0 + j * 8 + 2 * (lane & 3);
+            if (gr < ka) {
+                if (gc < kb) Pz[gr * kb + gc] = acc[i][j][0];
+                if (gc + 1 < kb) Pz[gr * kb + gc + 1] = acc[i][j][1];
+            }
+        }
+}
+
+static bool gram_big(const double* Z, int64_t ldz, int64_t ka, const double* W, int64_t ldw, int64_t kb) {
+    static const bool off = getenv("OCB_GRAM_SMALL_TILES") != nullptr;
+    return !off && ka >= 128 && kb >= 128 && (ldz & 1) == 0 && (ldw & 1) == 0 &&
+           ((uintptr_t)Z & 15) == 0 && ((uintptr_t)W & 15) == 0;
+}
+
+static void gram_plan2(int64_t n, int64_t ka, int64_t kb, bool sym, int* nsplit, int64_t* rps) {
+    const int64_t ta = (ka + G2_T - 1) / G2_T, tb = (kb + G2_T - 1) / G2_T;
+    const int64_t tiles = sym ? ta * (ta + 1) / 2 : ta * tb;
+    int64_t want = (2 * (int64_t)148 + tiles - 1) / tiles;          // ~2 CTAs per SM in total
+    const int64_t maxsplit = (n + 8 * G2_RK - 1) / (8 * G2_RK);     // >= 128 rows per split
+    want = std::max<int64_t>(1, std::min(want, std::max<int64_t>(1, maxsplit)));
+    int64_t r = (n + want - 1) / want;
+    r = align_up(std::max<int64_t>(r, 1), G2_RK);
+    *rps = r;
+    *nsplit = (int)std::max<int64_t>(1, (n + r - 1) / r);
 }
 
 static void gram_plan(int64_t n, int64_t ka, int64_t kb, int* nsplit, int64_t* rps) {
@@ -115,17 +228,34 @@ int gram_impl(const double* Z, int64_t ldz, int64_t ka, const double* W, int64_t
     const int sym = (Z == W && ldz == ldw && ka == kb && ka > GR_TM) ? 1 : 0;   // G = Z^T Z
     int nsplit;
     int64_t rps;
-    gram_plan(n, ka, kb, &nsplit, &rps);
+    const bool big = gram_big(Z, ldz, ka, W, ldw, kb);
+    if (big) gram_plan2(n, ka, kb, sym != 0, &nsplit, &rps);
+    else gram_plan(n, ka, kb, &nsplit, &rps);
     const int64_t need = (int64_t)nsplit * ka * kb * 8;
     if (!ws || ws_bytes < need) {
         set_error("gram: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
         return OCB_ERR_CAPACITY;
     }
+    if (big) {
+        const int smem = G2_ST * 2 * G2_RK * G2_LD * (int)sizeof(double);
+        static bool attr = false;
+        if (!attr) {
+            OCB_CUDA(cudaFuncSetAttribute(gram_partial_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr = true;
+        }
+        dim3 grid2((unsigned)((ka + G2_T - 1) / G2_T), (unsigned)((kb + G2_T - 1) / G2_T), nsplit);
+        gram_partial_kernel2<<<grid2, 256, smem, st>>>(Z, ldz, ka, W, ldw, kb, n, rps, (double*)ws, sym);
+        OCB_LAUNCH_CHECK();
+        gram_reduce_kernel<<<(unsigned)((ka * kb + 255) / 256), 256, 0, st>>>((const double*)ws, ka, kb,
+                                                                             nsplit, G, ldg, sym, G2_T);
+        OCB_LAUNCH_CHECK();
+        return OCB_OK;
+    }
     dim3 grid((unsigned)((ka + GR_TM - 1) / GR_TM), (unsigned)((kb + GR_TN - 1) / GR_TN), nsplit);
     gram_partial_kernel<<<grid, 256, 0, st>>>(Z, ldz, ka, W, ldw, kb, n, rps, (double*)ws, sym);
     OCB_LAUNCH_CHECK();
     gram_reduce_kernel<<<(unsigned)((ka * kb + 255) / 256), 256, 0, st>>>((const double*)ws, ka, kb,
-                                                                         nsplit, G, ldg, sym);
+                                                                         nsplit, G, ldg, sym, GR_TM);
     OCB_LAUNCH_CHECK();
     return OCB_OK;
 }
@@ -658,10 +788,13 @@ int ocb_fp64_peak(int kind, int64_t iters, int64_t ctas_per_sm, double* h_tflops
 }
 
 int64_t ocb_gram_ws_bytes(int64_t n, int64_t ka, int64_t kb) {
-    int nsplit;
+    int nsplit, nsplit2;
     int64_t rps;
     ocb::gram_plan(n, std::max<int64_t>(ka, 1), std::max<int64_t>(kb, 1), &nsplit, &rps);
-    return (int64_t)nsplit * ka * kb * 8;
+    ocb::gram_plan2(n, std::max<int64_t>(ka, 1), std::max<int64_t>(kb, 1), false, &nsplit2, &rps);
+    int nsplit3;
+    ocb::gram_plan2(n, std::max<int64_t>(ka, 1), std::max<int64_t>(kb, 1), true, &nsplit3, &rps);
+    return (int64_t)std::max(nsplit, std::max(nsplit2, nsplit3)) * ka * kb * 8;
 }
 
 int ocb_gram(const double* d_Z, int64_t ldz, int64_t ka, const double* d_W, int64_t ldw, int64_t kb,
