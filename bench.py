@@ -438,9 +438,9 @@ def run_sharded(rank, world, k_total, steps, nx, ny, peak_gbs):
             Zl, widths, rel = par.sharded_stein(cm, fac, Wd, d)
         ev[1].record()
         if cm is None:
-            Zc, cinfo = dv.compress(Zl, thresh=1e-8*float(np.sqrt(k_total)), k=None)
+            Zc, cinfo = dv._compress_once(Zl, None, 256, 1e-14, None)     # same single-level path as sharded
         else:
-            Zc, cinfo = par.sharded_compress(cm, Zl, widths, thresh=1e-8*float(np.sqrt(k_total)), k=None)
+            Zc, cinfo = par.sharded_compress(cm, Zl, widths, thresh=None, k=256)
         ev[2].record()
         torch.cuda.synchronize()
         t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], dtype=torch.float64,

@@ -193,6 +193,11 @@ __global__ void __launch_bounds__(256) gram_partial_kernel2(const double* __rest
         }
 }
 
+static bool gram_big_enabled() {
+    static const bool on = getenv("OCB_GRAM_BIG_TILES") != nullptr;
+    return on;
+}
+
 static bool gram_big(const double* Z, int64_t ldz, int64_t ka, const double* W, int64_t ldw, int64_t kb) {
     // opt-in (OCB_GRAM_BIG_TILES=1): measured equal to the 64 x 64 kernel (12.9 / 17.5 / 20.3 against
     // 12.5 / 17.3 / 19.7 TFLOP/s at K = 1296 / 1716 / 3072) - the Gram product is not bound by its staging
@@ -790,12 +795,13 @@ int ocb_fp64_peak(int kind, int64_t iters, int64_t ctas_per_sm, double* h_tflops
 }
 
 int64_t ocb_gram_ws_bytes(int64_t n, int64_t ka, int64_t kb) {
-    int nsplit, nsplit2;
+    int nsplit, nsplit2 = 0, nsplit3 = 0;
     int64_t rps;
     ocb::gram_plan(n, std::max<int64_t>(ka, 1), std::max<int64_t>(kb, 1), &nsplit, &rps);
-    ocb::gram_plan2(n, std::max<int64_t>(ka, 1), std::max<int64_t>(kb, 1), false, &nsplit2, &rps);
-    int nsplit3;
-    ocb::gram_plan2(n, std::max<int64_t>(ka, 1), std::max<int64_t>(kb, 1), true, &nsplit3, &rps);
+    if (ocb::gram_big_enabled() && ka >= 128 && kb >= 128) {
+        ocb::gram_plan2(n, ka, kb, false, &nsplit2, &rps);
+        ocb::gram_plan2(n, ka, kb, true, &nsplit3, &rps);
+    }
     return (int64_t)std::max(nsplit, std::max(nsplit2, nsplit3)) * ka * kb * 8;
 }
 
