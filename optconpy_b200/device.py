@@ -847,6 +847,12 @@ def _compress_once(Z, thresh, k, eta, rmax):
     sig = torch.zeros((rmax,), dtype=torch.float64, device=Z.device)
     info = (C.c_int64*3)()
     wsb = lib.ocb_compress_ws_bytes(n, K, rmax)
+    # the K x K Gram matrix grows with every DRE step (K = block width x ADI steps): ask for
+    # headroom, so that the buffer is not re-allocated (cudaFree + cudaMalloc: both synchronise)
+    # every few time steps
+    have = _WS.get('compress')
+    if have is None or have.buf is None or have.buf.numel() < wsb:
+        workspace('compress', int(wsb*1.6))
     ws = workspace('compress', wsb)
     _cabi.check(lib.ocb_compress(ptr(Z), Z.stride(0), n, K,
                                  -1.0 if thresh is None else float(thresh),
