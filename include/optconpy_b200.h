@@ -161,6 +161,32 @@ int ocb_lu_program_export(const ocb_lu_program* prog, int32_t* h_sub_ptr, int32_
 int ocb_lu_program_solve_host(const ocb_lu_program* prog, const int32_t* h_perm_r, const int32_t* h_perm_c,
                               const double* h_b, double* h_x, int64_t mode, double max_pad,
                               int64_t* h_stats4);
+/* ---- numeric-only refactorisation with symbolic reuse (host side) ----------
+ * Replaces, for the second and every later matrix of one sparsity pattern, the per-matrix
+ * `spsla.splu` of the reference's hot path (proj_ric_utils.py:108-111 factorises A + p_j M for every
+ * shift j; solve_dae_ric.py:147-163 rebuilds A for every time step: same pattern, new numbers).
+ * ocb_refactor_create takes the pattern of A (CSC) and the two permutations a first, pivoting
+ * factorisation produced, (P A Q)[perm_r[i], perm_c[j]] = A[i, j] with the pivots on the diagonal,
+ * and computes everything that depends on them only (elimination tree, supernodes, front
+ * structures, index maps, CSR structure of both factors).  ocb_refactor_numeric then factorises a
+ * matrix with these static pivots: one multifrontal pass over dense fronts; OCB_ERR_SINGULAR on a
+ * zero pivot.  Its outputs, together with ocb_refactor_structure's index arrays and permutations
+ * (the input ones composed with an elimination-tree postorder), are the L / U arguments of
+ * ocb_lu_pack_host* with flags bit 1 CLEAR (P A Q = L U, L unit lower).  The caller's residual
+ * guard (ocb_lu_pack_host_checked) decides whether the static pivots were good enough. */
+typedef struct ocb_refactor ocb_refactor;
+int ocb_refactor_create(ocb_refactor** out, int64_t n, const int32_t* h_A_colptr, const int32_t* h_A_rowidx,
+                        const int32_t* h_perm_r, const int32_t* h_perm_c);
+int ocb_refactor_destroy(ocb_refactor* rf);
+/* info8: n, nnz(L) incl. the unit diagonal, nnz(U), supernodes, largest front, peak stack
+ * entries, flops of one numeric pass, nnz(A) */
+int ocb_refactor_info(const ocb_refactor* rf, int64_t* info8);
+/* any pointer may be null; sizes from ocb_refactor_info */
+int ocb_refactor_structure(const ocb_refactor* rf, int32_t* h_L_rowptr, int32_t* h_L_colidx,
+                           int32_t* h_U_rowptr, int32_t* h_U_colidx, int32_t* h_perm_r, int32_t* h_perm_c);
+/* h_A_vals in the order of the CSC arrays given to ocb_refactor_create; not re-entrant per handle */
+int ocb_refactor_numeric(ocb_refactor* rf, const double* h_A_vals, double* h_L_vals, double* h_U_vals);
+
 /* bytes of device workspace ocb_lu_solve needs for k right-hand sides (0 when the column-panel
  * kernel is used; n_ext x roundup(k) doubles for the wide executor) */
 int64_t ocb_lu_solve_ws_bytes(const ocb_lu* lu, int64_t k);

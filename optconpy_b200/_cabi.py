@@ -37,6 +37,11 @@ PROTOTYPES = {
     'ocb_lu_program_info': (C.c_int, [vp, C.POINTER(i64)]),
     'ocb_lu_program_solve_host': (C.c_int, [vp, vp, vp, vp, vp, i64, C.c_double, C.POINTER(i64)]),
     'ocb_lu_program_export': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
+    'ocb_refactor_create': (C.c_int, [C.POINTER(vp), i64, vp, vp, vp, vp]),
+    'ocb_refactor_destroy': (C.c_int, [vp]),
+    'ocb_refactor_info': (C.c_int, [vp, C.POINTER(i64)]),
+    'ocb_refactor_structure': (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    'ocb_refactor_numeric': (C.c_int, [vp, vp, vp, vp]),
     'ocb_lu_solve_ws_bytes': (i64, [vp, i64]),
     'ocb_lu_solve': (C.c_int, [vp, f64p, i64, i64, f64p, i64, i64, i64, vp, i64, vp]),
     'ocb_prof_enable': (C.c_int, [C.c_int]),

@@ -293,10 +293,109 @@ def _safe_args(args):
     return args[:4] + (opts, args[5], flags) + tuple(args[7:])
 
 
+class _Refactor(object):
+    """Numeric-only factorisation of one sparsity pattern with the pivot order of a first SuperLU
+    run (``ocb_refactor_*``, csrc/refactor.cpp): the index arrays of both factors and the
+    permutations are fixed, ``numeric(data)`` fills in the numbers."""
+
+    def __init__(self, n, indptr, indices, perm_r, perm_c):
+        from optconpy_b200 import _cabi
+        self._lib = lib = _cabi.load()
+        self.n = n
+        ip = np.ascontiguousarray(indptr, dtype=np.int32)
+        ii = np.ascontiguousarray(indices, dtype=np.int32)
+        h = C.c_void_p()
+        _cabi.check(lib.ocb_refactor_create(C.byref(h), n, ip.ctypes.data, ii.ctypes.data,
+                                            perm_r.ctypes.data, perm_c.ctypes.data), 'ocb_refactor_create')
+        self._h = h
+        info = (C.c_int64*8)()
+        lib.ocb_refactor_info(h, info)
+        self.info = dict(nnzL=int(info[1]), nnzU=int(info[2]), supernodes=int(info[3]),
+                         max_front=int(info[4]), flops=int(info[6]))
+        self.Lrp, self.Urp = np.empty(n+1, np.int32), np.empty(n+1, np.int32)
+        self.Lci, self.Uci = np.empty(info[1], np.int32), np.empty(info[2], np.int32)
+        self.perm_r, self.perm_c = np.empty(n, np.int32), np.empty(n, np.int32)
+        lib.ocb_refactor_structure(h, self.Lrp.ctypes.data, self.Lci.ctypes.data, self.Urp.ctypes.data,
+                                   self.Uci.ctypes.data, self.perm_r.ctypes.data, self.perm_c.ctypes.data)
+        self.Lva, self.Uva = np.empty(info[1]), np.empty(info[2])
+
+    def numeric(self, data):
+        """The eight arrays ``ocb_lu_pack_host`` takes (layout: P A Q = L U, flags bit 1 clear),
+        or None if a static pivot vanished."""
+        d = np.ascontiguousarray(data, dtype=np.float64)
+        rc = self._lib.ocb_refactor_numeric(self._h, d.ctypes.data, self.Lva.ctypes.data, self.Uva.ctypes.data)
+        if rc != 0:
+            return None
+        return [self.Lrp, self.Lci, self.Lva, self.Urp, self.Uci, self.Uva, self.perm_r, self.perm_c]
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.ocb_refactor_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+# Static-pivot refactorisation (SURVEY 8 row f2): OCB_REFACTOR=0 switches it off.  Handles by
+# sparsity pattern + ordering, at most four (one run has one or two patterns).
+_REFAC = dict()
+REFACTOR_MAX_PATTERNS = 4
+
+
+def _refactor_enabled(args):
+    import os
+    flags = args[6] if len(args) > 6 else 0
+    q = args[7] if len(args) > 7 else None
+    return (os.environ.get('OCB_REFACTOR', '1') != '0' and q is not None and (flags & 2)
+            and not (flags & SAFE_FLAG) and args[3][0] > 0)
+
+
+def _refactor_key(args):
+    import zlib
+    return (args[3], len(args[1]), zlib.crc32(memoryview(np.ascontiguousarray(args[1]))),
+            zlib.crc32(memoryview(np.ascontiguousarray(args[2]))),
+            zlib.crc32(memoryview(np.ascontiguousarray(args[7]))))
+
+
+def _pack(lib, arrs, n, smem, flags, slot, amat):
+    """Analyse + pack one factorisation.  Returns (slot or None, image or None, nbytes, backerr)."""
+    from optconpy_b200 import _cabi
+    img, backerr, nbytes = None, None, 0
+    if slot is not None:
+        # build the image right in the pinned segment (no intermediate buffer, no copy)
+        seg = _attach(slot[0])
+        if slot[0] not in _ADDRESS:    # one exported view per segment, kept for the process lifetime
+            _ADDRESS[slot[0]] = C.addressof(C.c_char.from_buffer(seg.buf))
+        nb = C.c_int64(0)
+        if amat is None:
+            rc = lib.ocb_lu_pack_host_into(n, *[a.ctypes.data for a in arrs], int(smem), int(flags),
+                                           _ADDRESS[slot[0]], int(slot[1]), C.byref(nb))
+        else:
+            be = C.c_double(0.0)
+            rc = lib.ocb_lu_pack_host_checked(n, *[a.ctypes.data for a in arrs], int(smem),
+                                              int(flags), _ADDRESS[slot[0]], int(slot[1]), None,
+                                              C.byref(nb), *[a.ctypes.data for a in amat], C.byref(be))
+            backerr = be.value
+        if rc == 0:
+            nbytes = nb.value
+        elif rc != -5:                    # anything but "does not fit": a real error
+            _cabi.check(rc, 'ocb_lu_pack_host_checked')
+        else:
+            slot = None                   # too small: hand the image back another way
+    if slot is None:
+        ci = _CImage(arrs, n, smem, flags, amat=amat)
+        img, backerr, nbytes = ci.view.copy(), ci.backerr, ci.view.nbytes
+        ci.free()
+    return slot, img, nbytes, backerr
+
+
 def _build(args, slot=None):
     """Factorise + analyse + pack (guarded).  Returns (name-or-None, image-or-None, nbytes,
     seconds factor, seconds pack, ordering, guard) where guard = (backward error of the image
-    handed out, 1 if it is the safe re-factorisation else 0)."""
+    handed out, 1 if it is the safe re-factorisation else 0, 'static' if the numbers come from
+    the numeric-only refactorisation with static pivots else 'slu', 1 if a static-pivot image
+    was rejected by the guard first else 0)."""
     from optconpy_b200 import _cabi
     lib = _cabi.load()
     tol = _guard_tol()
@@ -304,6 +403,24 @@ def _build(args, slot=None):
     tf = tp = 0.0
     order = None
     safe = 0
+    rejected = 0
+    n = args[3][0]
+    rkey = _refactor_key(args) if _refactor_enabled(args) else None
+    rf = _REFAC.get(rkey) if rkey is not None else None
+    if rf is not None:
+        # second and later matrices of a pattern: numbers only, pivots as in the first one.  The
+        # guard is what makes static pivots safe, so it always runs here.
+        t0 = time.perf_counter()
+        arrs = rf.numeric(args[0])
+        t1 = time.perf_counter()
+        tf += t1 - t0
+        if arrs is not None:
+            am = amat if amat is not None else _amat_arrays(args)
+            used, img, nbytes, backerr = _pack(lib, arrs, n, args[5], args[6] & ~2, slot, am)
+            tp += time.perf_counter() - t1
+            if backerr <= (tol if tol > 0 else GUARD_TOL):
+                return used, img, nbytes, tf, tp, None, (backerr, 0, 'static', 0)
+        rejected = 1
     while True:
         t0 = time.perf_counter()
         flags = args[6] if len(args) > 6 else 0
@@ -311,36 +428,20 @@ def _build(args, slot=None):
         order = o2 if order is None else order
         t1 = time.perf_counter()
         tf += t1 - t0
-        n = args[3][0]
-        img, backerr, nbytes = None, None, 0
-        if slot is not None:
-            # build the image right in the pinned segment (no intermediate buffer, no copy)
-            seg = _attach(slot[0])
-            if slot[0] not in _ADDRESS:    # one exported view per segment, kept for the process lifetime
-                _ADDRESS[slot[0]] = C.addressof(C.c_char.from_buffer(seg.buf))
-            nb = C.c_int64(0)
-            if amat is None:
-                rc = lib.ocb_lu_pack_host_into(n, *[a.ctypes.data for a in arrs], int(args[5]), int(flags),
-                                               _ADDRESS[slot[0]], int(slot[1]), C.byref(nb))
-            else:
-                be = C.c_double(0.0)
-                rc = lib.ocb_lu_pack_host_checked(n, *[a.ctypes.data for a in arrs], int(args[5]),
-                                                  int(flags), _ADDRESS[slot[0]], int(slot[1]), None,
-                                                  C.byref(nb), *[a.ctypes.data for a in amat], C.byref(be))
-                backerr = be.value
-            if rc == 0:
-                nbytes = nb.value
-            elif rc != -5:                    # anything but "does not fit": a real error
-                _cabi.check(rc, 'ocb_lu_pack_host_checked')
-            else:
-                slot = None                   # too small: hand the image back another way
-        if slot is None:
-            ci = _CImage(arrs, n, args[5], flags, amat=amat)
-            img, backerr, nbytes = ci.view.copy(), ci.backerr, ci.view.nbytes
-            ci.free()
+        used, img, nbytes, backerr = _pack(lib, arrs, n, args[5], flags, slot, amat)
         tp += time.perf_counter() - t1
         if backerr is None or backerr <= tol or safe:
-            return slot, img, nbytes, tf, tp, order, (backerr, safe)
+            if rkey is not None and rf is None and not safe and rkey not in _REFAC:
+                # first good factorisation of this pattern: its pivots become the static ones
+                t2 = time.perf_counter()
+                if len(_REFAC) >= REFACTOR_MAX_PATTERNS:
+                    _REFAC.pop(next(iter(_REFAC)))
+                try:
+                    _REFAC[rkey] = _Refactor(n, args[2], args[1], arrs[6], arrs[7])
+                except RuntimeError:
+                    _REFAC[rkey] = None
+                tf += time.perf_counter() - t2
+            return used, img, nbytes, tf, tp, order, (backerr, safe, 'slu', rejected)
         args = _safe_args(args)
         safe = 1
 
@@ -366,6 +467,16 @@ def _attach(name):
     return seg
 
 
+def _timeline(t0, tf, tp):
+    """OCB_TIMELINE=<dir>: one line per job (wall-clock start, end, seconds factor / pack) in
+    <dir>/worker_<pid>.log, merged with the main process's events by tools/e2e_timeline.py."""
+    import os
+    d = os.environ.get('OCB_TIMELINE')
+    if d:
+        with open(os.path.join(d, 'worker_%d.log' % os.getpid()), 'a') as f:
+            f.write('%.6f %.6f %.6f %.6f\n' % (t0, time.time(), tf, tp))
+
+
 def factor_image_to_shm(args, slot=None):
     """Pool entry point: factorise, analyse, pack and hand the image back through POSIX shared
     memory (no pickling of ~10 MB through a pipe).  ``slot = (name, capacity)`` is a segment of
@@ -374,7 +485,9 @@ def factor_image_to_shm(args, slot=None):
     Returns (name or None if the slot was used, nbytes, seconds factor, seconds analyse+pack,
     ordering for later matrices of the same pattern or None, guard)."""
     from multiprocessing import shared_memory
+    t0 = time.time()
     used, img, nbytes, tf, tp, order, guard = _build(args, slot)
+    _timeline(t0, tf, tp)
     if used is not None:
         return None, nbytes, tf, tp, order, guard
     shm = shared_memory.SharedMemory(create=True, size=max(nbytes, 64))

@@ -205,7 +205,41 @@ struct FactorTemplate {
     std::vector<int32_t> q;           // program row
     std::vector<int32_t> base;        // position of the row's entry 0
     std::vector<uint8_t> g;           // log2(lanes per row)
+    // rows of kind 1 / 2 grouped by supernode (index_blocks): the refill computes one block
+    // inverse at a time into scratch buffers and writes its rows straight away
+    std::vector<int32_t> bl_level_ptr;   // block entries of recorded level j
+    std::vector<int32_t> bl_block, bl_ptr, bl_x;
+    void index_blocks(int nb);
 };
+
+void FactorTemplate::index_blocks(int nb) {
+    bl_level_ptr.assign(1, 0);
+    bl_ptr.assign(1, 0);
+    std::vector<int32_t> slot(nb, -1);
+    std::vector<std::vector<int32_t>> bucket;
+    std::vector<int32_t> order;
+    for (size_t lv = 0; lv + 1 < level_ptr.size(); ++lv) {
+        bucket.clear();
+        order.clear();
+        for (int32_t x = level_ptr[lv]; x < level_ptr[lv + 1]; ++x) {
+            const RowRef& rr = rows[x];
+            if (rr.kind != 1 && rr.kind != 2) continue;
+            if (slot[rr.block] < 0) {
+                slot[rr.block] = (int32_t)bucket.size();
+                bucket.emplace_back();
+                order.push_back(rr.block);
+            }
+            bucket[slot[rr.block]].push_back(x);
+        }
+        for (size_t j = 0; j < order.size(); ++j) {
+            bl_block.push_back(order[j]);
+            bl_x.insert(bl_x.end(), bucket[j].begin(), bucket[j].end());
+            bl_ptr.push_back((int32_t)bl_x.size());
+            slot[order[j]] = -1;
+        }
+        bl_level_ptr.push_back((int32_t)bl_block.size());
+    }
+}
 
 struct MergedBlock {            // inverse-multiplied form of one merged block
     std::vector<int32_t> cols;  // off-block columns in order of first appearance
@@ -437,80 +471,81 @@ int emit_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
 // Mirrors the value computations of emit_factor exactly (tests compare the images byte by byte).
 int refill_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                   const std::vector<BlockPlan>& plan, const FactorTemplate& rec, LuProgram* P) {
-    const int nb = (int)starts.size() - 1;
+    (void)plan;
     std::vector<double> D, X, Tbuf;
     std::vector<int32_t> posbuf;
-    std::vector<int32_t> inv_slot(nb, -1);
-    std::vector<std::vector<double>> inv;
-    std::vector<MergedBlock> mblocks;
+    MergedBlock mb;                       // scratch, reused by every merged block
     for (size_t lv = 0; lv + 1 < rec.level_ptr.size(); ++lv) {
         const int32_t a = rec.level_ptr[lv], b = rec.level_ptr[lv + 1];
-        inv.clear();
-        mblocks.clear();
-        const auto ti0 = std::chrono::steady_clock::now();
-        for (int32_t x = a; x < b; ++x) {
+        for (int32_t x = a; x < b; ++x) {        // plain rows: entries outside the diagonal block
             const RowRef& rr = rec.rows[x];
-            if (rr.k != 0) continue;
-            if (rr.kind == 1) {
-                invert_block(T, starts[rr.block], starts[rr.block + 1], &D, &X);
-                inv_slot[rr.block] = (int32_t)inv.size();
-                inv.push_back(X);
-            } else if (rr.kind == 2) {
-                inv_slot[rr.block] = (int32_t)mblocks.size();
-                mblocks.emplace_back();
-                multiply_block(n, T, starts[rr.block], starts[rr.block + 1], &posbuf, &D, &Tbuf, &mblocks.back());
-                const int w = starts[rr.block + 1] - starts[rr.block];
-                for (int j = 0; j < w && !T.unit; ++j)
-                    if (D[(size_t)j * w + j] == 0.0) {
-                        set_error("the %s factor has a zero pivot in row %d", T.upper ? "upper" : "lower",
-                                  starts[rr.block] + j);
-                        return OCB_ERR_SINGULAR;
-                    }
-            }
-        }
-        g_inv_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ti0).count();
-        for (int32_t x = a; x < b; ++x) {
-            const RowRef& rr = rec.rows[x];
+            if (rr.kind != 0) continue;
             const int32_t r0 = starts[rr.block], r1 = starts[rr.block + 1], w = r1 - r0;
             const int32_t i = r0 + rr.k;
             const int g = rec.g[x], G = 1 << g;
             double* vbase = P->val.data() + rec.base[x];
             int e = 0;
-            auto put = [&](double v) {
-                vbase[((size_t)(e >> g) << 5) + (size_t)(e & (G - 1))] = v;
-                ++e;
-            };
-            if (rr.kind == 0) {
-                double dg = 1.0;
-                for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) {
-                    const int32_t c = T.ci[p];
-                    if (c < r0 || c >= r1) {
-                        put(T.va[p]);
-                    } else if (c == i && !T.unit) {
-                        dg = T.va[p];
-                    }
+            double dg = 1.0;
+            for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) {
+                const int32_t c = T.ci[p];
+                if (c < r0 || c >= r1) {
+                    vbase[((size_t)(e >> g) << 5) + (size_t)(e & (G - 1))] = T.va[p];
+                    ++e;
+                } else if (c == i && !T.unit) {
+                    dg = T.va[p];
                 }
-                if (!T.unit && dg == 0.0) {
-                    set_error("the %s factor has a zero pivot in row %d", T.upper ? "upper" : "lower", i);
-                    return OCB_ERR_SINGULAR;
-                }
-                if (w == 1) P->scale[rec.q[x]] = 1.0 / dg;
-            } else if (rr.kind == 1) {
-                const std::vector<double>& Xi = inv[inv_slot[rr.block]];
-                const int j0 = T.upper ? rr.k : 0, j1 = T.upper ? w : rr.k + 1;
-                for (int j = j0; j < j1; ++j) put(-Xi[(size_t)rr.k * w + j]);
-            } else if (rr.kind == 2) {
-                const MergedBlock& mb = mblocks[inv_slot[rr.block]];
-                const int j0 = T.upper ? rr.k : 0, j1 = T.upper ? w : rr.k + 1;
-                for (int j = j0; j < j1; ++j) put(-mb.X[(size_t)rr.k * w + j]);
-                const size_t cu = mb.cols.size();
-                for (int32_t j = 0; j < mb.ncol[rr.k]; ++j) put(mb.Pm[(size_t)rr.k * cu + j]);
             }
-            if (e != rr.len && rr.kind != 3) {
+            if (!T.unit && dg == 0.0) {
+                set_error("the %s factor has a zero pivot in row %d", T.upper ? "upper" : "lower", i);
+                return OCB_ERR_SINGULAR;
+            }
+            if (w == 1) P->scale[rec.q[x]] = 1.0 / dg;
+            if (e != rr.len) {
                 set_error("program template does not match the factor (row %d)", i);
                 return OCB_ERR_ARG;
             }
         }
+        const auto ti0 = std::chrono::steady_clock::now();
+        for (int32_t bi = rec.bl_level_ptr[lv]; bi < rec.bl_level_ptr[lv + 1]; ++bi) {
+            const int32_t t = rec.bl_block[bi];
+            const int32_t r0 = starts[t], r1 = starts[t + 1], w = r1 - r0;
+            const int32_t xa = rec.bl_ptr[bi], xb = rec.bl_ptr[bi + 1];
+            const int kind = rec.rows[rec.bl_x[xa]].kind;
+            const double* Xm;
+            if (kind == 1) {
+                invert_block(T, r0, r1, &D, &X);
+                Xm = X.data();
+            } else {
+                multiply_block(n, T, r0, r1, &posbuf, &D, &Tbuf, &mb);
+                for (int j = 0; j < w && !T.unit; ++j)
+                    if (D[(size_t)j * w + j] == 0.0) {
+                        set_error("the %s factor has a zero pivot in row %d", T.upper ? "upper" : "lower", r0 + j);
+                        return OCB_ERR_SINGULAR;
+                    }
+                Xm = mb.X.data();
+            }
+            const size_t cu = mb.cols.size();
+            for (int32_t xi = xa; xi < xb; ++xi) {
+                const int32_t x = rec.bl_x[xi];
+                const RowRef& rr = rec.rows[x];
+                const int g = rec.g[x], G = 1 << g;
+                double* vbase = P->val.data() + rec.base[x];
+                int e = 0;
+                const int j0 = T.upper ? rr.k : 0, j1 = T.upper ? w : rr.k + 1;
+                const double* xr = Xm + (size_t)rr.k * w;
+                for (int j = j0; j < j1; ++j, ++e) vbase[((size_t)(e >> g) << 5) + (size_t)(e & (G - 1))] = -xr[j];
+                if (kind == 2) {
+                    const double* pr = mb.Pm.data() + (size_t)rr.k * cu;
+                    const int32_t nc = mb.ncol[rr.k];
+                    for (int32_t j = 0; j < nc; ++j, ++e) vbase[((size_t)(e >> g) << 5) + (size_t)(e & (G - 1))] = pr[j];
+                }
+                if (e != rr.len) {
+                    set_error("program template does not match the factor (row %d)", r0 + rr.k);
+                    return OCB_ERR_ARG;
+                }
+            }
+        }
+        g_inv_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ti0).count();
     }
     return OCB_OK;
 }
@@ -733,6 +768,8 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
         g_inv_ms = 0.0;
     }
     if (rc == OCB_OK && tmpl) {
+        tmpl->recL.index_blocks((int)starts.size() - 1);
+        tmpl->recU.index_blocks((int)starts.size() - 1);
         tmpl->starts = starts;
         tmpl->planL = planL;
         tmpl->planU = planU;

@@ -106,5 +106,8 @@ void execute_program_host(const LuProgram& P, const int32_t* perm_r, const int32
 void tri_times_dense(const double* X, const double* T, double* P, int w, int m, bool upper);
 // X = inverse of the w x w triangular D (row-major; X zero on entry).  host_dense.cpp.
 void tri_inverse(const double* D, double* X, int w, bool upper, bool unit);
+// C[M x N] += alpha * A[M x K] * B[K x N], row-major with leading dimensions.  host_dense.cpp.
+void gemm_acc(int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+              double alpha);
 
 }  // namespace ocb

@@ -27,11 +27,23 @@ STATS = dict(lu_factor_s=0.0,          # SuperLU seconds summed over the workers
              lu_arena_s=0.0,           # ... of which: device buffer from the caching allocator
              lu_unpinned_uploads=0,    # images that did not travel through a pinned pool segment
              lu_guard_refactors=0,     # residual guard: matrices factorised again in safe mode
+             lu_static_pivot=0,         # ... images whose numbers came from the numeric-only refactorisation
+             lu_static_rejected=0,      # ... static-pivot images the guard rejected (SuperLU took over)
              lu_guard_max_backerr=0.0,  # ... largest backward error of an image handed out
              n_factor=0, h2d_bytes=0, d2h_bytes=0)
 
 # wall seconds of the main thread per phase of the host API (diagnostics, bench.py e2e)
 PHASE = dict()
+
+
+# OCB_TIMELINE=<dir>: (thread, label, wall start, wall end) of the host-side events of a run
+# (diagnostics; tools/e2e_timeline.py merges them with the workers' logs)
+TIMELINE = [] if os.environ.get('OCB_TIMELINE') else None
+
+
+def timeline(label, t0, t1=None):
+    if TIMELINE is not None:
+        TIMELINE.append((threading.current_thread().name, label, t0, time.time() if t1 is None else t1))
 
 
 class phase(object):
@@ -42,9 +54,11 @@ class phase(object):
 
     def __enter__(self):
         self.t0 = time.perf_counter()
+        self.w0 = time.time()
 
     def __exit__(self, *a):
         PHASE[self.name] = PHASE.get(self.name, 0.0) + time.perf_counter() - self.t0
+        timeline(self.name, self.w0)
         return False
 
 # Host factorisation used for the (separately timed) setup step.  SuperLU with a
@@ -274,7 +288,10 @@ def _record_guard(guard):
     """Book-keeping of the workers' residual guard (``_lu_worker._build``)."""
     if guard is None or guard[0] is None:
         return
-    backerr, safe = guard
+    backerr, safe = guard[:2]
+    if len(guard) > 2:
+        STATS['lu_static_pivot'] += int(guard[2] == 'static')
+        STATS['lu_static_rejected'] += int(guard[3])
     from . import _lu_worker
     STATS['lu_guard_refactors'] += int(safe)
     STATS['lu_guard_max_backerr'] = max(STATS['lu_guard_max_backerr'], float(backerr))
@@ -514,6 +531,7 @@ class FactorJob(object):
                 self._async.append(pool.apply_async(_lu_worker.factor_image_to_shm, (a, slot)))
         STATS['lu_submit_s'] += time.perf_counter() - t0
         STATS['n_factor'] += self.n
+        timeline('submit %d' % self.n, time.time() - (time.perf_counter() - t0))
 
     def start_upload(self):
         """Collect the worker results and upload the images from a helper thread on its own
@@ -530,6 +548,7 @@ class FactorJob(object):
             t0 = time.perf_counter()
             out = self._future.result()
             STATS['lu_wait_s'] += time.perf_counter() - t0
+            timeline('result_wait', time.time() - (time.perf_counter() - t0))
             return out
         return self._collect()
 
@@ -568,6 +587,8 @@ class FactorJob(object):
                 if order is not None and key is not None:
                     _ORDER.setdefault(key, order)
                 STATS['lu_collect_wait_s'] += time.perf_counter() - t0
+                timeline('collect_wait', time.time() - (time.perf_counter() - t0))
+                tw0 = time.time()
                 STATS['lu_factor_s'] += tf
                 STATS['lu_worker_pack_s'] += tp
                 shp = _shm_pool(nbytes)
@@ -578,6 +599,7 @@ class FactorJob(object):
                     finally:
                         del img
                         shp.release(slot)
+                    timeline('upload', tw0)
                     continue
                 if slot is not None:
                     shp.release(slot)

@@ -420,7 +420,9 @@ def test_program_on_unstructured_pattern(cav10, flags):
     _execute(prog, X, check_hazards=True)
     got = X[arrs[7]]
     ref = spsla.splu(K).solve(B)
-    assert np.linalg.norm(got - ref) <= 1e-10*np.linalg.norm(ref)
+    # forward error: cond(K) * eps ~ 6e-9 is what any LU solve may show here; the program's is
+    # 3e-11 .. 1.2e-10 over seeds / layouts, with row substitution or the blocked block inverses alike
+    assert np.linalg.norm(got - ref) <= 5e-10*np.linalg.norm(ref)
     # cond(K) ~ 6e7 and ||x|| ~ 1e7 ||b||: the residual is measured normwise.  (Solving with the
     # explicit inverses of wide diagonal blocks is not backward stable row by row as
     # substitution is: relative to ||b|| this residual is 5e-7 where SuperLU reaches 3e-9.)
@@ -429,11 +431,13 @@ def test_program_on_unstructured_pattern(cav10, flags):
     assert img.nbytes > 0 and prog[0]['n_ext'] == n + 2*prog[0]['ymax']
 
 
-def test_worker_builds_the_image_in_the_callers_segment(cav10):
+def test_worker_builds_the_image_in_the_callers_segment(cav10, monkeypatch):
     """_lu_worker.factor_image_to_shm with a slot: ocb_lu_pack_host_into writes the image straight
     into the (pinned) shared-memory segment - same bytes as the malloc'ed image, fresh build and
-    template hit alike; a segment that is too small falls back to a one-off segment."""
+    template hit alike; a segment that is too small falls back to a one-off segment.  (SuperLU path
+    only: the static-pivot path has its own test in test_refactor.py.)"""
     from multiprocessing import shared_memory
+    monkeypatch.setenv('OCB_REFACTOR', '0')
     K = _saddle(cav10)
     n = K.shape[0]
     flags = 2 | (2 << 4)
@@ -493,7 +497,7 @@ def test_residual_guard_refactorises_in_safe_mode(monkeypatch):
     # guard off: the fast image is handed out, with the larger error
     monkeypatch.setenv('OCB_LU_GUARD_TOL', '-1')
     img2, tf, tp, order, guard2 = _lu_worker.factor_image(dv._csc_args(hard, dict(dv.LU_OPTIONS)) + (232448, flags))
-    assert guard2 == (None, 0) and img2.nbytes != img.nbytes
+    assert guard2[:2] == (None, 0) and img2.nbytes != img.nbytes
     # the safe layout itself: no supernode wider than 32 rows, still reproduces SuperLU
     n = hard.shape[0]
     arrs = _lu_worker.factor_arrays(_lu_worker._safe_args(dv._csc_args(hard, dict(dv.LU_OPTIONS)) + (232448, flags)),

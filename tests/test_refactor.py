@@ -1,0 +1,212 @@
+"""CPU suite: numeric-only refactorisation with symbolic reuse (csrc/refactor.cpp).
+
+The reference factorises ``A + p_j M`` from scratch for every shift and every time step
+(``proj_ric_utils.py:108-111`` inside ``solve_dae_ric.py:147-163``); all of these matrices share
+one sparsity pattern.  ``ocb_refactor_*`` keeps the pivot order of a first SuperLU run and redoes
+the numbers only.  Checked here without a GPU: ``L U = P A Q`` to rounding, solves against
+SuperLU, fixed structure, unsymmetric patterns, the zero-pivot and the guard fall-backs of the
+worker, and the image of the static-pivot path through the gather program."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import scipy.sparse.linalg as spsla
+
+from optconpy_b200 import _cabi, _lu_worker, device as dv, problems as pb
+from test_lu_program import _program, _execute
+
+
+@pytest.fixture(scope='module')
+def cav10():
+    return pb.drivcav_problem(10, 1e-2)
+
+
+def _shifted(prob, tau, p):
+    M, A, J = prob['M'], prob['A'], prob['J']
+    Nc = pb.convection_matrix(prob, pb.analytic_vortex)
+    return dv.sadpnt_matrix(-(0.5*M.T + tau*(A.T + Nc.T)) + p*M.T, J)
+
+
+def _csc(K):
+    K = sps.csc_matrix(K, dtype=np.float64)
+    K.sum_duplicates()
+    K.sort_indices()
+    return K
+
+
+def _lu_of(rf, K):
+    n = K.shape[0]
+    arrs = rf.numeric(K.data)
+    assert arrs is not None
+    L = sps.csr_matrix((arrs[2].copy(), arrs[1], arrs[0]), shape=(n, n))
+    U = sps.csr_matrix((arrs[5].copy(), arrs[4], arrs[3]), shape=(n, n))
+    return L, U, arrs[6], arrs[7]
+
+
+def _permuted(K, pr, pc):
+    co = K.tocoo()
+    return sps.csr_matrix((co.data, (pr[co.row], pc[co.col])), shape=K.shape)
+
+
+def test_static_pivots_reproduce_the_matrix_and_superlu(cav10):
+    """First matrix through SuperLU (ordering + pivots), the other shifts / step lengths through
+    the numeric-only pass: L U = P A Q, unit lower L, solves equal to SuperLU's."""
+    K0 = _csc(_shifted(cav10, 2e-3, -1.0))
+    n = K0.shape[0]
+    a = dv._csc_args(K0, dict(dv.LU_OPTIONS)) + (232448, 2)
+    q = _lu_worker.order_only(a)
+    arrs = _lu_worker.factor_arrays(a + (q,), transposed=True)
+    rf = _lu_worker._Refactor(n, K0.indptr, K0.indices, arrs[6], arrs[7])
+    assert rf.info['nnzL'] == rf.info['nnzU']                      # symmetric structure
+    # no more fill than SuperLU's own factors of this pivot order (+ a few accidental zeros it drops)
+    assert rf.info['nnzL'] + rf.info['nnzU'] <= 1.1*(len(arrs[1]) + len(arrs[4]))
+    rng = np.random.default_rng(0)
+    for tau, p in ((2e-3, -1.0), (3e-4, -5.0), (1e-3, -1.3), (5e-2, -2.0)):
+        K = _csc(_shifted(cav10, tau, p))
+        assert np.array_equal(K.indices, K0.indices) and np.array_equal(K.indptr, K0.indptr)
+        L, U, pr, pc = _lu_of(rf, K)
+        assert np.array_equal(L.diagonal(), np.ones(n))
+        assert sps.triu(L, 1).nnz == 0 and sps.tril(U, -1).nnz == 0
+        Cm = _permuted(K, pr, pc)
+        assert abs(L @ U - Cm).max() <= 1e-12*abs(Cm).max()
+        b = rng.standard_normal(n)
+        y = np.empty(n)
+        y[pr] = b
+        z = spsla.spsolve_triangular(U, spsla.spsolve_triangular(L, y, lower=True, unit_diagonal=True),
+                                     lower=False)
+        x = z[pc]
+        ref = spsla.splu(K).solve(b)
+        assert np.linalg.norm(x - ref) <= 1e-11*np.linalg.norm(ref)
+        assert np.linalg.norm(K @ x - b) <= 1e-12*np.linalg.norm(b)
+
+
+@pytest.mark.parametrize('n,density,seed', [(1, 1.0, 0), (7, 0.4, 1), (300, 0.02, 2), (900, 0.006, 3)])
+def test_unsymmetric_pattern_identity_pivots(n, density, seed):
+    """General sparse pattern (not symmetric), diagonally dominant values, identity permutations:
+    the structure is symmetrised internally, the product must still be exact; large supernodes
+    (dense trailing fronts) exercise the blocked kernels."""
+    rng = np.random.default_rng(seed)
+    S = sps.random(n, n, density=density, format='csc', random_state=seed)
+    S.data[:] = rng.standard_normal(S.nnz)
+    K = _csc(S + sps.identity(n)*(1.0 + abs(S).sum(axis=1).max()))
+    ident = np.arange(n, dtype=np.int32)
+    rf = _lu_worker._Refactor(n, K.indptr, K.indices, ident, ident)
+    L, U, pr, pc = _lu_of(rf, K)
+    assert sorted(pr) == list(range(n)) and np.array_equal(pr, pc)      # identity composed with a postorder
+    Cm = _permuted(K, pr, pc)
+    assert abs(L @ U - Cm).max() <= 1e-13*abs(Cm).max()
+    assert rf.info['supernodes'] >= 1 and rf.info['max_front'] <= n
+
+
+def test_dense_block_goes_through_the_blocked_kernels():
+    """One 150-column supernode with a 40-row border: five 32-pivot blocks, the inverse-based panel
+    updates, the in-place row panel and the register-blocked trailing update."""
+    rng = np.random.default_rng(5)
+    n = 190
+    D = rng.standard_normal((n, n))
+    D[150:, 150:] = 0.0
+    D += np.diag(np.full(n, 60.0))
+    K = _csc(sps.csc_matrix(D))
+    ident = np.arange(n, dtype=np.int32)
+    rf = _lu_worker._Refactor(n, K.indptr, K.indices, ident, ident)
+    assert rf.info['max_front'] == n
+    L, U, pr, pc = _lu_of(rf, K)
+    Cm = _permuted(K, pr, pc)
+    assert abs(L @ U - Cm).max() <= 1e-13*abs(Cm).max()
+
+
+def test_bad_arguments_and_zero_pivot():
+    lib = _cabi.load()
+    n = 4
+    K = _csc(sps.csc_matrix(np.array([[2.0, 1, 0, 0], [1, 2, 1, 0], [0, 1, 2, 1], [0, 0, 1, 2]])))
+    ip, ii = K.indptr.astype(np.int32), K.indices.astype(np.int32)
+    bad = np.array([0, 1, 1, 3], dtype=np.int32)
+    ident = np.arange(n, dtype=np.int32)
+    h = C.c_void_p()
+    assert lib.ocb_refactor_create(C.byref(h), n, ip.ctypes.data, ii.ctypes.data, bad.ctypes.data,
+                                   ident.ctypes.data) == -1
+    assert b'permutation' in lib.ocb_last_error()
+    rf = _lu_worker._Refactor(n, ip, ii, ident, ident)
+    assert rf.numeric(K.data) is not None
+    Z = K.copy()
+    Z.data[:] = K.data
+    Z[0, 0] = 0.0                     # stored zero on the first static pivot
+    Z = _csc(Z)
+    assert Z.nnz == K.nnz
+    assert rf.numeric(Z.data) is None
+    assert b'pivot' in lib.ocb_last_error()
+    nan = K.data.copy()
+    nan[3] = np.nan
+    assert rf.numeric(nan) is None
+    # empty system
+    e = np.zeros(1, dtype=np.int32)
+    rf0 = _lu_worker._Refactor(0, e, e, e, e)
+    assert rf0.info['nnzL'] == 0
+
+
+def test_worker_uses_static_pivots_from_the_second_matrix_on(cav10, monkeypatch):
+    """_lu_worker._build: the first matrix of a pattern goes through SuperLU and fixes the pivots,
+    later ones take the numeric-only path; every image is guarded, and its program reproduces
+    SuperLU's solve."""
+    monkeypatch.delenv('OCB_REFACTOR', raising=False)
+    monkeypatch.delenv('OCB_LU_GUARD_TOL', raising=False)
+    _lu_worker._REFAC.clear()
+    flags = 2 | 4 | (2 << 4)
+    K0 = _shifted(cav10, 2e-3, -1.0)
+    a0 = dv._csc_args(K0, dict(dv.LU_OPTIONS)) + (232448, flags)
+    q = _lu_worker.order_only(a0)
+    n = K0.shape[0]
+    paths = []
+    for tau, p in ((2e-3, -1.0), (3e-4, -5.0), (1e-3, -1.3)):
+        K = _shifted(cav10, tau, p)
+        a = dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, flags, q)
+        used, img, nbytes, tf, tp, order, guard = _lu_worker._build(a)
+        paths.append(guard[2])
+        assert guard[0] <= _lu_worker.GUARD_TOL and guard[1] == 0 and guard[3] == 0
+        assert img is not None and img.nbytes == nbytes
+    assert paths == ['slu', 'static', 'static']
+    # the static-pivot factors through the program builder and the numpy executor
+    rf = next(iter(_lu_worker._REFAC.values()))
+    K = _csc(_shifted(cav10, 7e-4, -3.0))
+    arrs = rf.numeric(K.data)
+    prog = _program(arrs, n, flags=flags & ~2)
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((n, 3))
+    X = np.zeros((prog[0]['n_ext'], 3))
+    X[arrs[6]] = B
+    _execute(prog, X, check_hazards=True)
+    got = X[arrs[7]]
+    ref = spsla.splu(K).solve(B)
+    assert np.linalg.norm(got - ref) <= 1e-11*np.linalg.norm(ref)
+    # switched off: SuperLU every time
+    monkeypatch.setenv('OCB_REFACTOR', '0')
+    a = dv._csc_args(_shifted(cav10, 3e-4, -5.0), dict(dv.LU_OPTIONS)) + (232448, flags, q)
+    assert _lu_worker._build(a)[6][2] == 'slu'
+    _lu_worker._REFAC.clear()
+
+
+def test_guard_rejects_bad_static_pivots_and_superlu_takes_over(cav10, monkeypatch):
+    """A later matrix of the same pattern whose values make the static pivot order unusable (a
+    velocity diagonal entry shrunk by fourteen orders of magnitude): the numeric-only image fails the
+    residual guard or hits a zero pivot, and the matrix is factorised by SuperLU again."""
+    monkeypatch.delenv('OCB_REFACTOR', raising=False)
+    monkeypatch.delenv('OCB_LU_GUARD_TOL', raising=False)
+    _lu_worker._REFAC.clear()
+    flags = 2 | 4 | (2 << 4)
+    K0 = _csc(_shifted(cav10, 2e-3, -1.0))
+    a0 = dv._csc_args(K0, dict(dv.LU_OPTIONS)) + (232448, flags)
+    q = _lu_worker.order_only(a0)
+    assert _lu_worker._build(a0 + (q,))[6][2] == 'slu'
+    K1 = K0.copy()
+    # the entry that is eliminated FIRST under the static order: nothing repairs it by fill
+    rf = next(iter(_lu_worker._REFAC.values()))
+    first = int(np.nonzero(rf.perm_r == 0)[0][0]), int(np.nonzero(rf.perm_c == 0)[0][0])
+    assert K1[first[0], first[1]] != 0.0
+    K1[first[0], first[1]] *= 1e-14
+    K1 = _csc(K1)
+    assert np.array_equal(K1.indices, K0.indices)
+    a1 = dv._csc_args(K1, dict(dv.LU_OPTIONS)) + (232448, flags, q)
+    used, img, nbytes, tf, tp, order, guard = _lu_worker._build(a1)
+    assert guard[2] == 'slu' and guard[3] == 1 and guard[0] <= _lu_worker.GUARD_TOL
+    _lu_worker._REFAC.clear()
