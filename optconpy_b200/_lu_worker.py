@@ -338,24 +338,38 @@ class _Refactor(object):
 
 
 # Static-pivot refactorisation: OCB_REFACTOR=0 switches it off.  Handles by
-# sparsity pattern + ordering, at most four (one run has one or two patterns).
+# sparsity pattern + pivots, at most four (one run has one or two patterns).
 _REFAC = dict()
 REFACTOR_MAX_PATTERNS = 4
 
 
-def _refactor_enabled(args):
+def refactor_wanted(flags):
+    """Static pivots are used with the default (transposed) SuperLU layout, unless OCB_REFACTOR=0."""
     import os
+    return os.environ.get('OCB_REFACTOR', '1') != '0' and bool(flags & 2) and not (flags & SAFE_FLAG)
+
+
+def static_pivots(args):
+    """The two permutations every later matrix of this pattern is factorised with: those of ONE
+    SuperLU run on the given matrix (ordering ``args[7]`` reused).  Computed once per pattern in
+    the main process and handed to every job, so that which worker runs which job - or whether
+    the look-ahead is on - cannot change a single bit of the results."""
+    arrs = factor_arrays(args[:8], transposed=True)
+    return arrs[6], arrs[7]
+
+
+def _refactor_enabled(args):
     flags = args[6] if len(args) > 6 else 0
-    q = args[7] if len(args) > 7 else None
-    return (os.environ.get('OCB_REFACTOR', '1') != '0' and q is not None and (flags & 2)
-            and not (flags & SAFE_FLAG) and args[3][0] > 0)
+    return (len(args) > 8 and args[8] is not None and args[7] is not None and refactor_wanted(flags)
+            and args[3][0] > 0)
 
 
 def _refactor_key(args):
     import zlib
     return (args[3], len(args[1]), zlib.crc32(memoryview(np.ascontiguousarray(args[1]))),
             zlib.crc32(memoryview(np.ascontiguousarray(args[2]))),
-            zlib.crc32(memoryview(np.ascontiguousarray(args[7]))))
+            zlib.crc32(memoryview(np.ascontiguousarray(args[8][0]))),
+            zlib.crc32(memoryview(np.ascontiguousarray(args[8][1]))))
 
 
 def _pack(lib, arrs, n, smem, flags, slot, amat):
@@ -407,9 +421,21 @@ def _build(args, slot=None):
     n = args[3][0]
     rkey = _refactor_key(args) if _refactor_enabled(args) else None
     rf = _REFAC.get(rkey) if rkey is not None else None
+    if rkey is not None and rkey not in _REFAC:
+        # first job of this pattern in this process: symbolic analysis for the given pivots
+        t0 = time.perf_counter()
+        if len(_REFAC) >= REFACTOR_MAX_PATTERNS:
+            _REFAC.pop(next(iter(_REFAC)))
+        try:
+            rf = _Refactor(n, args[2], args[1], np.ascontiguousarray(args[8][0], dtype=np.int32),
+                           np.ascontiguousarray(args[8][1], dtype=np.int32))
+        except RuntimeError:
+            rf = None
+        _REFAC[rkey] = rf
+        tf += time.perf_counter() - t0
     if rf is not None:
-        # second and later matrices of a pattern: numbers only, pivots as in the first one.  The
-        # guard is what makes static pivots safe, so it always runs here.
+        # numbers only, pivots as given.  The guard is what makes static pivots safe, so it
+        # always runs here.
         t0 = time.perf_counter()
         arrs = rf.numeric(args[0])
         t1 = time.perf_counter()
@@ -431,24 +457,14 @@ def _build(args, slot=None):
         used, img, nbytes, backerr = _pack(lib, arrs, n, args[5], flags, slot, amat)
         tp += time.perf_counter() - t1
         if backerr is None or backerr <= tol or safe:
-            if rkey is not None and rf is None and not safe and rkey not in _REFAC:
-                # first good factorisation of this pattern: its pivots become the static ones
-                t2 = time.perf_counter()
-                if len(_REFAC) >= REFACTOR_MAX_PATTERNS:
-                    _REFAC.pop(next(iter(_REFAC)))
-                try:
-                    _REFAC[rkey] = _Refactor(n, args[2], args[1], arrs[6], arrs[7])
-                except RuntimeError:
-                    _REFAC[rkey] = None
-                tf += time.perf_counter() - t2
             return used, img, nbytes, tf, tp, order, (backerr, safe, 'slu', rejected)
         args = _safe_args(args)
         safe = 1
 
 
 def factor_image(args):
-    """(data, indices, indptr, shape, lu_options, smem_optin[, flags, q]) -> (image, seconds
-    factor, seconds analyse+pack, ordering, guard)."""
+    """(data, indices, indptr, shape, lu_options, smem_optin[, flags, q, (perm_r, perm_c)]) ->
+    (image, seconds factor, seconds analyse+pack, ordering, guard)."""
     _, img, _, tf, tp, order, guard = _build(args)
     return img, tf, tp, order, guard
 

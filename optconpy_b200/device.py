@@ -336,19 +336,23 @@ def _pattern_key(a):
 
 
 def _with_order(a, opts):
-    """worker arguments (.., smem, flags, q) with the cached ordering of this pattern, if any"""
+    """worker arguments (.., smem, flags, q, pivots) with the cached ordering and the static
+    pivots (``_lu_worker.static_pivots``; None when switched off) of this pattern"""
     if os.environ.get('OCB_NO_ORDER_REUSE') or opts.get('permc_spec') == 'NATURAL':
         return a, None
     key = _pattern_key(a)
     with _LOCK:
         if key not in _ORDER:
             # first matrix of this pattern: get the ordering NOW (one synchronous SuperLU run), so
-            # that no queued job runs the slow path or produces the larger factor
+            # that no queued job runs the slow path or produces the larger factor; a second run
+            # fixes the pivot order of the numeric-only refactorisation (SURVEY 8 row f2)
             from . import _lu_worker
             t0 = time.perf_counter()
-            _ORDER[key] = _lu_worker.order_only(a)
+            q = _lu_worker.order_only(a)
+            piv = _lu_worker.static_pivots(a + (q,)) if _lu_worker.refactor_wanted(a[6]) else None
+            _ORDER[key] = (q, piv)
             STATS['lu_order_s'] += time.perf_counter() - t0
-        return a + (_ORDER[key],), key
+        return a + _ORDER[key], key
 
 
 _SMEM_OPTIN = dict()
@@ -564,7 +568,7 @@ class FactorJob(object):
                 STATS['lu_worker_pack_s'] += tp
                 _record_guard(guard)
                 if order is not None and key is not None:
-                    _ORDER.setdefault(key, order)
+                    _ORDER.setdefault(key, (order, None))
                 out.append(LU(None, image=img))
         else:
             from multiprocessing import shared_memory
@@ -585,7 +589,7 @@ class FactorJob(object):
                     raise RuntimeError('optconpy_b200: host LU worker failed or timed out: %r' % (exc,))
                 _record_guard(guard)
                 if order is not None and key is not None:
-                    _ORDER.setdefault(key, order)
+                    _ORDER.setdefault(key, (order, None))
                 STATS['lu_collect_wait_s'] += time.perf_counter() - t0
                 timeline('collect_wait', time.time() - (time.perf_counter() - t0))
                 tw0 = time.time()
@@ -653,9 +657,11 @@ def _new_arena(nbytes):
     key = (cls, torch.cuda.current_stream().cuda_stream, torch.cuda.current_device())
     if key not in _ARENA_WARM and cls >= (4 << 20):
         _ARENA_WARM.add(key)
+        tw = time.time()
         count = min(int(os.environ.get('OCB_ARENA_PREWARM', '64')), (1 << 30)//cls)
         warm = [torch.empty(cls, dtype=torch.uint8, device=cur_device()) for _ in range(count)]
         del warm
+        timeline('arena_prewarm %d x %d' % (count, cls), tw)
     return torch.empty(cls, dtype=torch.uint8, device=cur_device())
 
 
@@ -673,7 +679,7 @@ class LU(object):
             image, tf, tp, order, guard = _lu_worker.factor_image(a)
             _record_guard(guard)
             if order is not None and key is not None:
-                _ORDER.setdefault(key, order)
+                _ORDER.setdefault(key, (order, None))
             STATS['lu_factor_s'] += tf
             STATS['lu_worker_pack_s'] += tp
             STATS['n_factor'] += 1

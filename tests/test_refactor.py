@@ -145,10 +145,10 @@ def test_bad_arguments_and_zero_pivot():
     assert rf0.info['nnzL'] == 0
 
 
-def test_worker_uses_static_pivots_from_the_second_matrix_on(cav10, monkeypatch):
-    """_lu_worker._build: the first matrix of a pattern goes through SuperLU and fixes the pivots,
-    later ones take the numeric-only path; every image is guarded, and its program reproduces
-    SuperLU's solve."""
+def test_worker_uses_the_static_pivots_it_is_given(cav10, monkeypatch):
+    """_lu_worker._build: the main process fixes ordering and pivots once per pattern (one SuperLU
+    run on the first matrix, ``static_pivots``); every job then takes the numeric-only path, is
+    guarded, and its program reproduces SuperLU's solve.  Without pivots, or switched off: SuperLU."""
     monkeypatch.delenv('OCB_REFACTOR', raising=False)
     monkeypatch.delenv('OCB_LU_GUARD_TOL', raising=False)
     _lu_worker._REFAC.clear()
@@ -156,16 +156,25 @@ def test_worker_uses_static_pivots_from_the_second_matrix_on(cav10, monkeypatch)
     K0 = _shifted(cav10, 2e-3, -1.0)
     a0 = dv._csc_args(K0, dict(dv.LU_OPTIONS)) + (232448, flags)
     q = _lu_worker.order_only(a0)
+    piv = _lu_worker.static_pivots(a0 + (q,))
     n = K0.shape[0]
-    paths = []
+    paths, images = [], []
     for tau, p in ((2e-3, -1.0), (3e-4, -5.0), (1e-3, -1.3)):
         K = _shifted(cav10, tau, p)
-        a = dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, flags, q)
+        a = dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, flags, q, piv)
         used, img, nbytes, tf, tp, order, guard = _lu_worker._build(a)
         paths.append(guard[2])
+        images.append(img)
         assert guard[0] <= _lu_worker.GUARD_TOL and guard[1] == 0 and guard[3] == 0
         assert img is not None and img.nbytes == nbytes
-    assert paths == ['slu', 'static', 'static']
+    assert paths == ['static', 'static', 'static']
+    assert len({im.nbytes for im in images}) == 1                  # one structure, whatever the values
+    # the same job again, in a "fresh worker": bit-identical image (no dependence on job history)
+    _lu_worker._REFAC.clear()
+    again = _lu_worker._build(dv._csc_args(_shifted(cav10, 1e-3, -1.3), dict(dv.LU_OPTIONS))
+                              + (232448, flags, q, piv))[1]
+    assert np.array_equal(again, images[2])
+    assert _lu_worker._build(a0 + (q,))[6][2] == 'slu' and _lu_worker._build(a0 + (q, None))[6][2] == 'slu'
     # the static-pivot factors through the program builder and the numpy executor
     rf = next(iter(_lu_worker._REFAC.values()))
     K = _csc(_shifted(cav10, 7e-4, -3.0))
@@ -181,7 +190,7 @@ def test_worker_uses_static_pivots_from_the_second_matrix_on(cav10, monkeypatch)
     assert np.linalg.norm(got - ref) <= 1e-11*np.linalg.norm(ref)
     # switched off: SuperLU every time
     monkeypatch.setenv('OCB_REFACTOR', '0')
-    a = dv._csc_args(_shifted(cav10, 3e-4, -5.0), dict(dv.LU_OPTIONS)) + (232448, flags, q)
+    a = dv._csc_args(_shifted(cav10, 3e-4, -5.0), dict(dv.LU_OPTIONS)) + (232448, flags, q, piv)
     assert _lu_worker._build(a)[6][2] == 'slu'
     _lu_worker._REFAC.clear()
 
@@ -197,7 +206,8 @@ def test_guard_rejects_bad_static_pivots_and_superlu_takes_over(cav10, monkeypat
     K0 = _csc(_shifted(cav10, 2e-3, -1.0))
     a0 = dv._csc_args(K0, dict(dv.LU_OPTIONS)) + (232448, flags)
     q = _lu_worker.order_only(a0)
-    assert _lu_worker._build(a0 + (q,))[6][2] == 'slu'
+    piv = _lu_worker.static_pivots(a0 + (q,))
+    assert _lu_worker._build(a0 + (q, piv))[6][2] == 'static'
     K1 = K0.copy()
     # the entry that is eliminated FIRST under the static order: nothing repairs it by fill
     rf = next(iter(_lu_worker._REFAC.values()))
@@ -206,7 +216,7 @@ def test_guard_rejects_bad_static_pivots_and_superlu_takes_over(cav10, monkeypat
     K1[first[0], first[1]] *= 1e-14
     K1 = _csc(K1)
     assert np.array_equal(K1.indices, K0.indices)
-    a1 = dv._csc_args(K1, dict(dv.LU_OPTIONS)) + (232448, flags, q)
+    a1 = dv._csc_args(K1, dict(dv.LU_OPTIONS)) + (232448, flags, q, piv)
     used, img, nbytes, tf, tp, order, guard = _lu_worker._build(a1)
     assert guard[2] == 'slu' and guard[3] == 1 and guard[0] <= _lu_worker.GUARD_TOL
     _lu_worker._REFAC.clear()

@@ -74,7 +74,15 @@ def main():
           % (sum(wk)/max(len(wk), 1)/(hi - lo), min(wk)/(hi - lo), max(wk)/(hi - lo), len(wk)))
     for k in sorted(k for k in busy if not k.startswith('worker')):
         print('  %-55s %7.2f ms/step' % (k, 1e3*busy[k]/max(nst, 1)))
-    # event list of a few steady steps
+    # event list of the slowest step after the start-up and of a few steady steps
+    if len(steps_ms) > 3:
+        worst = max(range(2, len(steps_ms)), key=lambda i: steps_ms[i])
+        a0, b0 = stamps[worst], stamps[worst + 1]
+        print('--- slowest step %d (%.1f ms): events overlapping it (ms relative to its start) ---'
+              % (worst + 1, steps_ms[worst]))
+        for th, label, a, b in ev:
+            if b >= a0 and a <= b0:
+                print('%9.2f %9.2f  %-28s %s' % (1e3*(a - a0), 1e3*(b - a0), th[:28], label))
     i0 = min(la + 3, len(stamps) - 2)
     a0, b0 = stamps[i0], stamps[min(i0 + args.show, len(stamps) - 1)]
     print('--- events between step stamps %d and %d (ms relative) ---' % (i0, i0 + args.show))

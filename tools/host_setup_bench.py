@@ -29,8 +29,9 @@ def main():
     flags = dv._pack_flags(False, 40)
     a0 = dv._csc_args(mat(2e-3, -1.0), opts) + (232448, flags)
     q = w.order_only(a0)
+    piv = w.static_pivots(a0 + (q,))
     shifts = [(3e-4, -5.0), (1e-3, -1.3), (2e-4, -3.0), (2.5e-4, -1.1)]
-    jobs = [dv._csc_args(mat(t, p), opts) + (232448, flags, q) for t, p in shifts]
+    jobs = [dv._csc_args(mat(t, p), opts) + (232448, flags, q, piv) for t, p in shifts]
 
     def best(fn):
         ts = []
