@@ -601,11 +601,17 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
                      const int32_t* Urp, const int32_t* Uci, const double* Uva, int max_lanes,
                      bool transposed, bool merge, LuProgram* P, int wmax_cap) {
     const int wcap = wmax_cap > 0 ? std::min(wmax_cap, wmax()) : wmax();
-    *P = LuProgram();
-    P->n = n;
-    P->sub_ptr.push_back(0);
-    if (n == 0) return OCB_OK;
+    auto reset = [&] {
+        *P = LuProgram();
+        P->n = n;
+        P->sub_ptr.push_back(0);
+    };
+    if (n == 0) {
+        reset();
+        return OCB_OK;
+    }
     if ((int64_t)Lrp[n] + Urp[n] + 2 * n >= (int64_t)INT32_MAX / 2) {
+        reset();
         set_error("factor too large for int32 program indices");
         return OCB_ERR_ARG;
     }
@@ -633,8 +639,14 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
         if (hit) {
             const auto tt1 = tnow();
             hit->stamp = ++g_tmpl_clock;
-            *P = hit->P;                                  // structure; the numbers follow
-            P->val.assign((size_t)hit->nent, 0.0);
+            // structure; the numbers follow.  A caller that hands in the program of its previous
+            // call (ocb_lu_pack_host keeps one per thread) and hits the same structure again keeps
+            // it: every number is rewritten below and the padding is still zero - no 25 MB copy
+            if (!(P->structure_id != 0 && P->structure_id == hit->P.structure_id && P->n == n &&
+                  (int64_t)P->val.size() == hit->nent && P->nent() == hit->nent)) {
+                *P = hit->P;
+                P->val.assign((size_t)hit->nent, 0.0);
+            }
             const auto tt2 = tnow();
             std::vector<double> Uva_sorted;
             const int32_t* Ucs = Uci;
@@ -657,6 +669,7 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
             return rc;
         }
     }
+    reset();
     std::unique_ptr<ProgramTemplate> tmpl;
     if (use_templates) {
         tmpl.reset(new ProgramTemplate());
@@ -943,11 +956,21 @@ void execute_program_host(const LuProgram& P, const int32_t* perm_r, const int32
             const int g = sl.glog_nrows & 255, nr = sl.glog_nrows >> 8, G = 1 << g;
             for (int r = 0; r < nr; ++r) {
                 const int32_t q = sl.q0 + r;
-                double acc = 0.0;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four chains: the gathers overlap
                 for (int u = 0; u < sl.trips; ++u) {
                     const size_t base = (size_t)sl.ebase + ((size_t)u << 5) + ((size_t)r << g);
-                    for (int l = 0; l < G; ++l) acc = fma(P.val[base + l], xe[P.col[base + l]], acc);
+                    const double* v = P.val.data() + base;
+                    const int32_t* c = P.col.data() + base;
+                    int l = 0;
+                    for (; l + 4 <= G; l += 4) {
+                        a0 = fma(v[l], xe[c[l]], a0);
+                        a1 = fma(v[l + 1], xe[c[l + 1]], a1);
+                        a2 = fma(v[l + 2], xe[c[l + 2]], a2);
+                        a3 = fma(v[l + 3], xe[c[l + 3]], a3);
+                    }
+                    for (; l < G; ++l) a0 = fma(v[l], xe[c[l]], a0);
                 }
+                const double acc = (a0 + a1) + (a2 + a3);
                 const double ini = P.init[q] >= 0 ? xe[P.init[q]] : 0.0;
                 out.push_back((ini - acc) * P.scale[q]);
             }

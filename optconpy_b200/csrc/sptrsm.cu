@@ -605,6 +605,7 @@ static void write_record(const LuProgram& P, const std::vector<Piece>& b, int cl
 constexpr int64_t IMG_MAGIC = 0x4f43424c55303034LL;   // "OCBLU004"
 enum { M_MAGIC = 0, M_TOTAL, M_N, M_NEXT, M_NNZL, M_NNZU, M_NSUBL, M_NSUBU, M_NSUPER, M_MAXW, M_NSLICE,
        M_NROWS, M_NENT, M_OPR, M_OPC, M_CL, M_STAGEB, M_NSTAGES, M_KPSMEM, M_FLAT, M_NSUB,
+       M_SHASH,   // hash of everything in the image that does not depend on the numbers (0: none)
        M_OBO = 24, M_OST = 32, M_NBATCH = 40,                  // one slot per cluster rank
        M_F_SLICE = 48, M_F_ROWSLICE, M_F_DST, M_F_INIT, M_F_SCALE, M_F_COL, M_F_VAL, M_F_SUBROW,
        M_P_PANEL = 56, M_P_SCALE, M_P_COL, M_P_VAL, M_P_SUB, M_NPANEL, M_PENT, M_PENT_ACTUAL,
@@ -618,7 +619,20 @@ struct ImageTemplate {
     std::vector<unsigned char> img;
     std::vector<SliceDest> dests;
     int64_t o_pr = 0, o_pc = 0, o_fscale = -1, o_fval = -1;
+    uint64_t shash = 0;       // of img with the numbers and the permutations zeroed (never 0)
 };
+
+static uint64_t hash_words(const unsigned char* p, size_t bytes) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    const size_t nw = bytes / 8;
+    for (size_t i = 0; i < nw; ++i) {
+        uint64_t w;
+        memcpy(&w, p + 8 * i, 8);
+        h = (h ^ w) * 0x100000001b3ULL;
+        h ^= h >> 29;
+    }
+    return h ? h : 1;
+}
 static std::mutex g_img_mutex;
 static std::vector<std::unique_ptr<ImageTemplate>> g_img_templates;
 static uint64_t g_img_clock = 0;
@@ -636,13 +650,25 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         for (auto& t : g_img_templates)
             if (t->structure_id == P.structure_id && t->max_smem_optin == max_smem_optin && t->flags == flags) {
                 t->stamp = ++g_img_clock;
-                unsigned char* img = (dst && (int64_t)t->img.size() <= dst_capacity)
-                                         ? dst : (unsigned char*)malloc(t->img.size());
+                const size_t sz = t->img.size();
+                unsigned char* img = (dst && (int64_t)sz <= dst_capacity) ? dst : (unsigned char*)malloc(sz);
                 if (!img) {
                     set_error("lu_pack_host: out of memory");
                     return OCB_ERR_CAPACITY;
                 }
-                memcpy(img, t->img.data(), t->img.size());
+                // A caller-provided buffer (a segment of the workers' pinned pool) that already
+                // holds an image of this very structure keeps it: only the numbers and the
+                // permutations are rewritten below (6 of 10 MB instead of 16).  The header goes
+                // last, so that a half-written buffer never carries a valid hash.
+                static const bool no_reuse = getenv("OCB_NO_SLOT_REUSE") != nullptr;
+                const int64_t* old = (const int64_t*)img;
+                const bool same = img == dst && !no_reuse && old[M_MAGIC] == IMG_MAGIC &&
+                                  old[M_TOTAL] == (int64_t)sz && (uint64_t)old[M_SHASH] == t->shash;
+                if (!same) {
+                    ((int64_t*)img)[M_SHASH] = 0;
+                    memcpy(img + M_COUNT * 8, t->img.data() + M_COUNT * 8, sz - M_COUNT * 8);
+                    memcpy(img, t->img.data(), M_COUNT * 8);
+                }
                 if (P.n > 0) {
                     memcpy(img + t->o_pr, h_perm_r, (size_t)P.n * 4);
                     memcpy(img + t->o_pc, h_perm_c, (size_t)P.n * 4);
@@ -842,6 +868,26 @@ static int pack_image(const LuProgram& P, const int32_t* h_perm_r, const int32_t
         if (want_flat) {
             tmpl->o_fscale = o_f[4];
             tmpl->o_fval = o_f[6];
+        }
+        {   // the template keeps the structure only: numbers and permutations zeroed, then hashed
+            unsigned char* ti = tmpl->img.data();
+            if (P.n > 0) {
+                memset(ti + o_pr, 0, (size_t)P.n * 4);
+                memset(ti + o_pc, 0, (size_t)P.n * 4);
+            }
+            for (const SliceDest& d : tmpl->dests) {
+                const Slice& sl = P.slices[d.slice];
+                memset(ti + d.val_off, 0, (size_t)sl.trips * 32 * 8);
+                memset(ti + d.scale_off, 0, (size_t)(sl.glog_nrows >> 8) * 8);
+            }
+            if (want_flat) {
+                memset(ti + o_f[4], 0, (size_t)P.nrows() * 8);
+                memset(ti + o_f[6], 0, (size_t)P.nent() * 8);
+            }
+            ((int64_t*)ti)[M_SHASH] = 0;
+            tmpl->shash = hash_words(ti, (size_t)total);
+            ((int64_t*)ti)[M_SHASH] = (int64_t)tmpl->shash;
+            meta[M_SHASH] = (int64_t)tmpl->shash;
         }
         std::unique_lock<std::mutex> lock(g_img_mutex);
         tmpl->stamp = ++g_img_clock;
@@ -1798,7 +1844,7 @@ static int pack_common(int64_t n, const int32_t* Lrp, const int32_t* Lci, const 
                        int64_t dst_capacity, unsigned char** img_out, int64_t* out_bytes,
                        const int32_t* A_colptr, const int32_t* A_rowidx, const double* A_vals,
                        double* out_backerr) {
-    ocb::LuProgram P;
+    static thread_local ocb::LuProgram P;     // kept between calls: see the template hit in build_lu_program
     int rc = ocb::build_lu_program(n, Lrp, Lci, Lva, Urp, Uci, Uva, ocb::trsm_threads(), (flags & 2) != 0,
                                    (flags & 4) != 0 && !(flags & 8), &P, (flags & 8) ? 32 : 0);
     if (rc != OCB_OK) return rc;

@@ -687,11 +687,15 @@ class LU(object):
         h = C.c_void_p()
         # the device image lives in a torch buffer: the caching allocator makes creating and
         # dropping a factorisation free of cudaMalloc / cudaFree (both synchronise the device)
+        tw = time.time()
         self.arena = _new_arena(int(image.nbytes))
         STATS['lu_arena_s'] += time.perf_counter() - t1
+        timeline('arena', tw)
+        tw = time.time()
         _cabi.check(lib.ocb_lu_create_from_image(C.byref(h), image.ctypes.data, image.nbytes,
                                                  ptr(self.arena), stream_ptr()),
                     'ocb_lu_create_from_image')
+        timeline('create_from_image', tw)
         self.handle = h
         self._lib = lib
         info = (C.c_int64*8)()

@@ -220,3 +220,45 @@ def test_guard_rejects_bad_static_pivots_and_superlu_takes_over(cav10, monkeypat
     used, img, nbytes, tf, tp, order, guard = _lu_worker._build(a1)
     assert guard[2] == 'slu' and guard[3] == 1 and guard[0] <= _lu_worker.GUARD_TOL
     _lu_worker._REFAC.clear()
+
+
+def test_pinned_slot_keeps_the_structure_between_images(cav10, monkeypatch):
+    """ocb_lu_pack_host_into on a buffer that already holds an image of the same structure rewrites
+    numbers and permutations only (header slot 21 = structure hash); whatever the buffer held
+    before - the same structure with other numbers, another structure, garbage - the bytes are
+    those of a build into a fresh buffer."""
+    monkeypatch.delenv('OCB_NO_SLOT_REUSE', raising=False)
+    lib = _cabi.load()
+    flags = 4 | (2 << 4)
+    K0 = _csc(_shifted(cav10, 2e-3, -1.0))
+    n = K0.shape[0]
+    a0 = dv._csc_args(K0, dict(dv.LU_OPTIONS)) + (232448, flags | 2)
+    q = _lu_worker.order_only(a0)
+    pr, pc = _lu_worker.static_pivots(a0 + (q,))
+    rf = _lu_worker._Refactor(n, K0.indptr, K0.indices, pr, pc)
+
+    def arrays(tau, p):
+        return [x.copy() for x in rf.numeric(_csc(_shifted(cav10, tau, p)).data)]
+
+    def into(arrs, buf, fl=flags):
+        nb = C.c_int64(0)
+        _cabi.check(lib.ocb_lu_pack_host_into(n, *[x.ctypes.data for x in arrs], 232448, fl,
+                                              buf.ctypes.data, buf.nbytes, C.byref(nb)), 'pack_into')
+        return buf[:nb.value].copy()
+    A1, A2 = arrays(3e-4, -5.0), arrays(1e-3, -1.3)
+    ref1 = _lu_worker.pack_image(A1, n, 232448, flags)
+    ref2 = _lu_worker.pack_image(A2, n, 232448, flags)
+    assert ref1.nbytes == ref2.nbytes and not np.array_equal(ref1, ref2)
+    assert ref1[168:176].any() and np.array_equal(ref1[168:176], ref2[168:176])      # same structure hash
+    buf = np.full(ref1.nbytes + 4096, 0xAB, dtype=np.uint8)
+    assert np.array_equal(into(A1, buf), ref1)                       # garbage before
+    assert np.array_equal(into(A2, buf), ref2)                       # same structure before: numbers only
+    assert np.array_equal(into(A1, buf), ref1)
+    # another structure in between (other cluster size -> other stream layout)
+    other = into(A1, buf, fl=4 | (4 << 4))
+    assert not np.array_equal(other[168:176], ref1[168:176])
+    assert np.array_equal(into(A2, buf), ref2)
+    # a buffer whose header claims the structure but whose body is not trusted when the hash is off
+    buf[168:176] = 0
+    buf[4096:8192] = 0x55
+    assert np.array_equal(into(A1, buf), ref1)

@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--lookahead', type=int, default=4)
     ap.add_argument('--mesh', type=int, default=25)
     ap.add_argument('--show', type=int, default=3, help='steps printed event by event')
+    ap.add_argument('--dump', default=None, help='write every event (and the step stamps) to this file')
     args = ap.parse_args()
     tdir = os.environ.get('OCB_TIMELINE')
     assert tdir, 'set OCB_TIMELINE=<dir>'
@@ -37,11 +38,13 @@ def main():
     kw['tmesh'] = kw['tmesh'][-(S+la+1):]
     tmp = tempfile.mkdtemp(prefix='ocb_tl_')
     kw['gtdtstrargs'] = dict(kw['gtdtstrargs'], data_prfx=os.path.join(tmp, 'tdst_'))
-    stamps = []
+    stamps, mem = [], []
 
     def cb(tk):
         torch.cuda.synchronize()
         stamps.append(time.time())
+        ms = torch.cuda.memory_stats()
+        mem.append((ms.get('num_device_alloc', 0), ms.get('num_device_free', 0)))
     dv.reset_stats()
     stimes = {}
     try:
@@ -56,9 +59,17 @@ def main():
             a, b, tf, tp = [float(x) for x in line.split()]
             ev.append(('worker ' + pid, 'factor %.1f + pack %.1f ms' % (1e3*tf, 1e3*tp), a, b))
     ev.sort(key=lambda e: e[2])
+    if args.dump:
+        with open(args.dump, 'w') as f:
+            for th, label, a, b in ev:
+                f.write('%.3f %.3f | %s | %s\n' % (1e3*(a - stamps[0]), 1e3*(b - stamps[0]), th, label))
+            for i, s_ in enumerate(stamps):
+                f.write('%.3f %.3f | STEP | end of step %d\n' % (1e3*(s_ - stamps[0]), 1e3*(s_ - stamps[0]), i))
     steps_ms = [1e3*(b - a) for a, b in zip(stamps[:-1], stamps[1:])]
     print('step ms:', ' '.join('%.1f' % s for s in steps_ms))
     print('workers %d, lookahead %d' % (dv._POOL['workers'], la))
+    print('cudaMalloc/cudaFree counts at the step ends:', mem)
+    print('CUDA_MODULE_LOADING =', os.environ.get('CUDA_MODULE_LOADING'))
     # steady-state window: steps la+2 .. S-1
     lo, hi = stamps[min(la + 2, len(stamps) - 2)], stamps[-1 - la] if len(stamps) > 2*la + 3 else stamps[-1]
     nst = sum(1 for s in stamps if lo < s <= hi)
