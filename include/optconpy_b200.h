@@ -40,6 +40,11 @@ const char* ocb_last_error(void);
 int ocb_version(void);
 /* number of kernel launches issued by this library since process start (bench.py: gpu_launches) */
 int64_t ocb_launch_count(void);
+/* How host threads of this process wait for the CURRENT device (cudaStreamSynchronize and friends):
+ * blocking = 1 sleeps on an interrupt instead of spinning.  With one process per GPU and fewer than
+ * ~3 host cores per process the spinning main threads otherwise take the cores the host LU workers
+ * need (8 GPUs on a 16-core host: e2e 55 -> see DESIGN.md section 7). */
+int ocb_set_sync_mode(int blocking);
 
 /* ---- K2: CSR x dense block ---------------------------------------------------
  * Y = alpha * S * X + beta * Y,  S (nrows x ncols) CSR, X (ncols x k), Y (nrows x k).

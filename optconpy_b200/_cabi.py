@@ -26,6 +26,7 @@ PROTOTYPES = {
                                            C.POINTER(vp), C.POINTER(i64), vp, vp, vp,
                                            C.POINTER(C.c_double)]),
     'ocb_host_free': (None, [vp]),
+    'ocb_set_sync_mode': (C.c_int, [C.c_int]),
     'ocb_lu_create_from_image': (C.c_int, [C.POINTER(vp), vp, i64, vp, vp]),
     'ocb_lu_info': (C.c_int, [vp, C.POINTER(i64)]),
     'ocb_lu_stats': (C.c_int, [vp, C.POINTER(i64)]),

@@ -51,6 +51,11 @@ const char* ocb_last_error(void) { return ocb::g_err; }
 int ocb_version(void) { return 100; }
 int64_t ocb_launch_count(void) { return (int64_t)ocb::g_launches.load(); }
 
+int ocb_set_sync_mode(int blocking) {
+    OCB_CUDA(cudaSetDeviceFlags(blocking ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
+    return OCB_OK;
+}
+
 int ocb_sqnorm(const double* d_X, int64_t ldx, int64_t n, int64_t k, double* d_out, void* stream) {
     OCB_ARG(d_X && d_out && n >= 0 && k >= 0 && ldx >= k, "sqnorm");
     ocb::sqnorm_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_X, ldx, n, k, d_out);

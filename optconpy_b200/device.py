@@ -72,11 +72,26 @@ LU_OPTIONS = dict(permc_spec='MMD_AT_PLUS_A', diag_pivot_thresh=0.01,
                   options=dict(SymmetricMode=True), relax=4, panel_size=10)
 
 
+_SYNC_MODE = set()
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError('optconpy_b200: no CUDA device visible; this package has no '
                            'CPU path (the CPU oracle lives in oracle/ and is test-only)')
-    return _cabi.load()
+    lib = _cabi.load()
+    d = torch.cuda.current_device()
+    if d not in _SYNC_MODE:
+        # One process per GPU on a host with few cores per process: threads that wait for the
+        # device must sleep, not spin - the cores belong to the LU workers (OCB_BLOCKING_SYNC=0/1
+        # overrides; default: on when fewer than 6 cores per rank).
+        _SYNC_MODE.add(d)
+        world = max(int(os.environ.get('WORLD_SIZE', '1')), 1)
+        want = os.environ.get('OCB_BLOCKING_SYNC')
+        if (want == '1') or (want is None and (os.cpu_count() or 1) < 6*world):
+            torch.cuda.current_stream()          # the primary context exists from here on
+            _cabi.check(lib.ocb_set_sync_mode(1), 'ocb_set_sync_mode')
+    return lib
 
 
 def stream_ptr():
