@@ -179,6 +179,14 @@ int ocb_lu_program_solve_host(const ocb_lu_program* prog, const int32_t* h_perm_
  * (the input ones composed with an elimination-tree postorder), are the L / U arguments of
  * ocb_lu_pack_host* with flags bit 1 CLEAR (P A Q = L U, L unit lower).  The caller's residual
  * guard (ocb_lu_pack_host_checked) decides whether the static pivots were good enough. */
+/* Fill- AND depth-reducing ordering of a symmetric sparsity pattern (adjacency in CSR, both
+ * triangles, diagonal entries ignored): nested dissection by BFS level structures with thinned
+ * separators, sets of <= leaf nodes kept as they are.  h_order_out[k] = the node eliminated k-th.
+ * Replaces SuperLU's minimum-degree ordering inside the reference's `spsla.factorized` /
+ * `spsla.splu` calls (lin_alg_utils.py:95-96, proj_ric_utils.py:108-111): the solve kernels are
+ * bound by the height of the elimination tree, which this ordering halves. */
+int ocb_order_nd(int64_t n, const int32_t* h_adj_rowptr, const int32_t* h_adj_colidx, int64_t leaf,
+                 int32_t* h_order_out);
 typedef struct ocb_refactor ocb_refactor;
 int ocb_refactor_create(ocb_refactor** out, int64_t n, const int32_t* h_A_colptr, const int32_t* h_A_rowidx,
                         const int32_t* h_perm_r, const int32_t* h_perm_c);

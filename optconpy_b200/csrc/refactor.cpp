@@ -157,6 +157,159 @@ int partial_lu(double* F, int m, int w, double tiny, double* work) {
 }  // namespace
 }  // namespace ocb
 
+// ---------------------------------------------------------------------------------------------
+// Nested-dissection ordering by breadth-first level structures (George's automatic nested
+// dissection with thinned separators).  The solve kernels are bound by the NUMBER of dependent
+// sub-levels of the gather program, i.e. by the height of the supernodal elimination tree: minimum
+// degree keeps the fill low but grows tall trees (N=25 cavity saddle matrix: 90 sub-levels); this
+// ordering gives 37 sub-levels AND 13 % less fill on the same matrix (n = 22k: 130 -> 69, -24 %).
+//   set S:  components are ordered one after the other; a connected set is cut at the level of a
+//   BFS from a pseudo-peripheral node that balances the halves; separator nodes without a
+//   neighbour on one side move to the other side; order(S) = order(side 0), order(side 1), separator.
+// ---------------------------------------------------------------------------------------------
+namespace ocb {
+namespace {
+
+struct NdWork {
+    const int32_t* ap;
+    const int32_t* ai;
+    int leaf;
+    std::vector<int32_t> tag;       // current set id of a node (-1: already ordered / other set)
+    std::vector<int32_t> dist, queue, side;
+    int32_t next_tag = 0;
+    int32_t* out;
+    int64_t nout = 0;
+};
+
+// BFS inside the set tagged `tg`, from `start`; returns the last node reached, fills dist for the
+// reached nodes and W.queue with them in BFS order
+int32_t nd_bfs(NdWork& W, int32_t tg, int32_t start, int32_t* nreached, int32_t* depth) {
+    W.queue.clear();
+    W.queue.push_back(start);
+    W.dist[start] = 0;
+    size_t head = 0;
+    // visited marker: dist >= 0 while the node's tag is tg and it sits in the queue; reset by the caller
+    while (head < W.queue.size()) {
+        const int32_t v = W.queue[head++];
+        for (int32_t p = W.ap[v]; p < W.ap[v + 1]; ++p) {
+            const int32_t u = W.ai[p];
+            if (W.tag[u] == tg && W.dist[u] < 0) {
+                W.dist[u] = W.dist[v] + 1;
+                W.queue.push_back(u);
+            }
+        }
+    }
+    *nreached = (int32_t)W.queue.size();
+    *depth = W.dist[W.queue.back()];
+    return W.queue.back();
+}
+
+void nd_order(NdWork& W, std::vector<int32_t>& nodes) {
+    const int32_t m = (int32_t)nodes.size();
+    if (m == 0) return;
+    if (m <= W.leaf) {
+        for (int32_t v : nodes) { W.out[W.nout++] = v; W.tag[v] = -1; }
+        return;
+    }
+    const int32_t tg = W.next_tag++;
+    for (int32_t v : nodes) { W.tag[v] = tg; W.dist[v] = -1; }
+    // connected components: the first one is treated below, the others recursively
+    int32_t reached = 0, depth = 0;
+    int32_t far = nd_bfs(W, tg, nodes[0], &reached, &depth);
+    if (reached < m) {
+        std::vector<int32_t> comp(W.queue.begin(), W.queue.end()), rest;
+        rest.reserve(m - reached);
+        for (int32_t v : nodes)
+            if (W.dist[v] < 0) rest.push_back(v);
+        for (int32_t v : nodes) W.tag[v] = -1;
+        nd_order(W, comp);
+        nd_order(W, rest);
+        return;
+    }
+    // pseudo-peripheral start
+    int32_t start = nodes[0];
+    for (int it = 0; it < 4 && far != start; ++it) {
+        start = far;
+        for (int32_t v : nodes) W.dist[v] = -1;
+        const int32_t d0 = depth;
+        far = nd_bfs(W, tg, start, &reached, &depth);
+        if (depth <= d0 && it > 0) break;
+    }
+    if (depth < 2) {     // (nearly) complete graph: nothing to dissect
+        for (int32_t v : nodes) { W.out[W.nout++] = v; W.tag[v] = -1; }
+        return;
+    }
+    // the level that balances the two sides
+    std::vector<int32_t> cnt(depth + 1, 0);
+    for (int32_t v : nodes) ++cnt[W.dist[v]];
+    int32_t lev = 1;
+    {
+        double bestd = 1e300, cum = 0.0;
+        for (int32_t l = 0; l <= depth; ++l) {
+            cum += cnt[l];
+            const double d = fabs(cum - 0.5 * cnt[l] - 0.5 * m);
+            if (d < bestd && l >= 1 && l <= depth - 1) { bestd = d; lev = l; }
+        }
+    }
+    for (int32_t v : nodes) W.side[v] = W.dist[v] < lev ? 0 : (W.dist[v] > lev ? 1 : 2);
+    // thin the separator
+    for (int pass = 0; pass < 2; ++pass) {
+        const int other = pass == 0 ? 1 : 0;
+        for (int32_t v : nodes) {
+            if (W.side[v] != 2) continue;
+            bool touches = false;
+            for (int32_t p = W.ap[v]; p < W.ap[v + 1] && !touches; ++p) {
+                const int32_t u = W.ai[p];
+                touches = W.tag[u] == tg && W.side[u] == other;
+            }
+            if (!touches) W.side[v] = pass == 0 ? 0 : 1;
+        }
+    }
+    std::vector<int32_t> s0, s1, sep;
+    for (int32_t v : nodes) (W.side[v] == 0 ? s0 : (W.side[v] == 1 ? s1 : sep)).push_back(v);
+    for (int32_t v : nodes) W.tag[v] = -1;
+    std::vector<int32_t>().swap(nodes);
+    nd_order(W, s0);
+    nd_order(W, s1);
+    for (int32_t v : sep) W.out[W.nout++] = v;
+}
+
+}  // namespace
+}  // namespace ocb
+
+extern "C" int ocb_order_nd(int64_t n, const int32_t* adj_rowptr, const int32_t* adj_colidx, int64_t leaf,
+                            int32_t* order_out) {
+    using namespace ocb;
+    if (n < 0 || (n > 0 && (!adj_rowptr || !order_out)) || n >= INT32_MAX) {
+        set_error("order_nd: bad argument");
+        return OCB_ERR_ARG;
+    }
+    if (n == 0) return OCB_OK;
+    for (int64_t i = 0; i < n; ++i)
+        for (int32_t p = adj_rowptr[i]; p < adj_rowptr[i + 1]; ++p)
+            if (adj_colidx[p] < 0 || adj_colidx[p] >= n) {
+                set_error("order_nd: column index out of range");
+                return OCB_ERR_ARG;
+            }
+    NdWork W;
+    W.ap = adj_rowptr;
+    W.ai = adj_colidx;
+    W.leaf = (int)std::max<int64_t>(leaf, 1);
+    W.tag.assign(n, -1);
+    W.dist.assign(n, -1);
+    W.side.assign(n, 0);
+    W.queue.reserve(n);
+    W.out = order_out;
+    std::vector<int32_t> all(n);
+    std::iota(all.begin(), all.end(), 0);
+    nd_order(W, all);
+    if (W.nout != n) {
+        set_error("order_nd: internal error (%lld of %lld nodes ordered)", (long long)W.nout, (long long)n);
+        return OCB_ERR_ARG;
+    }
+    return OCB_OK;
+}
+
 struct ocb_refactor {
     int64_t n = 0;
     int64_t nnzA = 0;

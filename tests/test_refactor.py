@@ -262,3 +262,68 @@ def test_pinned_slot_keeps_the_structure_between_images(cav10, monkeypatch):
     buf[168:176] = 0
     buf[4096:8192] = 0x55
     assert np.array_equal(into(A1, buf), ref1)
+
+
+def _nd(G, leaf=4):
+    lib = _cabi.load()
+    G = sps.csr_matrix(G)
+    G.sort_indices()
+    n = G.shape[0]
+    ip, ii = G.indptr.astype(np.int32), G.indices.astype(np.int32)
+    q = np.empty(n, dtype=np.int32)
+    _cabi.check(lib.ocb_order_nd(n, ip.ctypes.data, ii.ctypes.data, leaf, q.ctypes.data), 'ocb_order_nd')
+    return q
+
+
+def _sublevels_and_fill(S, q):
+    """Sub-levels of the gather program and nnz(L+U) of the matrix S under the symmetric order q."""
+    n = S.shape[0]
+    a = dv._csc_args(S, dict(dv.LU_OPTIONS)) + (232448, 6, np.ascontiguousarray(q, dtype=np.int32))
+    arrs = _lu_worker.factor_arrays(a, transposed=True)
+    info = _program(arrs, n, flags=6)[0]
+    return info['nsub_L'] + info['nsub_U'], len(arrs[1]) + len(arrs[4])
+
+
+def test_nested_dissection_orders_every_node_once_and_flattens_the_tree(cav10):
+    """ocb_order_nd: a permutation whatever the graph (grid, path, disconnected, complete, empty
+    rows); on a 2-D grid the elimination tree is far lower than under minimum degree at no more
+    fill; on the cavity saddle pattern the gather program gets at most 60 % of the sub-levels."""
+    nx = 40
+    I = sps.identity(nx)
+    T = sps.diags([np.ones(nx-1), np.ones(nx-1)], [-1, 1])
+    grid = (sps.kron(I, T) + sps.kron(T, I)).tocsr()
+    q = _nd(grid)
+    assert sorted(q.tolist()) == list(range(nx*nx))
+    S = sps.csc_matrix(grid + sps.identity(nx*nx)*10.0)
+    qm = np.argsort(spsla.splu(S, permc_spec='MMD_AT_PLUS_A', diag_pivot_thresh=0.0,
+                               options=dict(SymmetricMode=True)).perm_c)
+    (l_nd, f_nd), (l_md, f_md) = _sublevels_and_fill(S, q), _sublevels_and_fill(S, qm)
+    assert l_nd <= 0.8*l_md and f_nd <= 1.25*f_md, (l_nd, l_md, f_nd, f_md)
+    # degenerate graphs
+    path = sps.diags([np.ones(99), np.ones(99)], [-1, 1]).tocsr()
+    assert sorted(_nd(path, leaf=1).tolist()) == list(range(100))
+    two = sps.block_diag([grid[:50][:, :50], path, sps.csr_matrix((3, 3))]).tocsr()   # components + isolated nodes
+    assert sorted(_nd(two).tolist()) == list(range(two.shape[0]))
+    full = sps.csr_matrix(np.ones((30, 30)) - np.eye(30))
+    assert sorted(_nd(full).tolist()) == list(range(30))
+    assert _nd(sps.csr_matrix((0, 0))).size == 0
+    lib = _cabi.load()
+    bad_ip, bad_ii, out = np.array([0, 1], np.int32), np.array([5], np.int32), np.empty(1, np.int32)
+    assert lib.ocb_order_nd(1, bad_ip.ctypes.data, bad_ii.ctypes.data, 4, out.ctypes.data) == -1
+    # the saddle-point pattern through order_only (ND + delayed zero diagonals) vs minimum degree
+    K = _shifted(cav10, 2e-3, -1.0)
+    n = K.shape[0]
+    a = dv._csc_args(K, dict(dv.LU_OPTIONS)) + (232448, 6)
+    levels = {}
+    import os
+    for which in ('nd', 'mmd'):
+        os.environ['OCB_ORDERING'] = which
+        try:
+            qq = _lu_worker.order_only(a)
+        finally:
+            os.environ.pop('OCB_ORDERING')
+        assert sorted(qq.tolist()) == list(range(n))
+        arrs = _lu_worker.factor_arrays(a + (qq,), transposed=True)
+        info = _program(arrs, n, flags=6)[0]
+        levels[which] = (info['nsub_L'] + info['nsub_U'], len(arrs[1]) + len(arrs[4]))
+    assert levels['nd'][0] <= 0.6*levels['mmd'][0] and levels['nd'][1] <= 1.25*levels['mmd'][1], levels   # (N=10: +15 % fill; N=25: -14 %, N=50: -24 %)
