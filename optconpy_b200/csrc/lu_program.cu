@@ -25,7 +25,20 @@ static int wmax() {           // widest supernode (its inverse block has w(w+1)/
     }
     return v;
 }
-constexpr int YCAP = 1024;   // y-scratch rows one sub-level may use (two such regions exist)
+// y-scratch rows one sub-level may use (two such regions exist): a supernode that finds its
+// sub-level full moves to the next one.  1024 rows keep the extended vector of the column-panel
+// kernel small (shared memory); large systems, whose vector lives in global memory anyway, get
+// n/8 rows - with nested dissection thousands of supernodes are ready at the same time, and a
+// small cap would spread them over many artificial sub-levels (N=100 cavity: 195 instead of ~100)
+static int ycap_for(int64_t n) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("OCB_YCAP");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0) return forced;
+    return n <= 16384 ? 1024 : (int)std::min<int64_t>(n / 8, 1 << 20);
+}
 
 struct BlockPlan {
     int32_t sA = -1;   // sub-level of the A rows (-1: block needs no work)
@@ -76,6 +89,7 @@ int find_supernodes(int64_t n, const int32_t* rp, const int32_t* ci, int wcap, s
 // assign the A sub-level (and y offset) of every block of one triangular factor
 int plan_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts, const MergeRule& rule,
                 std::vector<BlockPlan>* plan, int32_t* nsub, int64_t* ymax) {
+    const int YCAP = ycap_for(n);
     const int nb = (int)starts.size() - 1;
     plan->assign(nb, BlockPlan());
     std::vector<int32_t> done(n, -1);
