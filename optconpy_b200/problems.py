@@ -134,32 +134,61 @@ def convection_matrix(prob, vfun, newton_term=True):
     ``N1[i,j] = int (v.grad phi_j) phi_i`` per component, plus (if
     ``newton_term``) ``N2[(c,i),(d,j)] = int phi_j d_d v_c phi_i``; this is the
     synthetic stand-in for ``snu.get_v_conv_conts`` (``optcont_main.py:556-568``).
-    Returned on the inner (non-Dirichlet) velocity dofs, shape (NV, NV)."""
+    Returned on the inner (non-Dirichlet) velocity dofs, shape (NV, NV).
+
+    The time stepper calls this once per time step (``get_tdpart``), so everything that depends
+    on the mesh only - shape-function tables, and the map from the element entries of the four
+    velocity blocks to the entries of the condensed CSR matrix - is computed once per problem;
+    a call then costs the element integrals and one ``bincount``.  The sparsity pattern is the
+    same for every linearisation point (entries that happen to cancel stay as stored zeros)."""
+    cache = prob.setdefault('_conv_cache', {})
+    c = cache.get(bool(newton_term))
+    if c is None:
+        mesh = prob['mesh']
+        X, det, glam = mesh.geometry()
+        phi, dphi = _p2_shape(_QP)
+        nlat = mesh.xy.shape[0]
+        t = mesh.tri
+        inv = np.asarray(prob['invinds'])
+        pos = np.full(2*nlat, -1, dtype=np.int64)
+        pos[inv] = np.arange(inv.size)
+        NV = inv.size
+        blocks = [(0, 0), (0, 1), (1, 0), (1, 1)] if newton_term else [(0, 0), (1, 1)]
+        r6 = np.repeat(t[:, :, None], 6, 2)
+        c6 = np.repeat(t[:, None, :], 6, 1)
+        keys = []
+        for (cc, dd) in blocks:                     # interleaved dof = 2*node + component
+            rr, cl = pos[2*r6 + cc], pos[2*c6 + dd]
+            keys.append(np.where((rr >= 0) & (cl >= 0), rr*NV + cl, -1).ravel())
+        keys = np.concatenate(keys)
+        keep = np.flatnonzero(keys >= 0)
+        uniq, inverse = np.unique(keys[keep], return_inverse=True)
+        rows = uniq // NV
+        c = dict(phi=phi, gphi=np.einsum('qil,eld->eqid', dphi, glam),
+                 wq=0.5*det[:, None]*_QW[None, :], blocks=blocks, keep=keep, inverse=inverse,
+                 nnz=uniq.size, NV=NV, indices=(uniq % NV).astype(np.int32),
+                 indptr=np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=NV))]).astype(np.int32))
+        cache[bool(newton_term)] = c
     mesh = prob['mesh']
-    X, det, glam = mesh.geometry()
-    phi, dphi = _p2_shape(_QP)
-    gphi = np.einsum('qil,eld->eqid', dphi, glam)
-    wq = 0.5*det[:, None]*_QW[None, :]
+    phi, gphi, wq = c['phi'], c['gphi'], c['wq']
     vnod = vfun(mesh.xy)                                   # (nlat,2) P2 interpolant
     vel = vnod[mesh.tri]                                   # (nel,6,2)
     vq = np.einsum('qi,eic->eqc', phi, vel)                # (nel,nq,2)
-    gv = np.einsum('eqid,eic->eqcd', gphi, vel)            # d_d v_c
-    N1e = np.einsum('eq,qi,eqd,eqjd->eij', wq, phi, vq, gphi)
-    nlat = mesh.xy.shape[0]
-    t = mesh.tri
-    r6 = np.repeat(t[:, :, None], 6, 2)
-    c6 = np.repeat(t[:, None, :], 6, 1)
-    N1 = _assemble(r6, c6, N1e, (nlat, nlat))
-    blocks = [[N1, None], [None, N1]]
+    N1e = np.einsum('eq,qi,eqd,eqjd->eij', wq, phi, vq, gphi, optimize=True)
     if newton_term:
-        for c in range(2):
-            for d in range(2):
-                N2e = np.einsum('eq,qi,qj,eq->eij', wq, phi, phi, gv[:, :, c, d])
-                N2 = _assemble(r6, c6, N2e, (nlat, nlat))
-                blocks[c][d] = N2 if blocks[c][d] is None else blocks[c][d] + N2
-    Nfull = _interleave_blocks(blocks, nlat)
-    inv = prob['invinds']
-    return Nfull[inv, :][:, inv].tocsr()
+        gv = np.einsum('eqid,eic->eqcd', gphi, vel)        # d_d v_c
+        wpp = np.einsum('eq,qi,qj->eqij', wq, phi, phi)
+        vals = []
+        for (cc, dd) in c['blocks']:
+            E = np.einsum('eqij,eq->eij', wpp, gv[:, :, cc, dd])
+            vals.append((E + N1e if cc == dd else E).ravel())
+    else:
+        vals = [N1e.ravel(), N1e.ravel()]
+    vals = np.concatenate(vals)
+    data = np.bincount(c['inverse'], weights=vals[c['keep']], minlength=c['nnz'])
+    out = sps.csr_matrix((data, c['indices'].copy(), c['indptr'].copy()), shape=(c['NV'], c['NV']))
+    out.has_sorted_indices = True
+    return out
 
 
 def _interleave_blocks(blocks, nlat):
