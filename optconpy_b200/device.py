@@ -915,11 +915,35 @@ def _compress_once(Z, thresh, k, eta, rmax):
                               sigma=sig[:int(info[1])])
 
 
+_DEFLATION_WARM = set()
+
+
+def _warm_deflation_ops(Z):
+    """The deflation levels below run a handful of torch element-wise kernels that nothing else
+    in this package uses.  CUDA loads a kernel the first time it is launched, out of a library of
+    more than a gigabyte: on a box with a cold page cache that first launch stalled every CUDA
+    call of the process for 50 ms - in the middle of whichever time step first needed a second
+    level (bench.py e2e: one 50-80 ms step in every run).  So they are launched once, on two
+    columns, when the first factor is compressed."""
+    _DEFLATION_WARM.add(Z.device.index)
+    z = Z[:, :2].contiguous()
+    sg = torch.from_numpy(np.ones(2)).to(Z.device)
+    q = (z/sg).contiguous()
+    lam = torch.ones(2, dtype=torch.float64, device=Z.device)
+    w = (torch.eye(2, dtype=torch.float64, device=Z.device)/torch.sqrt(lam)).contiguous()
+    r = z - tall_gemm(q, w)
+    torch.cat([z[:, :1], r[:, :1]], dim=1).contiguous()
+    torch.cat([lam[:1], sg[:1]])
+    lam.cpu()
+
+
 def compress(Z, thresh=None, k=None, eta=1e-14, rmax=None, _smax0=None, _level=0):
     """Device version of ``compress_Zsvd``: returns (Zc device tensor, info dict).
     ``Zc = Z V`` with V the right singular vectors of the singular values ``> thresh`` (at most
     ``k``), computed from Gram matrices on the FP64 tensor pipe; thresholds below the resolution
     of one Gram matrix (``COMPRESS_DELTA * sigma_max``) are reached by deflation levels."""
+    if _level == 0 and Z.device.index not in _DEFLATION_WARM and Z.shape[1] >= 2:
+        _warm_deflation_ops(Z)
     Zc, info = _compress_once(Z, thresh, k, eta, rmax)
     info['levels'] = _level + 1
     if thresh is None or info['chol_rank'] == 0:
