@@ -72,26 +72,34 @@ LU_OPTIONS = dict(permc_spec='MMD_AT_PLUS_A', diag_pivot_thresh=0.01,
                   options=dict(SymmetricMode=True), relax=4, panel_size=10)
 
 
-_SYNC_MODE = set()
+# How threads of this process wait for the device.  Spinning (the CUDA default while there are
+# more cores than contexts) gives the lowest latency and is right for the device-resident loop;
+# but with one process per GPU and few host cores per process - 8 GPUs on a 16-core host - the
+# spinning main threads take the cores the LU workers need (e2e at 8 GPUs: 55 -> 88 steps/s with
+# sleeping waits, while the device-resident loop loses 20 % to the wake-up latency).  So the
+# waits sleep exactly while host factorisations are in flight.  OCB_BLOCKING_SYNC=0 / 1: never /
+# always while jobs are in flight; default: when a rank has fewer than 6 cores.
+_SYNC = dict(inflight=0, blocking=False, enabled=None)
+
+
+def _jobs_inflight(delta):
+    with _LOCK:
+        if _SYNC['enabled'] is None:
+            world = max(int(os.environ.get('WORLD_SIZE', '1')), 1)
+            want = os.environ.get('OCB_BLOCKING_SYNC')
+            _SYNC['enabled'] = (want == '1') or (want is None and (os.cpu_count() or 1) < 6*world)
+        _SYNC['inflight'] = max(0, _SYNC['inflight'] + delta)
+        want = _SYNC['enabled'] and _SYNC['inflight'] > 0
+        if want != _SYNC['blocking']:
+            _cabi.check(_cabi.load().ocb_set_sync_mode(1 if want else 0), 'ocb_set_sync_mode')
+            _SYNC['blocking'] = want
 
 
 def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError('optconpy_b200: no CUDA device visible; this package has no '
                            'CPU path (the CPU oracle lives in oracle/ and is test-only)')
-    lib = _cabi.load()
-    d = torch.cuda.current_device()
-    if d not in _SYNC_MODE:
-        # One process per GPU on a host with few cores per process: threads that wait for the
-        # device must sleep, not spin - the cores belong to the LU workers (OCB_BLOCKING_SYNC=0/1
-        # overrides; default: on when fewer than 6 cores per rank).
-        _SYNC_MODE.add(d)
-        world = max(int(os.environ.get('WORLD_SIZE', '1')), 1)
-        want = os.environ.get('OCB_BLOCKING_SYNC')
-        if (want == '1') or (want is None and (os.cpu_count() or 1) < 6*world):
-            torch.cuda.current_stream()          # the primary context exists from here on
-            _cabi.check(lib.ocb_set_sync_mode(1), 'ocb_set_sync_mode')
-    return lib
+    return _cabi.load()
 
 
 def stream_ptr():
@@ -548,6 +556,8 @@ class FactorJob(object):
                 slot = None if i is None else (shp.segs[i][0].name, shp.seg_bytes)
                 self._slots.append(i)
                 self._async.append(pool.apply_async(_lu_worker.factor_image_to_shm, (a, slot)))
+            self._counted = True
+            _jobs_inflight(+1)
         STATS['lu_submit_s'] += time.perf_counter() - t0
         STATS['n_factor'] += self.n
         timeline('submit %d' % self.n, time.time() - (time.perf_counter() - t0))
@@ -576,6 +586,14 @@ class FactorJob(object):
             return self._done
         if torch.cuda.current_device() != self.device:
             torch.cuda.set_device(self.device)
+        try:
+            return self._collect_inner()
+        finally:
+            if getattr(self, '_counted', False):
+                self._counted = False
+                _jobs_inflight(-1)
+
+    def _collect_inner(self):
         out = []
         if self._async is None:
             for (img, tf, tp, order, guard), key in zip(self._sync, self._keys):
