@@ -962,11 +962,13 @@ def compress(Z, thresh=None, k=None, eta=1e-14, rmax=None, _smax0=None, _level=0
     of one Gram matrix (``COMPRESS_DELTA * sigma_max``) are reached by deflation levels."""
     if _level == 0 and Z.device.index not in _DEFLATION_WARM and Z.shape[1] >= 2:
         _warm_deflation_ops(Z)
+    tw = time.time()
     Zc, info = _compress_once(Z, thresh, k, eta, rmax)
     info['levels'] = _level + 1
     if thresh is None or info['chol_rank'] == 0:
         return Zc, info
     sig = info['sigma'].cpu().numpy()
+    timeline('compress:level %d' % _level, tw)
     smax = float(sig[0])
     smax0 = smax if _smax0 is None else _smax0
     if (thresh >= COMPRESS_DELTA*smax or (k is not None and info['kept'] >= int(k))
@@ -976,12 +978,20 @@ def compress(Z, thresh=None, k=None, eta=1e-14, rmax=None, _smax0=None, _level=0
     k1 = int((sig > COMPRESS_DELTA*smax).sum())
     if k1 == 0 or k1 > info['kept']:
         return Zc, info
+    tw = time.time()
     Zc1 = Zc[:, :k1].contiguous()
     sg1 = torch.from_numpy(sig[:k1].copy()).to(Z.device)
     Q1 = (Zc1/sg1).contiguous()                       # ~ left singular vectors U_1
+    timeline('deflate:scale', tw)
+    tw = time.time()
     lam, Wq, _ = sym_eig(gram(Q1, Q1))                # re-orthonormalise: Q1 <- Q1 W lam^-1/2
+    timeline('deflate:gram+eig', tw)
+    tw = time.time()
     Q1 = tall_gemm(Q1, (Wq/torch.sqrt(lam)).contiguous())
+    timeline('deflate:orth', tw)
+    tw = time.time()
     Z2 = Z - tall_gemm(Q1, gram(Q1, Z))               # (I - Q1 Q1^T) Z
+    timeline('deflate:project', tw)
     t2 = max(float(thresh), COMPRESS_NOISE*smax0)
     Zc2, info2 = compress(Z2.contiguous(), thresh=t2, k=None if k is None else int(k) - k1, eta=eta,
                           rmax=rmax, _smax0=smax0, _level=_level + 1)
