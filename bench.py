@@ -624,12 +624,14 @@ def main():
                     launches=int(nl.value), mean_launch_ms=tot_ms.value/max(nl.value, 1),
                     kernel_share_of_step=tot_ms.value/ms, mean_rhs_cols=k_mean,
                     alg_bytes_per_launch=ab.value/max(nl.value, 1),
-                    note='n=5477: a cluster of 4 CTAs per column panel streams the 9.4 MB gather '
-                         'program (out of L2 after the first read) through ~140 dependent '
-                         'sub-levels; the kernel is bound by that latency chain and the '
-                         'shared-memory gather rate, not by HBM (DESIGN.md K1); '
-                         'nnzL+nnzU=%d, sub-levels L/U=%d/%d'
-                         % (lu0.info['nnzL']+lu0.info['nnzU'], lu0.info['levelsL'],
+                    note='n=%d: a cluster of 2-4 CTAs per column panel streams the %.1f MB gather '
+                         'program (out of L2 after the first read) through %d dependent '
+                         'sub-levels (nested-dissection ordering; 90 under minimum degree); the '
+                         'kernel is bound by that dependency chain and the shared-memory gather '
+                         'rate, not by HBM (DESIGN.md K1); nnzL+nnzU=%d, sub-levels L/U=%d/%d'
+                         % (lu0.info['n'], lu0.info['device_bytes']/1e6,
+                            lu0.info['levelsL']+lu0.info['levelsU'],
+                            lu0.info['nnzL']+lu0.info['nnzU'], lu0.info['levelsL'],
                             lu0.info['levelsU']))
     solves = sum(i['solves'] for i in info[W:])
     phase_ms = None
