@@ -455,13 +455,7 @@ int ocb_refactor_create(ocb_refactor** out, int64_t n, const int32_t* A_colptr, 
             std::sort(s.begin(), s.end());
         }
     }
-    // supernodes: column j+1 joins column j if it is j's parent and has the same structure below
-    int relax = 0;
-    {
-        const char* e = getenv("OCB_REFACTOR_RELAX");
-        relax = e ? atoi(e) : 0;
-    }
-    (void)relax;
+    // (fundamental) supernodes: column j+1 joins column j if it is j's parent and has the same structure below
     R->sn_start.push_back(0);
     for (int64_t j = 1; j < n; ++j)
         if (!(parent[j - 1] == j && cs[j].size() + 1 == cs[j - 1].size())) R->sn_start.push_back((int32_t)j);

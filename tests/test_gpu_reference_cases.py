@@ -221,7 +221,8 @@ def test_config4_fine_channel_first_newton_step(mods):
     (optcont_main.py:488-492: z0 = None, so the ADI block is trct_mat) with the built-in six
     shifts, cut to 12 ADI steps so that the oracle's column-by-column SuperLU solves finish in a
     minute.  The factors go through the all-columns executors (the column panel of n = 109 688 does
-    not fit shared memory) and the constrained minimum-degree ordering."""
+    not fit shared memory), the nested-dissection ordering with delayed pressure nodes and the
+    numeric-only refactorisation."""
     glau, gpru, olau, opru = mods
     from optconpy_b200 import scenarios as sc, device as dv
     prob, cs, kw = sc.config4(olau)
@@ -233,6 +234,9 @@ def test_config4_fine_channel_first_newton_step(mods):
     dv.reset_stats()
     got = gpru.proj_alg_ric_newtonadi(**args)
     assert dv.STATS['lu_guard_refactors'] == 0 and dv.STATS['lu_guard_max_backerr'] < 2e-15
+    # all six shifted factors came from the numeric-only refactorisation (static pivots of one
+    # SuperLU run, nested-dissection ordering) and passed the residual guard
+    assert dv.STATS['lu_static_pivot'] == 6 and dv.STATS['lu_static_rejected'] == 0
     ref = opru.proj_alg_ric_newtonadi(**args)
     assert got['adi_steps'] == ref['adi_steps'] == [12]
     assert got['zfac'].shape == ref['zfac'].shape
