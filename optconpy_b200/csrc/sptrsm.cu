@@ -340,9 +340,15 @@ __global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(cons
                     }
 #pragma unroll
                     for (int u = 0; u < UNR; ++u) {
-                        const double* xj = x + (size_t)j[u] * KP;
+                        if (KP == 2) {   // both columns of a row in ONE 16-byte shared-memory gather
+                            const double2 xx = *reinterpret_cast<const double2*>(x + (size_t)j[u] * 2);
+                            acc[u % NACC][0] = fma(v[u], xx.x, acc[u % NACC][0]);
+                            acc[u % NACC][KP - 1] = fma(v[u], xx.y, acc[u % NACC][KP - 1]);
+                        } else {
+                            const double* xj = x + (size_t)j[u] * KP;
 #pragma unroll
-                        for (int c = 0; c < KP; ++c) acc[u % NACC][c] = fma(v[u], xj[c], acc[u % NACC][c]);
+                            for (int c = 0; c < KP; ++c) acc[u % NACC][c] = fma(v[u], xj[c], acc[u % NACC][c]);
+                        }
                     }
                 }
                 if (u0 < trips) {   // remainder (warp-uniform): up to UNR-1 trips, loads first
@@ -358,10 +364,16 @@ __global__ void __launch_bounds__(TRSM_MAX_THREADS, 1) sptrsm_stream_kernel(cons
 #pragma unroll
                     for (int u = 0; u < UNR - 1; ++u) {
                         if (u0 + u < trips) {
-                            const double* xj = x + (size_t)j[u] * KP;
+                            if (KP == 2) {
+                                const double2 xx = *reinterpret_cast<const double2*>(x + (size_t)j[u] * 2);
+                                acc[u % NACC][0] = fma(v[u], xx.x, acc[u % NACC][0]);
+                                acc[u % NACC][KP - 1] = fma(v[u], xx.y, acc[u % NACC][KP - 1]);
+                            } else {
+                                const double* xj = x + (size_t)j[u] * KP;
 #pragma unroll
-                            for (int c = 0; c < KP; ++c)
-                                acc[u % NACC][c] = fma(v[u], xj[c], acc[u % NACC][c]);
+                                for (int c = 0; c < KP; ++c)
+                                    acc[u % NACC][c] = fma(v[u], xj[c], acc[u % NACC][c]);
+                            }
                         }
                     }
                 }

@@ -346,9 +346,25 @@ def _pack_flags(wide, k_hint=None):
     and take SuperLU's column-wise factors as they are (no CSC->CSR conversion on the host),
     bit 2 = small supernodes solved in one sub-level instead of two,
     bits 4..7 = cluster size of the column-panel kernel from the expected block width
-    (measured, N=25 factor: one column per cluster while one wave of clusters covers the block -
-    clusters of 4 up to 33 right-hand sides: 135 us, of 3 up to 44: 146 us, of 2 beyond: 175 us)."""
-    cl = 0 if k_hint is None else (4 if k_hint <= 33 else (3 if k_hint <= 44 else 2))
+    (measured on the N=25 factor, profiles/r02f_cluster_size_sweep.log + r02f_kp2_sweep.log: one
+    column per cluster while one wave of clusters covers the block, two columns - one 16-byte gather
+    per entry - beyond: clusters of 4 take 85 us up to 33 right-hand sides and 118-123 us up to 66,
+    clusters of 3 100 us up to 45 and 138-141 us up to 90, clusters of 2 128 us up to 74 and 171 us
+    up to 148)."""
+    if k_hint is None:
+        cl = 0
+    elif k_hint <= 33:
+        cl = 4
+    elif k_hint <= 44:
+        cl = 3
+    elif k_hint <= 60:      # (clusters of 4 fall off a cliff beyond 66 columns - 232 us -: the hint
+        cl = 4              # may lag the actual width by a few columns)
+    elif k_hint <= 74:
+        cl = 2
+    elif k_hint <= 90:
+        cl = 3
+    else:
+        cl = 2
     merge = 4 if os.environ.get('OCB_MERGE', MERGE_DEFAULT) == '1' else 0
     return (1 if wide else 0) | (0 if os.environ.get('OCB_NO_TRANSPOSED_LU') else 2) | merge | (cl << 4)
 
