@@ -55,9 +55,10 @@ static SideStream* side_stream() {
     return p;
 }
 
-// pinned host scratch for the few scalars that steer host-side loops
+// pinned host scratch for the few scalars that steer host-side loops; one per host thread (the
+// stepper's tail thread runs ocb_smw_solve while the main thread sits in ocb_adi_run)
 static double* pinned_scratch() {
-    static double* p = nullptr;
+    static thread_local double* p = nullptr;
     if (!p) {
         if (cudaHostAlloc((void**)&p, 16384, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
     }

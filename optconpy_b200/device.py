@@ -136,22 +136,26 @@ def remember_device_copy(host_arr, dev_tensor):
     import weakref
     if not isinstance(host_arr, np.ndarray) or host_arr.size == 0:
         return
-    if len(_DEV_CACHE) >= _DEV_CACHE_MAX:
-        _DEV_CACHE.pop(next(iter(_DEV_CACHE)))
     try:
         ref = weakref.ref(host_arr)
     except TypeError:
         return
-    _DEV_CACHE[id(host_arr)] = (ref, _fingerprint(host_arr), dev_tensor)
+    fp = _fingerprint(host_arr)
+    with _LOCK:
+        if len(_DEV_CACHE) >= _DEV_CACHE_MAX:
+            _DEV_CACHE.pop(next(iter(_DEV_CACHE)))
+        _DEV_CACHE[id(host_arr)] = (ref, fp, dev_tensor)
 
 
 def _cached_device_copy(arr):
-    ent = _DEV_CACHE.get(id(arr))
+    with _LOCK:
+        ent = _DEV_CACHE.get(id(arr))
     if ent is None:
         return None
     ref, fp, t = ent
     if ref() is not arr or t.device != cur_device() or fp != _fingerprint(arr):
-        _DEV_CACHE.pop(id(arr), None)
+        with _LOCK:
+            _DEV_CACHE.pop(id(arr), None)
         return None
     return t
 
@@ -174,7 +178,7 @@ def to_dev(arr):
     return torch.from_numpy(a).to(cur_device())
 
 
-_PINNED_STAGE = dict(buf=None)
+_PINNED_STAGE = dict()      # per host thread (the stepper's tail thread copies results out too)
 
 
 def to_host(t):
@@ -189,11 +193,12 @@ def to_host(t):
         return t.cpu().numpy()
     tc = t if t.is_contiguous() else t.contiguous()
     numel = tc.numel()
-    st = _PINNED_STAGE['buf']
+    me = threading.get_ident()
+    st = _PINNED_STAGE.get(me)
     if st is None or st.numel() < numel or st.dtype != tc.dtype:
         cap = 1 << max(int(numel - 1).bit_length(), 20)
         st = torch.empty(cap, dtype=tc.dtype, pin_memory=True)
-        _PINNED_STAGE['buf'] = st
+        _PINNED_STAGE[me] = st
     host = st[:numel].view(tc.shape)
     host.copy_(tc, non_blocking=True)
     torch.cuda.current_stream().synchronize()
@@ -242,7 +247,9 @@ def reserve_pool(nbytes):
 
 
 def workspace(name, nbytes):
-    ws = _WS.setdefault(name, Workspace())
+    """The growing buffer of purpose ``name`` of the CALLING host thread (two threads of one
+    process may drive the device at the same time, on different streams)."""
+    ws = _WS.setdefault((name, threading.get_ident()), Workspace())
     return ws.get(nbytes)
 
 
@@ -528,6 +535,19 @@ def bind_thread_to_device(index=None):
     index = _MAIN_DEVICE['index'] if index is None else index
     if index is not None:
         torch.cuda.set_device(index)
+
+
+def tail_thread_init():
+    """Called on the MAIN thread: returns the initializer of a helper thread that drives device
+    work of its own (``dre_stepper``: the feed-forward tail of a time step runs beside the
+    Riccati part of the next one): bound to the current device, on a stream of its own."""
+    require_cuda()
+    index = torch.cuda.current_device()
+
+    def init():
+        bind_thread_to_device(index)
+        torch.cuda.set_stream(torch.cuda.Stream())
+    return init
 
 
 def lookahead_thread_init():
@@ -931,7 +951,7 @@ def _compress_once(Z, thresh, k, eta, rmax):
     # the K x K Gram matrix grows with every DRE step (K = block width x ADI steps): ask for
     # headroom, so that the buffer is not re-allocated (cudaFree + cudaMalloc: both synchronise)
     # every few time steps
-    have = _WS.get('compress')
+    have = _WS.get(('compress', threading.get_ident()))
     if have is None or have.buf is None or have.buf.numel() < wsb:
         workspace('compress', int(wsb*1.6))
     ws = workspace('compress', wsb)

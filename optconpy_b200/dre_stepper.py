@@ -86,7 +86,7 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
                       check_c_consist=True,
                       lau=None, pru=None, store=None, verbose=False,
                       stepinfo=None, step_callback=None, lookahead=4, timing=None,
-                      private_extensions=True):
+                      private_extensions=True, overlap_tail=True):
     """Same keyword signature as the reference's ``solve_flow_daeric`` plus
     ``lau``/``pru`` (backend modules), ``store`` and ``stepinfo`` (optional list
     that receives per-step diagnostics).  Returns the ``feedbackthroughdict``
@@ -97,6 +97,11 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
     ``pru.factors_async`` / ``lau.sadlu_async`` the sparse LU setup of the next
     ``lookahead`` steps is started (host worker processes) before the device work of step
     ``k``; the numbers are the same with or without it.
+
+    ``overlap_tail`` (with look-ahead and a backend that offers ``pru.tail_thread_init``): the
+    feed-forward half of step ``k`` runs on a helper thread while this thread drives the Riccati
+    half of step ``k-1`` (independent chains); same numbers, ``step_callback`` is then called from
+    that thread.
 
     ``private_extensions=False`` (with ``lookahead=0``): call the backend through the
     reference's signatures ONLY - no ``_factors`` / ``_lazy_zfac`` / ``sadlu`` keywords - i.e.
@@ -192,58 +197,25 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
     depth = int(lookahead) if can_prefetch else 0
     zc_width = [Zc.shape[1]]        # latest factor width, read by the look-ahead thread
     ahead = {}
-    for tk in range(len(tmesh)-2, -1, -1):
-        t = tmesh[tk]
-        cts = tmesh[tk+1] - t
-        if verbose:
-            print('Time is {0}, timestep is {1}'.format(t, cts))
-        gtdtstrargs.update(time=t)
-        key = get_datastr(**gtdtstrargs)
-        for tj in range(tk-1, max(tk-1-depth, -1), -1):
-            if tj not in ahead:
-                ahead[tj] = pool.submit(prepare, tj)
-        if timing is not None:
-            _t0 = _time.perf_counter()
-        pre = ahead.pop(tk).result() if tk in ahead else prepare(tk)
-        if timing is not None:
-            timing['prepare_wait_s'] = timing.get('prepare_wait_s', 0.0) + _time.perf_counter() - _t0
-        nmattd, rhsvtd, NT = pre['nmattd'], pre['rhsvtd'], pre['NT']
 
-        cnsw, cnsmtxtb = None, None
-        if curnwtnsdict is not None:
-            try:
-                cnsw = store.load(curnwtnsdict[t]['w'])
-                cnsmtxtb = store.load(curnwtnsdict[t]['mtxtb'])
-            except IOError:
-                cnsw, cnsmtxtb = None, None
+    # The two halves of a time step are independent chains: the Riccati part (Newton-ADI,
+    # compression) of step k-1 needs Zc of step k only, the feed-forward part ("tail": gain,
+    # feed-forward solve, stores) of step k needs Zc of step k and the tail of step k+1.  With a
+    # backend that allows a second device-driving thread (``pru.tail_thread_init``) the tail of
+    # step k runs on that thread, on its own stream, while this thread already drives the Riccati
+    # part of step k-1; the numbers are the same (same operations on the same data, in the same
+    # order within each chain).  At most one tail is outstanding.
+    tail_pool = None
+    if overlap_tail and can_prefetch and hasattr(pru, 'tail_thread_init'):
+        from concurrent.futures import ThreadPoolExecutor as _TPE
+        tail_pool = _TPE(max_workers=1, initializer=pru.tail_thread_init())
+    tail_state = dict(wc=wc, mtxtb=mtxtb)
+    pending_tail = [None]
 
-        info = dict(t=t, tau=cts)
-        try:
-            Zc = store.load(key + '__Z')
-        except IOError:
-            ft_mat = pre['ft_mat']
-            w_mat = np.hstack([MT @ Zc, np.sqrt(cts)*tct_mat])
-            oldfb = np.sqrt(cts)*cnsmtxtb if cnsmtxtb is not None else None
-            xkw = dict(_factors=pre['fac']) if pre['fac'] is not None else {}
-            if private_extensions and hasattr(pru, 'DeviceFactor'):
-                # the uncompressed factor is only compressed below: leave it on the device
-                xkw['_lazy_zfac'] = True
-            nres = pru.proj_alg_ric_newtonadi(mmat=MT, amat=ft_mat, transposed=True,
-                                              mtxoldb=oldfb, jmat=jmat,
-                                              bmat=np.sqrt(cts)*tb_mat,
-                                              wmat=w_mat, z0=Zc,
-                                              nwtn_adi_dict=nwtn_adi_dict, **xkw)
-            Zp = nres['zfac']
-            info.update(nwtn_upd_fnorms=nres.get('nwtn_upd_fnorms'),
-                        adi_steps=nres.get('adi_steps'), zp_cols=Zp.shape[1])
-            if comprz_maxc is not None or comprz_thresh is not None:
-                Zc = pru.compress_Zsvd(Zp, thresh=comprz_thresh, k=comprz_maxc)
-            else:
-                Zc = Zp = np.asarray(Zp)
-            store.save(np.asarray(Zp) if save_full_z else Zc, key + '__Z')
-        info.update(zc_cols=Zc.shape[1])
-        zc_width[0] = Zc.shape[1]
-
+    def tail(tk, t, cts, key, pre, Zc, cnsw, cnsmtxtb, info):
+        """Feed-forward half of step tk (``solve_dae_ric.py:173-207``)."""
+        wc, mtxtb = tail_state['wc'], tail_state['mtxtb']
+        rhsvtd = pre['rhsvtd']
         at_mat = pre['at_mat']
         ftilde = rhsvtd + rhsv
         if cnsw is not None:
@@ -268,11 +240,80 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
 
         store.save(wc, key + '__w')
         store.save(mtxtb, key + '__mtxtb')
+        tail_state['wc'], tail_state['mtxtb'] = wc, mtxtb
         fbdict.update({t: dict(w=key + '__w', mtxtb=key + '__mtxtb')})
         if stepinfo is not None:
             stepinfo.append(info)
         if step_callback is not None:
             step_callback(tk)
+
+    def join_tail():
+        if pending_tail[0] is not None:
+            f, pending_tail[0] = pending_tail[0], None
+            f.result()          # re-raises what the tail raised
+
+    try:
+        for tk in range(len(tmesh)-2, -1, -1):
+            t = tmesh[tk]
+            cts = tmesh[tk+1] - t
+            if verbose:
+                print('Time is {0}, timestep is {1}'.format(t, cts))
+            key = get_datastr(**dict(gtdtstrargs, time=t))
+            for tj in range(tk-1, max(tk-1-depth, -1), -1):
+                if tj not in ahead:
+                    ahead[tj] = pool.submit(prepare, tj)
+            if timing is not None:
+                _t0 = _time.perf_counter()
+            pre = ahead.pop(tk).result() if tk in ahead else prepare(tk)
+            if timing is not None:
+                timing['prepare_wait_s'] = timing.get('prepare_wait_s', 0.0) + _time.perf_counter() - _t0
+
+            cnsw, cnsmtxtb = None, None
+            if curnwtnsdict is not None:
+                # written by the tail of this very time step in an earlier sweep only: no
+                # dependence on the tail that may still be running
+                try:
+                    cnsw = store.load(curnwtnsdict[t]['w'])
+                    cnsmtxtb = store.load(curnwtnsdict[t]['mtxtb'])
+                except IOError:
+                    cnsw, cnsmtxtb = None, None
+
+            info = dict(t=t, tau=cts)
+            try:
+                Zc = store.load(key + '__Z')
+            except IOError:
+                ft_mat = pre['ft_mat']
+                w_mat = np.hstack([MT @ Zc, np.sqrt(cts)*tct_mat])
+                oldfb = np.sqrt(cts)*cnsmtxtb if cnsmtxtb is not None else None
+                xkw = dict(_factors=pre['fac']) if pre['fac'] is not None else {}
+                if private_extensions and hasattr(pru, 'DeviceFactor'):
+                    # the uncompressed factor is only compressed below: leave it on the device
+                    xkw['_lazy_zfac'] = True
+                nres = pru.proj_alg_ric_newtonadi(mmat=MT, amat=ft_mat, transposed=True,
+                                                  mtxoldb=oldfb, jmat=jmat,
+                                                  bmat=np.sqrt(cts)*tb_mat,
+                                                  wmat=w_mat, z0=Zc,
+                                                  nwtn_adi_dict=nwtn_adi_dict, **xkw)
+                Zp = nres['zfac']
+                info.update(nwtn_upd_fnorms=nres.get('nwtn_upd_fnorms'),
+                            adi_steps=nres.get('adi_steps'), zp_cols=Zp.shape[1])
+                if comprz_maxc is not None or comprz_thresh is not None:
+                    Zc = pru.compress_Zsvd(Zp, thresh=comprz_thresh, k=comprz_maxc)
+                else:
+                    Zc = Zp = np.asarray(Zp)
+                store.save(np.asarray(Zp) if save_full_z else Zc, key + '__Z')
+            info.update(zc_cols=Zc.shape[1])
+            zc_width[0] = Zc.shape[1]
+
+            join_tail()                       # the tail of the previous step (it ran beside this Riccati part)
+            if tail_pool is not None:
+                pending_tail[0] = tail_pool.submit(tail, tk, t, cts, key, pre, Zc, cnsw, cnsmtxtb, info)
+            else:
+                tail(tk, t, cts, key, pre, Zc, cnsw, cnsmtxtb, info)
+        join_tail()
+    finally:
+        if tail_pool is not None:
+            tail_pool.shutdown(wait=True)
     if pool is not None:
         pool.shutdown(wait=True)
         sys.setswitchinterval(old_switch)

@@ -23,9 +23,13 @@ from . import device as dv
 from . import parallel as par
 
 __all__ = ['solve_proj_lyap_stein', 'proj_alg_ric_newtonadi', 'compress_Zsvd',
-           'get_mTzzTtb', 'comp_proj_lyap_res_norm', 'factors_async', 'lookahead_thread_init']
+           'get_mTzzTtb', 'comp_proj_lyap_res_norm', 'factors_async', 'lookahead_thread_init',
+           'tail_thread_init']
 
 lookahead_thread_init = dv.lookahead_thread_init
+# a second host thread may call get_mTzzTtb / lau.solve_sadpnt_smw while this one sits in
+# proj_alg_ric_newtonadi: workspaces, staging buffers and the C library's scratch are per thread
+tail_thread_init = dv.tail_thread_init
 
 DEFAULT_SHIFTS = [-30.0, -20.0, -10.0, -5.0, -3.0, -1.0]
 

@@ -151,6 +151,76 @@ def test_outer_newton_carry(cav6):
     assert sorted(fb1) == sorted(fb2) == sorted(tmesh)
 
 
+def test_overlapped_tail_gives_the_same_results(cav6):
+    """dre_stepper: with a backend that offers ``tail_thread_init`` the feed-forward half of step k
+    runs on a helper thread beside the Riccati half of step k-1.  Same stores, bit for bit, as the
+    sequential loop - also across two outer Newton passes (``curnwtnsdict``: the tail of a step
+    writes the carried entries the next pass reads) - and the callback sees every step in order."""
+    import threading
+    cs = pb.control_setup(cav6, olau, alphau=1e-4)
+    tmesh = pb.get_tint(0.0, 0.1, 4)
+    nd = dict(sc.DEFAULT_NWTN_ADI, adi_max_steps=60, nwtn_max_steps=3)
+    kw = sc.dre_kwargs(cav6, cs, tmesh, nd, 1e-3, sc._ystar_sin(cs['NY']))
+    tail_threads = set()
+
+    class AsyncPru(object):               # the oracle plus the three optional entry points
+        def __getattr__(self, name):
+            f = getattr(opru, name)
+            if name != 'get_mTzzTtb':
+                return f
+
+            def spy(*a, **k):
+                tail_threads.add(threading.current_thread().name)
+                return f(*a, **k)
+            return spy
+
+        def factors_async(self, **k):
+            return None
+
+        def tail_thread_init(self):
+            return lambda: None
+
+    class AsyncLau(object):
+        def __getattr__(self, name):
+            return getattr(olau, name)
+
+        def sadlu_async(self, **k):
+            return None
+
+    def run(overlap):
+        store, order = ds.MemStore(), []
+        cnd = {t: dict(v='cns_v_t%r' % t, mtxtb='cns_mtxtb_t%r' % t, w='cns_w_t%r' % t) for t in tmesh}
+        fbs = []
+        for cns in (0, 1):
+            g = dict(kw['gtdtstrargs'], data_prfx='cns%d_' % cns)
+            fbs.append(ds.solve_flow_daeric(lau=AsyncLau(), pru=AsyncPru(), store=store, curnwtnsdict=cnd,
+                                            lookahead=2, overlap_tail=overlap, step_callback=order.append,
+                                            **dict(kw, gtdtstrargs=g)))
+        return store, fbs, order
+    tail_threads.clear()
+    s_seq, fb_seq, o_seq = run(False)
+    assert tail_threads == {threading.current_thread().name}
+    tail_threads.clear()
+    s_ovl, fb_ovl, o_ovl = run(True)
+    assert any(n != threading.current_thread().name for n in tail_threads)      # really on a helper thread
+    assert o_seq == o_ovl == 2*list(range(len(tmesh)-2, -1, -1)) and fb_seq == fb_ovl
+    assert sorted(s_seq) == sorted(s_ovl)
+    for k in s_seq:
+        assert np.array_equal(s_seq[k], s_ovl[k]), k
+
+    # an exception in the tail surfaces in the caller
+    class Boom(AsyncLau):
+        def __getattr__(self, name):
+            if name == 'solve_sadpnt_smw':
+                def boom(**k):
+                    raise RuntimeError('tail failed')
+                return boom
+            return getattr(olau, name)
+    with pytest.raises(RuntimeError, match='tail failed'):
+        ds.solve_flow_daeric(lau=Boom(), pru=AsyncPru(), store=ds.MemStore(), lookahead=2,
+                             **dict(kw, gtdtstrargs=dict(kw['gtdtstrargs'])))
+
+
 def test_device_factor_handle_behaves_like_the_array():
     """proj_ric_utils.DeviceFactor (the lazily downloaded ADI factor): shape/dtype/len without a
     copy, ndarray on demand through the numpy protocol (np.asarray, np.save, slicing, hstack)."""
