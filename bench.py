@@ -657,11 +657,14 @@ def main():
             kw2['gtdtstrargs'] = dict(kw2['gtdtstrargs'], data_prfx=os.path.join(tmp, 'tdst_'))
             stamps, bytes_at = [], []
 
+            phase_at = []
+
             def cb(tk):
                 torch.cuda.synchronize()
                 stamps.append(time.perf_counter())
                 bytes_at.append((dv.STATS['h2d_bytes'], dv.STATS['d2h_bytes'],
                                  torch.cuda.memory_stats().get('num_device_alloc', 0)))
+                phase_at.append(dict(dv.PHASE, **stimes))
             dv.reset_stats()
             barrier()
             if args.phases:
@@ -690,6 +693,11 @@ def main():
                                             if k.startswith('lu_') or k == 'n_factor'},
                        lu_workers=dv._POOL['workers'], lookahead_steps=la,
                        step_ms=[round(1e3*(b - a), 2) for a, b in zip(stamps[max(W-1, 0):W+K-1], stamps[max(W, 1):W+K])],
+                       # wall ms per phase inside each timed step (main thread + the tail thread;
+                       # the callback runs on the tail thread, so a step's row holds the Riccati
+                       # phases of the step that ran beside its tail): where a slow step lost its time
+                       step_phase_ms=[{k: round(1e3*(phase_at[i][k] - phase_at[i-1].get(k, 0.0)), 1)
+                                       for k in phase_at[i]} for i in range(max(W, 1), W+K)],
                        cuda_mallocs_in_timed_region=int(bytes_at[W+K-1][2] - bytes_at[W-1][2]),
                        pinned_pool_segments=(len(dv._SHM['pool'].segs) if dv._SHM['pool'] is not None else 0),
                        main_thread_phase_s_per_step=dict({k: v/(S+la) for k, v in dv.PHASE.items()},
