@@ -973,22 +973,29 @@ _DEFLATION_WARM = set()
 
 
 def _warm_deflation_ops(Z):
-    """The deflation levels below run a handful of torch element-wise kernels that nothing else
-    in this package uses.  CUDA loads a kernel the first time it is launched, out of a library of
-    more than a gigabyte: on a box with a cold page cache that first launch stalled every CUDA
-    call of the process for 50 ms - in the middle of whichever time step first needed a second
-    level (bench.py e2e: one 50-80 ms step in every run).  So they are launched once, on two
-    columns, when the first factor is compressed."""
+    """The deflation levels below run kernels, and need device blocks and workspaces, that the
+    first time steps of a run do not: they start when sigma_max has grown past thresh / DELTA.
+    Whichever time step needed them first paid for it - CUDA loads a kernel on its first launch
+    (torch's element-wise kernels out of a library of more than a gigabyte: 50 ms on a cold page
+    cache), and the factor-sized temporaries and the larger Gram workspace were fresh cudaMallocs
+    (10-13 ms, synchronising) - i.e. one 40-80 ms step in every bench.py e2e run.  So the very
+    first compression of a process runs one deflation step on its own input (a 32-column
+    subspace; results discarded, ~1 ms) and leaves three factor-sized blocks with 50 % headroom
+    in the allocator's cache."""
     _DEFLATION_WARM.add(Z.device.index)
-    z = Z[:, :2].contiguous()
-    sg = torch.from_numpy(np.ones(2)).to(Z.device)
-    q = (z/sg).contiguous()
-    lam = torch.ones(2, dtype=torch.float64, device=Z.device)
-    w = (torch.eye(2, dtype=torch.float64, device=Z.device)/torch.sqrt(lam)).contiguous()
-    r = z - tall_gemm(q, w)
-    torch.cat([z[:, :1], r[:, :1]], dim=1).contiguous()
+    k1 = max(1, min(32, Z.shape[1]//2))
+    z1 = Z[:, :k1].contiguous()
+    sg = torch.from_numpy(np.ones(k1)).to(Z.device)
+    q = (z1/sg).contiguous()
+    lam, wq, _ = sym_eig(gram(q, q))
+    q = tall_gemm(q, (wq/torch.sqrt(lam.abs() + 1.0)).contiguous())
+    z2 = (Z - tall_gemm(q, gram(q, Z))).contiguous()
+    torch.cat([z1, z2[:, :1]], dim=1).contiguous()
     torch.cat([lam[:1], sg[:1]])
     lam.cpu()
+    del z2
+    spare = [torch.empty(int(1.5*Z.numel()), dtype=torch.float64, device=Z.device) for _ in range(3)]
+    del spare
 
 
 def compress(Z, thresh=None, k=None, eta=1e-14, rmax=None, _smax0=None, _level=0):
