@@ -211,6 +211,18 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
         tail_pool = _TPE(max_workers=1, initializer=pru.tail_thread_init())
     tail_state = dict(wc=wc, mtxtb=mtxtb)
     pending_tail = [None]
+    # A full (generation-2) pass of Python's cycle collector walks every object of the process -
+    # millions after importing torch / scipy - with the GIL held: 15-50 ms during which NO Python
+    # thread moves (measured: one time step of every run, always the same one, lost that much in
+    # whichever call happened to be active).  The objects alive now are long-lived; park them in
+    # the permanent generation for the duration of the loop, so that the passes that do happen
+    # only look at what the loop itself created.
+    frozen = False
+    if can_prefetch:
+        import gc
+        gc.collect()
+        gc.freeze()
+        frozen = True
 
     def tail(tk, t, cts, key, pre, Zc, cnsw, cnsmtxtb, info):
         """Feed-forward half of step tk (``solve_dae_ric.py:173-207``)."""
@@ -314,6 +326,8 @@ def solve_flow_daeric(mmat=None, amat=None, jmat=None, bmat=None,
     finally:
         if tail_pool is not None:
             tail_pool.shutdown(wait=True)
+        if frozen:
+            gc.unfreeze()
     if pool is not None:
         pool.shutdown(wait=True)
         sys.setswitchinterval(old_switch)
