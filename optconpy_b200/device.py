@@ -358,18 +358,14 @@ def _pack_flags(wide, k_hint=None):
     per entry - beyond: clusters of 4 take 85 us up to 33 right-hand sides and 118-123 us up to 66,
     clusters of 3 100 us up to 45 and 138-141 us up to 90, clusters of 2 128 us up to 74 and 171 us
     up to 148)."""
-    # k_hint: an estimate of the block width, or (width, True) for a guaranteed upper bound
-    exact = isinstance(k_hint, tuple) and bool(k_hint[1])
-    if isinstance(k_hint, tuple):
-        k_hint = k_hint[0]
     if k_hint is None:
         cl = 0
     elif k_hint <= 33:
         cl = 4
     elif k_hint <= 44:
         cl = 3
-    elif k_hint <= (66 if exact else 60):   # (clusters of 4 fall off a cliff beyond 66 columns -
-        cl = 4                              # 232 us -: an estimate may lag the actual width)
+    elif k_hint <= 60:      # (clusters of 4 fall off a cliff beyond 66 columns - 232 us -: the hint
+        cl = 4              # may lag the actual width by a few columns)
     elif k_hint <= 74:
         cl = 2
     elif k_hint <= 90:

@@ -70,7 +70,7 @@ class StepSetup(object):
         ft_mat = -(0.5*ctx.MT + cts*(ctx.AT + NT))
         khint = (ctx.maxc if ctx.maxc is not None else ctx.Zc.shape[1]) + ctx.tct.shape[1] + ctx.tb.shape[1]
         self.fac = pru.ShiftedFactors(sps.csr_matrix(ft_mat), ctx.MT, ctx.J, ctx.shifts,
-                                      Mt_dev=ctx.Mt_dev, k_hint=(khint, ctx.maxc is not None))
+                                      Mt_dev=ctx.Mt_dev, k_hint=khint)
         at_mat = ctx.MT + cts*(ctx.AT + NT)
         self._at_job = dv.FactorJob([dv.sadpnt_matrix(at_mat, ctx.J)]).start_upload()
         self.ftilde = dv.to_dev(np.asarray(rhsvtd) + ctx.rhsv)
