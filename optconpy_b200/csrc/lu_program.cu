@@ -223,12 +223,23 @@ struct FactorTemplate {
     // inverse at a time into scratch buffers and writes its rows straight away
     std::vector<int32_t> bl_level_ptr;   // block entries of recorded level j
     std::vector<int32_t> bl_block, bl_ptr, bl_x;
-    void index_blocks(int nb);
+    // merged (one-step) blocks: where every stored entry of the block's rows goes - index into the
+    // dense off-block matrix To (>= 0) or into the diagonal block D (-1 - index) -, the width of To
+    // and the column count of every row: all of it depends on the index arrays only
+    std::vector<int64_t> mb_ptr;         // per block entry (kind 2 only; equal neighbours otherwise)
+    std::vector<int32_t> mb_dst;
+    std::vector<int32_t> mb_cu;
+    std::vector<int64_t> mb_ncol_ptr;
+    std::vector<int32_t> mb_ncol;
+    void index_blocks(int nb, const Tri& T, const std::vector<int32_t>& starts);
 };
 
-void FactorTemplate::index_blocks(int nb) {
+void FactorTemplate::index_blocks(int nb, const Tri& T, const std::vector<int32_t>& starts) {
     bl_level_ptr.assign(1, 0);
     bl_ptr.assign(1, 0);
+    mb_ptr.assign(1, 0);
+    mb_ncol_ptr.assign(1, 0);
+    std::vector<int32_t> pos;            // column -> index in the block's column list
     std::vector<int32_t> slot(nb, -1);
     std::vector<std::vector<int32_t>> bucket;
     std::vector<int32_t> order;
@@ -250,6 +261,36 @@ void FactorTemplate::index_blocks(int nb) {
             bl_x.insert(bl_x.end(), bucket[j].begin(), bucket[j].end());
             bl_ptr.push_back((int32_t)bl_x.size());
             slot[order[j]] = -1;
+            int32_t cu = 0;
+            if (rows[bucket[j][0]].kind == 2) {
+                // the same walk as multiply_block: columns in order of first appearance over the
+                // rows in dependency order, then the destination of every stored entry
+                const int32_t r0 = starts[order[j]], r1 = starts[order[j] + 1], w = r1 - r0;
+                if (pos.empty()) pos.assign(T.rp ? (size_t)starts.back() : 0, -1);
+                std::vector<int32_t> cols, ncol(w, 0);
+                for (int kk = 0; kk < w; ++kk) {
+                    const int k = T.upper ? w - 1 - kk : kk;
+                    for (int32_t p = T.rp[r0 + k]; p < T.rp[r0 + k + 1]; ++p) {
+                        const int32_t c = T.ci[p];
+                        if ((c < r0 || c >= r1) && pos[c] < 0) {
+                            pos[c] = (int32_t)cols.size();
+                            cols.push_back(c);
+                        }
+                    }
+                    ncol[k] = (int32_t)cols.size();
+                }
+                cu = (int32_t)cols.size();
+                for (int k = 0; k < w; ++k)
+                    for (int32_t p = T.rp[r0 + k]; p < T.rp[r0 + k + 1]; ++p) {
+                        const int32_t c = T.ci[p];
+                        mb_dst.push_back((c < r0 || c >= r1) ? k * cu + pos[c] : -1 - (k * w + (c - r0)));
+                    }
+                for (int32_t c : cols) pos[c] = -1;
+                mb_ncol.insert(mb_ncol.end(), ncol.begin(), ncol.end());
+            }
+            mb_cu.push_back(cu);
+            mb_ptr.push_back((int64_t)mb_dst.size());
+            mb_ncol_ptr.push_back((int64_t)mb_ncol.size());
         }
         bl_level_ptr.push_back((int32_t)bl_block.size());
     }
@@ -530,15 +571,29 @@ int refill_factor(int64_t n, const Tri& T, const std::vector<int32_t>& starts,
                 invert_block(T, r0, r1, &D, &X);
                 Xm = X.data();
             } else {
-                multiply_block(n, T, r0, r1, &posbuf, &D, &Tbuf, &mb);
+                // multiply_block with the recorded destinations: one pass over the stored entries
+                const int32_t cu_ = rec.mb_cu[bi];
+                const int32_t* dstp = rec.mb_dst.data() + rec.mb_ptr[bi];
+                D.assign((size_t)w * w, 0.0);
+                Tbuf.assign((size_t)w * cu_, 0.0);
+                for (int32_t i = r0; i < r1; ++i)
+                    for (int32_t p = T.rp[i]; p < T.rp[i + 1]; ++p) {
+                        const int32_t d = *dstp++;
+                        if (d >= 0) Tbuf[d] = T.va[p]; else D[-1 - d] = T.va[p];
+                    }
                 for (int j = 0; j < w && !T.unit; ++j)
                     if (D[(size_t)j * w + j] == 0.0) {
                         set_error("the %s factor has a zero pivot in row %d", T.upper ? "upper" : "lower", r0 + j);
                         return OCB_ERR_SINGULAR;
                     }
+                mb.X.assign((size_t)w * w, 0.0);
+                tri_inverse(D.data(), mb.X.data(), w, T.upper, T.unit);
+                mb.Pm.assign((size_t)w * cu_, 0.0);
+                tri_times_dense(mb.X.data(), Tbuf.data(), mb.Pm.data(), w, cu_, T.upper);
+                mb.ncol.assign(rec.mb_ncol.begin() + rec.mb_ncol_ptr[bi], rec.mb_ncol.begin() + rec.mb_ncol_ptr[bi + 1]);
                 Xm = mb.X.data();
             }
-            const size_t cu = mb.cols.size();
+            const size_t cu = kind == 2 ? (size_t)rec.mb_cu[bi] : 0;
             for (int32_t xi = xa; xi < xb; ++xi) {
                 const int32_t x = rec.bl_x[xi];
                 const RowRef& rr = rec.rows[x];
@@ -795,8 +850,8 @@ int build_lu_program(int64_t n, const int32_t* Lrp, const int32_t* Lci, const do
         g_inv_ms = 0.0;
     }
     if (rc == OCB_OK && tmpl) {
-        tmpl->recL.index_blocks((int)starts.size() - 1);
-        tmpl->recU.index_blocks((int)starts.size() - 1);
+        tmpl->recL.index_blocks((int)starts.size() - 1, TL, starts);
+        tmpl->recU.index_blocks((int)starts.size() - 1, TU, starts);
         tmpl->starts = starts;
         tmpl->planL = planL;
         tmpl->planU = planU;
