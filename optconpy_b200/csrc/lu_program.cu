@@ -1023,23 +1023,18 @@ void execute_program_host(const LuProgram& P, const int32_t* perm_r, const int32
         for (int32_t s = P.sub_ptr[sb]; s < P.sub_ptr[sb + 1]; ++s) {
             const Slice& sl = P.slices[s];
             const int g = sl.glog_nrows & 255, nr = sl.glog_nrows >> 8, G = 1 << g;
+            // the 32 lanes of the slice side by side, as the warp does it (padding entries are
+            // val = 0, col = 0): a fixed-width inner loop instead of one short loop per row
+            double lane[32];
+            for (int l = 0; l < 32; ++l) lane[l] = 0.0;
+            const double* v = P.val.data() + sl.ebase;
+            const int32_t* c = P.col.data() + sl.ebase;
+            for (int u = 0; u < sl.trips; ++u, v += 32, c += 32)
+                for (int l = 0; l < 32; ++l) lane[l] = fma(v[l], xe[c[l]], lane[l]);
             for (int r = 0; r < nr; ++r) {
                 const int32_t q = sl.q0 + r;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four chains: the gathers overlap
-                for (int u = 0; u < sl.trips; ++u) {
-                    const size_t base = (size_t)sl.ebase + ((size_t)u << 5) + ((size_t)r << g);
-                    const double* v = P.val.data() + base;
-                    const int32_t* c = P.col.data() + base;
-                    int l = 0;
-                    for (; l + 4 <= G; l += 4) {
-                        a0 = fma(v[l], xe[c[l]], a0);
-                        a1 = fma(v[l + 1], xe[c[l + 1]], a1);
-                        a2 = fma(v[l + 2], xe[c[l + 2]], a2);
-                        a3 = fma(v[l + 3], xe[c[l + 3]], a3);
-                    }
-                    for (; l < G; ++l) a0 = fma(v[l], xe[c[l]], a0);
-                }
-                const double acc = (a0 + a1) + (a2 + a3);
+                double acc = 0.0;
+                for (int l = 0; l < G; ++l) acc += lane[(r << g) + l];
                 const double ini = P.init[q] >= 0 ? xe[P.init[q]] : 0.0;
                 out.push_back((ini - acc) * P.scale[q]);
             }
