@@ -327,3 +327,59 @@ def test_nested_dissection_orders_every_node_once_and_flattens_the_tree(cav10):
         info = _program(arrs, n, flags=6)[0]
         levels[which] = (info['nsub_L'] + info['nsub_U'], len(arrs[1]) + len(arrs[4]))
     assert levels['nd'][0] <= 0.6*levels['mmd'][0] and levels['nd'][1] <= 1.25*levels['mmd'][1], levels   # (N=10: +15 % fill; N=25: -14 %, N=50: -24 %)
+
+
+def test_random_patterns_and_pivot_orders_property():
+    """Property test (hypothesis): for random sparse patterns, random row / column permutations
+    that put a dominant entry on every pivot position, and random values, the numeric-only
+    factorisation reproduces ``P A Q`` and solves ``A x = b``; a second matrix with the same
+    pattern reuses the handle."""
+    hyp = pytest.importorskip('hypothesis')
+    st = pytest.importorskip('hypothesis.strategies')
+
+    @hyp.settings(max_examples=25, deadline=None)
+    @hyp.given(n=st.integers(2, 60), dens=st.floats(0.02, 0.5), seed=st.integers(0, 10**6))
+    def check(n, dens, seed):
+        rng = np.random.default_rng(seed)
+        S = sps.random(n, n, density=dens, format='coo', random_state=seed)
+        pr, pc = rng.permutation(n).astype(np.int32), rng.permutation(n).astype(np.int32)
+        # pivot positions: entry (i, j) of A lands on the diagonal of P A Q iff pr[i] == pc[j]
+        inv_pc = np.empty(n, dtype=np.int64)
+        inv_pc[pc] = np.arange(n)
+        rows = np.arange(n)
+        cols = inv_pc[pr[rows]]
+        mats = []
+        for rep in range(2):
+            vals = rng.standard_normal(S.nnz)
+            A = sps.coo_matrix((vals, (S.row, S.col)), shape=(n, n)).tocsc()
+            A = A + sps.coo_matrix((np.full(n, 2.0 + abs(vals).sum()), (rows, cols)), shape=(n, n)).tocsc()
+            mats.append(_csc(A))
+        assert np.array_equal(mats[0].indices, mats[1].indices)
+        rf = _lu_worker._Refactor(n, mats[0].indptr, mats[0].indices, pr, pc)
+        for A in mats:
+            L, U, qr, qc = _lu_of(rf, A)
+            Cm = _permuted(A, qr, qc)
+            assert abs(L @ U - Cm).max() <= 1e-12*abs(Cm).max()
+            b = rng.standard_normal(n)
+            y = np.empty(n)
+            y[qr] = b
+            z = spsla.spsolve_triangular(sps.csr_matrix(U), spsla.spsolve_triangular(
+                sps.csr_matrix(L), y, lower=True, unit_diagonal=True), lower=False)
+            assert np.linalg.norm(A @ z[qc] - b) <= 1e-10*np.linalg.norm(b)
+    check()
+
+
+def test_nested_dissection_random_graphs_property():
+    """Property test: whatever the (symmetric) graph and the leaf size, ``ocb_order_nd`` returns a
+    permutation, and it is deterministic."""
+    hyp = pytest.importorskip('hypothesis')
+    st = pytest.importorskip('hypothesis.strategies')
+
+    @hyp.settings(max_examples=40, deadline=None)
+    @hyp.given(n=st.integers(1, 400), dens=st.floats(0.0, 0.2), leaf=st.integers(1, 64), seed=st.integers(0, 10**6))
+    def check(n, dens, leaf, seed):
+        S = sps.random(n, n, density=dens, format='csr', random_state=seed)
+        G = ((S + S.T) != 0).astype(np.float64).tocsr()
+        q1, q2 = _nd(G, leaf), _nd(G, leaf)
+        assert np.array_equal(np.sort(q1), np.arange(n)) and np.array_equal(q1, q2)
+    check()
