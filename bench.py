@@ -51,11 +51,14 @@ def _config(N):
                 NP=(N+1)**2-1,
                 parallelism='independent DRE replica per GPU',
                 l2_policy='no flush: every timed step works on inputs that were never touched '
-                          'before - its own 8 factor images (~75 MB, uploaded during setup) and a '
+                          'before - its own 8 factor images (~64 MB, uploaded during setup) and a '
                           'new 40-60 MB factor Z - so each step starts cold in L2; re-reading the '
                           '7 shifted factors out of L2 across the ~80 ADI iterations WITHIN a step '
                           'is the reuse the algorithm has',
-                lu_setup='host SuperLU (MMD_AT_PLUS_A, symmetric mode) in worker processes, timed separately')
+                lu_setup='host, in worker processes, timed separately: nested-dissection ordering and one '
+                         'SuperLU run (pivot order) per sparsity pattern, then a numeric-only multifrontal '
+                         'factorisation with those static pivots per matrix, residual guard with SuperLU '
+                         '(symmetric mode, diag_pivot_thresh 0.01) as fall-back')
 
 
 class ClockSampler(object):
