@@ -187,6 +187,12 @@ int ocb_lu_program_solve_host(const ocb_lu_program* prog, const int32_t* h_perm_
  * bound by the height of the elimination tree, which this ordering halves. */
 int ocb_order_nd(int64_t n, const int32_t* h_adj_rowptr, const int32_t* h_adj_colidx, int64_t leaf,
                  int32_t* h_order_out);
+/* Saddle-point constraint on an elimination order: nodes with a zero diagonal (h_diag_is_zero[v] != 0: the
+ * pressure block of [[A, J^T], [J, 0]]) are delayed until right after their first neighbour with a
+ * non-zero diagonal, so that their pivot is the Schur-complement entry and never an exact zero. */
+int ocb_order_delay_zero_diagonals(int64_t n, const int32_t* h_adj_rowptr, const int32_t* h_adj_colidx,
+                                   const uint8_t* h_diag_is_zero, const int32_t* h_order_in,
+                                   int32_t* h_order_out);
 typedef struct ocb_refactor ocb_refactor;
 int ocb_refactor_create(ocb_refactor** out, int64_t n, const int32_t* h_A_colptr, const int32_t* h_A_rowidx,
                         const int32_t* h_perm_r, const int32_t* h_perm_c);

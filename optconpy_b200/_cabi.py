@@ -39,6 +39,7 @@ PROTOTYPES = {
     'ocb_lu_program_solve_host': (C.c_int, [vp, vp, vp, vp, vp, i64, C.c_double, C.POINTER(i64)]),
     'ocb_lu_program_export': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     'ocb_order_nd': (C.c_int, [i64, vp, vp, i64, vp]),
+    'ocb_order_delay_zero_diagonals': (C.c_int, [i64, vp, vp, vp, vp, vp]),
     'ocb_refactor_create': (C.c_int, [C.POINTER(vp), i64, vp, vp, vp, vp]),
     'ocb_refactor_destroy': (C.c_int, [vp]),
     'ocb_refactor_info': (C.c_int, [vp, C.POINTER(i64)]),

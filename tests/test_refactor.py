@@ -383,3 +383,37 @@ def test_nested_dissection_random_graphs_property():
         q1, q2 = _nd(G, leaf), _nd(G, leaf)
         assert np.array_equal(np.sort(q1), np.arange(n)) and np.array_equal(q1, q2)
     check()
+
+
+def test_zero_diagonal_delay_matches_the_python_statement(cav10):
+    """``ocb_order_delay_zero_diagonals`` (used by ``order_only``) against the Python statement of
+    the rule, ``_lu_worker._delay_zero_diagonals``, on the saddle-point pattern and random orders;
+    every pressure node ends up right after a velocity neighbour or at the end."""
+    lib = _cabi.load()
+    K = sps.csr_matrix(_shifted(cav10, 2e-3, -1.0))
+    n = K.shape[0]
+    P = sps.csr_matrix((np.ones(K.nnz), K.indices, K.indptr), shape=K.shape)
+    P = ((P + P.T) != 0).astype(np.float64).tocsr()
+    P.setdiag(0.0)
+    P.eliminate_zeros()
+    P.sort_indices()
+    ip, ii = P.indptr.astype(np.int32), P.indices.astype(np.int32)
+    dz = (K.diagonal() == 0.0)
+    assert dz.any() and not dz.all()
+    dz8 = np.ascontiguousarray(dz, dtype=np.uint8)
+    for seed in range(4):
+        q = np.random.default_rng(seed).permutation(n).astype(np.int32)
+        ref = _lu_worker._delay_zero_diagonals(ip, ii, dz, q)
+        out = np.empty(n, dtype=np.int32)
+        _cabi.check(lib.ocb_order_delay_zero_diagonals(n, ip.ctypes.data, ii.ctypes.data, dz8.ctypes.data,
+                                                       q.ctypes.data, out.ctypes.data), 'delay')
+        assert np.array_equal(ref, out)
+        pos = np.empty(n, dtype=np.int64)
+        pos[out] = np.arange(n)
+        for v in np.flatnonzero(dz)[:50]:
+            nb = ii[ip[v]:ip[v+1]]
+            nb = nb[~dz[nb]]
+            assert nb.size == 0 or pos[nb].min() < pos[v]       # a velocity neighbour goes first
+    bad = np.zeros(n, dtype=np.int32)
+    assert lib.ocb_order_delay_zero_diagonals(n, ip.ctypes.data, ii.ctypes.data, dz8.ctypes.data,
+                                              bad.ctypes.data, out.ctypes.data) == -1
