@@ -667,7 +667,14 @@ def main():
                 stamps.append(time.perf_counter())
                 bytes_at.append((dv.STATS['h2d_bytes'], dv.STATS['d2h_bytes'],
                                  torch.cuda.memory_stats().get('num_device_alloc', 0)))
-                phase_at.append(dict(dv.PHASE, **stimes))
+                for _ in range(3):      # (called on the stepper's tail thread; the main thread may be adding a key)
+                    try:
+                        phase_at.append(dict(dv.PHASE, **stimes))
+                        break
+                    except RuntimeError:
+                        continue
+                else:
+                    phase_at.append(dict(phase_at[-1]) if phase_at else {})
             dv.reset_stats()
             barrier()
             if args.phases:
